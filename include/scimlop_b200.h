@@ -1,0 +1,202 @@
+/* scimlop_b200.h -- C ABI of libscimlop_b200.so, the B200-native evaluation backend for the cached
+ * in-place `mul!` path of SciMLOperators.jl (TensorProductOperator and Added/Composed/Scaled trees
+ * over Matrix/Diagonal/BatchedDiagonal/Identity/Null operators).
+ *
+ * Conventions:
+ *   - every array pointer is a DEVICE pointer unless the function name ends in `_host`;
+ *   - all matrices are column-major with explicit leading dimensions (in elements);
+ *   - `alpha`/`beta` are HOST pointers to one scalar of the operand dtype; `beta == NULL` or `*beta == 0`
+ *     means "3-arg mul!": W is overwritten and never read (src/batch.jl:222-223, src/basic.jl:251,521,
+ *     BLAS convention at src/matrix.jl:349); `alpha == NULL` means 1;
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*); nothing allocates;
+ *     scratch is caller-owned (`*_workspace_bytes` says how much) -- mirrors `cache_operator`
+ *     allocating once and `mul!` being allocation-free (test/Downstream/alloccheck.jl);
+ *   - every function returns an int status (SCIMLOP_OK == 0); no exception crosses the boundary;
+ *   - a handle is per device and is not thread-safe, like a cached operator's scratch
+ *     (src/SciMLOperators.jl:131-132).
+ *
+ * The reference is pure Julia and has no FFI of its own; each entry point below names the reference
+ * method whose body it replaces (file:line under the SciMLOperators.jl tree).  INTEGRATION.md shows the
+ * `ccall` stubs of the package extension that binds them.
+ */
+#ifndef SCIMLOP_B200_H
+#define SCIMLOP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCIMLOP_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ------------------------------------------------------------------------------ */
+enum {
+  SCIMLOP_OK = 0,
+  SCIMLOP_ERR_NULL_POINTER = 1,  /* a required pointer is NULL */
+  SCIMLOP_ERR_BAD_SHAPE = 2,     /* negative size, ld < rows, inconsistent factor dims (the @assert's) */
+  SCIMLOP_ERR_WORKSPACE = 3,     /* workspace missing or too small (`@assert iscached(L)`, tensor.jl:548) */
+  SCIMLOP_ERR_UNSUPPORTED = 4,   /* dtype / precision / factor kind not supported */
+  SCIMLOP_ERR_CUDA = 5,          /* a CUDA runtime/driver call failed; see scimlop_last_error */
+  SCIMLOP_ERR_NCCL = 6,          /* NCCL missing or a collective failed */
+  SCIMLOP_ERR_BAD_HANDLE = 7,
+  SCIMLOP_ERR_NO_DEVICE = 8      /* no usable sm_100 device: there is NO CPU fallback */
+};
+
+/* ---- element types & precision modes ------------------------------------------------------------- */
+enum { SCIMLOP_F64 = 0, SCIMLOP_F32 = 1 };
+enum {
+  SCIMLOP_PREC_DEFAULT = 0, /* F64: DMMA (mma.sync f64) tensor path; F32: exact-FP32 FFMA path     */
+  SCIMLOP_PREC_TF32X3 = 1,  /* F32 only, opt-in: 3xTF32 split on tensor cores (rel. err <= 1e-5)   */
+  SCIMLOP_PREC_TF32 = 2     /* F32 only, opt-in: single-pass TF32 (rel. err ~1e-3)                 */
+};
+
+/* ---- factor kinds (kron factors and tree leaves) --------------------------------------------------- */
+enum {
+  SCIMLOP_DENSE = 0,    /* MatrixOperator over a dense matrix            src/matrix.jl:116-133        */
+  SCIMLOP_IDENTITY = 1, /* IdentityOperator                              src/basic.jl:28-30           */
+  SCIMLOP_DIAG = 2,     /* DiagonalOperator(::Vector): data = n entries  src/matrix.jl:438-459        */
+  SCIMLOP_BDIAG = 3,    /* BatchedDiagonalOperator: data = n x k, ld     src/batch.jl:11-28           */
+  SCIMLOP_NULL = 4      /* NullOperator                                  src/basic.jl:185-188         */
+};
+/* OR-ed into a kron factor kind: the factor is the lazy adjoint/transpose of the stored matrix
+ * (`adjoint(::MatrixOperator)` wraps the array, src/matrix.jl:174-175; TPO adjoint maps over factors,
+ * src/tensor.jl:181-191).  dims[] are those of the OPERATOR; the stored matrix is cols x rows. */
+#define SCIMLOP_TRANS 0x100
+
+typedef struct scimlop_context* scimlop_handle_t;
+
+/* ---- handle ------------------------------------------------------------------------------------------ */
+int scimlop_version(void);
+const char* scimlop_status_string(int status);
+/* Binds the handle to CUDA device `device`; fails with SCIMLOP_ERR_NO_DEVICE unless it is sm_100. */
+int scimlop_create(scimlop_handle_t* out, int device);
+int scimlop_destroy(scimlop_handle_t h);
+/* Copies the text of the last failure recorded on `h` (empty string if none). */
+int scimlop_last_error(scimlop_handle_t h, char* buf, size_t len);
+/* Number of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
+int scimlop_launch_count(scimlop_handle_t h, int64_t* count);
+
+/* ---- leaves ---------------------------------------------------------------------------------------- */
+/* MatrixOperator mul!: W(m x k) = alpha * op(A) * V(n x k) + beta * W.    Replaces src/matrix.jl:337-350
+ * (`mul!(w, L.A, v[, α, β])` -> BLAS gemm!); transA != 0 is the lazy Adjoint/Transpose wrapper that
+ * `adjoint(::MatrixOperator)` of a constant operator builds (src/matrix.jl:174-175): op(A) = A^T with A
+ * stored n x m. */
+int scimlop_matmul(scimlop_handle_t h, int dtype, int precision, int transA, int64_t m, int64_t n,
+                   int64_t k, const void* A, int64_t lda, const void* V, int64_t ldv, void* W,
+                   int64_t ldw, const void* alpha, const void* beta, void* stream);
+
+/* Strided-batched GEMM engine: C_b(M x N) = alpha * op(A_b)(M x K) * op(B_b)(K x N) + beta * C_b,
+ * b = 0..batch-1, operand b at base + b*stride (elements; stride 0 = shared operand).  This is what the
+ * extension binds for `mul!(::DevMat, ::DevMat, ::DevMat, α, β)` and the transposed-destination form
+ * src/matrix.jl:354-361. */
+int scimlop_gemm_strided_batched(scimlop_handle_t h, int dtype, int precision, int transA, int transB,
+                                 int64_t M, int64_t N, int64_t K, const void* alpha, const void* A,
+                                 int64_t lda, int64_t strideA, const void* B, int64_t ldb,
+                                 int64_t strideB, const void* beta, void* C, int64_t ldc,
+                                 int64_t strideC, int64_t batch, void* stream);
+
+/* Diagonal / batched-diagonal mul!: W(n x k) = alpha * (d .* V) + beta * W.  ldd == 0: d has n entries
+ * broadcast along the k columns (stdlib Diagonal mul!, src/matrix.jl:340,349 with A::Diagonal);
+ * ldd >= n: d is n x k (src/batch.jl:151-179, call forms :203-228). */
+int scimlop_diag_mul(scimlop_handle_t h, int dtype, int64_t n, int64_t k, const void* d, int64_t ldd,
+                     const void* V, int64_t ldv, void* W, int64_t ldw, const void* alpha,
+                     const void* beta, void* stream);
+
+/* Identity / Null mul!: W(n x k) = alpha * V + beta * W   (src/basic.jl:74-90); V == NULL gives the
+ * NullOperator form W = beta * W with a strong zero for beta == 0 (src/basic.jl:248-264). */
+int scimlop_axpby(scimlop_handle_t h, int dtype, int64_t n, int64_t k, const void* V, int64_t ldv,
+                  void* W, int64_t ldw, const void* alpha, const void* beta, void* stream);
+
+/* ---- TensorProductOperator ------------------------------------------------------------------------- */
+/* Scratch needed by scimlop_kron_mul for these factors and k columns (replaces the 7-slot cache tuple of
+ * `cache_self`, src/tensor.jl:460-518: at most two ping-pong buffers, none when <= 1 factor is
+ * non-identity).  dims[2*f] = rows, dims[2*f+1] = cols of factor f, outermost factor first. */
+int scimlop_kron_workspace_bytes(int dtype, int nfactors, const int64_t* dims, const int32_t* kinds,
+                                 int64_t k, size_t* bytes);
+
+/* W(prod rows x k) = alpha * (F_1 (x) F_2 (x) ... (x) F_n) * V(prod cols x k) + beta * W.
+ * Replaces `mul!(w, L::TensorProductOperator, v[, α, β])` src/tensor.jl:543-574 / :576-610 including
+ * `outer_mul!` :750-834 and the right-fold nesting of the N-ary constructor (:121).  factors[f] is a
+ * dense rows x cols matrix (lds[f] >= rows), a length-rows diagonal (SCIMLOP_DIAG) or ignored
+ * (SCIMLOP_IDENTITY).  1 <= nfactors <= 8. */
+int scimlop_kron_mul(scimlop_handle_t h, int dtype, int precision, int nfactors,
+                     const void* const* factors, const int64_t* dims, const int64_t* lds,
+                     const int32_t* kinds, const void* V, int64_t ldv, void* W, int64_t ldw, int64_t k,
+                     const void* alpha, const void* beta, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* The reference's own plugin hook, same contract: W[i,m,j] = sum_o A[m,o] * C[i,o,j]  (then
+ * alpha*acc + beta*W[i,m,j]); W is (mi*mo) x k, C is (mi*no) x k, A is mo x no.
+ * Replaces `tensor_outer_mul_fast!(w, outer, C, mi, mo, no, k[, α, β])` src/tensor.jl:719, implemented
+ * today by ext/SciMLOperatorsLoopVectorizationExt.jl:10-44. */
+int scimlop_outer_mul_fast(scimlop_handle_t h, int dtype, int precision, void* W, const void* A,
+                           int64_t lda, const void* C, int64_t mi, int64_t mo, int64_t no, int64_t k,
+                           const void* alpha, const void* beta, void* stream);
+
+/* TensorSumOperator / kron(A,I) + kron(I,B):  W_j(mi x mo) = alpha*(B*V_j + V_j*A^T) + beta*W_j for
+ * every column j, V_j = reshape(V[:,j], mi, mo); A is mo x mo (outer), B is mi x mi (inner).
+ * Replaces src/tensor.jl:387-403 (and the AddedOperator of two TPOs of config 5). No workspace. */
+int scimlop_kronsum_mul(scimlop_handle_t h, int dtype, int precision, const void* A, int64_t lda,
+                        int64_t mo, const void* B, int64_t ldb, int64_t mi, const void* V, int64_t ldv,
+                        void* W, int64_t ldw, int64_t k, const void* alpha, const void* beta,
+                        void* stream);
+
+/* ---- operator trees --------------------------------------------------------------------------------- */
+/* A tree is handed over flattened (the host does what src/basic.jl:619-635 does for sums and :936-939
+ * for products): a sum of terms, each term = scale * f_1 * f_2 * ... * f_n (applied right to left). */
+typedef struct {
+  int32_t kind;     /* SCIMLOP_DENSE / IDENTITY / DIAG / BDIAG / NULL */
+  int32_t trans;    /* DENSE only: apply data^T (data stored cols x rows)  */
+  const void* data; /* device pointer (NULL for IDENTITY / NULL)          */
+  int64_t ld;       /* DENSE: leading dim; BDIAG: leading dim of the n x k diagonal; else ignored */
+  int64_t rows;     /* operator rows    */
+  int64_t cols;     /* operator columns */
+} scimlop_factor_t;
+
+typedef struct {
+  double scale; /* product of the ScaledOperator λ's above this term (src/basic.jl:518-536) */
+  int32_t nfactors;
+  const scimlop_factor_t* factors; /* host array, leftmost factor first */
+} scimlop_term_t;
+
+int scimlop_tree_workspace_bytes(int dtype, const scimlop_term_t* terms, int nterms, int64_t k,
+                                 size_t* bytes);
+
+/* W(rows x k) = alpha * (sum_t scale_t * prod_f factor_{t,f}) * V + beta * W.
+ * Replaces `mul!(w, ::AddedOperator, v[, α, β])` src/basic.jl:834-854, `::ComposedOperator`
+ * :1160-1207, `::ScaledOperator` :518-536 and the leaves they recurse into, in one pass over W for the
+ * elementwise terms plus one fused-epilogue GEMM per dense term. */
+int scimlop_tree_mul(scimlop_handle_t h, int dtype, int precision, const scimlop_term_t* terms,
+                     int nterms, const void* V, int64_t ldv, void* W, int64_t ldw, int64_t k,
+                     const void* alpha, const void* beta, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ---- host-buffer entry (end-to-end path) ------------------------------------------------------------- */
+/* Same as scimlop_kron_mul but V, W and the factors live in (ideally pinned) HOST memory: columns are
+ * streamed through the device in chunks of `chunk_cols` (0 = library default) with H2D copy, compute and
+ * D2H copy overlapped on three streams.  Device staging is owned by the handle and grown on demand
+ * (first call allocates; later calls of the same shape do not).  Blocks until W is complete. */
+int scimlop_kron_mul_host(scimlop_handle_t h, int dtype, int precision, int nfactors,
+                          const void* const* factors, const int64_t* dims, const int64_t* lds,
+                          const int32_t* kinds, const void* V, int64_t ldv, void* W, int64_t ldw,
+                          int64_t k, const void* alpha, const void* beta, int64_t chunk_cols);
+
+/* ---- multi-GPU: column sharding ---------------------------------------------------- */
+/* Columns [first, first+count) of a k-column batch owned by `rank` of `nranks` (contiguous slabs). */
+int scimlop_shard_columns(int64_t k, int nranks, int rank, int64_t* first, int64_t* count);
+/* NCCL communicator over one process per GPU.  `unique_id` is the 128-byte ncclUniqueId produced by
+ * scimlop_comm_unique_id on rank 0 and broadcast by the caller (torch.distributed / MPI / Julia Distributed). */
+int scimlop_comm_unique_id(void* unique_id_128B);
+int scimlop_comm_init(scimlop_handle_t h, int nranks, int rank, const void* unique_id_128B);
+int scimlop_comm_destroy(scimlop_handle_t h);
+/* In-place all-gather of equal column slabs: W_full is rows x (cols_per_rank*nranks) with ld == rows;
+ * rank r's slab already sits at column r*cols_per_rank.  Only used when the caller wants a replicated W. */
+int scimlop_allgather_cols(scimlop_handle_t h, int dtype, void* W_full, int64_t rows,
+                           int64_t cols_per_rank, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCIMLOP_B200_H */

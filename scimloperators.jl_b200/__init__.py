@@ -1,0 +1,16 @@
+"""scimloperators.jl_b200 -- B200-native evaluation backend for the cached in-place `mul!` path of
+SciMLOperators.jl (TensorProductOperator and Added/Composed/Scaled operator trees).
+
+The product is `libscimlop_b200.so` (csrc/, C ABI in include/scimlop_b200.h); this package is the host-side
+mirror of the reference's operator interface over that ABI.  The directory name contains a dot, so import it
+through the `scimlop_b200` shim at the repo root (`import scimlop_b200 as sb`)."""
+from . import _lib
+from ._lib import Handle, ScimlopError, handle, load
+from .array import DeviceArray
+from .operators import (AbstractSciMLOperator, AddedOperator, BatchedDiagonalOperator, ComposedOperator,
+                        DiagonalOperator, IdentityOperator, MatrixOperator, NullOperator, ScalarOperator,
+                        ScaledOperator, TensorProductOperator, TensorSumOperator, cache_operator, iscached, kron,
+                        kronsum, mul_, update_coefficients_)
+from .distributed import ColumnShard, allgather_cols, shard_columns
+
+__all__ = [n for n in dir() if not n.startswith("_")]

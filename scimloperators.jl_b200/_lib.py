@@ -1,0 +1,140 @@
+"""ctypes binding of libscimlop_b200.so (include/scimlop_b200.h) -- the same entry points the Julia package
+extension `ccall`s.  There is no CPU fallback: if the shared library is missing, or no
+sm_100 GPU is present when a handle is requested, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libscimlop_b200.so")
+
+# enums of include/scimlop_b200.h
+OK = 0
+ERR_NULL_POINTER, ERR_BAD_SHAPE, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_BAD_HANDLE, ERR_NO_DEVICE = range(1, 9)
+F64, F32 = 0, 1
+PREC_DEFAULT, PREC_TF32X3, PREC_TF32 = 0, 1, 2
+DENSE, IDENTITY, DIAG, BDIAG, NULL = 0, 1, 2, 3, 4
+TRANS = 0x100
+
+
+class Factor(C.Structure):  # scimlop_factor_t
+    _fields_ = [("kind", C.c_int32), ("trans", C.c_int32), ("data", C.c_void_p), ("ld", C.c_int64),
+                ("rows", C.c_int64), ("cols", C.c_int64)]
+
+
+class Term(C.Structure):  # scimlop_term_t
+    _fields_ = [("scale", C.c_double), ("nfactors", C.c_int32), ("factors", C.POINTER(Factor))]
+
+
+class ScimlopError(RuntimeError):
+    def __init__(self, status, where, detail=""):
+        self.status = status
+        super().__init__(f"{where}: status {status} ({status_string(status)})" + (f": {detail}" if detail else ""))
+
+
+_P, _I64, _I32, _INT, _SZ = C.c_void_p, C.c_int64, C.c_int32, C.c_int, C.c_size_t
+_I64P, _I32P = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+
+# name -> argtypes; every function returns int except scimlop_status_string
+SIGNATURES = {
+    "scimlop_version": [],
+    "scimlop_status_string": [_INT],
+    "scimlop_create": [C.POINTER(_P), _INT],
+    "scimlop_destroy": [_P],
+    "scimlop_last_error": [_P, C.c_char_p, _SZ],
+    "scimlop_launch_count": [_P, _I64P],
+    "scimlop_matmul": [_P, _INT, _INT, _INT, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P],
+    "scimlop_gemm_strided_batched": [_P, _INT, _INT, _INT, _INT, _I64, _I64, _I64, _P, _P, _I64, _I64, _P, _I64,
+                                     _I64, _P, _P, _I64, _I64, _I64, _P],
+    "scimlop_diag_mul": [_P, _INT, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P],
+    "scimlop_axpby": [_P, _INT, _I64, _I64, _P, _I64, _P, _I64, _P, _P, _P],
+    "scimlop_kron_workspace_bytes": [_INT, _INT, _I64P, _I32P, _I64, C.POINTER(_SZ)],
+    "scimlop_kron_mul": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _I64, _P, _I64, _I64, _P,
+                         _P, _P, _SZ, _P],
+    "scimlop_outer_mul_fast": [_P, _INT, _INT, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P],
+    "scimlop_kronsum_mul": [_P, _INT, _INT, _P, _I64, _I64, _P, _I64, _I64, _P, _I64, _P, _I64, _I64, _P, _P, _P],
+    "scimlop_tree_workspace_bytes": [_INT, C.POINTER(Term), _INT, _I64, C.POINTER(_SZ)],
+    "scimlop_tree_mul": [_P, _INT, _INT, C.POINTER(Term), _INT, _P, _I64, _P, _I64, _I64, _P, _P, _P, _SZ, _P],
+    "scimlop_kron_mul_host": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _I64, _P, _I64, _I64,
+                              _P, _P, _I64],
+    "scimlop_shard_columns": [_I64, _INT, _INT, _I64P, _I64P],
+    "scimlop_comm_unique_id": [_P],
+    "scimlop_comm_init": [_P, _INT, _INT, _P],
+    "scimlop_comm_destroy": [_P],
+    "scimlop_allgather_cols": [_P, _INT, _P, _I64, _I64, _P],
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the shared library and declare every entry point of the header. Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = header and library disagree
+            fn.argtypes = args
+            fn.restype = C.c_char_p if name == "scimlop_status_string" else C.c_int
+        _lib = lib
+    return _lib
+
+
+def status_string(status):
+    return load().scimlop_status_string(int(status)).decode()
+
+
+class Handle:
+    """Per-device library handle (scimlop_create / scimlop_destroy)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self._h = _P()
+        rc = self.lib.scimlop_create(C.byref(self._h), int(device))
+        if rc != OK:
+            raise ScimlopError(rc, "scimlop_create")
+        self.device = int(device)
+
+    @property
+    def ptr(self):
+        return self._h
+
+    def check(self, rc, where):
+        if rc != OK:
+            buf = C.create_string_buffer(512)
+            self.lib.scimlop_last_error(self._h, buf, 512)
+            raise ScimlopError(rc, where, buf.value.decode(errors="replace"))
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        self.check(self.lib.scimlop_launch_count(self._h, C.byref(n)), "scimlop_launch_count")
+        return n.value
+
+    def close(self):
+        if self._h:
+            self.lib.scimlop_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_handles = {}
+
+
+def handle(device=None):
+    """The process-wide handle of a CUDA device (default: torch's current device)."""
+    if device is None:
+        import torch
+        device = torch.cuda.current_device()
+    device = int(device)
+    if device not in _handles:
+        _handles[device] = Handle(device)
+    return _handles[device]

@@ -1,0 +1,79 @@
+// context.h -- library handle and error plumbing shared by the translation units of libscimlop_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/scimlop_b200.h"
+
+typedef CUresult (*scimlop_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                            const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                            const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                            CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+constexpr int SCIMLOP_HOST_SLOTS = 3;
+
+struct scimlop_context {
+  uint32_t magic;
+  int device;
+  int sm_count;
+  scimlop_encode_tiled_fn encode_tiled;
+  char last_error[512];
+  int64_t launches;
+
+  // ---- host-streaming state (scimlop_kron_mul_host) ----
+  cudaStream_t s_h2d, s_comp, s_d2h;
+  cudaEvent_t ev_h2d[SCIMLOP_HOST_SLOTS], ev_comp[SCIMLOP_HOST_SLOTS], ev_d2h[SCIMLOP_HOST_SLOTS];
+  bool host_streams_ready;
+  void* stage;  // one device allocation carved into V/W slots, factors and workspace
+  size_t stage_bytes;
+
+  // ---- NCCL (loaded with dlopen on first use) ----
+  void* nccl_lib;
+  void* nccl_comm;
+  int nranks, rank;
+};
+
+constexpr uint32_t SCIMLOP_MAGIC = 0x5C1B200u;
+
+inline int scimlop_fail(scimlop_context* c, int status, const char* fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->last_error, sizeof(c->last_error), fmt, ap);
+    va_end(ap);
+  }
+  return status;
+}
+
+#define SCIMLOP_CUDA(c, call)                                                                      \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return scimlop_fail((c), SCIMLOP_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                   \
+                          cudaGetErrorString(e__), __FILE__, __LINE__);                            \
+  } while (0)
+
+// RAII: make the handle's device current for the duration of a call.
+struct scimlop_device_guard {
+  int prev = -1;
+  bool switched = false;
+  explicit scimlop_device_guard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~scimlop_device_guard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+inline bool scimlop_valid(scimlop_context* c) { return c && c->magic == SCIMLOP_MAGIC; }
+
+// internal entry shared between scimlop.cu and extras.cu
+int scimlop_kron_mul_impl(scimlop_context* c, int dtype, int precision, int nfactors,
+                          const void* const* factors, const int64_t* dims, const int64_t* lds,
+                          const int32_t* kinds, const void* V, int64_t ldv, void* W, int64_t ldw, int64_t k,
+                          const void* alpha, const void* beta, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream);

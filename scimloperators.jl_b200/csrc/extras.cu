@@ -1,0 +1,235 @@
+// extras.cu -- handle teardown, the host-buffer (end-to-end) entry point and the optional NCCL all-gather.
+//
+// scimlop_kron_mul_host streams the columns of V through the device in chunks (H2D copy, the kron kernels
+// and the D2H copy of the previous chunks overlap on three streams): columns are independent units of the
+// operator (src/SciMLOperators.jl:177-198), so chunking is exact.
+#include <dlfcn.h>
+
+#include <algorithm>
+
+#include "context.h"
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int ensure_host_streams(scimlop_context* c) {
+  if (c->host_streams_ready) return SCIMLOP_OK;
+  SCIMLOP_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  SCIMLOP_CUDA(c, cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+  SCIMLOP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < SCIMLOP_HOST_SLOTS; i++) {
+    SCIMLOP_CUDA(c, cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+    SCIMLOP_CUDA(c, cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+    SCIMLOP_CUDA(c, cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+  }
+  c->host_streams_ready = true;
+  return SCIMLOP_OK;
+}
+
+}  // namespace
+
+extern "C" int scimlop_kron_mul_host(scimlop_handle_t h, int dtype, int precision, int nfactors,
+                                     const void* const* factors, const int64_t* dims, const int64_t* lds,
+                                     const int32_t* kinds, const void* V, int64_t ldv, void* W, int64_t ldw,
+                                     int64_t k, const void* alpha, const void* beta, int64_t chunk_cols) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (dtype != SCIMLOP_F64 && dtype != SCIMLOP_F32) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "unsupported dtype %d", dtype);
+  if (nfactors < 1 || nfactors > 8 || !dims || !kinds || !lds || !factors)
+    return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_mul_host: bad factor description");
+  if (k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kron_mul_host: negative k");
+  const size_t es = dtype == SCIMLOP_F64 ? 8 : 4;
+  long long rows = 1, cols = 1;
+  for (int f = 0; f < nfactors; f++) {
+    if (dims[2 * f] < 0 || dims[2 * f + 1] < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kron_mul_host: negative size");
+    rows *= dims[2 * f]; cols *= dims[2 * f + 1];
+  }
+  if (k == 0 || rows == 0) return SCIMLOP_OK;
+  if (!V || !W) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_mul_host: V/W null");
+  if (ldv != cols || ldw != rows) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kron_mul_host: V and W must be contiguous");
+  scimlop_device_guard guard(h->device);
+  if (int rc = ensure_host_streams(h)) return rc;
+
+  double beta_val = 0.0;
+  if (beta) beta_val = dtype == SCIMLOP_F64 ? *static_cast<const double*>(beta) : (double)*static_cast<const float*>(beta);
+  const bool readw = beta_val != 0.0;
+
+  // chunk size: ~32 MiB of V per chunk by default, at least 1 column
+  long long cc = chunk_cols > 0 ? chunk_cols : std::max<long long>(1, (32ll << 20) / std::max<long long>(1, cols * (long long)es));
+  cc = std::min<long long>(cc, k);
+
+  // ---- carve the staging allocation: factors | V slots | W slots | workspace ----
+  size_t off = 0;
+  size_t fac_off[8];
+  for (int f = 0; f < nfactors; f++) {
+    fac_off[f] = off;
+    if ((kinds[f] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE) {
+      const int64_t srows = (kinds[f] & SCIMLOP_TRANS) ? dims[2 * f + 1] : dims[2 * f];
+      if (!factors[f] || lds[f] < std::max<int64_t>(1, srows)) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kron_mul_host: bad dense factor %d", f);
+      off += align_up((size_t)lds[f] * (size_t)(dims[2 * f] + dims[2 * f + 1] - srows) * es, 256);
+    } else if (kinds[f] == SCIMLOP_DIAG) {
+      if (!factors[f]) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_mul_host: null diagonal factor %d", f);
+      off += align_up((size_t)dims[2 * f] * es, 256);
+    }
+  }
+  const size_t vslot = align_up((size_t)cols * cc * es, 256), wslot = align_up((size_t)rows * cc * es, 256);
+  const size_t v_off = off; off += vslot * SCIMLOP_HOST_SLOTS;
+  const size_t w_off = off; off += wslot * SCIMLOP_HOST_SLOTS;
+  size_t ws_bytes = 0;
+  if (int rc = scimlop_kron_workspace_bytes(dtype, nfactors, dims, kinds, cc, &ws_bytes)) return scimlop_fail(h, rc, "kron_mul_host: bad factors");
+  const size_t ws_off = off; off += ws_bytes;
+  if (off > h->stage_bytes) {
+    if (h->stage) { SCIMLOP_CUDA(h, cudaDeviceSynchronize()); SCIMLOP_CUDA(h, cudaFree(h->stage)); h->stage = nullptr; h->stage_bytes = 0; }
+    SCIMLOP_CUDA(h, cudaMalloc(&h->stage, off));
+    h->stage_bytes = off;
+  }
+  char* base = static_cast<char*>(h->stage);
+
+  // factors: uploaded once per call on the H2D stream
+  const void* dfac[8];
+  for (int f = 0; f < nfactors; f++) {
+    dfac[f] = nullptr;
+    size_t bytes = 0;
+    if ((kinds[f] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE)
+      bytes = (size_t)lds[f] * (size_t)((kinds[f] & SCIMLOP_TRANS) ? dims[2 * f] : dims[2 * f + 1]) * es;
+    else if (kinds[f] == SCIMLOP_DIAG) bytes = (size_t)dims[2 * f] * es;
+    if (bytes) {
+      dfac[f] = base + fac_off[f];
+      SCIMLOP_CUDA(h, cudaMemcpyAsync(base + fac_off[f], factors[f], bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    }
+  }
+
+  const long long nchunks = (k + cc - 1) / cc;
+  for (long long ci = 0; ci < nchunks; ci++) {
+    const int slot = (int)(ci % SCIMLOP_HOST_SLOTS);
+    const long long c0 = ci * cc, nc = std::min<long long>(cc, k - c0);
+    char* dV = base + v_off + vslot * slot;
+    char* dW = base + w_off + wslot * slot;
+    if (ci >= SCIMLOP_HOST_SLOTS) {
+      // the slot is free once its previous compute (V) / download (W) finished
+      SCIMLOP_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_comp[slot], 0));
+      if (readw) SCIMLOP_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_d2h[slot], 0));
+    }
+    SCIMLOP_CUDA(h, cudaMemcpyAsync(dV, static_cast<const char*>(V) + (size_t)c0 * cols * es, (size_t)nc * cols * es,
+                                    cudaMemcpyHostToDevice, h->s_h2d));
+    if (readw)
+      SCIMLOP_CUDA(h, cudaMemcpyAsync(dW, static_cast<const char*>(W) + (size_t)c0 * rows * es, (size_t)nc * rows * es,
+                                      cudaMemcpyHostToDevice, h->s_h2d));
+    SCIMLOP_CUDA(h, cudaEventRecord(h->ev_h2d[slot], h->s_h2d));
+    SCIMLOP_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_h2d[slot], 0));
+    if (ci >= SCIMLOP_HOST_SLOTS) SCIMLOP_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_d2h[slot], 0));
+    int rc = scimlop_kron_mul_impl(h, dtype, precision, nfactors, dfac, dims, lds, kinds, dV, cols, dW, rows, nc, alpha,
+                                   beta, base + ws_off, ws_bytes, h->s_comp);
+    if (rc) return rc;
+    SCIMLOP_CUDA(h, cudaEventRecord(h->ev_comp[slot], h->s_comp));
+    SCIMLOP_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_comp[slot], 0));
+    SCIMLOP_CUDA(h, cudaMemcpyAsync(static_cast<char*>(W) + (size_t)c0 * rows * es, dW, (size_t)nc * rows * es,
+                                    cudaMemcpyDeviceToHost, h->s_d2h));
+    SCIMLOP_CUDA(h, cudaEventRecord(h->ev_d2h[slot], h->s_d2h));
+  }
+  SCIMLOP_CUDA(h, cudaStreamSynchronize(h->s_d2h));
+  SCIMLOP_CUDA(h, cudaStreamSynchronize(h->s_comp));
+  SCIMLOP_CUDA(h, cudaStreamSynchronize(h->s_h2d));
+  return SCIMLOP_OK;
+}
+
+// ================================================================================================
+// NCCL (dlopen'ed: the library must load, and the single-GPU path must work, without libnccl)
+// ================================================================================================
+namespace {
+
+typedef struct { char internal[128]; } nccl_unique_id;
+typedef int (*nccl_get_unique_id_fn)(nccl_unique_id*);
+typedef int (*nccl_comm_init_rank_fn)(void**, int, nccl_unique_id, int);
+typedef int (*nccl_comm_destroy_fn)(void*);
+typedef int (*nccl_all_gather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char* (*nccl_get_error_string_fn)(int);
+constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8;  // ncclDataType_t (nccl.h)
+
+void* g_nccl = nullptr;
+
+void* nccl_sym(const char* name) {
+  if (!g_nccl) {
+    g_nccl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl) g_nccl = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  }
+  return g_nccl ? dlsym(g_nccl, name) : nullptr;
+}
+
+}  // namespace
+
+extern "C" int scimlop_comm_unique_id(void* id) {
+  if (!id) return SCIMLOP_ERR_NULL_POINTER;
+  auto fn = reinterpret_cast<nccl_get_unique_id_fn>(nccl_sym("ncclGetUniqueId"));
+  if (!fn) return SCIMLOP_ERR_NCCL;
+  return fn(static_cast<nccl_unique_id*>(id)) == 0 ? SCIMLOP_OK : SCIMLOP_ERR_NCCL;
+}
+
+extern "C" int scimlop_comm_init(scimlop_handle_t h, int nranks, int rank, const void* id) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (!id) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "comm_init: unique id is null");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "comm_init: bad rank %d of %d", rank, nranks);
+  auto fn = reinterpret_cast<nccl_comm_init_rank_fn>(nccl_sym("ncclCommInitRank"));
+  if (!fn) return scimlop_fail(h, SCIMLOP_ERR_NCCL, "libnccl.so.2 not found: %s", dlerror());
+  scimlop_device_guard guard(h->device);
+  nccl_unique_id uid;
+  memcpy(&uid, id, sizeof(uid));
+  void* comm = nullptr;
+  int r = fn(&comm, nranks, uid, rank);
+  if (r != 0) {
+    auto es = reinterpret_cast<nccl_get_error_string_fn>(nccl_sym("ncclGetErrorString"));
+    return scimlop_fail(h, SCIMLOP_ERR_NCCL, "ncclCommInitRank failed: %s", es ? es(r) : "?");
+  }
+  h->nccl_comm = comm; h->nranks = nranks; h->rank = rank;
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_comm_destroy(scimlop_handle_t h) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (h->nccl_comm) {
+    auto fn = reinterpret_cast<nccl_comm_destroy_fn>(nccl_sym("ncclCommDestroy"));
+    if (fn) fn(h->nccl_comm);
+    h->nccl_comm = nullptr;
+  }
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_allgather_cols(scimlop_handle_t h, int dtype, void* W_full, int64_t rows, int64_t cols_per_rank,
+                                      void* stream) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (!h->nccl_comm) return scimlop_fail(h, SCIMLOP_ERR_NCCL, "allgather_cols: call scimlop_comm_init first");
+  if (dtype != SCIMLOP_F64 && dtype != SCIMLOP_F32) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "unsupported dtype %d", dtype);
+  if (rows < 0 || cols_per_rank < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "allgather_cols: negative size");
+  if (rows == 0 || cols_per_rank == 0) return SCIMLOP_OK;
+  if (!W_full) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "allgather_cols: W_full null");
+  auto fn = reinterpret_cast<nccl_all_gather_fn>(nccl_sym("ncclAllGather"));
+  if (!fn) return scimlop_fail(h, SCIMLOP_ERR_NCCL, "ncclAllGather not found");
+  scimlop_device_guard guard(h->device);
+  const size_t es = dtype == SCIMLOP_F64 ? 8 : 4;
+  const size_t count = (size_t)rows * (size_t)cols_per_rank;
+  const char* send = static_cast<const char*>(W_full) + (size_t)h->rank * count * es;  // in-place form
+  int r = fn(send, W_full, count, dtype == SCIMLOP_F64 ? NCCL_FLOAT64 : NCCL_FLOAT32, h->nccl_comm,
+             static_cast<cudaStream_t>(stream));
+  if (r != 0) {
+    auto es2 = reinterpret_cast<nccl_get_error_string_fn>(nccl_sym("ncclGetErrorString"));
+    return scimlop_fail(h, SCIMLOP_ERR_NCCL, "ncclAllGather failed: %s", es2 ? es2(r) : "?");
+  }
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_destroy(scimlop_handle_t h) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  scimlop_device_guard guard(h->device);
+  scimlop_comm_destroy(h);
+  if (h->host_streams_ready) {
+    cudaStreamSynchronize(h->s_h2d); cudaStreamSynchronize(h->s_comp); cudaStreamSynchronize(h->s_d2h);
+    for (int i = 0; i < SCIMLOP_HOST_SLOTS; i++) {
+      cudaEventDestroy(h->ev_h2d[i]); cudaEventDestroy(h->ev_comp[i]); cudaEventDestroy(h->ev_d2h[i]);
+    }
+    cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_comp); cudaStreamDestroy(h->s_d2h);
+  }
+  if (h->stage) cudaFree(h->stage);
+  h->magic = 0;
+  delete h;
+  return SCIMLOP_OK;
+}

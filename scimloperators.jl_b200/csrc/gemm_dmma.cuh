@@ -1,0 +1,230 @@
+// gemm_dmma.cuh -- FP64 strided-batched GEMM for sm_100a: TMA-staged operand tiles (128B-swizzled),
+// mbarrier producer/consumer ring, DMMA (mma.sync.m8n8k4.f64) math, fused epilogue.
+//
+//   C_b(M x N) = alpha * rowscale .* (A_b(M x K) * B_b(K x N)) + beta * C_b          (column-major C)
+//
+// This is the engine behind every contraction of the hot path: the reshape /
+// permutedims! of src/tensor.jl:558,780-787 become pure tensor-map geometry (an operand is either
+// "outer-contiguous" or "k-contiguous" in global memory and TMA lays it out in shared memory for us),
+// and copy!/axpby! (src/tensor.jl:829-831), the ScaledOperator λ (src/basic.jl:518-536) and a left
+// DiagonalOperator / BatchedDiagonalOperator (src/basic.jl:1160-1189) live in the epilogue.
+//
+// tcgen05 has no FP64 kind, so FP64 tensor math on Blackwell is the warp-level DMMA.8x8x4 (all larger
+// mma.sync f64 shapes lower to it; measured peak 37.1 TFLOP/s, profiles/r01_peaks_microbench.json).
+#pragma once
+#include "ptx.cuh"
+
+namespace scimlop {
+namespace dmma {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int STAGES = 5;
+constexpr int TILE_BYTES = BM * BK * 8;      // 16 KB per operand tile
+constexpr int STAGE_BYTES = 2 * TILE_BYTES;  // A + B
+constexpr int CONSUMER_WARPS = 8;            // 2 (m) x 4 (n), warp tile 64 x 32
+constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int MAX_SCALES = 3;
+
+struct Scale {
+  const double* ptr;
+  long long ld;  // 0: vector indexed by row m; else matrix indexed m + n*ld
+};
+
+struct Params {
+  int M, N, K, batch;
+  int tiles_m, tiles_n;
+  long long total_tiles;
+  double* C;
+  long long ldc, strideC;
+  double alpha, beta;  // beta == 0: C is never read
+  int nscale;
+  Scale scale[MAX_SCALES];
+  int vec_ok;  // C base, ldc, strideC allow 16-byte stores
+  int a_batched, b_batched;
+};
+
+// k index used by lane t in MMA step s of a BK=16 block.  The permutation makes the 64-bit fragment
+// loads bank-conflict-free for BOTH swizzled tile layouts (see tile_off): the four k's of a step hit
+// four different {2c,2c+1} pairs mod 8 (outer-contiguous tiles) and come as two even + two odd values
+// whose halves differ in bit 2 (k-contiguous tiles).  Any permutation of k is legal for a dot product.
+__device__ __forceinline__ int kperm(int s, int t) {
+  // s0 {0,10,5,15}  s1 {1,11,4,14}  s2 {2,8,7,13}  s3 {3,9,6,12}   (one nibble per t)
+  const uint32_t tab = (s == 0) ? 0xF5A0u : (s == 1) ? 0xE4B1u : (s == 2) ? 0xD782u : 0xC693u;
+  return (int)((tab >> (4 * t)) & 15u);
+}
+
+// Byte offset of element (o, k) inside one 16 KB operand tile.
+//  KC (k-contiguous source):   one TMA box {16 k, 128 outer}: row o = 128 B, 16-byte chunks XOR (o & 7).
+//  OC (outer-contiguous source): eight TMA boxes {16 outer, 16 k} of 2 KB: row k = 128 B, chunks XOR (k & 7).
+template <bool KC>
+__device__ __forceinline__ uint32_t tile_off(int o, int k) {
+  if (KC) return o * 128 + ((((k >> 1) ^ (o & 7))) << 4) + ((k & 1) << 3);
+  return (o >> 4) * 2048 + k * 128 + (((((o & 15) >> 1) ^ (k & 7))) << 4) + ((o & 1) << 3);
+}
+
+template <bool A_KC, bool B_OC>
+__global__ void __maxnreg__(224)
+    gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle patterns repeat every 1024 B: align the tile ring.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], CONSUMER_WARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int nk = (p.K + BK - 1) / BK;
+
+  if (warp == CONSUMER_WARPS) {
+    // ================= TMA producer (one elected lane) =================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int mt = (int)(tile % p.tiles_m);
+        const long long r = tile / p.tiles_m;
+        const int nt = (int)(r % p.tiles_n);
+        const int b = (int)(r / p.tiles_n);
+        const int m0 = mt * BM, n0 = nt * BN;
+        const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
+        for (int kb = 0; kb < nk; kb++) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * STAGE_BYTES;
+          uint8_t* sB = sA + TILE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (A_KC) {
+            tma_load_3d(sA, &tmA, &full_bar[stage], k0, m0, ba);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) tma_load_3d(sA + q * 2048, &tmA, &full_bar[stage], m0 + 16 * q, k0, ba);
+          }
+          if (!B_OC) {
+            tma_load_3d(sB, &tmB, &full_bar[stage], k0, n0, bb);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) tma_load_3d(sB + q * 2048, &tmB, &full_bar[stage], n0 + 16 * q, k0, bb);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================= DMMA consumers =================
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 1;   // 64-row half of the tile
+  const int wn = warp >> 1;  // 32-column quarter of the tile
+
+  // per-lane fragment offsets for the four MMA steps of a stage (sub-tile 0 and 1; the rest are immediates)
+  uint32_t offA[4][2], offB[4][2];
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const int k = kperm(s, t);
+    offA[s][0] = tile_off<A_KC>(wm * 64 + g, k);
+    offA[s][1] = tile_off<A_KC>(wm * 64 + 8 + g, k);
+    offB[s][0] = TILE_BYTES + tile_off<!B_OC>(wn * 32 + g, k);
+    offB[s][1] = TILE_BYTES + tile_off<!B_OC>(wn * 32 + 8 + g, k);
+  }
+  // sub-tile i = 2*(i>>1) + (i&1): +16 outer rows per pair
+  constexpr uint32_t pairA = A_KC ? 16 * 128 : 2048;
+  constexpr uint32_t pairB = (!B_OC) ? 16 * 128 : 2048;
+
+  int stage = 0;
+  uint32_t phase = 0;
+
+  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int mt = (int)(tile % p.tiles_m);
+    const long long r = tile / p.tiles_m;
+    const int nt = (int)(r % p.tiles_n);
+    const int b = (int)(r / p.tiles_n);
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kb = 0; kb < nk; kb++) {
+      mbar_wait(&full_bar[stage], phase);
+      const uint8_t* st = smem + stage * STAGE_BYTES;
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        double a[8], bf[4];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          a[i] = *reinterpret_cast<const double*>(st + offA[s][i & 1] + (i >> 1) * pairA);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          bf[j] = *reinterpret_cast<const double*>(st + offB[s][j & 1] + (j >> 1) * pairB);
+        // MMA rows <- n (B operand), MMA cols <- m (A operand): lane owns C[m = 2t, 2t+1][n = g]
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], bf[j], a[i]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    // ---- fused epilogue: rowscale, alpha, beta, store (the producer is already prefetching the next tile) ----
+    const int mbase = mt * BM + wm * 64 + 2 * t;
+    const int nbase = nt * BN + wn * 32 + g;
+    double* Cb = p.C + (long long)b * p.strideC;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int n = nbase + 8 * j;
+      if (n >= p.N) continue;
+      double* col = Cb + (long long)n * p.ldc;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int m = mbase + 8 * i;
+        if (m >= p.M) continue;
+        double v0 = acc[i][j][0], v1 = acc[i][j][1];
+        const bool pair = (m + 1 < p.M);
+        for (int q = 0; q < p.nscale; q++) {
+          const double* sp = p.scale[q].ptr + (p.scale[q].ld ? (long long)n * p.scale[q].ld : 0) + m;
+          v0 *= sp[0];
+          if (pair) v1 *= sp[1];
+        }
+        v0 *= p.alpha;
+        v1 *= p.alpha;
+        if (pair && p.vec_ok) {
+          double2* dst = reinterpret_cast<double2*>(col + m);
+          if (p.beta != 0.0) {
+            const double2 old = *dst;
+            v0 += p.beta * old.x;
+            v1 += p.beta * old.y;
+          }
+          *dst = make_double2(v0, v1);
+        } else {
+          if (p.beta != 0.0) {
+            v0 += p.beta * col[m];
+            if (pair) v1 += p.beta * col[m + 1];
+          }
+          col[m] = v0;
+          if (pair) col[m + 1] = v1;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace dmma
+}  // namespace scimlop

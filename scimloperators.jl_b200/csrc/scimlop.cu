@@ -1,0 +1,830 @@
+// scimlop.cu -- C ABI of libscimlop_b200.so: handle, GEMM dispatch, elementwise pass, and the host-side
+// planners that turn a TensorProductOperator / operator tree into kernel launches.
+//
+// Reference behaviour being replaced (SciMLOperators.jl): src/tensor.jl:543-610,750-834 (TPO mul! and
+// outer_mul!), src/matrix.jl:337-361, src/batch.jl:151-179, src/basic.jl:74-90,248-264,518-536,834-854,
+// 1160-1207.  No CPU fallback: every path ends in a CUDA kernel launch or an error status.
+#include <algorithm>
+#include <new>
+
+#include "context.h"
+#include "eltwise.cuh"
+#include "gemm_dmma.cuh"
+#include "gemm_simt.cuh"
+
+using namespace scimlop;
+
+// ================================================================================================
+// small helpers
+// ================================================================================================
+namespace {
+
+template <typename T>
+T scalar_or(const void* p, T dflt) {
+  return p ? *static_cast<const T*>(p) : dflt;
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline size_t elem_size(int dtype) { return dtype == SCIMLOP_F64 ? 8 : 4; }
+
+struct ScaleArg {
+  const void* ptr;
+  long long ld;
+};
+
+// ---- elementwise launcher -------------------------------------------------------------------------
+template <typename T>
+int launch_eltwise(scimlop_context* c, elt::Params<T>& p, cudaStream_t st) {
+  if (p.n <= 0 || p.k <= 0) return SCIMLOP_OK;
+  constexpr int VMAX = (sizeof(T) == 8) ? 2 : 4;
+  bool vec = (p.n % VMAX == 0) && (p.ldw % VMAX == 0) && aligned16(p.W);
+  if (p.nterms > 0) vec = vec && (p.ldv % VMAX == 0) && aligned16(p.V);
+  for (int t = 0; t < p.nterms; t++)
+    for (int f = p.nvec[t]; f < p.nfac[t]; f++)
+      vec = vec && (p.fac[t][f].ld % VMAX == 0) && aligned16(p.fac[t][f].ptr);
+  const int V = vec ? VMAX : 1;
+  const long long rows = (p.n + V - 1) / V;
+  const long long row_blocks = (rows + elt::THREADS - 1) / elt::THREADS;
+  // enough blocks to fill the machine several times over, each looping over a multiple of UNROLL columns
+  const long long target = (long long)c->sm_count * 16;
+  long long col_blocks = std::max<long long>(1, std::min<long long>((target + row_blocks - 1) / row_blocks, 65535));
+  long long cpb = (p.k + col_blocks - 1) / col_blocks;
+  cpb = std::max<long long>(elt::UNROLL, (cpb + elt::UNROLL - 1) / elt::UNROLL * elt::UNROLL);
+  col_blocks = (p.k + cpb - 1) / cpb;
+  if (col_blocks > 65535) {
+    cpb = ((p.k + 65534) / 65535 + elt::UNROLL - 1) / elt::UNROLL * elt::UNROLL;
+    col_blocks = (p.k + cpb - 1) / cpb;
+  }
+  if (row_blocks > 2147483647LL) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "eltwise: too many rows");
+  p.cols_per_block = (int)cpb;
+  dim3 grid((unsigned)row_blocks, (unsigned)col_blocks);
+  if (vec)
+    elt::eltwise_kernel<T, VMAX><<<grid, elt::THREADS, 0, st>>>(p);
+  else
+    elt::eltwise_kernel<T, 1><<<grid, elt::THREADS, 0, st>>>(p);
+  c->launches++;
+  SCIMLOP_CUDA(c, cudaGetLastError());
+  return SCIMLOP_OK;
+}
+
+// W = alpha * V + beta * W  (V may be NULL with alpha ignored: W = beta * W)
+template <typename T>
+int eltwise_axpby(scimlop_context* c, long long n, long long k, const T* V, long long ldv, T* W, long long ldw,
+                  T alpha, T beta, cudaStream_t st) {
+  elt::Params<T> p;
+  memset(&p, 0, sizeof(p));
+  p.n = n; p.k = k; p.V = V; p.ldv = ldv; p.W = W; p.ldw = ldw; p.alpha = alpha; p.beta = beta;
+  if (V) { p.nterms = 1; p.coef[0] = T(1); }
+  return launch_eltwise(c, p, st);
+}
+
+// ---- DMMA (FP64, TMA) launcher ------------------------------------------------------------------------
+int make_map_f64(scimlop_context* c, CUtensorMap* map, const double* base, bool kc, long long outer, long long K,
+                 long long ld, long long stride, long long nb) {
+  cuuint64_t gdim[3];
+  cuuint64_t gstr[2];
+  cuuint32_t box[3];
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (kc) {
+    gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)outer;
+    box[0] = dmma::BK; box[1] = dmma::BM;
+  } else {
+    gdim[0] = (cuuint64_t)outer; gdim[1] = (cuuint64_t)K;
+    box[0] = 16; box[1] = dmma::BK;
+  }
+  gdim[2] = (cuuint64_t)nb;
+  box[2] = 1;
+  gstr[0] = (cuuint64_t)ld * 8;
+  gstr[1] = (nb > 1) ? (cuuint64_t)stride * 8 : (cuuint64_t)ld * 8 * gdim[1];
+  CUresult r = c->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), gdim, gstr, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return scimlop_fail(c, SCIMLOP_ERR_CUDA,
+                        "cuTensorMapEncodeTiled failed (CUresult %d): dims {%llu,%llu,%llu} strides {%llu,%llu}",
+                        (int)r, (unsigned long long)gdim[0], (unsigned long long)gdim[1],
+                        (unsigned long long)gdim[2], (unsigned long long)gstr[0], (unsigned long long)gstr[1]);
+  return SCIMLOP_OK;
+}
+
+bool dmma_eligible(long long M, long long N, long long K, const double* A, long long lda, long long sA,
+                   const double* B, long long ldb, long long sB, long long batch) {
+  if (M < 16 || N < 16 || K < 4) return false;
+  if (!aligned16(A) || !aligned16(B)) return false;
+  if ((lda & 1) || (ldb & 1)) return false;
+  if (batch > 1 && ((sA & 1) || (sB & 1))) return false;
+  const long long lim = 2147483647LL;
+  if (M > lim || N > lim || K > lim || batch > lim) return false;
+  if (lda > (1LL << 36) || ldb > (1LL << 36) || sA > (1LL << 36) || sB > (1LL << 36)) return false;
+  return true;
+}
+
+int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long long N, long long K, double alpha,
+                const double* A, long long lda, long long sA, const double* B, long long ldb, long long sB,
+                double beta, double* C, long long ldc, long long sC, long long batch, int nscale,
+                const ScaleArg* scales, cudaStream_t st) {
+  const bool a_batched = batch > 1 && sA != 0, b_batched = batch > 1 && sB != 0;
+  CUtensorMap tmA, tmB;
+  int rc = make_map_f64(c, &tmA, A, /*kc=*/transA, M, K, lda, sA, a_batched ? batch : 1);
+  if (rc) return rc;
+  rc = make_map_f64(c, &tmB, B, /*kc=*/!transB, N, K, ldb, sB, b_batched ? batch : 1);
+  if (rc) return rc;
+  dmma::Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.batch = (int)batch;
+  p.tiles_m = (int)((M + dmma::BM - 1) / dmma::BM);
+  p.tiles_n = (int)((N + dmma::BN - 1) / dmma::BN);
+  p.total_tiles = (long long)p.tiles_m * p.tiles_n * batch;
+  p.C = C; p.ldc = ldc; p.strideC = sC;
+  p.alpha = alpha; p.beta = beta;
+  p.nscale = nscale;
+  for (int q = 0; q < nscale; q++) { p.scale[q].ptr = static_cast<const double*>(scales[q].ptr); p.scale[q].ld = scales[q].ld; }
+  p.vec_ok = aligned16(C) && !(ldc & 1) && (batch == 1 || !(sC & 1));
+  p.a_batched = a_batched; p.b_batched = b_batched;
+  const int grid = (int)std::min<long long>(p.total_tiles, c->sm_count);
+  if (!transA && !transB) dmma::gemm_dmma_kernel<false, false><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
+  else if (!transA && transB) dmma::gemm_dmma_kernel<false, true><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
+  else if (transA && !transB) dmma::gemm_dmma_kernel<true, false><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
+  else dmma::gemm_dmma_kernel<true, true><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
+  c->launches++;
+  SCIMLOP_CUDA(c, cudaGetLastError());
+  return SCIMLOP_OK;
+}
+
+template <typename T>
+int launch_simt(scimlop_context* c, bool transA, bool transB, long long M, long long N, long long K, T alpha,
+                const T* A, long long lda, long long sA, const T* B, long long ldb, long long sB, T beta, T* C,
+                long long ldc, long long sC, long long batch, int nscale, const ScaleArg* scales, cudaStream_t st) {
+  simt::Params<T> p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.batch = (int)batch;
+  p.tiles_m = (int)((M + simt::TM - 1) / simt::TM);
+  p.tiles_n = (int)((N + simt::TN - 1) / simt::TN);
+  const long long total = (long long)p.tiles_m * p.tiles_n * batch;
+  if (total > 2147483647LL) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "gemm: too many tiles (%lld)", total);
+  p.A = A; p.lda = lda; p.strideA = sA;
+  p.B = B; p.ldb = ldb; p.strideB = sB;
+  p.C = C; p.ldc = ldc; p.strideC = sC;
+  p.alpha = alpha; p.beta = beta; p.nscale = nscale;
+  for (int q = 0; q < nscale; q++) { p.scale[q].ptr = static_cast<const T*>(scales[q].ptr); p.scale[q].ld = scales[q].ld; }
+  const unsigned grid = (unsigned)total;
+  if (!transA && !transB) simt::gemm_simt_kernel<T, false, false><<<grid, simt::THREADS, 0, st>>>(p);
+  else if (!transA && transB) simt::gemm_simt_kernel<T, false, true><<<grid, simt::THREADS, 0, st>>>(p);
+  else if (transA && !transB) simt::gemm_simt_kernel<T, true, false><<<grid, simt::THREADS, 0, st>>>(p);
+  else simt::gemm_simt_kernel<T, true, true><<<grid, simt::THREADS, 0, st>>>(p);
+  c->launches++;
+  SCIMLOP_CUDA(c, cudaGetLastError());
+  return SCIMLOP_OK;
+}
+
+// C_b = alpha * rowscale .* (op(A_b) op(B_b)) + beta * C_b
+template <typename T>
+int gemm_dispatch(scimlop_context* c, int precision, bool transA, bool transB, long long M, long long N,
+                  long long K, T alpha, const T* A, long long lda, long long sA, const T* B, long long ldb,
+                  long long sB, T beta, T* C, long long ldc, long long sC, long long batch, int nscale,
+                  const ScaleArg* scales, cudaStream_t st);
+
+template <>
+int gemm_dispatch<double>(scimlop_context* c, int precision, bool transA, bool transB, long long M, long long N,
+                          long long K, double alpha, const double* A, long long lda, long long sA,
+                          const double* B, long long ldb, long long sB, double beta, double* C, long long ldc,
+                          long long sC, long long batch, int nscale, const ScaleArg* scales, cudaStream_t st) {
+  if (precision != SCIMLOP_PREC_DEFAULT)
+    return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "Float64 only supports SCIMLOP_PREC_DEFAULT (got %d)", precision);
+  if (M <= 0 || N <= 0 || batch <= 0) return SCIMLOP_OK;
+  if (dmma_eligible(M, N, K, A, lda, sA, B, ldb, sB, batch))
+    return launch_dmma(c, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, nscale,
+                       scales, st);
+  return launch_simt<double>(c, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
+                             nscale, scales, st);
+}
+
+template <>
+int gemm_dispatch<float>(scimlop_context* c, int precision, bool transA, bool transB, long long M, long long N,
+                         long long K, float alpha, const float* A, long long lda, long long sA, const float* B,
+                         long long ldb, long long sB, float beta, float* C, long long ldc, long long sC,
+                         long long batch, int nscale, const ScaleArg* scales, cudaStream_t st) {
+  if (precision != SCIMLOP_PREC_DEFAULT)
+    return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED,
+                        "Float32 tensor-core modes (TF32x3 / TF32) are not built yet; use SCIMLOP_PREC_DEFAULT");
+  if (M <= 0 || N <= 0 || batch <= 0) return SCIMLOP_OK;
+  return launch_simt<float>(c, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
+                            nscale, scales, st);
+}
+
+int check_handle(scimlop_context* c) { return scimlop_valid(c) ? SCIMLOP_OK : SCIMLOP_ERR_BAD_HANDLE; }
+int check_dtype(scimlop_context* c, int dtype) {
+  if (dtype != SCIMLOP_F64 && dtype != SCIMLOP_F32)
+    return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "unsupported dtype %d (Float64 = 0, Float32 = 1)", dtype);
+  return SCIMLOP_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// handle
+// ================================================================================================
+extern "C" int scimlop_version(void) { return SCIMLOP_VERSION; }
+
+extern "C" const char* scimlop_status_string(int s) {
+  switch (s) {
+    case SCIMLOP_OK: return "ok";
+    case SCIMLOP_ERR_NULL_POINTER: return "null pointer";
+    case SCIMLOP_ERR_BAD_SHAPE: return "bad shape";
+    case SCIMLOP_ERR_WORKSPACE: return "workspace missing or too small (operator not cached)";
+    case SCIMLOP_ERR_UNSUPPORTED: return "unsupported dtype / precision / factor kind";
+    case SCIMLOP_ERR_CUDA: return "CUDA error";
+    case SCIMLOP_ERR_NCCL: return "NCCL error";
+    case SCIMLOP_ERR_BAD_HANDLE: return "bad handle";
+    case SCIMLOP_ERR_NO_DEVICE: return "no sm_100 device (there is no CPU fallback)";
+    default: return "unknown status";
+  }
+}
+
+extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
+  if (!out) return SCIMLOP_ERR_NULL_POINTER;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return SCIMLOP_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SCIMLOP_ERR_NO_DEVICE;
+  if (prop.major != 10) return SCIMLOP_ERR_NO_DEVICE;  // sm_100a cubins only
+  scimlop_context* c = new (std::nothrow) scimlop_context();
+  if (!c) return SCIMLOP_ERR_CUDA;
+  memset(c, 0, sizeof(*c));
+  c->magic = SCIMLOP_MAGIC;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  scimlop_device_guard guard(device);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    delete c;
+    return SCIMLOP_ERR_CUDA;
+  }
+  c->encode_tiled = reinterpret_cast<scimlop_encode_tiled_fn>(fn);
+  cudaError_t e = cudaSuccess;
+  auto optin = [&](const void* f) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, dmma::SMEM_BYTES);
+  };
+  optin((const void*)dmma::gemm_dmma_kernel<false, false>);
+  optin((const void*)dmma::gemm_dmma_kernel<false, true>);
+  optin((const void*)dmma::gemm_dmma_kernel<true, false>);
+  optin((const void*)dmma::gemm_dmma_kernel<true, true>);
+  if (e != cudaSuccess) {
+    delete c;
+    return SCIMLOP_ERR_CUDA;
+  }
+  *out = c;
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_last_error(scimlop_handle_t h, char* buf, size_t len) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (!buf || len == 0) return SCIMLOP_ERR_NULL_POINTER;
+  snprintf(buf, len, "%s", h->last_error);
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_launch_count(scimlop_handle_t h, int64_t* count) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (!count) return SCIMLOP_ERR_NULL_POINTER;
+  *count = h->launches;
+  return SCIMLOP_OK;
+}
+
+// ================================================================================================
+// leaves
+// ================================================================================================
+extern "C" int scimlop_gemm_strided_batched(scimlop_handle_t h, int dtype, int precision, int transA, int transB,
+                                            int64_t M, int64_t N, int64_t K, const void* alpha, const void* A,
+                                            int64_t lda, int64_t strideA, const void* B, int64_t ldb,
+                                            int64_t strideB, const void* beta, void* C, int64_t ldc,
+                                            int64_t strideC, int64_t batch, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_dtype(h, dtype)) return rc;
+  if (M < 0 || N < 0 || K < 0 || batch < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "gemm: negative size");
+  if (M == 0 || N == 0 || batch == 0) return SCIMLOP_OK;
+  if (!C || (K > 0 && (!A || !B))) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "gemm: null operand");
+  const int64_t a_rows = transA ? K : M, b_rows = transB ? N : K;
+  if ((K > 0 && (lda < std::max<int64_t>(1, a_rows) || ldb < std::max<int64_t>(1, b_rows))) || ldc < M)
+    return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "gemm: leading dimension smaller than rows (lda=%lld ldb=%lld ldc=%lld)",
+                        (long long)lda, (long long)ldb, (long long)ldc);
+  scimlop_device_guard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SCIMLOP_F64)
+    return gemm_dispatch<double>(h, precision, transA != 0, transB != 0, M, N, K, scalar_or<double>(alpha, 1.0),
+                                 (const double*)A, lda, strideA, (const double*)B, ldb, strideB,
+                                 scalar_or<double>(beta, 0.0), (double*)C, ldc, strideC, batch, 0, nullptr, st);
+  return gemm_dispatch<float>(h, precision, transA != 0, transB != 0, M, N, K, scalar_or<float>(alpha, 1.f),
+                              (const float*)A, lda, strideA, (const float*)B, ldb, strideB,
+                              scalar_or<float>(beta, 0.f), (float*)C, ldc, strideC, batch, 0, nullptr, st);
+}
+
+extern "C" int scimlop_matmul(scimlop_handle_t h, int dtype, int precision, int transA, int64_t m, int64_t n,
+                              int64_t k, const void* A, int64_t lda, const void* V, int64_t ldv, void* W,
+                              int64_t ldw, const void* alpha, const void* beta, void* stream) {
+  return scimlop_gemm_strided_batched(h, dtype, precision, transA, 0, m, k, n, alpha, A, lda, 0, V, ldv, 0, beta, W,
+                                      ldw, 0, 1, stream);
+}
+
+template <typename T>
+static int diag_mul_t(scimlop_context* h, int64_t n, int64_t k, const void* d, int64_t ldd, const void* V,
+                      int64_t ldv, void* W, int64_t ldw, const void* alpha, const void* beta, cudaStream_t st) {
+  elt::Params<T> p;
+  memset(&p, 0, sizeof(p));
+  p.n = n; p.k = k; p.V = (const T*)V; p.ldv = ldv; p.W = (T*)W; p.ldw = ldw;
+  p.alpha = scalar_or<T>(alpha, T(1)); p.beta = scalar_or<T>(beta, T(0));
+  p.nterms = 1; p.coef[0] = T(1); p.nfac[0] = 1;
+  p.fac[0][0].ptr = (const T*)d;
+  if (ldd == 0) { p.nvec[0] = 1; p.fac[0][0].ld = 0; p.fac[0][0].div = 1; p.fac[0][0].mod = n; }
+  else { p.nvec[0] = 0; p.fac[0][0].ld = ldd; p.fac[0][0].div = 1; p.fac[0][0].mod = 1; }
+  return launch_eltwise(h, p, st);
+}
+
+extern "C" int scimlop_diag_mul(scimlop_handle_t h, int dtype, int64_t n, int64_t k, const void* d, int64_t ldd,
+                                const void* V, int64_t ldv, void* W, int64_t ldw, const void* alpha,
+                                const void* beta, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_dtype(h, dtype)) return rc;
+  if (n < 0 || k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "diag_mul: negative size");
+  if (n == 0 || k == 0) return SCIMLOP_OK;
+  if (!d || !V || !W) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "diag_mul: null operand");
+  if (ldv < n || ldw < n || (ldd != 0 && ldd < n))
+    return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "diag_mul: leading dimension smaller than n");
+  scimlop_device_guard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return dtype == SCIMLOP_F64 ? diag_mul_t<double>(h, n, k, d, ldd, V, ldv, W, ldw, alpha, beta, st)
+                              : diag_mul_t<float>(h, n, k, d, ldd, V, ldv, W, ldw, alpha, beta, st);
+}
+
+extern "C" int scimlop_axpby(scimlop_handle_t h, int dtype, int64_t n, int64_t k, const void* V, int64_t ldv,
+                             void* W, int64_t ldw, const void* alpha, const void* beta, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_dtype(h, dtype)) return rc;
+  if (n < 0 || k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "axpby: negative size");
+  if (n == 0 || k == 0) return SCIMLOP_OK;
+  if (!W) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "axpby: W is null");
+  if (ldw < n || (V && ldv < n)) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "axpby: leading dimension smaller than n");
+  scimlop_device_guard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SCIMLOP_F64)
+    return eltwise_axpby<double>(h, n, k, (const double*)V, ldv, (double*)W, ldw, scalar_or<double>(alpha, 1.0),
+                                 scalar_or<double>(beta, 0.0), st);
+  return eltwise_axpby<float>(h, n, k, (const float*)V, ldv, (float*)W, ldw, scalar_or<float>(alpha, 1.f),
+                              scalar_or<float>(beta, 0.f), st);
+}
+
+// ================================================================================================
+// TensorProductOperator
+// ================================================================================================
+namespace {
+
+constexpr int MAX_KRON_FACTORS = 8;
+
+struct KronPlan {
+  int nops;                // non-identity factors
+  long long rows, cols;    // prod of factor rows / cols
+  long long max_inter;     // largest intermediate (elements per k column count included)
+};
+
+int kron_plan(scimlop_context* c, int nfactors, const int64_t* dims, const int32_t* kinds, int64_t k, KronPlan* pl) {
+  if (nfactors < 1 || nfactors > MAX_KRON_FACTORS)
+    return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "kron: nfactors must be in 1..%d (got %d)", MAX_KRON_FACTORS, nfactors);
+  if (!dims || !kinds) return scimlop_fail(c, SCIMLOP_ERR_NULL_POINTER, "kron: dims/kinds null");
+  if (k < 0) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "kron: negative k");
+  pl->nops = 0; pl->rows = 1; pl->cols = 1; pl->max_inter = 0;
+  for (int f = 0; f < nfactors; f++) {
+    const int64_t m = dims[2 * f], n = dims[2 * f + 1];
+    if (m < 0 || n < 0) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "kron: negative factor size");
+    if (kinds[f] == SCIMLOP_IDENTITY || kinds[f] == SCIMLOP_DIAG) {
+      if (m != n) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "kron: identity/diagonal factor %d must be square", f);
+    } else if ((kinds[f] & ~SCIMLOP_TRANS) != SCIMLOP_DENSE) {
+      return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "kron: factor kind %d not supported inside a tensor product", kinds[f]);
+    }
+    if (kinds[f] != SCIMLOP_IDENTITY) pl->nops++;
+    pl->rows *= m; pl->cols *= n;
+  }
+  // intermediates: after applying modes nfactors-1 .. p the tensor has prod_{q>=p} m_q * prod_{q<p} n_q * k entries
+  long long done = 0;
+  for (int p = nfactors - 1; p >= 0; p--) {
+    if (kinds[p] == SCIMLOP_IDENTITY) continue;
+    done++;
+    if (done == pl->nops) break;  // the last op writes W
+    long long e = k;
+    for (int q = 0; q < nfactors; q++) e *= (q >= p) ? dims[2 * q] : dims[2 * q + 1];
+    pl->max_inter = std::max(pl->max_inter, e);
+  }
+  return SCIMLOP_OK;
+}
+
+template <typename T>
+int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* const* factors, const int64_t* dims,
+               const int64_t* lds, const int32_t* kinds, const T* V, T* W, long long k, T alpha, T beta,
+               void* workspace, size_t ws_bytes, const KronPlan& pl, cudaStream_t st) {
+  if (pl.nops == 0) return eltwise_axpby<T>(c, pl.rows, k, V, pl.cols, W, pl.rows, alpha, beta, st);
+  const size_t buf_bytes = align_up((size_t)pl.max_inter * sizeof(T), 256);
+  const int nbuf = pl.nops >= 3 ? 2 : (pl.nops == 2 ? 1 : 0);
+  if (nbuf > 0 && (!workspace || ws_bytes < buf_bytes * nbuf))
+    return scimlop_fail(c, SCIMLOP_ERR_WORKSPACE, "kron: workspace %zu B < required %zu B (call cache_operator first)",
+                        ws_bytes, buf_bytes * nbuf);
+  T* bufs[2] = {static_cast<T*>(workspace),
+                reinterpret_cast<T*>(static_cast<char*>(workspace) + buf_bytes)};
+  const T* cur = V;
+  int done = 0, flip = 0;
+  long long L = 1;  // product of rows of the modes already applied (faster indices)
+  for (int p = nfactors - 1; p >= 0; p--) {
+    const long long m = dims[2 * p], n = dims[2 * p + 1];
+    if (kinds[p] == SCIMLOP_IDENTITY) { L *= m; continue; }
+    long long R = k;  // product of the slower, not yet applied modes and the batch
+    for (int q = 0; q < p; q++) R *= dims[2 * q + 1];
+    done++;
+    const bool last = (done == pl.nops);
+    T* out = last ? W : bufs[flip];
+    const T a = last ? alpha : T(1), bt = last ? beta : T(0);
+    const bool tr = (kinds[p] & SCIMLOP_TRANS) != 0;
+    int rc;
+    if (kinds[p] == SCIMLOP_DIAG) {
+      // mode product with a diagonal: scale along index (i / L) % n of every column of the L*n x R view
+      elt::Params<T> ep;
+      memset(&ep, 0, sizeof(ep));
+      ep.n = L * n; ep.k = R; ep.V = cur; ep.ldv = L * n; ep.W = out; ep.ldw = L * n; ep.alpha = a; ep.beta = bt;
+      ep.nterms = 1; ep.coef[0] = T(1); ep.nvec[0] = 1; ep.nfac[0] = 1;
+      ep.fac[0][0].ptr = static_cast<const T*>(factors[p]); ep.fac[0][0].ld = 0; ep.fac[0][0].div = L; ep.fac[0][0].mod = n;
+      rc = launch_eltwise(c, ep, st);
+    } else if (L == 1) {
+      // innermost applied mode: out(m x R) = op(F)(m x n) * cur(n x R)    [src/tensor.jl:568,603]
+      rc = gemm_dispatch<T>(c, precision, tr, false, m, R, n, a, static_cast<const T*>(factors[p]), lds[p], 0, cur,
+                            n, 0, bt, out, m, 0, 1, 0, nullptr, st);
+    } else {
+      // out_r(L x m) = cur_r(L x n) * op(F)^T for every slab r           [src/tensor.jl:778-788, no permutedims]
+      rc = gemm_dispatch<T>(c, precision, false, !tr, L, m, n, a, cur, L, L * n, static_cast<const T*>(factors[p]),
+                            lds[p], 0, bt, out, L, L * m, R, 0, nullptr, st);
+    }
+    if (rc) return rc;
+    cur = out;
+    flip ^= 1;
+    L *= m;
+  }
+  return SCIMLOP_OK;
+}
+
+}  // namespace
+
+extern "C" int scimlop_kron_workspace_bytes(int dtype, int nfactors, const int64_t* dims, const int32_t* kinds,
+                                            int64_t k, size_t* bytes) {
+  if (!bytes) return SCIMLOP_ERR_NULL_POINTER;
+  if (dtype != SCIMLOP_F64 && dtype != SCIMLOP_F32) return SCIMLOP_ERR_UNSUPPORTED;
+  KronPlan pl;
+  if (int rc = kron_plan(nullptr, nfactors, dims, kinds, k, &pl)) return rc;
+  const int nbuf = pl.nops >= 3 ? 2 : (pl.nops == 2 ? 1 : 0);
+  *bytes = nbuf * align_up((size_t)pl.max_inter * elem_size(dtype), 256);
+  return SCIMLOP_OK;
+}
+
+int scimlop_kron_mul_impl(scimlop_context* h, int dtype, int precision, int nfactors, const void* const* factors,
+                          const int64_t* dims, const int64_t* lds, const int32_t* kinds, const void* V, int64_t ldv,
+                          void* W, int64_t ldw, int64_t k, const void* alpha, const void* beta, void* workspace,
+                          size_t workspace_bytes, cudaStream_t st) {
+  if (int rc = check_dtype(h, dtype)) return rc;
+  KronPlan pl;
+  if (int rc = kron_plan(h, nfactors, dims, kinds, k, &pl)) return rc;
+  if (!factors || !lds) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron: factors/lds null");
+  for (int f = 0; f < nfactors; f++) {
+    if (kinds[f] == SCIMLOP_IDENTITY) continue;
+    if (!factors[f]) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron: factor %d is null", f);
+    if ((kinds[f] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE &&
+        lds[f] < std::max<int64_t>(1, (kinds[f] & SCIMLOP_TRANS) ? dims[2 * f + 1] : dims[2 * f]))
+      return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kron: ld of factor %d smaller than its stored rows", f);
+  }
+  if (k == 0 || pl.rows == 0) return SCIMLOP_OK;
+  if (!W || (!V && pl.cols > 0)) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron: V/W null");
+  // the reshape views of src/tensor.jl:558,593 need contiguous columns
+  if (ldv != pl.cols || ldw != pl.rows)
+    return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE,
+                        "kron: V and W must be contiguous (ldv=%lld, cols=%lld; ldw=%lld, rows=%lld)", (long long)ldv,
+                        pl.cols, (long long)ldw, pl.rows);
+  if (pl.cols == 0) {  // empty contraction: W = beta * W
+    if (dtype == SCIMLOP_F64)
+      return eltwise_axpby<double>(h, pl.rows, k, nullptr, 0, (double*)W, ldw, 0.0, scalar_or<double>(beta, 0.0), st);
+    return eltwise_axpby<float>(h, pl.rows, k, nullptr, 0, (float*)W, ldw, 0.f, scalar_or<float>(beta, 0.f), st);
+  }
+  if (dtype == SCIMLOP_F64)
+    return kron_mul_t<double>(h, precision, nfactors, factors, dims, lds, kinds, (const double*)V, (double*)W, k,
+                              scalar_or<double>(alpha, 1.0), scalar_or<double>(beta, 0.0), workspace, workspace_bytes,
+                              pl, st);
+  return kron_mul_t<float>(h, precision, nfactors, factors, dims, lds, kinds, (const float*)V, (float*)W, k,
+                           scalar_or<float>(alpha, 1.f), scalar_or<float>(beta, 0.f), workspace, workspace_bytes, pl,
+                           st);
+}
+
+extern "C" int scimlop_kron_mul(scimlop_handle_t h, int dtype, int precision, int nfactors,
+                                const void* const* factors, const int64_t* dims, const int64_t* lds,
+                                const int32_t* kinds, const void* V, int64_t ldv, void* W, int64_t ldw, int64_t k,
+                                const void* alpha, const void* beta, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  scimlop_device_guard guard(h->device);
+  return scimlop_kron_mul_impl(h, dtype, precision, nfactors, factors, dims, lds, kinds, V, ldv, W, ldw, k, alpha,
+                               beta, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int scimlop_outer_mul_fast(scimlop_handle_t h, int dtype, int precision, void* W, const void* A,
+                                      int64_t lda, const void* C, int64_t mi, int64_t mo, int64_t no, int64_t k,
+                                      const void* alpha, const void* beta, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_dtype(h, dtype)) return rc;
+  if (mi < 0 || mo < 0 || no < 0 || k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "outer_mul: negative size");
+  if (mi == 0 || mo == 0 || k == 0) return SCIMLOP_OK;
+  if (!W || (no > 0 && (!A || !C))) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "outer_mul: null operand");
+  if (no > 0 && lda < mo) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "outer_mul: lda < mo");
+  scimlop_device_guard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // W_j(mi x mo) = alpha * C_j(mi x no) * A^T + beta * W_j, j = 1..k
+  if (dtype == SCIMLOP_F64)
+    return gemm_dispatch<double>(h, precision, false, true, mi, mo, no, scalar_or<double>(alpha, 1.0),
+                                 (const double*)C, mi, mi * no, (const double*)A, lda, 0, scalar_or<double>(beta, 0.0),
+                                 (double*)W, mi, mi * mo, k, 0, nullptr, st);
+  return gemm_dispatch<float>(h, precision, false, true, mi, mo, no, scalar_or<float>(alpha, 1.f), (const float*)C, mi,
+                              mi * no, (const float*)A, lda, 0, scalar_or<float>(beta, 0.f), (float*)W, mi, mi * mo, k,
+                              0, nullptr, st);
+}
+
+template <typename T>
+static int kronsum_t(scimlop_context* h, int precision, const T* A, int64_t lda, int64_t mo, const T* B, int64_t ldb,
+                     int64_t mi, const T* V, T* W, int64_t k, T alpha, T beta, cudaStream_t st) {
+  // I (x) B : W(mi x mo*k) = alpha * B * V + beta * W                         [src/tensor.jl:389,401 / K6]
+  int rc = gemm_dispatch<T>(h, precision, false, false, mi, mo * k, mi, alpha, B, ldb, 0, V, mi, 0, beta, W, mi, 0, 1, 0,
+                            nullptr, st);
+  if (rc) return rc;
+  // A (x) I : W_j += alpha * V_j * A^T                                        [src/tensor.jl:388,400 / K7+K2]
+  return gemm_dispatch<T>(h, precision, false, true, mi, mo, mo, alpha, V, mi, mi * mo, A, lda, 0, T(1), W, mi, mi * mo,
+                          k, 0, nullptr, st);
+}
+
+extern "C" int scimlop_kronsum_mul(scimlop_handle_t h, int dtype, int precision, const void* A, int64_t lda,
+                                   int64_t mo, const void* B, int64_t ldb, int64_t mi, const void* V, int64_t ldv,
+                                   void* W, int64_t ldw, int64_t k, const void* alpha, const void* beta,
+                                   void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_dtype(h, dtype)) return rc;
+  if (mo < 0 || mi < 0 || k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kronsum: negative size");
+  if (mo == 0 || mi == 0 || k == 0) return SCIMLOP_OK;
+  if (!A || !B || !V || !W) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kronsum: null operand");
+  if (lda < mo || ldb < mi) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kronsum: leading dimension smaller than rows");
+  if (ldv != mi * mo || ldw != mi * mo)
+    return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kronsum: V and W must be contiguous (ld == mi*mo)");
+  scimlop_device_guard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SCIMLOP_F64)
+    return kronsum_t<double>(h, precision, (const double*)A, lda, mo, (const double*)B, ldb, mi, (const double*)V,
+                             (double*)W, k, scalar_or<double>(alpha, 1.0), scalar_or<double>(beta, 0.0), st);
+  return kronsum_t<float>(h, precision, (const float*)A, lda, mo, (const float*)B, ldb, mi, (const float*)V, (float*)W,
+                          k, scalar_or<float>(alpha, 1.f), scalar_or<float>(beta, 0.f), st);
+}
+
+// ================================================================================================
+// operator trees
+// ================================================================================================
+namespace {
+
+inline bool is_elementwise(int kind) { return kind == SCIMLOP_IDENTITY || kind == SCIMLOP_DIAG || kind == SCIMLOP_BDIAG; }
+
+struct TreeInfo {
+  long long rows, cols;
+  long long max_inter;  // largest chain intermediate (rows), 0 if none
+  int nbuf;
+};
+
+int tree_analyse(scimlop_context* c, const scimlop_term_t* terms, int nterms, TreeInfo* ti) {
+  if (nterms < 0 || (nterms > 0 && !terms)) return scimlop_fail(c, SCIMLOP_ERR_NULL_POINTER, "tree: terms null");
+  ti->rows = -1; ti->cols = -1; ti->max_inter = 0; ti->nbuf = 0;
+  for (int t = 0; t < nterms; t++) {
+    const scimlop_term_t& T = terms[t];
+    if (T.nfactors < 1 || !T.factors) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "tree: term %d has no factors", t);
+    long long rows = T.factors[0].rows, cols = T.factors[T.nfactors - 1].cols;
+    int ndense = 0;
+    for (int f = 0; f < T.nfactors; f++) {
+      const scimlop_factor_t& F = T.factors[f];
+      if (F.kind < SCIMLOP_DENSE || F.kind > SCIMLOP_NULL) return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "tree: factor kind %d", F.kind);
+      if (F.rows < 0 || F.cols < 0) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "tree: negative factor size");
+      if (is_elementwise(F.kind) && F.rows != F.cols) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "tree: elementwise factor must be square");
+      if (f + 1 < T.nfactors && F.cols != T.factors[f + 1].rows)
+        return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "tree: term %d: factor %d cols (%lld) != factor %d rows (%lld)", t, f,
+                            (long long)F.cols, f + 1, (long long)T.factors[f + 1].rows);
+      if (F.kind == SCIMLOP_DENSE) ndense++;
+    }
+    if (ti->rows < 0) { ti->rows = rows; ti->cols = cols; }
+    else if (ti->rows != rows || ti->cols != cols)
+      return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "tree: summands have different sizes");
+    if (ndense > 0) {
+      // intermediates of the chain: the right-hand diagonal run applied to V (if any) and the output of
+      // every dense factor except the leftmost one; they ping-pong between at most two buffers
+      int ninter = 0;
+      int last_dense = -1, first_dense = -1;
+      for (int f = 0; f < T.nfactors; f++)
+        if (T.factors[f].kind == SCIMLOP_DENSE) { if (first_dense < 0) first_dense = f; last_dense = f; }
+      for (int f = last_dense + 1; f < T.nfactors; f++)
+        if (T.factors[f].kind == SCIMLOP_DIAG || T.factors[f].kind == SCIMLOP_BDIAG) {
+          ninter++; ti->max_inter = std::max<long long>(ti->max_inter, T.factors[last_dense].cols); break;
+        }
+      for (int f = first_dense + 1; f <= last_dense; f++)
+        if (T.factors[f].kind == SCIMLOP_DENSE) { ninter++; ti->max_inter = std::max<long long>(ti->max_inter, T.factors[f].rows); }
+      ti->nbuf = std::max(ti->nbuf, std::min(ninter, 2));
+    }
+  }
+  if (ti->rows < 0) { ti->rows = 0; ti->cols = 0; }
+  return SCIMLOP_OK;
+}
+
+template <typename T>
+void set_factor(elt::Factor<T>& dst, const scimlop_factor_t& F) {
+  dst.ptr = static_cast<const T*>(F.data);
+  if (F.kind == SCIMLOP_BDIAG) { dst.ld = F.ld; dst.div = 1; dst.mod = 1; }
+  else { dst.ld = 0; dst.div = 1; dst.mod = F.rows; }
+}
+
+// add the elementwise factors [first, last) of a term to (nvec-sorted) slot t of an eltwise program
+template <typename T>
+int add_elt_factors(scimlop_context* c, elt::Params<T>& p, int t, const scimlop_factor_t* f, int first, int last) {
+  int nv = 0, nb = 0;
+  const scimlop_factor_t* vec[elt::MAX_FAC];
+  const scimlop_factor_t* bat[elt::MAX_FAC];
+  for (int i = first; i < last; i++) {
+    if (f[i].kind == SCIMLOP_IDENTITY) continue;
+    if (nv + nb == elt::MAX_FAC) return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "tree: more than %d diagonal factors in one product", elt::MAX_FAC);
+    if (!f[i].data) return scimlop_fail(c, SCIMLOP_ERR_NULL_POINTER, "tree: diagonal factor without data");
+    if (f[i].kind == SCIMLOP_DIAG) vec[nv++] = &f[i]; else bat[nb++] = &f[i];
+  }
+  for (int i = 0; i < nv; i++) set_factor(p.fac[t][i], *vec[i]);
+  for (int i = 0; i < nb; i++) set_factor(p.fac[t][nv + i], *bat[i]);
+  p.nvec[t] = nv; p.nfac[t] = nv + nb;
+  return SCIMLOP_OK;
+}
+
+template <typename T>
+int tree_mul_t(scimlop_context* c, int precision, const scimlop_term_t* terms, int nterms, const T* V, long long ldv,
+               T* W, long long ldw, long long k, T alpha, T beta, void* workspace, size_t ws_bytes, const TreeInfo& ti,
+               cudaStream_t st) {
+  const long long rows = ti.rows;
+  const size_t buf_bytes = align_up((size_t)ti.max_inter * (size_t)k * sizeof(T), 256);
+  if (ti.nbuf > 0 && (!workspace || ws_bytes < buf_bytes * ti.nbuf))
+    return scimlop_fail(c, SCIMLOP_ERR_WORKSPACE, "tree: workspace %zu B < required %zu B (call cache_operator first)",
+                        ws_bytes, buf_bytes * ti.nbuf);
+  T* bufs[2] = {static_cast<T*>(workspace), reinterpret_cast<T*>(static_cast<char*>(workspace) + buf_bytes)};
+
+  // ---- pass 1: all elementwise terms in one sweep (also carries beta * W) ----
+  bool w_started = false;  // has W already received beta*W_in ?
+  {
+    elt::Params<T> p;
+    memset(&p, 0, sizeof(p));
+    p.n = rows; p.k = k; p.V = V; p.ldv = ldv; p.W = W; p.ldw = ldw; p.alpha = alpha; p.beta = beta;
+    int ne = 0, ndense_terms = 0;
+    for (int t = 0; t < nterms; t++) {
+      const scimlop_term_t& Tm = terms[t];
+      bool dense = false, null = false;
+      for (int f = 0; f < Tm.nfactors; f++) {
+        dense = dense || Tm.factors[f].kind == SCIMLOP_DENSE;
+        null = null || Tm.factors[f].kind == SCIMLOP_NULL;
+      }
+      if (null || Tm.scale == 0.0) continue;  // NullOperator / iszero(λ) short-circuit (src/basic.jl:521-523)
+      if (dense) { ndense_terms++; continue; }
+      if (ne == elt::MAX_TERMS) {
+        int rc = launch_eltwise(c, p, st);
+        if (rc) return rc;
+        w_started = true;
+        p.beta = T(1); ne = 0; p.nterms = 0;
+      }
+      p.coef[ne] = (T)Tm.scale;
+      if (int rc = add_elt_factors(c, p, ne, Tm.factors, 0, Tm.nfactors)) return rc;
+      ne++;
+      p.nterms = ne;
+    }
+    if (ne > 0 || ndense_terms == 0) {
+      // ndense_terms == 0 && ne == 0: the whole tree is null -> W = beta * W with a strong zero
+      if (!(w_started && ne == 0)) {
+        int rc = launch_eltwise(c, p, st);
+        if (rc) return rc;
+        w_started = true;
+      }
+    }
+  }
+
+  // ---- pass 2: one fused-epilogue GEMM chain per dense term ----
+  for (int t = 0; t < nterms; t++) {
+    const scimlop_term_t& Tm = terms[t];
+    bool dense = false, null = false;
+    int first_dense = -1;
+    for (int f = 0; f < Tm.nfactors; f++) {
+      if (Tm.factors[f].kind == SCIMLOP_DENSE && first_dense < 0) first_dense = f;
+      dense = dense || Tm.factors[f].kind == SCIMLOP_DENSE;
+      null = null || Tm.factors[f].kind == SCIMLOP_NULL;
+    }
+    if (!dense || null || Tm.scale == 0.0) continue;
+    const T* cur = V;
+    long long cur_ld = ldv;
+    int flip = 0;
+    int last_dense = first_dense;
+    for (int f = first_dense; f < Tm.nfactors; f++) if (Tm.factors[f].kind == SCIMLOP_DENSE) last_dense = f;
+    // diagonal factors right of the rightmost dense factor act on V: one elementwise pass into scratch
+    {
+      bool any = false;
+      for (int f = last_dense + 1; f < Tm.nfactors; f++)
+        any = any || Tm.factors[f].kind == SCIMLOP_DIAG || Tm.factors[f].kind == SCIMLOP_BDIAG;
+      if (any) {
+        elt::Params<T> p;
+        memset(&p, 0, sizeof(p));
+        const long long in_rows = Tm.factors[last_dense].cols;
+        T* tmp = bufs[flip]; flip ^= 1;
+        p.n = in_rows; p.k = k; p.V = cur; p.ldv = cur_ld; p.W = tmp; p.ldw = in_rows; p.alpha = T(1); p.beta = T(0);
+        p.nterms = 1; p.coef[0] = T(1);
+        if (int rc = add_elt_factors(c, p, 0, Tm.factors, last_dense + 1, Tm.nfactors)) return rc;
+        if (int rc = launch_eltwise(c, p, st)) return rc;
+        cur = tmp; cur_ld = in_rows;
+      }
+    }
+    for (int f = last_dense; f >= first_dense; f--) {
+      const scimlop_factor_t& F = Tm.factors[f];
+      if (F.kind != SCIMLOP_DENSE) continue;
+      if (!F.data) return scimlop_fail(c, SCIMLOP_ERR_NULL_POINTER, "tree: dense factor without data");
+      const long long in_rows = F.cols, out_rows = F.rows;
+      if (F.ld < std::max<long long>(1, F.trans ? F.cols : F.rows))
+        return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "tree: dense factor ld too small");
+      // the diagonal factors between this dense factor and the next one to its left scale the rows of its
+      // output: they ride in the GEMM epilogue
+      ScaleArg sc[dmma::MAX_SCALES];
+      int ns = 0;
+      for (int q = f - 1; q >= 0 && Tm.factors[q].kind != SCIMLOP_DENSE; q--) {
+        const scimlop_factor_t& D = Tm.factors[q];
+        if (D.kind == SCIMLOP_IDENTITY) continue;
+        if (ns == dmma::MAX_SCALES)
+          return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "tree: more than %d diagonal factors left of a dense factor", dmma::MAX_SCALES);
+        if (!D.data) return scimlop_fail(c, SCIMLOP_ERR_NULL_POINTER, "tree: diagonal factor without data");
+        sc[ns].ptr = D.data; sc[ns].ld = (D.kind == SCIMLOP_BDIAG) ? D.ld : 0; ns++;
+      }
+      if (f == first_dense) {
+        // leftmost dense factor: writes W with λ, α and β fused as well
+        const T b2 = w_started ? T(1) : beta;
+        int rc = gemm_dispatch<T>(c, precision, F.trans != 0, false, out_rows, k, in_rows, (T)(alpha * (T)Tm.scale),
+                                  static_cast<const T*>(F.data), F.ld, 0, cur, cur_ld, 0, b2, W, ldw, 0, 1, ns, sc, st);
+        if (rc) return rc;
+        w_started = true;
+      } else {
+        T* out = bufs[flip]; flip ^= 1;
+        int rc = gemm_dispatch<T>(c, precision, F.trans != 0, false, out_rows, k, in_rows, T(1),
+                                  static_cast<const T*>(F.data), F.ld, 0, cur, cur_ld, 0, T(0), out, out_rows, 0, 1, ns,
+                                  sc, st);
+        if (rc) return rc;
+        cur = out; cur_ld = out_rows;
+      }
+    }
+  }
+  return SCIMLOP_OK;
+}
+
+}  // namespace
+
+extern "C" int scimlop_tree_workspace_bytes(int dtype, const scimlop_term_t* terms, int nterms, int64_t k,
+                                            size_t* bytes) {
+  if (!bytes) return SCIMLOP_ERR_NULL_POINTER;
+  if (dtype != SCIMLOP_F64 && dtype != SCIMLOP_F32) return SCIMLOP_ERR_UNSUPPORTED;
+  if (k < 0) return SCIMLOP_ERR_BAD_SHAPE;
+  TreeInfo ti;
+  if (int rc = tree_analyse(nullptr, terms, nterms, &ti)) return rc;
+  *bytes = ti.nbuf * align_up((size_t)ti.max_inter * (size_t)k * elem_size(dtype), 256);
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_tree_mul(scimlop_handle_t h, int dtype, int precision, const scimlop_term_t* terms, int nterms,
+                                const void* V, int64_t ldv, void* W, int64_t ldw, int64_t k, const void* alpha,
+                                const void* beta, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_dtype(h, dtype)) return rc;
+  if (k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "tree: negative k");
+  TreeInfo ti;
+  if (int rc = tree_analyse(h, terms, nterms, &ti)) return rc;
+  if (nterms == 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "tree: no terms (use scimlop_axpby for a pure beta*W)");
+  if (k == 0 || ti.rows == 0) return SCIMLOP_OK;
+  if (!W || !V) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "tree: V/W null");
+  if (ldw < ti.rows || ldv < ti.cols) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "tree: leading dimension smaller than rows");
+  scimlop_device_guard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SCIMLOP_F64)
+    return tree_mul_t<double>(h, precision, terms, nterms, (const double*)V, ldv, (double*)W, ldw, k,
+                              scalar_or<double>(alpha, 1.0), scalar_or<double>(beta, 0.0), workspace, workspace_bytes, ti, st);
+  return tree_mul_t<float>(h, precision, terms, nterms, (const float*)V, ldv, (float*)W, ldw, k,
+                           scalar_or<float>(alpha, 1.f), scalar_or<float>(beta, 0.f), workspace, workspace_bytes, ti, st);
+}
+
+extern "C" int scimlop_shard_columns(int64_t k, int nranks, int rank, int64_t* first, int64_t* count) {
+  if (!first || !count) return SCIMLOP_ERR_NULL_POINTER;
+  if (k < 0 || nranks < 1 || rank < 0 || rank >= nranks) return SCIMLOP_ERR_BAD_SHAPE;
+  const int64_t base = k / nranks, rem = k % nranks;
+  *first = rank * base + std::min<int64_t>(rank, rem);
+  *count = base + (rank < rem ? 1 : 0);
+  return SCIMLOP_OK;
+}

@@ -1,0 +1,61 @@
+"""Multi-GPU: column sharding with replicated factors.
+
+Every operator of the path acts column-wise on V (src/SciMLOperators.jl:177-198), and columns are
+contiguous in column-major storage, so a shard is a contiguous slab of V and of W.  One process per GPU;
+no collective on the compute path.  `allgather_cols` (NCCL over NVLink) exists only for callers that want
+the whole W replicated on every rank."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def shard_columns(k, nranks, rank):
+    """(first, count): rank's contiguous column slab of a k-column batch (scimlop_shard_columns)."""
+    first, count = C.c_int64(0), C.c_int64(0)
+    rc = _lib.load().scimlop_shard_columns(int(k), int(nranks), int(rank), C.byref(first), C.byref(count))
+    if rc != _lib.OK:
+        raise _lib.ScimlopError(rc, "scimlop_shard_columns")
+    return first.value, count.value
+
+
+class ColumnShard:
+    """This rank's view of a globally (n x k) batch: columns [first, first+count)."""
+
+    def __init__(self, k, nranks, rank):
+        self.k, self.nranks, self.rank = int(k), int(nranks), int(rank)
+        self.first, self.count = shard_columns(k, nranks, rank)
+
+    def take(self, host_matrix):
+        """Slice this rank's columns out of a host (NumPy) matrix."""
+        return np.asfortranarray(host_matrix[:, self.first:self.first + self.count])
+
+    def shard_batched_diag(self, host_diag):
+        """A BatchedDiagonalOperator's diagonal is batch-shaped, so it shards with V (src/batch.jl:6,44-47)."""
+        return self.take(host_diag)
+
+
+def init_comm(handle, nranks, rank, broadcast_bytes):
+    """Create the NCCL communicator. `broadcast_bytes(b: bytes|None) -> bytes` broadcasts rank 0's 128-byte
+    unique id (e.g. via torch.distributed.broadcast_object_list)."""
+    lib = handle.lib
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        handle.check(lib.scimlop_comm_unique_id(buf), "scimlop_comm_unique_id")
+    uid = broadcast_bytes(bytes(buf.raw) if rank == 0 else None)
+    buf2 = C.create_string_buffer(uid, 128)
+    handle.check(lib.scimlop_comm_init(handle.ptr, nranks, rank, buf2), "scimlop_comm_init")
+
+
+def allgather_cols(handle, W_full, cols_per_rank, stream=None):
+    """In-place all-gather of equal column slabs of W_full (rows x cols_per_rank*nranks, contiguous)."""
+    import torch
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+    rows = W_full.shape[0]
+    handle.check(handle.lib.scimlop_allgather_cols(handle.ptr, _lib.F64 if W_full.dtype == np.float64 else _lib.F32,
+                                                   C.c_void_p(W_full.ptr), rows, int(cols_per_rank), st),
+                 "scimlop_allgather_cols")
+    return W_full

@@ -1,0 +1,893 @@
+"""Host-side mirror of the SciMLOperators.jl operator interface for the hot path, over the C ABI.
+
+Julia is not installed in this image, so the package extension that a SciMLOperators.jl maintainer would
+add (julia/ext/SciMLOperatorsB200Ext.jl) cannot run here; this module is its executable
+twin: the same operator types, constructors, algebra, `cache_operator` / `update_coefficients!` /
+`mul!` protocol and error behaviour, with every `mul!` ending in a `ccall`-equivalent ctypes call into
+libscimlop_b200.so.  Names follow the reference (`!` becomes a trailing underscore).
+
+  reference                                             here
+  ----------------------------------------------------  ----------------------------------------------
+  MatrixOperator            src/matrix.jl:116-133       MatrixOperator
+  DiagonalOperator          src/matrix.jl:438-459       DiagonalOperator (vector) -> batch.jl:30 for 2-D
+  BatchedDiagonalOperator   src/batch.jl:11-40          BatchedDiagonalOperator
+  IdentityOperator / NullOperator  src/basic.jl:28,185  IdentityOperator / NullOperator
+  ScalarOperator            src/scalar.jl:124-127       ScalarOperator
+  ScaledOperator            src/basic.jl:357-372        ScaledOperator
+  AddedOperator             src/basic.jl:596-635        AddedOperator
+  ComposedOperator          src/basic.jl:909-939        ComposedOperator
+  TensorProductOperator     src/tensor.jl:88-142        TensorProductOperator, kron
+  TensorSumOperator         src/tensor.jl:269-298       TensorSumOperator, kronsum
+  cache_operator            src/interface.jl:245-252    cache_operator
+  update_coefficients!      src/interface.jl:150-154    update_coefficients_
+  mul!(w, L, v[, α, β])                                 mul_(w, L, v[, alpha, beta])
+  L(w, v, u, p, t[, α, β])  src/interface.jl:161-171    L(w, v, u, p, t[, alpha, beta])
+
+No arithmetic happens on the host: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .array import DeviceArray
+
+_DT = {np.dtype("float64"): _lib.F64, np.dtype("float32"): _lib.F32}
+_CT = {np.dtype("float64"): C.c_double, np.dtype("float32"): C.c_float}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _scalar(dtype, x):
+    """Host scalar in the operand dtype, by reference (the ABI takes α/β as host pointers). None -> NULL."""
+    if x is None:
+        return None
+    return C.byref(_CT[np.dtype(dtype)](float(x)))
+
+
+def _as_device(a):
+    return a if isinstance(a, DeviceArray) else DeviceArray.from_numpy(np.asarray(a))
+
+
+def _ncols(v):
+    return v.shape[1] if v.ndim == 2 else 1
+
+
+def _check_vw(L, w, v):
+    m, n = L.size()
+    if v.shape[0] != n or w.shape[0] != m or _ncols(v) != _ncols(w):
+        raise AssertionError(f"DimensionMismatch: operator {m}x{n}, v {v.shape}, w {w.shape}")
+    if v.dtype != w.dtype:
+        raise TypeError("v and w must have the same element type")
+    dt = L.dtype
+    if dt is not None and dt != v.dtype:
+        raise TypeError(f"operator eltype {dt} != array eltype {v.dtype}: the native ABI takes one dtype "
+                        "(SURVEY.md §8 pitfalls); the Julia wrapper falls back to the generic path here")
+    if w.t.data_ptr() == v.t.data_ptr() and w.t.numel() > 0:
+        raise AssertionError("mul!: w and v must not alias")
+
+
+class ScalarOperator:
+    """src/scalar.jl:124-127 -- mutable scalar; `update_func(old, u, p, t)` gives the new value (:267-270)."""
+
+    def __init__(self, val, update_func=None):
+        self.val = val
+        self.update_func = update_func
+
+    def convert(self):
+        return self.val  # convert(Number, λ), src/scalar.jl:219
+
+    def update_coefficients_(self, u, p, t):
+        if self.update_func is not None:
+            self.val = self.update_func(self.val, u, p, t)
+
+
+class AbstractSciMLOperator:
+    precision = _lib.PREC_DEFAULT
+    dtype = None  # np.dtype of the stored arrays; None for Identity/Null (Bool eltype in the reference)
+
+    # ---- interface ---------------------------------------------------------------------------------
+    def size(self):
+        raise NotImplementedError
+
+    def getops(self):
+        return ()
+
+    def iscached(self):  # src/interface.jl:199-204
+        return all(op.iscached() for op in self.getops() if isinstance(op, AbstractSciMLOperator))
+
+    def cache_operator(self, v):  # src/interface.jl:245-252
+        return self
+
+    def update_coefficients_(self, u=None, p=None, t=None):  # src/interface.jl:150-154
+        for op in self.getops():
+            op.update_coefficients_(u, p, t)
+        return self
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        raise NotImplementedError
+
+    def _flat_terms(self):
+        """[(scale, [leaf, ...]), ...] if this operator is a sum of products of native leaves, else None."""
+        return None
+
+    # ---- call forms: src/interface.jl:161-171 --------------------------------------------------------
+    def __call__(self, *args):
+        if len(args) == 4:      # L(v, u, p, t): out of place
+            v, u, p, t = args
+            self.update_coefficients_(u, p, t)
+            return self * v
+        if len(args) == 5:      # L(w, v, u, p, t)
+            w, v, u, p, t = args
+            self.update_coefficients_(u, p, t)
+            return self.mul_(w, v)
+        if len(args) == 7:      # L(w, v, u, p, t, α, β)
+            w, v, u, p, t, a, b = args
+            self.update_coefficients_(u, p, t)
+            return self.mul_(w, v, a, b)
+        raise TypeError("call forms: L(v,u,p,t), L(w,v,u,p,t), L(w,v,u,p,t,α,β)")
+
+    # ---- algebra: src/basic.jl:375-390, 711-720, 936-939; src/tensor.jl:149-164 -----------------------
+    def __add__(self, other):
+        if isinstance(other, AbstractSciMLOperator):
+            return AddedOperator(self, other)
+        if np.isscalar(other):  # L + λ  ==  L + λ*I  (src/basic.jl:711-720)
+            return AddedOperator(self, ScaledOperator(other, IdentityOperator(self.size()[0])))
+        return NotImplemented
+
+    __radd__ = __add__
+
+    def __neg__(self):
+        return ScaledOperator(-1.0, self)
+
+    def __sub__(self, other):
+        if isinstance(other, AbstractSciMLOperator):
+            return AddedOperator(self, ScaledOperator(-1.0, other))
+        if np.isscalar(other):
+            return AddedOperator(self, ScaledOperator(-other, IdentityOperator(self.size()[0])))
+        return NotImplemented
+
+    def __mul__(self, other):
+        if isinstance(other, AbstractSciMLOperator):
+            return ComposedOperator(self, other)
+        if isinstance(other, ScalarOperator) or np.isscalar(other):
+            return ScaledOperator(other, self)
+        if isinstance(other, DeviceArray):  # out-of-place L * v
+            if not self.iscached():
+                self.cache_operator(other)
+            m = self.size()[0]
+            w = DeviceArray.empty((m,) + other.shape[1:], other.dtype, other.device_index)
+            return self.mul_(w, other)
+        return NotImplemented
+
+    def __rmul__(self, other):
+        if isinstance(other, ScalarOperator) or np.isscalar(other):
+            return ScaledOperator(other, self)
+        return NotImplemented
+
+    __matmul__ = __mul__
+
+    def __truediv__(self, other):
+        if np.isscalar(other):
+            return ScaledOperator(1.0 / other, self)
+        return NotImplemented
+
+    def adjoint(self):
+        raise NotImplementedError(f"adjoint of {type(self).__name__} is outside the B200 hot path")
+
+    @property
+    def T(self):
+        return self.adjoint()  # real element types only: adjoint == transpose
+
+
+def _beta_is_zero(beta):
+    return beta is None or beta is False or float(beta) == 0.0
+
+
+def _lmul(w, beta, h):
+    """lmul!(β, w) with a strong zero (src/basic.jl:251,263) -> scimlop_axpby with V == NULL."""
+    n, k = w.shape[0], _ncols(w)
+    b = 0.0 if _beta_is_zero(beta) else float(beta)
+    h.check(h.lib.scimlop_axpby(h.ptr, _DT[w.dtype], n, k, None, 0, C.c_void_p(w.ptr), w.ld, None,
+                                _scalar(w.dtype, b), _stream()), "scimlop_axpby")
+    return w
+
+
+# ====================================================================================================
+# leaves
+# ====================================================================================================
+class MatrixOperator(AbstractSciMLOperator):
+    """src/matrix.jl:116-133; `mul!` :337-350.  `trans=True` is the lazy Adjoint wrapper produced by
+    `adjoint(::MatrixOperator)` on a constant operator (:174-175).  `update_func(A, u, p, t)` mutates the
+    device matrix in place (:257-271)."""
+
+    def __init__(self, A, trans=False, update_func=None):
+        self.A = _as_device(A)
+        if self.A.ndim != 2:
+            raise ValueError("MatrixOperator needs a matrix")
+        self.trans = bool(trans)
+        self.update_func = update_func
+
+    @property
+    def dtype(self):
+        return self.A.dtype
+
+    def size(self):
+        m, n = self.A.shape
+        return (n, m) if self.trans else (m, n)
+
+    def adjoint(self):
+        if self.update_func is not None:
+            raise NotImplementedError("adjoint of a time-dependent MatrixOperator builds an AdjointOperator (src/left.jl) -- out of scope")
+        return MatrixOperator(self.A, not self.trans)
+
+    def update_coefficients_(self, u=None, p=None, t=None):
+        if self.update_func is not None:
+            self.update_func(self.A, u, p, t)
+        return self
+
+    def _flat_terms(self):
+        return [(1.0, [self])]
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        _check_vw(self, w, v)
+        h = _lib.handle(w.device_index)
+        m, n = self.size()
+        h.check(h.lib.scimlop_matmul(h.ptr, _DT[w.dtype], self.precision, int(self.trans), m, n, _ncols(v),
+                                     C.c_void_p(self.A.ptr), self.A.ld, C.c_void_p(v.ptr), v.ld,
+                                     C.c_void_p(w.ptr), w.ld, _scalar(w.dtype, alpha), _scalar(w.dtype, beta),
+                                     _stream()), "scimlop_matmul")
+        return w
+
+
+class _VectorDiagonalOperator(AbstractSciMLOperator):
+    """`DiagonalOperator(::AbstractVector)` = MatrixOperator(Diagonal(d)), src/matrix.jl:438-459."""
+
+    def __init__(self, d, update_func=None):
+        self.diag = _as_device(d)
+        if self.diag.ndim != 1:
+            raise ValueError("vector diagonal expected")
+        self.update_func = update_func
+
+    @property
+    def dtype(self):
+        return self.diag.dtype
+
+    def size(self):
+        n = self.diag.shape[0]
+        return (n, n)
+
+    def adjoint(self):
+        return self
+
+    def update_coefficients_(self, u=None, p=None, t=None):
+        if self.update_func is not None:
+            self.update_func(self.diag, u, p, t)
+        return self
+
+    def _flat_terms(self):
+        return [(1.0, [self])]
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        _check_vw(self, w, v)
+        h = _lib.handle(w.device_index)
+        n = self.diag.shape[0]
+        h.check(h.lib.scimlop_diag_mul(h.ptr, _DT[w.dtype], n, _ncols(v), C.c_void_p(self.diag.ptr), 0,
+                                       C.c_void_p(v.ptr), v.ld, C.c_void_p(w.ptr), w.ld,
+                                       _scalar(w.dtype, alpha), _scalar(w.dtype, beta), _stream()),
+                "scimlop_diag_mul")
+        return w
+
+
+class BatchedDiagonalOperator(AbstractSciMLOperator):
+    """src/batch.jl:11-28: the diagonal has the same shape as the (N x K) input; `mul!` :151-179."""
+
+    def __init__(self, diag, update_func=None):
+        self.diag = _as_device(diag)
+        if self.diag.ndim != 2:
+            raise ValueError("BatchedDiagonalOperator needs an N x K diagonal")
+        self.update_func = update_func
+
+    @property
+    def dtype(self):
+        return self.diag.dtype
+
+    def size(self):
+        n = self.diag.shape[0]
+        return (n, n)
+
+    def adjoint(self):
+        return self  # src/batch.jl:49-50 (real eltype)
+
+    def update_coefficients_(self, u=None, p=None, t=None):
+        if self.update_func is not None:
+            self.update_func(self.diag, u, p, t)
+        return self
+
+    def _flat_terms(self):
+        return [(1.0, [self])]
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        _check_vw(self, w, v)
+        if tuple(v.shape) != tuple(self.diag.shape):
+            raise AssertionError(f"BatchedDiagonalOperator: v {v.shape} must match diag {self.diag.shape}")
+        h = _lib.handle(w.device_index)
+        n, k = self.diag.shape
+        h.check(h.lib.scimlop_diag_mul(h.ptr, _DT[w.dtype], n, k, C.c_void_p(self.diag.ptr), self.diag.ld,
+                                       C.c_void_p(v.ptr), v.ld, C.c_void_p(w.ptr), w.ld,
+                                       _scalar(w.dtype, alpha), _scalar(w.dtype, beta), _stream()),
+                "scimlop_diag_mul")
+        return w
+
+
+def DiagonalOperator(d, update_func=None):
+    """Vector -> diagonal MatrixOperator (src/matrix.jl:438); array -> BatchedDiagonalOperator (src/batch.jl:30)."""
+    d = _as_device(d)
+    if d.ndim == 1:
+        return _VectorDiagonalOperator(d, update_func)
+    return BatchedDiagonalOperator(d, update_func)
+
+
+class IdentityOperator(AbstractSciMLOperator):
+    """src/basic.jl:28-30; `mul!` :74-90."""
+
+    def __init__(self, n):
+        self.len = int(n)
+
+    def size(self):
+        return (self.len, self.len)
+
+    def adjoint(self):
+        return self
+
+    def _flat_terms(self):
+        return [(1.0, [self])]
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        _check_vw(self, w, v)
+        h = _lib.handle(w.device_index)
+        h.check(h.lib.scimlop_axpby(h.ptr, _DT[w.dtype], self.len, _ncols(v), C.c_void_p(v.ptr), v.ld,
+                                    C.c_void_p(w.ptr), w.ld, _scalar(w.dtype, alpha), _scalar(w.dtype, beta),
+                                    _stream()), "scimlop_axpby")
+        return w
+
+
+class NullOperator(AbstractSciMLOperator):
+    """src/basic.jl:185-188; `mul!` :248-264 (`lmul!(false, w)` / `lmul!(β, w)`)."""
+
+    def __init__(self, n):
+        self.len = int(n)
+
+    def size(self):
+        return (self.len, self.len)
+
+    def adjoint(self):
+        return self
+
+    def _flat_terms(self):
+        return [(1.0, [self])]
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        _check_vw(self, w, v)
+        return _lmul(w, beta, _lib.handle(w.device_index))
+
+
+_LEAVES = (MatrixOperator, _VectorDiagonalOperator, BatchedDiagonalOperator, IdentityOperator, NullOperator)
+
+
+# ====================================================================================================
+# tree plan: an operator that flattens to Σ_t λ_t Π_f leaf  ->  ONE scimlop_tree_mul call
+# ====================================================================================================
+class _TreePlan:
+    def __init__(self, owner, terms, v):
+        self.owner = owner
+        self.terms = terms  # [(scale_getter, [leaf...])]
+        self.k = _ncols(v)
+        self.dtype = v.dtype
+        nt = len(terms)
+        self.c_terms = (_lib.Term * nt)()
+        self._keep = []
+        for i, (_, leaves) in enumerate(terms):
+            arr = (_lib.Factor * len(leaves))()
+            for j, leaf in enumerate(leaves):
+                m, n = leaf.size()
+                f = arr[j]
+                f.rows, f.cols, f.trans, f.data, f.ld = m, n, 0, None, 0
+                if isinstance(leaf, MatrixOperator):
+                    f.kind, f.trans, f.data, f.ld = _lib.DENSE, int(leaf.trans), leaf.A.ptr, leaf.A.ld
+                elif isinstance(leaf, _VectorDiagonalOperator):
+                    f.kind, f.data = _lib.DIAG, leaf.diag.ptr
+                elif isinstance(leaf, BatchedDiagonalOperator):
+                    if leaf.diag.shape[1] != self.k:
+                        raise AssertionError(f"BatchedDiagonalOperator diag {leaf.diag.shape} does not match k={self.k}")
+                    f.kind, f.data, f.ld = _lib.BDIAG, leaf.diag.ptr, leaf.diag.ld
+                elif isinstance(leaf, IdentityOperator):
+                    f.kind = _lib.IDENTITY
+                else:
+                    f.kind = _lib.NULL
+                if leaf.dtype is not None and leaf.dtype != self.dtype:
+                    raise TypeError(f"operator eltype {leaf.dtype} != array eltype {self.dtype}")
+            self._keep.append(arr)
+            self.c_terms[i].nfactors = len(leaves)
+            self.c_terms[i].factors = arr
+        self._refresh_scales()
+        nbytes = C.c_size_t(0)
+        lib = _lib.load()
+        rc = lib.scimlop_tree_workspace_bytes(_DT[self.dtype], self.c_terms, nt, self.k, C.byref(nbytes))
+        if rc != _lib.OK:
+            raise _lib.ScimlopError(rc, "scimlop_tree_workspace_bytes")
+        self.ws_bytes = nbytes.value
+        self.ws = torch.empty(max(1, self.ws_bytes), dtype=torch.uint8, device=v.t.device)
+
+    def _refresh_scales(self):
+        for i, (scale, _) in enumerate(self.terms):
+            self.c_terms[i].scale = float(scale())
+
+    def mul_(self, w, v, alpha, beta, precision):
+        if _ncols(v) != self.k or v.dtype != self.dtype:
+            raise AssertionError("operator was cached for a different input shape / eltype: call cache_operator again")
+        self._refresh_scales()  # ScalarOperators may have been updated (src/scalar.jl:267-270)
+        h = _lib.handle(w.device_index)
+        h.check(h.lib.scimlop_tree_mul(h.ptr, _DT[w.dtype], precision, self.c_terms, len(self.terms),
+                                       C.c_void_p(v.ptr), v.ld, C.c_void_p(w.ptr), w.ld, self.k,
+                                       _scalar(w.dtype, alpha), _scalar(w.dtype, beta),
+                                       C.c_void_p(self.ws.data_ptr()), self.ws_bytes, _stream()),
+                "scimlop_tree_mul")
+        return w
+
+
+def _scale_getter(scalars):
+    def get():
+        x = 1.0
+        for s in scalars:
+            x *= s.convert() if isinstance(s, ScalarOperator) else s
+        return x
+    return get
+
+
+def _terms_with_scalars(L, scalars=()):
+    """Flatten like src/basic.jl:619-635 (sums) and :936-939 (products); returns [(scalars, leaves)] or None."""
+    if isinstance(L, _LEAVES):
+        return [(tuple(scalars), [L])]
+    if isinstance(L, ScaledOperator):
+        return _terms_with_scalars(L.L, tuple(scalars) + (L.lam,))
+    if isinstance(L, AddedOperator):
+        out = []
+        for op in L.ops:
+            t = _terms_with_scalars(op, scalars)
+            if t is None:
+                return None
+            out.extend(t)
+        return out
+    if isinstance(L, ComposedOperator):
+        sc, leaves = tuple(scalars), []
+        for op in L.ops:
+            t = _terms_with_scalars(op, ())
+            if t is None or len(t) != 1:  # distributing a sum over a product would duplicate work
+                return None
+            sc += t[0][0]
+            leaves.extend(t[0][1])
+        return [(sc, leaves)]
+    return None
+
+
+class _TreeMixin:
+    """Shared by Scaled/Added/Composed: try the one-call native plan, else recurse like the reference."""
+    _plan = None
+
+    def _try_plan(self, v):
+        terms = _terms_with_scalars(self)
+        if terms is None:
+            self._plan = None
+            return False
+        self._plan = _TreePlan(self, [(_scale_getter(sc), leaves) for sc, leaves in terms], v)
+        return True
+
+
+# ====================================================================================================
+# lazy algebra
+# ====================================================================================================
+class ScaledOperator(_TreeMixin, AbstractSciMLOperator):
+    """src/basic.jl:357-372; `mul!` :518-536: `mul!(w, L.L, v, λ·α, β)`, `iszero(λ)` short-circuits."""
+
+    def __init__(self, lam, L):
+        self.lam = lam if isinstance(lam, ScalarOperator) else ScalarOperator(lam)
+        self.L = L
+
+    @property
+    def dtype(self):
+        return self.L.dtype
+
+    def size(self):
+        return self.L.size()
+
+    def getops(self):
+        return (self.lam, self.L)
+
+    def iscached(self):
+        return self.L.iscached()
+
+    def adjoint(self):
+        return ScaledOperator(self.lam, self.L.adjoint())  # src/basic.jl:434-439 (real λ)
+
+    def cache_operator(self, v):
+        self.L = self.L.cache_operator(v)
+        self._try_plan(v)
+        return self
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        _check_vw(self, w, v)
+        if self._plan is not None:
+            return self._plan.mul_(w, v, alpha, beta, self.precision)
+        lam = self.lam.convert()
+        if lam == 0:
+            return _lmul(w, beta, _lib.handle(w.device_index))
+        a = lam if alpha is None else lam * float(alpha)
+        return self.L.mul_(w, v, a, False if beta is None else beta)
+
+
+class AddedOperator(_TreeMixin, AbstractSciMLOperator):
+    """src/basic.jl:596-610; nested sums are flattened (:619-635); `mul!` :834-854."""
+
+    def __init__(self, *ops):
+        flat = []
+        for op in ops:
+            flat.extend(op.ops if isinstance(op, AddedOperator) else [op])
+        sizes = {op.size() for op in flat}
+        if len(sizes) != 1:
+            raise AssertionError(f"AddedOperator: size mismatch {sizes}")
+        self.ops = tuple(flat)
+
+    @property
+    def dtype(self):
+        for op in self.ops:
+            if op.dtype is not None:
+                return op.dtype
+        return None
+
+    def size(self):
+        return self.ops[0].size()
+
+    def getops(self):
+        return self.ops
+
+    def adjoint(self):
+        return AddedOperator(*[op.adjoint() for op in self.ops])  # src/basic.jl:766-771
+
+    def cache_operator(self, v):
+        self.ops = tuple(op.cache_operator(v) for op in self.ops)
+        self._try_plan(v)
+        return self
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        _check_vw(self, w, v)
+        if self._plan is not None:
+            return self._plan.mul_(w, v, alpha, beta, self.precision)
+        # summands that are not native leaves (e.g. TensorProductOperators): accumulate like
+        # src/basic.jl:839-840 / :875-885 -- first summand carries β, the rest add with β = 1
+        a = True if alpha is None else alpha
+        self.ops[0].mul_(w, v, a, False if beta is None else beta)
+        for op in self.ops[1:]:
+            op.mul_(w, v, a, True)
+        return w
+
+
+class ComposedOperator(_TreeMixin, AbstractSciMLOperator):
+    """src/basic.jl:909-927; `cache_self` :1104-1138; `mul!` :1160-1207."""
+
+    def __init__(self, *ops):
+        flat = []
+        for op in ops:
+            flat.extend(op.ops if isinstance(op, ComposedOperator) else [op])
+        for a, b in zip(flat[:-1], flat[1:]):
+            if a.size()[1] != b.size()[0]:
+                raise AssertionError(f"ComposedOperator: size mismatch {a.size()} * {b.size()}")
+        self.ops = tuple(flat)
+        self.cache = None
+
+    @property
+    def dtype(self):
+        for op in self.ops:
+            if op.dtype is not None:
+                return op.dtype
+        return None
+
+    def size(self):
+        return (self.ops[0].size()[0], self.ops[-1].size()[1])
+
+    def getops(self):
+        return self.ops
+
+    def adjoint(self):
+        return ComposedOperator(*[op.adjoint() for op in reversed(self.ops)])  # src/basic.jl:1003-1011
+
+    def iscached(self):
+        return (self._plan is not None or self.cache is not None) and all(op.iscached() for op in self.ops)
+
+    def cache_operator(self, v):
+        if self._try_plan(v):
+            self.ops = tuple(self.ops)
+            # children are leaves here; nothing else to cache
+            return self
+        # generic chain: one scratch per intermediate (src/basic.jl:1104-1138), the last slot stashes w
+        k = v.shape[1:]
+        vecs = [v]
+        for op in reversed(self.ops[1:]):
+            vecs.insert(0, DeviceArray.zeros((op.size()[0],) + tuple(k), v.dtype, v.device_index))
+        self.cache = vecs[:-1]  # no stash slot: α and β ride on the last stage instead of copy!/axpy! sweeps
+        n = len(self.ops)
+        inputs = vecs  # input of op i is vecs[i]
+        self.ops = tuple(self.ops[i].cache_operator(inputs[i]) for i in range(n))
+        return self
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        _check_vw(self, w, v)
+        if not self.iscached():
+            raise AssertionError("cache needs to be set up for operator of type ComposedOperator: "
+                                 "call cache_operator(L, v) first")  # src/basic.jl:1183,1198
+        if self._plan is not None:
+            return self._plan.mul_(w, v, alpha, beta, self.precision)
+        n = len(self.ops)
+        if alpha is None:  # 3-arg: chain through the scratch, src/basic.jl:1172-1178
+            vecs = [w] + self.cache[: n - 1] + [v]
+            for i in reversed(range(n)):
+                self.ops[i].mul_(vecs[i], vecs[i + 1])
+            return w
+        # 5-arg without the reference's copy!/lmul!/axpy! sweeps: α and β ride on the last stage
+        vecs = [w] + self.cache[: n - 1] + [v]
+        for i in reversed(range(1, n)):
+            self.ops[i].mul_(vecs[i], vecs[i + 1])
+        return self.ops[0].mul_(w, vecs[1], alpha, beta)
+
+
+# ====================================================================================================
+# tensor products
+# ====================================================================================================
+def _kron_leaf(op):
+    """(kind, data_ptr, ld) if `op` can be a native Kronecker factor, else None."""
+    if isinstance(op, MatrixOperator):
+        return (_lib.DENSE | (_lib.TRANS if op.trans else 0), op.A.ptr, op.A.ld)
+    if isinstance(op, IdentityOperator):
+        return (_lib.IDENTITY, None, 0)
+    if isinstance(op, _VectorDiagonalOperator):
+        return (_lib.DIAG, op.diag.ptr, 0)
+    return None
+
+
+class TensorProductOperator(AbstractSciMLOperator):
+    """src/tensor.jl:88-107.  `ops = (outer, inner)`; matrices are wrapped in MatrixOperator (:109-118); the
+    N-ary constructor is a right fold (:121).  `mul!` :543-610 needs `cache_operator` first (:548,:583)."""
+
+    def __init__(self, *ops):
+        ops = [op if isinstance(op, AbstractSciMLOperator) else MatrixOperator(op) for op in ops]
+        if len(ops) < 2:
+            raise ValueError("TensorProductOperator needs at least two factors")
+        if len(ops) > 2:
+            ops = [ops[0], TensorProductOperator(*ops[1:])]
+        self.ops = tuple(ops)
+        self._native = None   # (factors..., workspace) when the whole product is native
+        self.cache = None     # c1 of the reference when falling back to the two-stage algorithm
+        self._k = None
+
+    @property
+    def dtype(self):
+        for op in self.ops:
+            if op.dtype is not None:
+                return op.dtype
+        return None
+
+    def size(self):
+        (mo, no), (mi, ni) = self.ops[0].size(), self.ops[1].size()
+        return (mo * mi, no * ni)  # src/tensor.jl:179
+
+    def getops(self):
+        return self.ops
+
+    def adjoint(self):
+        return TensorProductOperator(*[op.adjoint() for op in self.ops])  # src/tensor.jl:181-191
+
+    # ---- flattening into native factors (with the ScaledOperator λ's pulled out) ----------------------
+    def _flatten(self):
+        """([(leaf op)...], [scalars...]) outermost first, or None if some factor is not native."""
+        leaves, scalars = [], []
+
+        def walk(op):
+            if isinstance(op, ScaledOperator):
+                scalars.append(op.lam)
+                return walk(op.L)
+            if isinstance(op, TensorProductOperator):
+                return all(walk(o) for o in op.ops)
+            if _kron_leaf(op) is None:
+                return False
+            leaves.append(op)
+            return True
+
+        return (leaves, scalars) if walk(self) else None
+
+    def iscached(self):
+        return self._native is not None or (self.cache is not None and all(op.iscached() for op in self.ops))
+
+    def cache_operator(self, v):
+        """`cache_self` + `cache_internals` (src/tensor.jl:460-541).  Native path: ask the library for its
+        workspace (<= 2 ping-pong buffers instead of the reference's 7 scratch tensors)."""
+        k = _ncols(v)
+        if v.shape[0] != self.size()[1]:
+            raise AssertionError(f"cache_operator: v has {v.shape[0]} rows, operator has {self.size()[1]} columns")
+        self._k = k
+        flat = self._flatten()
+        if flat is not None:
+            leaves, scalars = flat
+            nf = len(leaves)
+            dims = (C.c_int64 * (2 * nf))()
+            lds = (C.c_int64 * nf)()
+            kinds = (C.c_int32 * nf)()
+            ptrs = (C.c_void_p * nf)()
+            for i, op in enumerate(leaves):
+                m, n = op.size()
+                dims[2 * i], dims[2 * i + 1] = m, n
+                kinds[i], ptrs[i], lds[i] = _kron_leaf(op)
+                if op.dtype is not None and op.dtype != v.dtype:
+                    raise TypeError(f"factor eltype {op.dtype} != array eltype {v.dtype}")
+            nbytes = C.c_size_t(0)
+            lib = _lib.load()
+            rc = lib.scimlop_kron_workspace_bytes(_DT[v.dtype], nf, dims, kinds, k, C.byref(nbytes))
+            if rc != _lib.OK:
+                raise _lib.ScimlopError(rc, "scimlop_kron_workspace_bytes")
+            ws = torch.empty(max(1, nbytes.value), dtype=torch.uint8, device=v.t.device)
+            self._native = dict(nf=nf, dims=dims, lds=lds, kinds=kinds, ptrs=ptrs, ws=ws, ws_bytes=nbytes.value,
+                                scalars=scalars, dtype=v.dtype)
+            return self
+        # two-stage algorithm of the reference with the native outer stage (the `tensor_outer_mul_fast!` hook)
+        outer, inner = self.ops
+        mi, ni = inner.size()
+        mo, no = outer.size()
+        self.cache = DeviceArray.zeros((mi, no * k), v.dtype, v.device_index)     # c1, src/tensor.jl:460-476
+        inner = inner.cache_operator(v.reshape(ni, no * k))                        # :538
+        outer = outer.cache_operator(DeviceArray.zeros((no, mi * k), v.dtype, v.device_index))  # :536,:539
+        self.ops = (outer, inner)
+        return self
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        _check_vw(self, w, v)
+        if not self.iscached():
+            raise AssertionError("cache needs to be set up for operator of type TensorProductOperator: "
+                                 "call cache_operator(L, v) first")  # src/tensor.jl:548,583
+        k = _ncols(v)
+        if k != self._k:
+            raise AssertionError("operator was cached for a different number of columns: call cache_operator again")
+        h = _lib.handle(w.device_index)
+        if self._native is not None:
+            nat = self._native
+            a = alpha
+            for s in nat["scalars"]:  # ScaledOperator factors fold into α (the intended src/tensor.jl:800-804)
+                a = s.convert() * (1.0 if a is None else float(a))
+            m, n = self.size()
+            h.check(h.lib.scimlop_kron_mul(h.ptr, _DT[w.dtype], self.precision, nat["nf"], nat["ptrs"], nat["dims"],
+                                           nat["lds"], nat["kinds"], C.c_void_p(v.ptr), n, C.c_void_p(w.ptr), m, k,
+                                           _scalar(w.dtype, a), _scalar(w.dtype, beta),
+                                           C.c_void_p(nat["ws"].data_ptr()), nat["ws_bytes"], _stream()),
+                    "scimlop_kron_mul")
+            return w
+        # ---- reference algorithm, src/tensor.jl:543-610 ----
+        outer, inner = self.ops
+        mi, ni = inner.size()
+        mo, no = outer.size()
+        U = v.reshape(ni, no * k)
+        if isinstance(outer, IdentityOperator):
+            inner.mul_(w.reshape(mi, no * k), U, alpha, beta)                      # :565 / :600
+            return w
+        C1 = self.cache
+        inner.mul_(C1, U)                                                          # :568 / :603
+        lam = 1.0
+        while isinstance(outer, ScaledOperator):                                   # :755-759 / :800-804 (intended)
+            lam *= outer.lam.convert()
+            outer = outer.L
+        if not isinstance(outer, MatrixOperator):
+            raise NotImplementedError(f"outer factor {type(outer).__name__} is not supported by the B200 backend "
+                                      "(the Julia wrapper keeps the generic path for it)")
+        a = alpha if lam == 1.0 else lam * (1.0 if alpha is None else float(alpha))
+        if outer.trans:
+            # W_j = C1_j * op(A)^T with op(A) = A^T  ->  plain (non-transposed B) batched GEMM
+            h.check(h.lib.scimlop_gemm_strided_batched(
+                h.ptr, _DT[w.dtype], self.precision, 0, 0, mi, mo, no, _scalar(w.dtype, a), C.c_void_p(C1.ptr), mi,
+                mi * no, C.c_void_p(outer.A.ptr), outer.A.ld, 0, _scalar(w.dtype, beta), C.c_void_p(w.ptr), mi,
+                mi * mo, k, _stream()), "scimlop_gemm_strided_batched")
+        else:
+            h.check(h.lib.scimlop_outer_mul_fast(h.ptr, _DT[w.dtype], self.precision, C.c_void_p(w.ptr),
+                                                 C.c_void_p(outer.A.ptr), outer.A.ld, C.c_void_p(C1.ptr), mi, mo, no,
+                                                 k, _scalar(w.dtype, a), _scalar(w.dtype, beta), _stream()),
+                    "scimlop_outer_mul_fast")                                      # :773-776 / :816-819
+        return w
+
+
+class TensorSumOperator(AbstractSciMLOperator):
+    """src/tensor.jl:269-298: `outer (x) I + I (x) inner`; `mul!` :387-403."""
+
+    def __init__(self, outer, inner):
+        outer = outer if isinstance(outer, AbstractSciMLOperator) else MatrixOperator(outer)
+        inner = inner if isinstance(inner, AbstractSciMLOperator) else MatrixOperator(inner)
+        for op in (outer, inner):
+            m, n = op.size()
+            if m != n:
+                raise AssertionError("TensorSumOperator needs square factors")
+        self.ops = (outer, inner)
+        self._native = (isinstance(outer, MatrixOperator) and isinstance(inner, MatrixOperator)
+                        and not outer.trans and not inner.trans)
+        self.products = None
+        if not self._native:
+            self.products = (TensorProductOperator(outer, IdentityOperator(inner.size()[0])),
+                             TensorProductOperator(IdentityOperator(outer.size()[0]), inner))
+        self._cached = False
+
+    @property
+    def dtype(self):
+        return self.ops[0].dtype or self.ops[1].dtype
+
+    def size(self):
+        n = self.ops[0].size()[0] * self.ops[1].size()[0]
+        return (n, n)
+
+    def getops(self):
+        return self.ops
+
+    def iscached(self):
+        return self._cached
+
+    def cache_operator(self, v):
+        if not self._native:
+            self.products = tuple(p.cache_operator(v) for p in self.products)
+        self._cached = True
+        return self
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        _check_vw(self, w, v)
+        if not self._native:
+            a = True if alpha is None else alpha
+            self.products[0].mul_(w, v, a, False if beta is None else beta)      # :388 / :400
+            self.products[1].mul_(w, v, a, True)                                 # :389 / :401
+            return w
+        h = _lib.handle(w.device_index)
+        A, B = self.ops[0].A, self.ops[1].A
+        mo, mi = A.shape[0], B.shape[0]
+        n = mo * mi
+        h.check(h.lib.scimlop_kronsum_mul(h.ptr, _DT[w.dtype], self.precision, C.c_void_p(A.ptr), A.ld, mo,
+                                          C.c_void_p(B.ptr), B.ld, mi, C.c_void_p(v.ptr), n, C.c_void_p(w.ptr), n,
+                                          _ncols(v), _scalar(w.dtype, alpha), _scalar(w.dtype, beta), _stream()),
+                "scimlop_kronsum_mul")
+        return w
+
+
+# ====================================================================================================
+# module-level protocol (the reference's free functions)
+# ====================================================================================================
+def kron(*ops):
+    """`kron(A, B, ...)` / `⊗` over operators or matrices: src/tensor.jl:149-164."""
+    return TensorProductOperator(*ops)
+
+
+def kronsum(outer, inner):
+    """src/tensor.jl:334."""
+    return TensorSumOperator(outer, inner)
+
+
+def cache_operator(L, v):
+    return L.cache_operator(v)
+
+
+def iscached(L):
+    return L.iscached()
+
+
+def update_coefficients_(L, u=None, p=None, t=None):
+    return L.update_coefficients_(u, p, t)
+
+
+def mul_(w, L, v, alpha=None, beta=None):
+    """`mul!(w, L, v)` / `mul!(w, L, v, α, β)`; returns w."""
+    if (alpha is None) != (beta is None):
+        raise TypeError("mul!: give both α and β or neither")
+    return L.mul_(w, v, alpha, beta)
