@@ -22,7 +22,7 @@ constexpr int STAGES = 5;
 constexpr int TILE_BYTES = BM * BK * 8;      // 16 KB per operand tile
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;  // A + B
 constexpr int CONSUMER_WARPS = 8;            // 2 (m) x 4 (n), warp tile 64 x 32
-constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int THREADS = CONSUMER_WARPS * 32;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int MAX_SCALES = 3;
 
@@ -63,8 +63,40 @@ __device__ __forceinline__ uint32_t tile_off(int o, int k) {
   return (o >> 4) * 2048 + k * 128 + (((((o & 15) >> 1) ^ (k & 7))) << 4) + ((o & 1) << 3);
 }
 
+// Issue the TMA loads of one pipeline stage: the A and B tiles of k-block `kb` of output tile `tile`.
 template <bool A_KC, bool B_OC>
-__global__ void __maxnreg__(224)
+__device__ __forceinline__ void produce_stage(const CUtensorMap* tmA, const CUtensorMap* tmB, const Params& p,
+                                              uint8_t* smem, uint64_t* full_bar, int slot, long long tile, int kb) {
+  const int mt = (int)(tile % p.tiles_m);
+  const long long r = tile / p.tiles_m;
+  const int nt = (int)(r % p.tiles_n);
+  const int b = (int)(r / p.tiles_n);
+  const int m0 = mt * BM, n0 = nt * BN, k0 = kb * BK;
+  const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
+  uint8_t* sA = smem + slot * STAGE_BYTES;
+  uint8_t* sB = sA + TILE_BYTES;
+  uint64_t* bar = &full_bar[slot];
+  mbar_arrive_expect_tx(bar, STAGE_BYTES);
+  if (A_KC) {
+    tma_load_3d(sA, tmA, bar, k0, m0, ba);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; q++) tma_load_3d(sA + q * 2048, tmA, bar, m0 + 16 * q, k0, ba);
+  }
+  if (!B_OC) {
+    tma_load_3d(sB, tmB, bar, k0, n0, bb);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; q++) tma_load_3d(sB + q * 2048, tmB, bar, n0 + 16 * q, k0, bb);
+  }
+}
+
+// 8 warps, all of them DMMA consumers (2 per SM sub-partition, so each may hold up to 255 registers: a
+// dedicated 9th producer warp would put 3 warps on one sub-partition and cap everybody at 168).  Lane 0 of
+// warp 0 doubles as the TMA producer: at pipeline iteration `it` it refills the slot that iteration it-1
+// released with the data of iteration it+STAGES-1, so STAGES-1 stages are always in flight.
+template <bool A_KC, bool B_OC>
+__global__ void __launch_bounds__(THREADS, 1)
     gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -75,58 +107,32 @@ __global__ void __maxnreg__(224)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool producer = (threadIdx.x == 0);
 
-  if (threadIdx.x == 0) {
+  const int nk = (p.K + BK - 1) / BK;
+  const long long my_tiles = (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const long long total_iters = my_tiles * nk;
+
+  // producer cursor: next (tile, kb) to load and its global iteration number
+  long long p_it = 0, p_tile = blockIdx.x;
+  int p_kb = 0;
+
+  if (producer) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], CONSUMER_WARPS);
     }
     fence_barrier_init();
+    // prologue: fill STAGES-1 slots (first use of each slot, nothing to wait for)
+    for (; p_it < STAGES - 1 && p_it < total_iters; p_it++) {
+      produce_stage<A_KC, B_OC>(&tmA, &tmB, p, smem, full_bar, (int)p_it, p_tile, p_kb);
+      if (++p_kb == nk) { p_kb = 0; p_tile += gridDim.x; }
+    }
   }
   __syncthreads();
 
-  const int nk = (p.K + BK - 1) / BK;
-
-  if (warp == CONSUMER_WARPS) {
-    // ================= TMA producer (one elected lane) =================
-    if (lane == 0) {
-      tma_prefetch_desc(&tmA);
-      tma_prefetch_desc(&tmB);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int mt = (int)(tile % p.tiles_m);
-        const long long r = tile / p.tiles_m;
-        const int nt = (int)(r % p.tiles_n);
-        const int b = (int)(r / p.tiles_n);
-        const int m0 = mt * BM, n0 = nt * BN;
-        const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
-        for (int kb = 0; kb < nk; kb++) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * STAGE_BYTES;
-          uint8_t* sB = sA + TILE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          const int k0 = kb * BK;
-          if (A_KC) {
-            tma_load_3d(sA, &tmA, &full_bar[stage], k0, m0, ba);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; q++) tma_load_3d(sA + q * 2048, &tmA, &full_bar[stage], m0 + 16 * q, k0, ba);
-          }
-          if (!B_OC) {
-            tma_load_3d(sB, &tmB, &full_bar[stage], k0, n0, bb);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; q++) tma_load_3d(sB + q * 2048, &tmB, &full_bar[stage], n0 + 16 * q, k0, bb);
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-    return;
-  }
-
-  // ================= DMMA consumers =================
   const int g = lane >> 2, t = lane & 3;
   const int wm = warp & 1;   // 64-row half of the tile
   const int wn = warp >> 1;  // 32-column quarter of the tile
@@ -141,12 +147,11 @@ __global__ void __maxnreg__(224)
     offB[s][0] = TILE_BYTES + tile_off<!B_OC>(wn * 32 + g, k);
     offB[s][1] = TILE_BYTES + tile_off<!B_OC>(wn * 32 + 8 + g, k);
   }
-  // sub-tile i = 2*(i>>1) + (i&1): +16 outer rows per pair
-  constexpr uint32_t pairA = A_KC ? 16 * 128 : 2048;
-  constexpr uint32_t pairB = (!B_OC) ? 16 * 128 : 2048;
+  constexpr uint32_t pairStride = 2048;  // +16 outer rows in either layout
 
   int stage = 0;
   uint32_t phase = 0;
+  long long it = 0;
 
   for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const int mt = (int)(tile % p.tiles_m);
@@ -160,7 +165,16 @@ __global__ void __maxnreg__(224)
 #pragma unroll
       for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int kb = 0; kb < nk; kb++) {
+    for (int kb = 0; kb < nk; kb++, it++) {
+      if (producer && p_it < total_iters) {
+        // slot of iteration it-1 (== p_it - STAGES): wait until all 8 warps released it, then refill
+        const int slot = (int)(p_it % STAGES);
+        if (p_it >= STAGES) mbar_wait(&empty_bar[slot], (uint32_t)((p_it / STAGES - 1) & 1));
+        produce_stage<A_KC, B_OC>(&tmA, &tmB, p, smem, full_bar, slot, p_tile, p_kb);
+        p_it++;
+        if (++p_kb == nk) { p_kb = 0; p_tile += gridDim.x; }
+      }
+      __syncwarp();
       mbar_wait(&full_bar[stage], phase);
       const uint8_t* st = smem + stage * STAGE_BYTES;
 #pragma unroll
@@ -168,10 +182,10 @@ __global__ void __maxnreg__(224)
         double a[8], bf[4];
 #pragma unroll
         for (int i = 0; i < 8; i++)
-          a[i] = *reinterpret_cast<const double*>(st + offA[s][i & 1] + (i >> 1) * pairA);
+          a[i] = *reinterpret_cast<const double*>(st + offA[s][i & 1] + (i >> 1) * pairStride);
 #pragma unroll
         for (int j = 0; j < 4; j++)
-          bf[j] = *reinterpret_cast<const double*>(st + offB[s][j & 1] + (j >> 1) * pairB);
+          bf[j] = *reinterpret_cast<const double*>(st + offB[s][j & 1] + (j >> 1) * pairStride);
         // MMA rows <- n (B operand), MMA cols <- m (A operand): lane owns C[m = 2t, 2t+1][n = g]
 #pragma unroll
         for (int i = 0; i < 8; i++)
@@ -183,7 +197,7 @@ __global__ void __maxnreg__(224)
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
 
-    // ---- fused epilogue: rowscale, alpha, beta, store (the producer is already prefetching the next tile) ----
+    // ---- fused epilogue: rowscale, alpha, beta, store (the next tile's first stages are already in flight) ----
     const int mbase = mt * BM + wm * 64 + 2 * t;
     const int nbase = nt * BN + wn * 32 + g;
     double* Cb = p.C + (long long)b * p.strideC;

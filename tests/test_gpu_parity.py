@@ -160,7 +160,7 @@ def test_tpo_matches_dense_kron(sb, dtype, square, vector_input):
             ref = R.TensorProductOperator(*[np.asarray(x, dtype=np.float64) for x in mats], lv=lv)
             v64 = np.asfortranarray(v.astype(np.float64))
             ref = ref.cache_operator(v64)
-            wr = np.asfortranarray(w0.astype(np.float64))
+            wr = np.array(w0, dtype=np.float64, order="F", copy=True)
             ref.mul5(wr, v64, alpha, beta)
             w = dev(sb, w0)
             check(sb.mul_(w, L, dv, alpha, beta).numpy(), wr, dtype, f"vs restated reference lv={lv}")
@@ -360,7 +360,7 @@ def test_operator_trees(sb, dtype, N, K):
         check(sb.mul_(dev(sb, w0), L, dv, 0.7, 0.3).numpy(), 0.7 * want + 0.3 * f(w0), dtype, f"{name} 5-arg")
         # and the literal sequential evaluation of the reference (sweep by sweep) agrees
         Lref = Lref.cache_operator(np.asfortranarray(f(v)))
-        wr = np.asfortranarray(f(w0))
+        wr = np.array(f(w0), order="F", copy=True)
         Lref.mul5(wr, np.asfortranarray(f(v)), 0.7, 0.3)
         check(sb.mul_(dev(sb, w0), L, dv, 0.7, 0.3).numpy(), wr, dtype, f"{name} vs restated reference")
 
