@@ -22,7 +22,8 @@ constexpr int STAGES = 5;
 constexpr int TILE_BYTES = BM * BK * 8;      // 16 KB per operand tile
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;  // A + B
 constexpr int CONSUMER_WARPS = 8;            // 2 (m) x 4 (n), warp tile 64 x 32
-constexpr int THREADS = CONSUMER_WARPS * 32;
+constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;    // + one producer warpgroup
+constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int MAX_SCALES = 3;
 
@@ -63,76 +64,81 @@ __device__ __forceinline__ uint32_t tile_off(int o, int k) {
   return (o >> 4) * 2048 + k * 128 + (((((o & 15) >> 1) ^ (k & 7))) << 4) + ((o & 1) << 3);
 }
 
-// Issue the TMA loads of one pipeline stage: the A and B tiles of k-block `kb` of output tile `tile`.
-template <bool A_KC, bool B_OC>
-__device__ __forceinline__ void produce_stage(const CUtensorMap* tmA, const CUtensorMap* tmB, const Params& p,
-                                              uint8_t* smem, uint64_t* full_bar, int slot, long long tile, int kb) {
-  const int mt = (int)(tile % p.tiles_m);
-  const long long r = tile / p.tiles_m;
-  const int nt = (int)(r % p.tiles_n);
-  const int b = (int)(r / p.tiles_n);
-  const int m0 = mt * BM, n0 = nt * BN, k0 = kb * BK;
-  const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
-  uint8_t* sA = smem + slot * STAGE_BYTES;
-  uint8_t* sB = sA + TILE_BYTES;
-  uint64_t* bar = &full_bar[slot];
-  mbar_arrive_expect_tx(bar, STAGE_BYTES);
-  if (A_KC) {
-    tma_load_3d(sA, tmA, bar, k0, m0, ba);
-  } else {
-#pragma unroll
-    for (int q = 0; q < 8; q++) tma_load_3d(sA + q * 2048, tmA, bar, m0 + 16 * q, k0, ba);
-  }
-  if (!B_OC) {
-    tma_load_3d(sB, tmB, bar, k0, n0, bb);
-  } else {
-#pragma unroll
-    for (int q = 0; q < 8; q++) tma_load_3d(sB + q * 2048, tmB, bar, n0 + 16 * q, k0, bb);
-  }
-}
-
-// 8 warps, all of them DMMA consumers (2 per SM sub-partition, so each may hold up to 255 registers: a
-// dedicated 9th producer warp would put 3 warps on one sub-partition and cap everybody at 168).  Lane 0 of
-// warp 0 doubles as the TMA producer: at pipeline iteration `it` it refills the slot that iteration it-1
-// released with the data of iteration it+STAGES-1, so STAGES-1 stages are always in flight.
+// Warp-specialised: warps 0-7 (two warpgroups) are DMMA consumers, warpgroup 2 (warps 8-11) is the TMA
+// producer (one elected lane).  An SM sub-partition owns 16K registers, so three resident warps per
+// sub-partition launch at <= 168 registers each; the producer group then drops to PRODUCER_REGS with
+// setmaxnreg.dec and the consumers grow to CONSUMER_REGS with setmaxnreg.inc (2*232 + 40 <= 512), which is
+// what lets a 64x32 FP64 warp tile (128 accumulator registers) plus double-buffered fragments live in
+// registers without spilling.
 template <bool A_KC, bool B_OC>
 __global__ void __launch_bounds__(THREADS, 1)
     gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  // 128B swizzle patterns repeat every 1024 B: align the tile ring.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 128B swizzle patterns repeat every 1024 B: align the tile ring (in the 32-bit shared window).
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t full_bar = smem + STAGES * STAGE_BYTES;  // STAGES x 8 B
+  const uint32_t empty_bar = full_bar + STAGES * 8;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool producer = (threadIdx.x == 0);
 
-  const int nk = (p.K + BK - 1) / BK;
-  const long long my_tiles = (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  const long long total_iters = my_tiles * nk;
-
-  // producer cursor: next (tile, kb) to load and its global iteration number
-  long long p_it = 0, p_tile = blockIdx.x;
-  int p_kb = 0;
-
-  if (producer) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+  if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CONSUMER_WARPS);
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, CONSUMER_WARPS);
     }
     fence_barrier_init();
-    // prologue: fill STAGES-1 slots (first use of each slot, nothing to wait for)
-    for (; p_it < STAGES - 1 && p_it < total_iters; p_it++) {
-      produce_stage<A_KC, B_OC>(&tmA, &tmB, p, smem, full_bar, (int)p_it, p_tile, p_kb);
-      if (++p_kb == nk) { p_kb = 0; p_tile += gridDim.x; }
-    }
   }
   __syncthreads();
 
+  const int nk = (p.K + BK - 1) / BK;
+  const int ntiles = (int)p.total_tiles;
+
+  if (warp >= CONSUMER_WARPS) {
+    // ================= TMA producer warpgroup =================
+    setmaxnreg_dec<PRODUCER_REGS>();
+    if (warp == CONSUMER_WARPS && lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      const int tiles_mn = p.tiles_m * p.tiles_n;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / tiles_mn;
+        const int rem = tile - b * tiles_mn;
+        const int nt = rem / p.tiles_m;
+        const int mt = rem - nt * p.tiles_m;
+        const int m0 = mt * BM, n0 = nt * BN;
+        const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
+        for (int kb = 0; kb < nk; kb++) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t sA = smem + stage * STAGE_BYTES;
+          const uint32_t sB = sA + TILE_BYTES;
+          const uint32_t bar = full_bar + 8 * stage;
+          mbar_arrive_expect_tx(bar, STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (A_KC) {
+            tma_load_3d(sA, &tmA, bar, k0, m0, ba);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) tma_load_3d(sA + q * 2048, &tmA, bar, m0 + 16 * q, k0, ba);
+          }
+          if (!B_OC) {
+            tma_load_3d(sB, &tmB, bar, k0, n0, bb);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) tma_load_3d(sB + q * 2048, &tmB, bar, n0 + 16 * q, k0, bb);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================= DMMA consumers =================
+  setmaxnreg_inc<CONSUMER_REGS>();
   const int g = lane >> 2, t = lane & 3;
   const int wm = warp & 1;   // 64-row half of the tile
   const int wn = warp >> 1;  // 32-column quarter of the tile
@@ -142,22 +148,46 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
   for (int s = 0; s < 4; s++) {
     const int k = kperm(s, t);
-    offA[s][0] = tile_off<A_KC>(wm * 64 + g, k);
-    offA[s][1] = tile_off<A_KC>(wm * 64 + 8 + g, k);
-    offB[s][0] = TILE_BYTES + tile_off<!B_OC>(wn * 32 + g, k);
-    offB[s][1] = TILE_BYTES + tile_off<!B_OC>(wn * 32 + 8 + g, k);
+    offA[s][0] = smem + tile_off<A_KC>(wm * 64 + g, k);
+    offA[s][1] = smem + tile_off<A_KC>(wm * 64 + 8 + g, k);
+    offB[s][0] = smem + TILE_BYTES + tile_off<!B_OC>(wn * 32 + g, k);
+    offB[s][1] = smem + TILE_BYTES + tile_off<!B_OC>(wn * 32 + 8 + g, k);
   }
-  constexpr uint32_t pairStride = 2048;  // +16 outer rows in either layout
+  constexpr uint32_t PAIR = 2048;  // +16 outer rows in either layout
+
+  // fragments of MMA step s of the stage at byte offset `so`
+#define SCIMLOP_LOAD_FRAGS(A_, B_, so, s)                                               \
+  {                                                                                     \
+    _Pragma("unroll") for (int i = 0; i < 8; i++)                                       \
+        A_[i] = lds_f64(offA[s][i & 1] + (so) + (i >> 1) * PAIR);                       \
+    _Pragma("unroll") for (int j = 0; j < 4; j++)                                       \
+        B_[j] = lds_f64(offB[s][j & 1] + (so) + (j >> 1) * PAIR);                       \
+  }
+  // MMA rows <- n (B operand), MMA cols <- m (A operand): lane owns C[m = 2t, 2t+1][n = g]
+#define SCIMLOP_MMA_STEP(A_, B_)                                                        \
+  {                                                                                     \
+    _Pragma("unroll") for (int i = 0; i < 8; i++)                                       \
+        _Pragma("unroll") for (int j = 0; j < 4; j++)                                   \
+            dmma884(acc[i][j][0], acc[i][j][1], B_[j], A_[i]);                          \
+  }
 
   int stage = 0;
   uint32_t phase = 0;
-  long long it = 0;
+  double a0[8], b0[4], a1[8], b1[4];  // double-buffered fragments: step s computes while step s+1 loads
 
-  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    const int mt = (int)(tile % p.tiles_m);
-    const long long r = tile / p.tiles_m;
-    const int nt = (int)(r % p.tiles_n);
-    const int b = (int)(r / p.tiles_n);
+  // prime the software pipeline with the first fragments of this CTA's first stage
+  if ((int)blockIdx.x < ntiles && nk > 0) {
+    mbar_wait(full_bar, 0);
+    SCIMLOP_LOAD_FRAGS(a0, b0, 0u, 0);
+  }
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tiles_mn = p.tiles_m * p.tiles_n;
+    const int b = tile / tiles_mn;
+    const int rem = tile - b * tiles_mn;
+    const int nt = rem / p.tiles_m;
+    const int mt = rem - nt * p.tiles_m;
+    const bool last_tile = tile + (int)gridDim.x >= ntiles;
 
     double acc[8][4][2];
 #pragma unroll
@@ -165,37 +195,27 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
       for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int kb = 0; kb < nk; kb++, it++) {
-      if (producer && p_it < total_iters) {
-        // slot of iteration it-1 (== p_it - STAGES): wait until all 8 warps released it, then refill
-        const int slot = (int)(p_it % STAGES);
-        if (p_it >= STAGES) mbar_wait(&empty_bar[slot], (uint32_t)((p_it / STAGES - 1) & 1));
-        produce_stage<A_KC, B_OC>(&tmA, &tmB, p, smem, full_bar, slot, p_tile, p_kb);
-        p_it++;
-        if (++p_kb == nk) { p_kb = 0; p_tile += gridDim.x; }
-      }
+    for (int kb = 0; kb < nk; kb++) {
+      const uint32_t so = stage * STAGE_BYTES;
+      SCIMLOP_LOAD_FRAGS(a1, b1, so, 1);
+      SCIMLOP_MMA_STEP(a0, b0);
+      SCIMLOP_LOAD_FRAGS(a0, b0, so, 2);
+      SCIMLOP_MMA_STEP(a1, b1);
+      SCIMLOP_LOAD_FRAGS(a1, b1, so, 3);
+      SCIMLOP_MMA_STEP(a0, b0);
+      // all of this stage's fragments are in registers: hand the slot back to the producer
       __syncwarp();
-      mbar_wait(&full_bar[stage], phase);
-      const uint8_t* st = smem + stage * STAGE_BYTES;
-#pragma unroll
-      for (int s = 0; s < 4; s++) {
-        double a[8], bf[4];
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-          a[i] = *reinterpret_cast<const double*>(st + offA[s][i & 1] + (i >> 1) * pairStride);
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-          bf[j] = *reinterpret_cast<const double*>(st + offB[s][j & 1] + (j >> 1) * pairStride);
-        // MMA rows <- n (B operand), MMA cols <- m (A operand): lane owns C[m = 2t, 2t+1][n = g]
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-#pragma unroll
-          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], bf[j], a[i]);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      // prefetch step 0 of the next stage (next k-block, or the first k-block of this CTA's next tile)
+      if (!(last_tile && kb == nk - 1)) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        SCIMLOP_LOAD_FRAGS(a0, b0, stage * STAGE_BYTES, 0);
+      }
+      SCIMLOP_MMA_STEP(a1, b1);
     }
+#undef SCIMLOP_LOAD_FRAGS
+#undef SCIMLOP_MMA_STEP
 
     // ---- fused epilogue: rowscale, alpha, beta, store (the next tile's first stages are already in flight) ----
     const int mbase = mt * BM + wm * 64 + 2 * t;
