@@ -165,5 +165,64 @@ __global__ void __launch_bounds__(THREADS) eltwise_kernel(const Params<T> p) {
   }
 }
 
+// Specialisation for programs without batched diagonals (Diagonal / Identity / Null / axpby and any sum of
+// products of vector diagonals): the whole tree collapses to one per-row coefficient, so the kernel streams
+// only V (and W when beta != 0).  Few registers -> 8 columns in flight per thread at full occupancy, which is
+// what a pure-streaming pass needs to approach the HBM roofline.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(THREADS) eltwise_rowcoef_kernel(const Params<T> p) {
+  constexpr int U = 8;
+  const long long i0 = ((long long)blockIdx.x * THREADS + threadIdx.x) * VEC;
+  if (i0 >= p.n) return;
+  const long long j_begin = (long long)blockIdx.y * p.cols_per_block;
+  const long long j_end = min(p.k, j_begin + (long long)p.cols_per_block);
+  T base[VEC];
+#pragma unroll
+  for (int q = 0; q < VEC; q++) base[q] = T(0);
+  for (int t = 0; t < p.nterms; t++) {
+    T c[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; q++) c[q] = p.coef[t];
+    for (int f = 0; f < p.nfac[t]; f++) {
+      const Factor<T> F = p.fac[t][f];
+#pragma unroll
+      for (int q = 0; q < VEC; q++) c[q] *= __ldg(F.ptr + ((i0 + q) / F.div) % F.mod);
+    }
+#pragma unroll
+    for (int q = 0; q < VEC; q++) base[q] += c[q];
+  }
+#pragma unroll
+  for (int q = 0; q < VEC; q++) base[q] *= p.alpha;
+  const bool readw = (p.beta != T(0));
+  const bool readv = (p.nterms > 0);
+  const T* vp = p.V + j_begin * p.ldv + i0;
+  T* wp = p.W + j_begin * p.ldw + i0;
+  for (long long j = j_begin; j < j_end; j += U, vp += U * p.ldv, wp += U * p.ldw) {
+    T v[U][VEC], w[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+#pragma unroll
+      for (int q = 0; q < VEC; q++) { v[u][q] = T(0); w[u][q] = T(0); }
+      if (j + u < j_end) {
+        if (readv) ld_stream<T, VEC>(v[u], vp + u * p.ldv);
+        if (readw) ld_stream<T, VEC>(w[u], wp + u * p.ldw);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (j + u < j_end) {
+        T o[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; q++) {
+          T x = readv ? base[q] * v[u][q] : T(0);
+          if (readw) x += p.beta * w[u][q];
+          o[q] = x;
+        }
+        st_stream<T, VEC>(wp + u * p.ldw, o);
+      }
+    }
+  }
+}
+
 }  // namespace elt
 }  // namespace scimlop

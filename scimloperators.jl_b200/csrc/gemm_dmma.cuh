@@ -220,40 +220,68 @@ __global__ void __launch_bounds__(THREADS, 1)
     // ---- fused epilogue: rowscale, alpha, beta, store (the next tile's first stages are already in flight) ----
     const int mbase = mt * BM + wm * 64 + 2 * t;
     const int nbase = nt * BN + wn * 32 + g;
-    double* Cb = p.C + (long long)b * p.strideC;
+    double* Cb = p.C + (long long)b * p.strideC + (long long)nbase * p.ldc + mbase;
+    const bool interior = p.vec_ok && (mt + 1) * BM <= p.M && (nt + 1) * BN <= p.N;
+    if (interior && p.nscale == 0) {
+      // fast path (every tile of the headline shapes): 32 x 16-byte stores per lane, no bounds checks
+      const double alpha = p.alpha, beta = p.beta;
+      if (beta == 0.0) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int n = nbase + 8 * j;
-      if (n >= p.N) continue;
-      double* col = Cb + (long long)n * p.ldc;
+        for (int j = 0; j < 4; j++) {
+          double* col = Cb + (long long)(8 * j) * p.ldc;
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int m = mbase + 8 * i;
-        if (m >= p.M) continue;
-        double v0 = acc[i][j][0], v1 = acc[i][j][1];
-        const bool pair = (m + 1 < p.M);
-        for (int q = 0; q < p.nscale; q++) {
-          const double* sp = p.scale[q].ptr + (p.scale[q].ld ? (long long)n * p.scale[q].ld : 0) + m;
-          v0 *= sp[0];
-          if (pair) v1 *= sp[1];
+          for (int i = 0; i < 8; i++)
+            *reinterpret_cast<double2*>(col + 8 * i) = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
         }
-        v0 *= p.alpha;
-        v1 *= p.alpha;
-        if (pair && p.vec_ok) {
-          double2* dst = reinterpret_cast<double2*>(col + m);
-          if (p.beta != 0.0) {
-            const double2 old = *dst;
-            v0 += p.beta * old.x;
-            v1 += p.beta * old.y;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          double* col = Cb + (long long)(8 * j) * p.ldc;
+          double2 old[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) old[i] = *reinterpret_cast<const double2*>(col + 8 * i);
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            *reinterpret_cast<double2*>(col + 8 * i) =
+                make_double2(fma(alpha, acc[i][j][0], beta * old[i].x), fma(alpha, acc[i][j][1], beta * old[i].y));
+        }
+      }
+    } else {
+      // general path: edge tiles, unaligned C, diagonal row scalings
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int n = nbase + 8 * j;
+        if (n >= p.N) continue;
+        double* col = Cb + (long long)(8 * j) * p.ldc;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int m = mbase + 8 * i;
+          if (m >= p.M) continue;
+          double v0 = acc[i][j][0], v1 = acc[i][j][1];
+          const bool pair = (m + 1 < p.M);
+          for (int q = 0; q < p.nscale; q++) {
+            const double* sp = p.scale[q].ptr + (p.scale[q].ld ? (long long)n * p.scale[q].ld : 0) + m;
+            v0 *= sp[0];
+            if (pair) v1 *= sp[1];
           }
-          *dst = make_double2(v0, v1);
-        } else {
-          if (p.beta != 0.0) {
-            v0 += p.beta * col[m];
-            if (pair) v1 += p.beta * col[m + 1];
+          v0 *= p.alpha;
+          v1 *= p.alpha;
+          double* dst = col + 8 * i;
+          if (pair && p.vec_ok) {
+            if (p.beta != 0.0) {
+              const double2 old = *reinterpret_cast<const double2*>(dst);
+              v0 += p.beta * old.x;
+              v1 += p.beta * old.y;
+            }
+            *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+          } else {
+            if (p.beta != 0.0) {
+              v0 += p.beta * dst[0];
+              if (pair) v1 += p.beta * dst[1];
+            }
+            dst[0] = v0;
+            if (pair) dst[1] = v1;
           }
-          col[m] = v0;
-          if (pair) col[m + 1] = v1;
         }
       }
     }

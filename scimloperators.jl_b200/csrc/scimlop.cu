@@ -49,16 +49,22 @@ int launch_eltwise(scimlop_context* c, elt::Params<T>& p, cudaStream_t st) {
   const long long target = (long long)c->sm_count * 16;
   long long col_blocks = std::max<long long>(1, std::min<long long>((target + row_blocks - 1) / row_blocks, 65535));
   long long cpb = (p.k + col_blocks - 1) / col_blocks;
-  cpb = std::max<long long>(elt::UNROLL, (cpb + elt::UNROLL - 1) / elt::UNROLL * elt::UNROLL);
+  constexpr long long CU = 8;  // column unroll of the widest kernel
+  cpb = std::max<long long>(CU, (cpb + CU - 1) / CU * CU);
   col_blocks = (p.k + cpb - 1) / cpb;
   if (col_blocks > 65535) {
-    cpb = ((p.k + 65534) / 65535 + elt::UNROLL - 1) / elt::UNROLL * elt::UNROLL;
+    cpb = ((p.k + 65534) / 65535 + CU - 1) / CU * CU;
     col_blocks = (p.k + cpb - 1) / cpb;
   }
   if (row_blocks > 2147483647LL) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "eltwise: too many rows");
   p.cols_per_block = (int)cpb;
   dim3 grid((unsigned)row_blocks, (unsigned)col_blocks);
-  if (vec)
+  bool batched = false;
+  for (int t = 0; t < p.nterms; t++) batched = batched || (p.nfac[t] > p.nvec[t]);
+  if (!batched) {
+    if (vec) elt::eltwise_rowcoef_kernel<T, VMAX><<<grid, elt::THREADS, 0, st>>>(p);
+    else elt::eltwise_rowcoef_kernel<T, 1><<<grid, elt::THREADS, 0, st>>>(p);
+  } else if (vec)
     elt::eltwise_kernel<T, VMAX><<<grid, elt::THREADS, 0, st>>>(p);
   else
     elt::eltwise_kernel<T, 1><<<grid, elt::THREADS, 0, st>>>(p);

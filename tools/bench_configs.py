@@ -1,0 +1,172 @@
+"""Times every BASELINE.json config (plus the sub-variants SURVEY.md §8(d) asks for) on one B200 through the
+host mirror / C ABI, device-resident, CUDA events, and prints one JSON line per config with the roofline
+fraction that bounds it.  Not the headline bench (that is bench.py); this is the per-path scoreboard that
+goes into profiles/.
+
+    python tools/bench_configs.py [--only c2,c4elt] [--reps 10]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import scimlop_b200 as sb  # noqa: E402
+
+PEAKS = {"f64_dmma_tflops": 37.1, "f32_ffma_tflops": 72.3}
+try:
+    _mp = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    PEAKS["hbm_gbs"] = float(_mp["hbm_gbs"])
+    PEAKS["hbm_source"] = "MEASURED_PEAKS.json"
+except Exception:
+    PEAKS["hbm_gbs"] = 6650.0
+    PEAKS["hbm_source"] = "fallback (B200_PROFILING.md)"
+
+
+def dev_rand(shape, dtype, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    n = int(np.prod(shape))
+    t = torch.rand(n, dtype=torch.float64 if dtype == np.float64 else torch.float32, device="cuda", generator=g)
+    return sb.DeviceArray(t, shape)
+
+
+def timeit(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    return float(np.min(times)), float(np.median(times))
+
+
+def report(name, flops, nbytes, tmin, tmed, bound, extra=None):
+    h = sb.handle()
+    line = {"config": name, "ms_min": tmin, "ms_median": tmed, "tflops": flops / (tmed * 1e-3) / 1e12,
+            "gbs": nbytes / (tmed * 1e-3) / 1e9, "bound": bound}
+    if bound == "hbm":
+        line["frac"] = line["gbs"] / PEAKS["hbm_gbs"]
+        line["peak"] = f'{PEAKS["hbm_gbs"]} GB/s ({PEAKS["hbm_source"]})'
+    elif bound == "f64":
+        line["frac"] = line["tflops"] / PEAKS["f64_dmma_tflops"]
+        line["peak"] = "37.1 TFLOP/s FP64 DMMA (profiles/r01_peaks_microbench.json)"
+    else:
+        line["frac"] = line["tflops"] / PEAKS["f32_ffma_tflops"]
+        line["peak"] = "72.3 TFLOP/s FP32 FFMA (profiles/r01_peaks_microbench.json)"
+    line["launches_total"] = h.launch_count()
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def c1(reps):
+    A, B = dev_rand((100, 100), np.float64, 0), dev_rand((100, 100), np.float64, 10)
+    V = dev_rand((10 ** 4, 100), np.float64, 1)
+    W = dev_rand((10 ** 4, 100), np.float64, 2)
+    L = sb.cache_operator(sb.kron(sb.MatrixOperator(A), sb.MatrixOperator(B)), V)
+    for tag, fn in (("3arg", lambda: sb.mul_(W, L, V)), ("5arg", lambda: sb.mul_(W, L, V, 0.7, 0.3))):
+        t = timeit(fn, reps)
+        report(f"c1 100x100(x)100x100 f64 k=100 {tag}", 4.0e8, 1.616e7 + (8e6 if tag == "5arg" else 0), *t, "f64")
+
+
+def c2(reps):
+    A, B = dev_rand((512, 512), np.float64, 0), dev_rand((512, 512), np.float64, 10)
+    V = dev_rand((512 * 512, 256), np.float64, 1)
+    W = dev_rand((512 * 512, 256), np.float64, 2)
+    L = sb.cache_operator(sb.kron(sb.MatrixOperator(A), sb.MatrixOperator(B)), V)
+    for tag, fn in (("3arg", lambda: sb.mul_(W, L, V)), ("5arg", lambda: sb.mul_(W, L, V, 0.7, 0.3))):
+        t = timeit(fn, reps)
+        report(f"c2 512x512(x)512x512 f64 k=256 {tag}", 1.374e11, 1.078e9 + (5.37e8 if tag == "5arg" else 0), *t, "f64")
+
+
+def c3(reps, k=512):
+    F = [dev_rand((128, 128), np.float32, s) for s in (0, 10, 20)]
+    n = 128 ** 3
+    V = dev_rand((n, k), np.float32, 1)
+    W = sb.DeviceArray.empty((n, k), np.float32)
+    L = sb.cache_operator(sb.TensorProductOperator(*[sb.MatrixOperator(f) for f in F]), V)
+    t = timeit(lambda: sb.mul_(W, L, V), max(2, reps // 3), warm=1)
+    report(f"c3 128^3 three-factor f32 k={k} 3arg", 3 * 2 * 128.0 * n * k, 2.0 * n * k * 4, *t, "f32")
+
+
+def c4elt(reps):
+    N, K = 2 ** 16, 1024
+    d1, d2 = dev_rand((N,), np.float64, 3), dev_rand((N,), np.float64, 4)
+    Dk = dev_rand((N, K), np.float64, 5)
+    V, W = dev_rand((N, K), np.float64, 1), dev_rand((N, K), np.float64, 2)
+    L = sb.cache_operator(sb.DiagonalOperator(d1) * sb.DiagonalOperator(Dk) + 2.0 * sb.DiagonalOperator(d2)
+                          + sb.IdentityOperator(N), V)
+    nb = N * K * 8
+    t = timeit(lambda: sb.mul_(W, L, V, 0.7, 0.3), reps)
+    report("c4-elt alpha*(D1*Dk + 2*D2 + I)*v + beta*w f64 N=65536 K=1024", 5.0 * N * K, 4.0 * nb, *t, "hbm")
+    t = timeit(lambda: sb.mul_(W, L, V), reps)
+    report("c4-elt 3-arg (no read of w)", 4.0 * N * K, 3.0 * nb, *t, "hbm")
+    Lb = sb.DiagonalOperator(Dk)
+    t = timeit(lambda: sb.mul_(W, Lb, V, 0.7, 0.3), reps)
+    report("BatchedDiagonalOperator 5-arg", 3.0 * N * K, 4.0 * nb, *t, "hbm")
+    Ld = sb.DiagonalOperator(d1)
+    t = timeit(lambda: sb.mul_(W, Ld, V), reps)
+    report("DiagonalOperator 3-arg", 1.0 * N * K, 2.0 * nb, *t, "hbm")
+    Li = sb.IdentityOperator(N)
+    t = timeit(lambda: sb.mul_(W, Li, V, 0.7, 0.3), reps)
+    report("IdentityOperator 5-arg (axpby)", 2.0 * N * K, 3.0 * nb, *t, "hbm")
+
+
+def c4dense(reps, N=32768, K=1024):
+    Mm = dev_rand((N, N), np.float64, 6)
+    d = dev_rand((N,), np.float64, 3)
+    V, W = dev_rand((N, K), np.float64, 1), dev_rand((N, K), np.float64, 2)
+    Mop = sb.MatrixOperator(Mm)
+    L = sb.cache_operator(sb.DiagonalOperator(d) * Mop.adjoint() + 2.0 * Mop + sb.IdentityOperator(N), V)
+    t = timeit(lambda: sb.mul_(W, L, V, 0.7, 0.3), max(2, reps // 4), warm=1)
+    report(f"c4-dense alpha*(D*M' + 2M + I)*v + beta*w f64 N={N} K={K}", 2 * 2.0 * N * N * K,
+           2.0 * N * N * 8 + 3.0 * N * K * 8, *t, "f64")
+
+
+def c5(reps, k=8):
+    n = 4096
+    Dxx, Dyy = dev_rand((n, n), np.float64, 7), dev_rand((n, n), np.float64, 8)
+    V, W = dev_rand((n * n, k), np.float64, 1), dev_rand((n * n, k), np.float64, 2)
+    L = sb.cache_operator(sb.kron(sb.MatrixOperator(Dxx), sb.IdentityOperator(n))
+                          + sb.kron(sb.IdentityOperator(n), sb.MatrixOperator(Dyy)), V)
+    t = timeit(lambda: sb.mul_(W, L, V), max(2, reps // 4), warm=1)
+    report(f"c5 kron(Dxx,I)+kron(I,Dyy) 4096^2 grid f64 k={k} (AddedOperator of two TPOs)", 2 * 2.0 * n ** 3 * k,
+           2.0 * n * n * k * 8 + 2.0 * n * n * 8, *t, "f64")
+    Ls = sb.cache_operator(sb.kronsum(sb.MatrixOperator(Dxx), sb.MatrixOperator(Dyy)), V)
+    t = timeit(lambda: sb.mul_(W, Ls, V), max(2, reps // 4), warm=1)
+    report(f"c5 kronsum(Dxx,Dyy) k={k} (scimlop_kronsum_mul)", 2 * 2.0 * n ** 3 * k, 2.0 * n * n * k * 8 + 2.0 * n * n * 8,
+           *t, "f64")
+    # the Krylov/ODE loop: R matvecs captured in one CUDA graph
+    R = 20
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        sb.mul_(W, Ls, V)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(R):
+                sb.mul_(W, Ls, V)
+    t = timeit(lambda: g.replay(), 3, warm=1)
+    report(f"c5 kronsum k={k}: {R} matvecs in one CUDA graph (per matvec)", 2 * 2.0 * n ** 3 * k,
+           2.0 * n * n * k * 8 + 2.0 * n * n * 8, t[0] / R, t[1] / R, "f64")
+
+
+ALL = {"c1": c1, "c2": c2, "c3": c3, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=",".join(ALL))
+    ap.add_argument("--reps", type=int, default=10)
+    a = ap.parse_args()
+    torch.cuda.set_device(0)
+    for name in a.only.split(","):
+        ALL[name](a.reps)
+        torch.cuda.empty_cache()
