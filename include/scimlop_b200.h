@@ -47,9 +47,12 @@ enum {
 /* ---- element types & precision modes ------------------------------------------------------------- */
 enum { SCIMLOP_F64 = 0, SCIMLOP_F32 = 1 };
 enum {
-  SCIMLOP_PREC_DEFAULT = 0, /* F64: DMMA (mma.sync f64) tensor path; F32: exact-FP32 FFMA path     */
-  SCIMLOP_PREC_TF32X3 = 1,  /* F32 only, opt-in: 3xTF32 split on tensor cores (rel. err <= 1e-5)   */
-  SCIMLOP_PREC_TF32 = 2     /* F32 only, opt-in: single-pass TF32 (rel. err ~1e-3)                 */
+  SCIMLOP_PREC_DEFAULT = 0,   /* F64: DMMA (mma.sync f64) tensor path.  F32: the fastest path that holds the
+                                 1e-5 relative-error contract: 3xTF32 split on tcgen05 tensor cores where the
+                                 shape is eligible, exact-FP32 FFMA otherwise                               */
+  SCIMLOP_PREC_TF32X3 = 1,    /* F32 only: 3xTF32 split on tcgen05 (same as DEFAULT where eligible)          */
+  SCIMLOP_PREC_TF32 = 2,      /* F32 only, explicit opt-in: single-pass TF32 on tcgen05 (rel. err ~1e-3)     */
+  SCIMLOP_PREC_FP32_EXACT = 3 /* F32 only: force the exact-FP32 FFMA path                                    */
 };
 
 /* ---- factor kinds (kron factors and tree leaves) --------------------------------------------------- */

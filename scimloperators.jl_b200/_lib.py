@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libscimlop_b200.so")
 OK = 0
 ERR_NULL_POINTER, ERR_BAD_SHAPE, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_BAD_HANDLE, ERR_NO_DEVICE = range(1, 9)
 F64, F32 = 0, 1
-PREC_DEFAULT, PREC_TF32X3, PREC_TF32 = 0, 1, 2
+PREC_DEFAULT, PREC_TF32X3, PREC_TF32, PREC_FP32_EXACT = 0, 1, 2, 3
 DENSE, IDENTITY, DIAG, BDIAG, NULL = 0, 1, 2, 3, 4
 TRANS = 0x100
 

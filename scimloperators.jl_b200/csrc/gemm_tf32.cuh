@@ -1,0 +1,327 @@
+// gemm_tf32.cuh -- Float32 "streaming operand x resident factor" GEMM on the 5th-generation tensor cores:
+// tcgen05.mma (kind::tf32) with TMEM accumulators, TMA-staged operands, 3xTF32 split for FP32-grade accuracy.
+//
+//   D(r, c) = alpha * sum_k X(r, k) * Fop(c, k)  +  beta * D(r, c)            r < rows, c < m, k < n
+//
+// X is the big streamed operand (a mode-unfolding of V, src/tensor.jl:558,780), Fop = op(F) is one small
+// Kronecker factor / MatrixOperator (m x n, both <= 128) that stays resident in shared memory, split once
+// per CTA into F_hi + F_lo.  Each X tile is split on the fly (x = hi + lo, both exactly representable in
+// TF32) and the product is accumulated as  lo*Fhi + hi*Flo + hi*Fhi  in FP32 inside TMEM (rel. error ~1e-6,
+// inside the 1e-5 budget of the north_star; the dropped lo*lo term is O(2^-22)).
+//
+// Two geometries, both pure tensor-map / descriptor choices (no data is ever transposed in memory):
+//   XK  (innermost Kronecker mode, MatrixOperator mul!):  X(r,k) at k + ldx*r      -> K-major A operand
+//   XMN (any other Kronecker mode, batched):              X(r,k) at r + ldx*k (+b) -> MN-major A operand
+// and the factor as B operand: MN-major for a plain factor (F(c,k) at c + ldf*k), K-major for a transposed one.
+//
+// Warp roles (10 warps): 0 TMA producer, 1 MMA issuer (+TMEM owner), 2-5 hi/lo splitters, 6-9 epilogue.
+#pragma once
+#include "ptx.cuh"
+
+namespace scimlop {
+namespace tf32 {
+
+constexpr int TM = 128;                 // rows of X per tile = UMMA M = TMEM lanes
+constexpr int BK = 32;                  // k per stage (128 bytes)
+constexpr int MAXF = 128;               // factor extents supported (m, n <= 128)
+constexpr int STAGES = 3;
+constexpr int XT_BYTES = TM * BK * 4;   // 16 KB: one X tile (raw -> hi in place), same again for lo
+constexpr int STAGE_BYTES = 2 * XT_BYTES;
+constexpr int F_BYTES = MAXF * MAXF * 4;  // 64 KB each for F_hi and F_lo
+constexpr int NBAR = 3 * STAGES + 4 + 1;
+constexpr int SMEM_BYTES = 1024 + 2 * F_BYTES + STAGES * STAGE_BYTES + 8 * NBAR + 16;
+constexpr int THREADS = 320;
+constexpr int TMEM_COLS = 256;          // two 128-column FP32 accumulators
+
+struct Params {
+  long long rows;        // extent of r per batch
+  int m, n;              // factor extents (output columns, contraction length)
+  int batch;
+  int tiles_r;           // ceil(rows / 128)
+  long long total_tiles; // tiles_r * batch
+  float* D;
+  long long d_rs, d_cs, d_bs;  // D(r, c, b) at r*d_rs + c*d_cs + b*d_bs
+  float alpha, beta;
+  int vec_ok;            // d_cs == 1 and 16-byte alignment holds: float4 stores along c
+  int x_batched;
+  int passes;            // 3: lo*Fhi + hi*Flo + hi*Fhi (FP32-grade);  1: hi*Fhi only (plain TF32, opt-in)
+};
+
+// ---- tcgen05 wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 64-bit shared-memory matrix descriptor (SM100 format, version 1), SWIZZLE_128B.
+//   K-major : rows of 128 B, 8-row groups SBO bytes apart; LBO unused (1).
+//   MN-major: atoms of (32 elements along MN = 128 B) x (8 k); LBO = bytes between atoms along MN,
+//             SBO = bytes between atoms along K.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, M = 128, N = n_mma
+__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int n_mma) {
+  uint32_t d = 0;
+  d |= 1u << 4;                        // c_format  = F32
+  d |= 2u << 7;                        // a_format  = TF32
+  d |= 2u << 10;                       // b_format  = TF32
+  d |= (a_mn ? 1u : 0u) << 15;         // a_major   (0 = K, 1 = MN)
+  d |= (b_mn ? 1u : 0u) << 16;         // b_major
+  d |= (uint32_t)(n_mma >> 3) << 17;   // N >> 3
+  d |= (uint32_t)(TM >> 4) << 24;      // M >> 4
+  return d;
+}
+
+__device__ __forceinline__ void split4(float4 x, float4& hi, float4& lo) {
+  auto h = [](float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+  hi = make_float4(h(x.x), h(x.y), h(x.z), h(x.w));
+  lo = make_float4(h(x.x - hi.x), h(x.y - hi.y), h(x.z - hi.z), h(x.w - hi.w));
+}
+
+// X_MN: X is MN-major (r contiguous); else K-major (k contiguous).  F_K: factor is K-major (transposed factor).
+template <bool X_MN, bool F_K>
+__global__ void __launch_bounds__(THREADS, 1)
+    gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmF, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));  // generic pointer to the aligned base
+  const uint32_t sFhi = smem, sFlo = smem + F_BYTES, sX = smem + 2 * F_BYTES;
+  const uint32_t bars = sX + STAGES * STAGE_BYTES;
+  const uint32_t raw_full = bars, split_done = bars + 8 * STAGES, stage_free = bars + 16 * STAGES;
+  const uint32_t tmem_full = bars + 24 * STAGES, tmem_empty = tmem_full + 16, f_full = tmem_empty + 16;
+  const uint32_t tmem_slot = f_full + 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(raw_full + 8 * s, 1);
+      mbar_init(split_done + 8 * s, 4);   // one arrival per splitter warp
+      mbar_init(stage_free + 8 * s, 1);   // tcgen05.commit
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tmem_full + 8 * a, 1);    // tcgen05.commit
+      mbar_init(tmem_empty + 8 * a, 4);   // one arrival per epilogue warp
+    }
+    mbar_init(f_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // ---- resident factor: TMA the raw FP32 factor into the F_hi region, then split it in place ----
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmF);
+    mbar_arrive_expect_tx(f_full, F_BYTES);
+    // four 16 KB boxes: F_K: {32 k, 128 c} per k-block; else {32 c, 128 k} per c-group
+    for (int q = 0; q < 4; q++) tma_load_3d(sFhi + q * 16384, &tmF, f_full, 32 * q, 0, 0);
+  }
+  mbar_wait(f_full, 0);
+  {
+    float4* hi = reinterpret_cast<float4*>(smem_gen);
+    float4* lo = reinterpret_cast<float4*>(smem_gen + F_BYTES);
+    for (int i = threadIdx.x; i < F_BYTES / 16; i += THREADS) {
+      float4 h, l;
+      split4(hi[i], h, l);
+      hi[i] = h;
+      lo[i] = l;
+    }
+  }
+  fence_async_smem();
+  __syncthreads();
+
+  const int nkb = (p.n + BK - 1) / BK;                 // k-blocks of 32
+  const int n_mma = ((p.m + 15) / 16) * 16;            // UMMA N
+  const uint32_t idesc = make_idesc(X_MN, !F_K, n_mma);
+
+  if (warp == 0) {
+    // ===================== TMA producer: raw X tiles =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int b = (int)(tile / p.tiles_r);
+        const int r0 = (int)(tile - (long long)b * p.tiles_r) * TM;
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(stage_free + 8 * stage, phase ^ 1);
+          const uint32_t dst = sX + stage * STAGE_BYTES;
+          const uint32_t bar = raw_full + 8 * stage;
+          mbar_arrive_expect_tx(bar, XT_BYTES);
+          if (X_MN) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) tma_load_3d(dst + q * 4096, &tmX, bar, r0 + 32 * q, kb * BK, p.x_batched ? b : 0);
+          } else {
+            tma_load_3d(dst, &tmX, bar, kb * BK, r0, p.x_batched ? b : 0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+        const int a = it & 1;
+        const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(tmem_empty + 8 * a, aphase ^ 1);   // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * 128;
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(split_done + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t xhi = sX + stage * STAGE_BYTES, xlo = xhi + XT_BYTES;
+          const int ksteps = min(4, (p.n - kb * BK + 7) / 8);
+          for (int ks = 0; ks < ksteps; ks++) {
+            uint64_t ahi, alo, bhi, blo;
+            if (X_MN) {   // atoms of 32 r x 8 k: next k atom +1024 B, next r atom +4096 B
+              ahi = make_desc(xhi + ks * 1024, 4096, 1024);
+              alo = make_desc(xlo + ks * 1024, 4096, 1024);
+            } else {      // rows of 128 B, +32 B per k-step inside the swizzle span
+              ahi = make_desc(xhi + ks * 32, 16, 1024);
+              alo = make_desc(xlo + ks * 32, 16, 1024);
+            }
+            if (F_K) {    // per k-block a [128 c][32 k] tile of 16 KB
+              bhi = make_desc(sFhi + kb * 16384 + ks * 32, 16, 1024);
+              blo = make_desc(sFlo + kb * 16384 + ks * 32, 16, 1024);
+            } else {      // four c-groups of [128 k][32 c] (16 KB apart); k atoms 1024 B apart
+              bhi = make_desc(sFhi + (kb * 4 + ks) * 1024, 16384, 1024);
+              blo = make_desc(sFlo + (kb * 4 + ks) * 1024, 16384, 1024);
+            }
+            const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+            if (p.passes == 3) {
+              tc_mma_tf32(d_tmem, alo, bhi, idesc, first);
+              tc_mma_tf32(d_tmem, ahi, blo, idesc, 1u);
+              tc_mma_tf32(d_tmem, ahi, bhi, idesc, 1u);
+            } else {
+              tc_mma_tf32(d_tmem, ahi, bhi, idesc, first);
+            }
+          }
+          tc_commit(stage_free + 8 * stage);          // smem slot reusable once these MMAs retire
+          if (kb == nkb - 1) tc_commit(tmem_full + 8 * a);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== splitters: raw X tile -> hi (in place) + lo =====================
+    const int st = threadIdx.x - 64;  // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < nkb; kb++) {
+        mbar_wait(raw_full + 8 * stage, phase);
+        float4* hi = reinterpret_cast<float4*>(smem_gen + 2 * F_BYTES + stage * STAGE_BYTES);
+        float4* lo = hi + XT_BYTES / 16;
+        float4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = hi[st + 128 * i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          float4 h, l;
+          split4(x[i], h, l);
+          hi[st + 128 * i] = h;
+          lo[st + 128 * i] = l;
+        }
+        fence_async_smem();       // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_done + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global (alpha, beta fused) =====================
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+      const int a = it & 1;
+      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+      const int b = (int)(tile / p.tiles_r);
+      const long long r = (tile - (long long)b * p.tiles_r) * TM + quarter * 32 + lane;
+      mbar_wait(tmem_full + 8 * a, aphase);
+      tc_fence_after();
+      float* drow = p.D + (long long)b * p.d_bs + r * p.d_rs;
+      const bool row_ok = r < p.rows;
+      for (int c0 = 0; c0 < p.m; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * 128 + c0, v);
+        tc_wait_ld();
+        if (row_ok) {
+          if (p.vec_ok && c0 + 32 <= p.m) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              float4 o = make_float4(p.alpha * __uint_as_float(v[c]), p.alpha * __uint_as_float(v[c + 1]),
+                                     p.alpha * __uint_as_float(v[c + 2]), p.alpha * __uint_as_float(v[c + 3]));
+              float4* dst = reinterpret_cast<float4*>(drow + c0 + c);
+              if (p.beta != 0.f) {
+                const float4 old = *dst;
+                o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+              }
+              *dst = o;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+              if (c0 + c < p.m) {
+                float* dst = drow + (long long)(c0 + c) * p.d_cs;
+                float o = p.alpha * __uint_as_float(v[c]);
+                if (p.beta != 0.f) o += p.beta * *dst;
+                *dst = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + 8 * a);
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace tf32
+}  // namespace scimlop

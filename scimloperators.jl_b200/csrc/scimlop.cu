@@ -11,6 +11,7 @@
 #include "eltwise.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tf32.cuh"
 
 using namespace scimlop;
 
@@ -205,17 +206,83 @@ int gemm_dispatch<double>(scimlop_context* c, int precision, bool transA, bool t
                              nscale, scales, st);
 }
 
+// ---- tcgen05 TF32 launcher (Float32, streamed operand x resident factor) ----------------------------------
+int make_map_f32(scimlop_context* c, CUtensorMap* map, const float* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2,
+                 cuuint64_t s1_bytes, cuuint64_t s2_bytes, cuuint32_t b0, cuuint32_t b1) {
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstr[2] = {s1_bytes, d2 > 1 ? s2_bytes : s1_bytes * d1};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = c->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return scimlop_fail(c, SCIMLOP_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed (CUresult %d): dims {%llu,%llu,%llu}",
+                        (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
+  return SCIMLOP_OK;
+}
+
+// D(r,c,b) = alpha * sum_k X(r,k,b) * Fop(c,k) + beta * D;  x_mn: X(r,k) at r + ldx*k, else at k + ldx*r;
+// f_k: Fop(c,k) at k + ldf*c, else at c + ldf*k.
+int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, int n, long long batch, const float* X,
+                long long ldx, long long xbs, const float* F, long long ldf, float* D, long long d_rs, long long d_cs,
+                long long d_bs, float alpha, float beta, int passes, cudaStream_t st) {
+  CUtensorMap tmX, tmF;
+  const bool xb = batch > 1 && xbs != 0;
+  int rc;
+  if (x_mn) rc = make_map_f32(c, &tmX, X, rows, n, xb ? batch : 1, ldx * 4, xbs * 4, 32, 32);
+  else rc = make_map_f32(c, &tmX, X, n, rows, xb ? batch : 1, ldx * 4, xbs * 4, 32, 128);
+  if (rc) return rc;
+  if (f_k) rc = make_map_f32(c, &tmF, F, n, m, 1, ldf * 4, 0, 32, 128);
+  else rc = make_map_f32(c, &tmF, F, m, n, 1, ldf * 4, 0, 32, 128);
+  if (rc) return rc;
+  tf32::Params p;
+  memset(&p, 0, sizeof(p));
+  p.rows = rows; p.m = m; p.n = n; p.batch = (int)batch;
+  p.tiles_r = (int)((rows + tf32::TM - 1) / tf32::TM);
+  p.total_tiles = (long long)p.tiles_r * batch;
+  p.D = D; p.d_rs = d_rs; p.d_cs = d_cs; p.d_bs = d_bs;
+  p.alpha = alpha; p.beta = beta;
+  p.vec_ok = (d_cs == 1) && aligned16(D) && (d_rs % 4 == 0) && (d_bs % 4 == 0);
+  p.x_batched = xb;
+  p.passes = passes;
+  const int grid = (int)std::min<long long>(p.total_tiles, c->sm_count);
+  if (x_mn && f_k) tf32::gemm_tf32x3_kernel<true, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, p);
+  else if (x_mn) tf32::gemm_tf32x3_kernel<true, false><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, p);
+  else if (f_k) tf32::gemm_tf32x3_kernel<false, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, p);
+  else tf32::gemm_tf32x3_kernel<false, false><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, p);
+  c->launches++;
+  SCIMLOP_CUDA(c, cudaGetLastError());
+  return SCIMLOP_OK;
+}
+
 template <>
 int gemm_dispatch<float>(scimlop_context* c, int precision, bool transA, bool transB, long long M, long long N,
                          long long K, float alpha, const float* A, long long lda, long long sA, const float* B,
                          long long ldb, long long sB, float beta, float* C, long long ldc, long long sC,
                          long long batch, int nscale, const ScaleArg* scales, cudaStream_t st) {
-  if (precision != SCIMLOP_PREC_DEFAULT)
-    return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED,
-                        "Float32 tensor-core modes (TF32x3 / TF32) are not built yet; use SCIMLOP_PREC_DEFAULT");
+  if (precision < SCIMLOP_PREC_DEFAULT || precision > SCIMLOP_PREC_FP32_EXACT)
+    return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "unknown precision mode %d", precision);
   if (M <= 0 || N <= 0 || batch <= 0) return SCIMLOP_OK;
-  return launch_simt<float>(c, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
-                            nscale, scales, st);
+  if (precision != SCIMLOP_PREC_FP32_EXACT && nscale == 0 && K >= 8 && K <= tf32::MAXF) {
+    const int passes = (precision == SCIMLOP_PREC_TF32) ? 1 : 3;
+    const long long lim = 2147483647LL;
+    // (a) the factor is A (innermost Kronecker mode, MatrixOperator mul!): stream B's columns
+    if (batch == 1 && !transB && M <= tf32::MAXF && N >= 256 && N < lim && aligned16(A) && aligned16(B) &&
+        lda % 4 == 0 && ldb % 4 == 0)
+      return launch_tf32(c, /*x_mn=*/false, /*f_k=*/transA, N, (int)M, (int)K, 1, B, ldb, 0, A, lda, C, ldc, 1, 0, alpha,
+                         beta, passes, st);
+    // (b) the factor is B, shared by all batches (any other Kronecker mode): stream A's rows
+    if (!transA && (sB == 0 || batch == 1) && N <= tf32::MAXF && M * batch >= 256 && M < lim && batch < lim &&
+        aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0 && sA % 4 == 0)
+      return launch_tf32(c, /*x_mn=*/true, /*f_k=*/!transB, M, (int)N, (int)K, batch, A, lda, sA, B, ldb, C, 1, ldc, sC,
+                         alpha, beta, passes, st);
+  }
+  if (precision == SCIMLOP_PREC_TF32)
+    return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED,
+                        "single-pass TF32 was requested but this shape is not eligible for the tcgen05 path");
+  return launch_simt<float>(c, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, nscale,
+                            scales, st);
 }
 
 int check_handle(scimlop_context* c) { return scimlop_valid(c) ? SCIMLOP_OK : SCIMLOP_ERR_BAD_HANDLE; }
@@ -281,6 +348,13 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   optin((const void*)dmma::gemm_dmma_kernel<false, true>);
   optin((const void*)dmma::gemm_dmma_kernel<true, false>);
   optin((const void*)dmma::gemm_dmma_kernel<true, true>);
+  auto optin2 = [&](const void* f) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, tf32::SMEM_BYTES);
+  };
+  optin2((const void*)tf32::gemm_tf32x3_kernel<false, false>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<false, true>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<true, false>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<true, true>);
   if (e != cudaSuccess) {
     delete c;
     return SCIMLOP_ERR_CUDA;

@@ -83,6 +83,55 @@ def test_gemm_strided_batched(sb, case, dtype):
         check(got, want, dtype, f"gemm {case} alpha={a} beta={b}")
 
 
+TF32_CASES = [
+    # M, N, K, batch, transA, transB  -- shapes that are eligible for the tcgen05 (3xTF32) path
+    (128, 4096, 128, 1, 0, 0),    # (a) factor = A, K-major X, MN-major factor     [innermost Kronecker mode]
+    (128, 4096, 128, 1, 1, 0),    # (a) transposed factor -> K-major factor
+    (100, 1000, 72, 1, 0, 0),     # (a) ragged: m, n, rows not multiples of the tile
+    (48, 300, 12, 1, 1, 0),       # (a) tiny factor, K tail
+    (128, 128, 128, 64, 0, 1),    # (b) factor = B shared, MN-major X              [outer Kronecker modes]
+    (16384, 128, 128, 2, 0, 1),   # (b) many row tiles per batch
+    (300, 40, 20, 3, 0, 0),       # (b) K-major factor, ragged rows
+    (1000, 100, 72, 5, 0, 1),     # (b) ragged everything
+]
+
+
+@pytest.mark.parametrize("case", TF32_CASES)
+@pytest.mark.parametrize("precision,tol", [(0, 1e-5), (1, 1e-5), (3, 1e-5), (2, 3e-3)])
+def test_gemm_f32_tensor_core_paths(sb, case, precision, tol):
+    """Float32: DEFAULT / TF32X3 run the tcgen05 3xTF32 kernel and must hold 1e-5; FP32_EXACT forces FFMA;
+    single-pass TF32 is opt-in with its own (documented) tolerance."""
+    import torch
+    M, N, K, batch, ta, tb = case
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    A = rnd(rng, *((K, M) if ta else (M, K)), batch, dtype=np.float32)
+    shared_b = batch > 1          # path (b) needs the factor shared across the batch
+    B = rnd(rng, *((N, K) if tb else (K, N)), 1 if shared_b else batch, dtype=np.float32)
+    C0 = rnd(rng, M, N, batch, dtype=np.float32)
+    h = sb.handle(0)
+    for (a, b) in ((0.7, 0.3), (None, None)):
+        dA, dB = dev(sb, A), dev(sb, B)
+        dC = dev(sb, C0 if b else np.full_like(C0, np.nan))
+        pa = C.byref(C.c_float(a)) if a is not None else None
+        pb = C.byref(C.c_float(b)) if b is not None else None
+        n0 = h.launch_count()
+        rc = h.lib.scimlop_gemm_strided_batched(
+            h.ptr, 1, precision, ta, tb, M, N, K, pa, C.c_void_p(dA.ptr), A.shape[0], A.shape[0] * A.shape[1],
+            C.c_void_p(dB.ptr), B.shape[0], 0 if shared_b else B.shape[0] * B.shape[1], pb, C.c_void_p(dC.ptr), M, M * N,
+            batch, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        h.check(rc, "gemm f32")
+        assert h.launch_count() == n0 + 1
+        want = np.empty((M, N, batch))
+        for i in range(batch):
+            opA = (A[:, :, i].T if ta else A[:, :, i]).astype(np.float64)
+            Bi = B[:, :, 0 if shared_b else i]
+            opB = (Bi.T if tb else Bi).astype(np.float64)
+            want[:, :, i] = (1.0 if a is None else a) * (opA @ opB) + (b * C0[:, :, i] if b else 0.0)
+        err = R.rel_err(dC.numpy(), want)
+        assert np.isfinite(dC.numpy()).all()
+        assert err <= tol, f"{case} precision={precision} alpha={a}: rel err {err:.3e}"
+
+
 def test_gemm_shared_operand_and_odd_ld(sb):
     """stride 0 = shared operand; odd leading dimensions / unaligned bases take the shape-agnostic kernel."""
     rng = np.random.default_rng(5)
