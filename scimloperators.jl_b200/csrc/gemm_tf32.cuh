@@ -77,15 +77,22 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 //   K-major : rows of 128 B, 8-row groups SBO bytes apart; LBO unused (1).
 //   MN-major: atoms of (32 elements along MN = 128 B) x (8 k); LBO = bytes between atoms along MN,
 //             SBO = bytes between atoms along K.
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//
+// 32-bit MN-major operands have exactly one legal layout: SWIZZLE_128B_BASE32B (layout type 1): rows of
+// 128 B (32 elements along MN) per k, 32-byte chunks XOR (k & 3), K atoms of 4 rows (SBO = 512 B when the k rows
+// are contiguous), LBO = bytes between successive 32-element MN groups.  TMA writes it with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  (Plain SWIZZLE_128B silently yields zeros: tools/tc_probe.cu.)
+__device__ __forceinline__ uint64_t make_desc_raw(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  d |= (uint64_t)1 << 46;       // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;  // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t addr) { return make_desc_raw(addr, 16, 1024, 2); }
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t addr, uint32_t lbo_bytes) { return make_desc_raw(addr, lbo_bytes, 512, 1); }
 // instruction descriptor: D = F32, A = B = TF32, M = 128, N = n_mma
 __device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int n_mma) {
   uint32_t d = 0;
@@ -212,18 +219,18 @@ __global__ void __launch_bounds__(THREADS, 1)
           for (int ks = 0; ks < ksteps; ks++) {
             uint64_t ahi, alo, bhi, blo;
             if (X_MN) {   // atoms of 32 r x 8 k: next k atom +1024 B, next r atom +4096 B
-              ahi = make_desc(xhi + ks * 1024, 4096, 1024);
-              alo = make_desc(xlo + ks * 1024, 4096, 1024);
+              ahi = make_desc_mn(xhi + ks * 1024, 4096);
+              alo = make_desc_mn(xlo + ks * 1024, 4096);
             } else {      // rows of 128 B, +32 B per k-step inside the swizzle span
-              ahi = make_desc(xhi + ks * 32, 16, 1024);
-              alo = make_desc(xlo + ks * 32, 16, 1024);
+              ahi = make_desc_k(xhi + ks * 32);
+              alo = make_desc_k(xlo + ks * 32);
             }
             if (F_K) {    // per k-block a [128 c][32 k] tile of 16 KB
-              bhi = make_desc(sFhi + kb * 16384 + ks * 32, 16, 1024);
-              blo = make_desc(sFlo + kb * 16384 + ks * 32, 16, 1024);
+              bhi = make_desc_k(sFhi + kb * 16384 + ks * 32);
+              blo = make_desc_k(sFlo + kb * 16384 + ks * 32);
             } else {      // four c-groups of [128 k][32 c] (16 KB apart); k atoms 1024 B apart
-              bhi = make_desc(sFhi + (kb * 4 + ks) * 1024, 16384, 1024);
-              blo = make_desc(sFlo + (kb * 4 + ks) * 1024, 16384, 1024);
+              bhi = make_desc_mn(sFhi + (kb * 4 + ks) * 1024, 16384);
+              blo = make_desc_mn(sFlo + (kb * 4 + ks) * 1024, 16384);
             }
             const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
             if (p.passes == 3) {

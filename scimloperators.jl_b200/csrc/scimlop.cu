@@ -208,13 +208,15 @@ int gemm_dispatch<double>(scimlop_context* c, int precision, bool transA, bool t
 
 // ---- tcgen05 TF32 launcher (Float32, streamed operand x resident factor) ----------------------------------
 int make_map_f32(scimlop_context* c, CUtensorMap* map, const float* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2,
-                 cuuint64_t s1_bytes, cuuint64_t s2_bytes, cuuint32_t b0, cuuint32_t b1) {
+                 cuuint64_t s1_bytes, cuuint64_t s2_bytes, cuuint32_t b0, cuuint32_t b1, bool mn_major) {
   cuuint64_t gdim[3] = {d0, d1, d2};
   cuuint64_t gstr[2] = {s1_bytes, d2 > 1 ? s2_bytes : s1_bytes * d1};
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = c->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               // 32-bit MN-major UMMA operands need the 32-byte-atom flavour of the 128B swizzle
+                               mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return scimlop_fail(c, SCIMLOP_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed (CUresult %d): dims {%llu,%llu,%llu}",
@@ -230,11 +232,11 @@ int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, 
   CUtensorMap tmX, tmF;
   const bool xb = batch > 1 && xbs != 0;
   int rc;
-  if (x_mn) rc = make_map_f32(c, &tmX, X, rows, n, xb ? batch : 1, ldx * 4, xbs * 4, 32, 32);
-  else rc = make_map_f32(c, &tmX, X, n, rows, xb ? batch : 1, ldx * 4, xbs * 4, 32, 128);
+  if (x_mn) rc = make_map_f32(c, &tmX, X, rows, n, xb ? batch : 1, ldx * 4, xbs * 4, 32, 32, true);
+  else rc = make_map_f32(c, &tmX, X, n, rows, xb ? batch : 1, ldx * 4, xbs * 4, 32, 128, false);
   if (rc) return rc;
-  if (f_k) rc = make_map_f32(c, &tmF, F, n, m, 1, ldf * 4, 0, 32, 128);
-  else rc = make_map_f32(c, &tmF, F, m, n, 1, ldf * 4, 0, 32, 128);
+  if (f_k) rc = make_map_f32(c, &tmF, F, n, m, 1, ldf * 4, 0, 32, 128, false);
+  else rc = make_map_f32(c, &tmF, F, m, n, 1, ldf * 4, 0, 32, 128, true);
   if (rc) return rc;
   tf32::Params p;
   memset(&p, 0, sizeof(p));
