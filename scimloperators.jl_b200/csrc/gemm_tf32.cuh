@@ -14,6 +14,15 @@
 //   XMN (any other Kronecker mode, batched):              X(r,k) at r + ldx*k (+b) -> MN-major A operand
 // and the factor as B operand: MN-major for a plain factor (F(c,k) at c + ldf*k), K-major for a transposed one.
 //
+// The split X operand is handed to the tensor core through TENSOR MEMORY (tcgen05.mma with the A operand in
+// TMEM, written by tcgen05.st), not through shared memory: shared memory then only holds the resident factor
+// (128 KB) and a 6-deep ring of raw 16 KB X tiles whose slots are released as soon as the splitters have read
+// them -- a deep TMA prefetch queue, which is what an HBM-bound kernel needs.  (A first version kept hi/lo in
+// shared memory: 3 stages only, latency-bound at 45 % of HBM; profiles/r01_ncu_tf32_v1_summary.txt.)
+//
+// TMEM map (512 columns): [0,128) accumulator 0, [128,256) accumulator 1, [256,512) four A stages of
+// 64 columns (32 k of X_hi, 32 k of X_lo; lane = row of the tile, column = k).
+//
 // Warp roles (10 warps): 0 TMA producer, 1 MMA issuer (+TMEM owner), 2-5 hi/lo splitters, 6-9 epilogue.
 #pragma once
 #include "ptx.cuh"
@@ -24,14 +33,15 @@ namespace tf32 {
 constexpr int TM = 128;                 // rows of X per tile = UMMA M = TMEM lanes
 constexpr int BK = 32;                  // k per stage (128 bytes)
 constexpr int MAXF = 128;               // factor extents supported (m, n <= 128)
-constexpr int STAGES = 3;
-constexpr int XT_BYTES = TM * BK * 4;   // 16 KB: one X tile (raw -> hi in place), same again for lo
-constexpr int STAGE_BYTES = 2 * XT_BYTES;
+constexpr int RSTAGES = 6;              // raw X tiles in flight (shared memory ring)
+constexpr int ASTAGES = 4;              // split A tiles in flight (tensor memory ring)
+constexpr int XT_BYTES = TM * BK * 4;   // 16 KB: one raw X tile
 constexpr int F_BYTES = MAXF * MAXF * 4;  // 64 KB each for F_hi and F_lo
-constexpr int NBAR = 3 * STAGES + 4 + 1;
-constexpr int SMEM_BYTES = 1024 + 2 * F_BYTES + STAGES * STAGE_BYTES + 8 * NBAR + 16;
+constexpr int NBAR = 2 * RSTAGES + 2 * ASTAGES + 4 + 1;
+constexpr int SMEM_BYTES = 1024 + 2 * F_BYTES + RSTAGES * XT_BYTES + 8 * NBAR + 16;
 constexpr int THREADS = 320;
-constexpr int TMEM_COLS = 256;          // two 128-column FP32 accumulators
+constexpr int TMEM_COLS = 512;          // 2 x 128 accumulator columns + 4 x 64 A-operand columns
+constexpr int TMEM_A0 = 256;
 
 struct Params {
   long long rows;        // extent of r per batch
@@ -70,6 +80,25 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand from tensor memory (lane = row, column = k), B from a shared-memory descriptor
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -120,18 +149,22 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));  // generic pointer to the aligned base
   const uint32_t sFhi = smem, sFlo = smem + F_BYTES, sX = smem + 2 * F_BYTES;
-  const uint32_t bars = sX + STAGES * STAGE_BYTES;
-  const uint32_t raw_full = bars, split_done = bars + 8 * STAGES, stage_free = bars + 16 * STAGES;
-  const uint32_t tmem_full = bars + 24 * STAGES, tmem_empty = tmem_full + 16, f_full = tmem_empty + 16;
+  const uint32_t bars = sX + RSTAGES * XT_BYTES;
+  const uint32_t raw_full = bars, raw_free = raw_full + 8 * RSTAGES;
+  const uint32_t a_full = raw_free + 8 * RSTAGES, a_free = a_full + 8 * ASTAGES;
+  const uint32_t tmem_full = a_free + 8 * ASTAGES, tmem_empty = tmem_full + 16, f_full = tmem_empty + 16;
   const uint32_t tmem_slot = f_full + 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) {
-      mbar_init(raw_full + 8 * s, 1);
-      mbar_init(split_done + 8 * s, 4);   // one arrival per splitter warp
-      mbar_init(stage_free + 8 * s, 1);   // tcgen05.commit
+    for (int s = 0; s < RSTAGES; s++) {
+      mbar_init(raw_full + 8 * s, 1);   // TMA transaction bytes
+      mbar_init(raw_free + 8 * s, 4);   // one arrival per splitter warp
+    }
+    for (int s = 0; s < ASTAGES; s++) {
+      mbar_init(a_full + 8 * s, 4);     // one arrival per splitter warp
+      mbar_init(a_free + 8 * s, 1);     // tcgen05.commit
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tmem_full + 8 * a, 1);    // tcgen05.commit
@@ -174,7 +207,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 
   const int nkb = (p.n + BK - 1) / BK;                 // k-blocks of 32
   const int n_mma = ((p.m + 15) / 16) * 16;            // UMMA N
-  const uint32_t idesc = make_idesc(X_MN, !F_K, n_mma);
+  const uint32_t idesc = make_idesc(false, !F_K, n_mma);   // A comes from TMEM (row = lane, k = column)
 
   if (warp == 0) {
     // ===================== TMA producer: raw X tiles =====================
@@ -185,8 +218,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         const int b = (int)(tile / p.tiles_r);
         const int r0 = (int)(tile - (long long)b * p.tiles_r) * TM;
         for (int kb = 0; kb < nkb; kb++) {
-          mbar_wait(stage_free + 8 * stage, phase ^ 1);
-          const uint32_t dst = sX + stage * STAGE_BYTES;
+          mbar_wait(raw_free + 8 * stage, phase ^ 1);
+          const uint32_t dst = sX + stage * XT_BYTES;
           const uint32_t bar = raw_full + 8 * stage;
           mbar_arrive_expect_tx(bar, XT_BYTES);
           if (X_MN) {
@@ -195,15 +228,15 @@ __global__ void __launch_bounds__(THREADS, 1)
           } else {
             tma_load_3d(dst, &tmX, bar, kb * BK, r0, p.x_batched ? b : 0);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == RSTAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int at = 0;
+      uint32_t aph = 0;
       int it = 0;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
         const int a = it & 1;
@@ -212,65 +245,83 @@ __global__ void __launch_bounds__(THREADS, 1)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * 128;
         for (int kb = 0; kb < nkb; kb++) {
-          mbar_wait(split_done + 8 * stage, phase);
+          mbar_wait(a_full + 8 * at, aph);
           tc_fence_after();
-          const uint32_t xhi = sX + stage * STAGE_BYTES, xlo = xhi + XT_BYTES;
+          const uint32_t ahi = tmem_base + TMEM_A0 + at * 64, alo = ahi + 32;
           const int ksteps = min(4, (p.n - kb * BK + 7) / 8);
           for (int ks = 0; ks < ksteps; ks++) {
-            uint64_t ahi, alo, bhi, blo;
-            if (X_MN) {   // atoms of 32 r x 8 k: next k atom +1024 B, next r atom +4096 B
-              ahi = make_desc_mn(xhi + ks * 1024, 4096);
-              alo = make_desc_mn(xlo + ks * 1024, 4096);
-            } else {      // rows of 128 B, +32 B per k-step inside the swizzle span
-              ahi = make_desc_k(xhi + ks * 32);
-              alo = make_desc_k(xlo + ks * 32);
-            }
-            if (F_K) {    // per k-block a [128 c][32 k] tile of 16 KB
+            uint64_t bhi, blo;
+            if (F_K) {    // per k-block a [128 c][32 k] tile of 16 KB, +32 B per k-step inside the swizzle span
               bhi = make_desc_k(sFhi + kb * 16384 + ks * 32);
               blo = make_desc_k(sFlo + kb * 16384 + ks * 32);
-            } else {      // four c-groups of [128 k][32 c] (16 KB apart); k atoms 1024 B apart
+            } else {      // four c-groups of [128 k][32 c] (16 KB apart); 8 k rows = 1024 B per k-step
               bhi = make_desc_mn(sFhi + (kb * 4 + ks) * 1024, 16384);
               blo = make_desc_mn(sFlo + (kb * 4 + ks) * 1024, 16384);
             }
             const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
             if (p.passes == 3) {
-              tc_mma_tf32(d_tmem, alo, bhi, idesc, first);
-              tc_mma_tf32(d_tmem, ahi, blo, idesc, 1u);
-              tc_mma_tf32(d_tmem, ahi, bhi, idesc, 1u);
+              tc_mma_tf32_ts(d_tmem, alo + ks * 8, bhi, idesc, first);
+              tc_mma_tf32_ts(d_tmem, ahi + ks * 8, blo, idesc, 1u);
+              tc_mma_tf32_ts(d_tmem, ahi + ks * 8, bhi, idesc, 1u);
             } else {
-              tc_mma_tf32(d_tmem, ahi, bhi, idesc, first);
+              tc_mma_tf32_ts(d_tmem, ahi + ks * 8, bhi, idesc, first);
             }
           }
-          tc_commit(stage_free + 8 * stage);          // smem slot reusable once these MMAs retire
+          tc_commit(a_free + 8 * at);                 // TMEM A stage reusable once these MMAs retire
           if (kb == nkb - 1) tc_commit(tmem_full + 8 * a);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++at == ASTAGES) { at = 0; aph ^= 1; }
         }
       }
     }
   } else if (warp < 6) {
-    // ===================== splitters: raw X tile -> hi (in place) + lo =====================
-    const int st = threadIdx.x - 64;  // 0..127
-    int stage = 0;
-    uint32_t phase = 0;
+    // ===================== splitters: raw X tile (smem) -> hi, lo (TMEM A operand) =====================
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;     // tile row handled by this thread
+    int rs = 0, at = 0;
+    uint32_t rph = 0, aph = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < nkb; kb++) {
-        mbar_wait(raw_full + 8 * stage, phase);
-        float4* hi = reinterpret_cast<float4*>(smem_gen + 2 * F_BYTES + stage * STAGE_BYTES);
-        float4* lo = hi + XT_BYTES / 16;
-        float4 x[8];
+        mbar_wait(raw_full + 8 * rs, rph);
+        const uint8_t* src = smem_gen + 2 * F_BYTES + rs * XT_BYTES;
+        uint32_t hi[32], lo[32];
+        if (X_MN) {
+          // [4 r-groups][32 k rows][128 B of 32 r], 32-byte chunks XOR (k & 3): lane reads its r for every k
+          const uint8_t* g = src + quarter * 4096 + ((lane & 7) << 2);
 #pragma unroll
-        for (int i = 0; i < 8; i++) x[i] = hi[st + 128 * i];
+          for (int k = 0; k < 32; k++) {
+            const float x = *reinterpret_cast<const float*>(g + k * 128 + ((((lane >> 3) ^ (k & 3))) << 5));
+            hi[k] = __float_as_uint(x) & 0xFFFFE000u;
+            lo[k] = __float_as_uint(x - __uint_as_float(hi[k])) & 0xFFFFE000u;
+          }
+        } else {
+          // [128 rows][128 B of 32 k], 16-byte chunks XOR (row & 7): lane reads its whole row
+          const uint8_t* g = src + row * 128;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          float4 h, l;
-          split4(x[i], h, l);
-          hi[st + 128 * i] = h;
-          lo[st + 128 * i] = l;
+          for (int cidx = 0; cidx < 8; cidx++) {
+            const float4 x = *reinterpret_cast<const float4*>(g + ((cidx ^ (row & 7)) << 4));
+            float4 h, l;
+            split4(x, h, l);
+            hi[4 * cidx + 0] = __float_as_uint(h.x); hi[4 * cidx + 1] = __float_as_uint(h.y);
+            hi[4 * cidx + 2] = __float_as_uint(h.z); hi[4 * cidx + 3] = __float_as_uint(h.w);
+            lo[4 * cidx + 0] = __float_as_uint(l.x); lo[4 * cidx + 1] = __float_as_uint(l.y);
+            lo[4 * cidx + 2] = __float_as_uint(l.z); lo[4 * cidx + 3] = __float_as_uint(l.w);
+          }
         }
-        fence_async_smem();       // generic-proxy writes -> visible to the tensor core (async proxy)
+        // the raw slot is free as soon as every lane holds its values in registers
         __syncwarp();
-        if (lane == 0) mbar_arrive(split_done + 8 * stage);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (lane == 0) mbar_arrive(raw_free + 8 * rs);
+        if (++rs == RSTAGES) { rs = 0; rph ^= 1; }
+        // hand hi / lo to the tensor core through TMEM
+        mbar_wait(a_free + 8 * at, aph ^ 1);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + TMEM_A0 + at * 64;
+        tc_st32(ta, hi);
+        tc_st32(ta + 32, lo);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + 8 * at);
+        if (++at == ASTAGES) { at = 0; aph ^= 1; }
       }
     }
   } else {

@@ -165,8 +165,12 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=",".join(ALL))
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--c3k", type=int, default=512, help="columns for config 3 (smaller for ncu runs)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     for name in a.only.split(","):
-        ALL[name](a.reps)
+        if name == "c3":
+            c3(a.reps, a.c3k)
+        else:
+            ALL[name](a.reps)
         torch.cuda.empty_cache()
