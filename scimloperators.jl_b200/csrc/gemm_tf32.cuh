@@ -23,7 +23,9 @@
 // TMEM map (512 columns): [0,128) accumulator 0, [128,256) accumulator 1, [256,512) four A stages of
 // 64 columns (32 k of X_hi, 32 k of X_lo; lane = row of the tile, column = k).
 //
-// Warp roles (10 warps): 0 TMA producer, 1 MMA issuer (+TMEM owner), 2-5 hi/lo splitters, 6-9 epilogue.
+// Warp roles (20 warps): 0 TMA producer, 1 MMA issuer (+TMEM owner), two splitter groups of 4 warps that
+// alternate over k-blocks (their LDS -> ALU -> tcgen05.st -> barrier chains overlap), two epilogue groups of 4
+// warps (group e drains accumulator e), so no role is a serial latency chain on the tile path.
 #pragma once
 #include "ptx.cuh"
 
@@ -39,7 +41,9 @@ constexpr int XT_BYTES = TM * BK * 4;   // 16 KB: one raw X tile
 constexpr int F_BYTES = MAXF * MAXF * 4;  // 64 KB each for F_hi and F_lo
 constexpr int NBAR = 2 * RSTAGES + 2 * ASTAGES + 4 + 1;
 constexpr int SMEM_BYTES = 1024 + 2 * F_BYTES + RSTAGES * XT_BYTES + 8 * NBAR + 16;
-constexpr int THREADS = 320;
+constexpr int NSG = 2;                  // splitter groups (4 warps each) alternating over k-blocks
+constexpr int NEG = 2;                  // epilogue groups (4 warps each), group e owns accumulator e
+constexpr int THREADS = 32 * (4 + 4 * NSG + 4 * NEG);   // warps 0 producer, 1 MMA, 2-3 idle, then the groups
 constexpr int TMEM_COLS = 512;          // 2 x 128 accumulator columns + 4 x 64 A-operand columns
 constexpr int TMEM_A0 = 256;
 
@@ -273,14 +277,17 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp >= 4 && warp < 4 + 4 * NSG) {
     // ===================== splitters: raw X tile (smem) -> hi, lo (TMEM A operand) =====================
+    const int grp = (warp - 4) >> 2;         // this group handles k-blocks with (global index % NSG) == grp
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;     // tile row handled by this thread
-    int rs = 0, at = 0;
-    uint32_t rph = 0, aph = 0;
+    long long kbg = 0;                       // global k-block counter of this CTA
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < nkb; kb++) {
+      for (int kb = 0; kb < nkb; kb++, kbg++) {
+        if ((int)(kbg % NSG) != grp) continue;
+        const int rs = (int)(kbg % RSTAGES), at = (int)(kbg % ASTAGES);
+        const uint32_t rph = (uint32_t)((kbg / RSTAGES) & 1), aph = (uint32_t)((kbg / ASTAGES) & 1);
         mbar_wait(raw_full + 8 * rs, rph);
         const uint8_t* src = smem_gen + 2 * F_BYTES + rs * XT_BYTES;
         uint32_t hi[32], lo[32];
@@ -310,7 +317,6 @@ __global__ void __launch_bounds__(THREADS, 1)
         // the raw slot is free as soon as every lane holds its values in registers
         __syncwarp();
         if (lane == 0) mbar_arrive(raw_free + 8 * rs);
-        if (++rs == RSTAGES) { rs = 0; rph ^= 1; }
         // hand hi / lo to the tensor core through TMEM
         mbar_wait(a_free + 8 * at, aph ^ 1);
         tc_fence_after();
@@ -321,15 +327,16 @@ __global__ void __launch_bounds__(THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full + 8 * at);
-        if (++at == ASTAGES) { at = 0; aph ^= 1; }
       }
     }
-  } else {
+  } else if (warp >= 4 + 4 * NSG) {
     // ===================== epilogue: TMEM -> registers -> global (alpha, beta fused) =====================
+    const int grp = (warp - 4 - 4 * NSG) >> 2;      // group e drains accumulator e (tiles with it % 2 == e)
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
       const int a = it & 1;
+      if (a != grp) continue;
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
       const int b = (int)(tile / p.tiles_r);
       const long long r = (tile - (long long)b * p.tiles_r) * TM + quarter * 32 + lane;
