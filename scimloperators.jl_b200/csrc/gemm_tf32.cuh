@@ -214,67 +214,72 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t idesc = make_idesc(false, !F_K, n_mma);   // A comes from TMEM (row = lane, k = column)
 
   if (warp == 0) {
-    // ===================== TMA producer: raw X tiles =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int b = (int)(tile / p.tiles_r);
-        const int r0 = (int)(tile - (long long)b * p.tiles_r) * TM;
-        for (int kb = 0; kb < nkb; kb++) {
-          mbar_wait(raw_free + 8 * stage, phase ^ 1);
+    // ===================== TMA producer: raw X tiles (warp-uniform loop, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = (int)(tile / p.tiles_r);
+      const int r0 = (int)(tile - (long long)b * p.tiles_r) * TM;
+      const int bx = p.x_batched ? b : 0;
+      for (int kb = 0; kb < nkb; kb++) {
+        mbar_wait(raw_free + 8 * stage, phase ^ 1);
+        if (elect_one()) {
           const uint32_t dst = sX + stage * XT_BYTES;
           const uint32_t bar = raw_full + 8 * stage;
           mbar_arrive_expect_tx(bar, XT_BYTES);
           if (X_MN) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) tma_load_3d(dst + q * 4096, &tmX, bar, r0 + 32 * q, kb * BK, p.x_batched ? b : 0);
+            for (int q = 0; q < 4; q++) tma_load_3d(dst + q * 4096, &tmX, bar, r0 + 32 * q, kb * BK, bx);
           } else {
-            tma_load_3d(dst, &tmX, bar, kb * BK, r0, p.x_batched ? b : 0);
+            tma_load_3d(dst, &tmX, bar, kb * BK, r0, bx);
           }
-          if (++stage == RSTAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == RSTAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int at = 0;
-      uint32_t aph = 0;
-      int it = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
-        const int a = it & 1;
-        const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-        mbar_wait(tmem_empty + 8 * a, aphase ^ 1);   // epilogue drained this accumulator
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    // factor descriptors: only the 14-bit start-address field (units of 16 B) changes per k-step
+    const uint64_t bhi0 = F_K ? make_desc_k(sFhi) : make_desc_mn(sFhi, 16384);
+    const uint64_t blo0 = F_K ? make_desc_k(sFlo) : make_desc_mn(sFlo, 16384);
+    constexpr uint32_t KB_INC = F_K ? (16384 >> 4) : (4096 >> 4);   // next k-block of 32
+    constexpr uint32_t KS_INC = F_K ? (32 >> 4) : (1024 >> 4);      // next k-step of 8
+    int at = 0;
+    uint32_t aph = 0;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+      const int a = it & 1;
+      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+      mbar_wait(tmem_empty + 8 * a, aphase ^ 1);   // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + a * 128;
+      for (int kb = 0; kb < nkb; kb++) {
+        mbar_wait(a_full + 8 * at, aph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * 128;
-        for (int kb = 0; kb < nkb; kb++) {
-          mbar_wait(a_full + 8 * at, aph);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t ahi = tmem_base + TMEM_A0 + at * 64, alo = ahi + 32;
           const int ksteps = min(4, (p.n - kb * BK + 7) / 8);
-          for (int ks = 0; ks < ksteps; ks++) {
-            uint64_t bhi, blo;
-            if (F_K) {    // per k-block a [128 c][32 k] tile of 16 KB, +32 B per k-step inside the swizzle span
-              bhi = make_desc_k(sFhi + kb * 16384 + ks * 32);
-              blo = make_desc_k(sFlo + kb * 16384 + ks * 32);
-            } else {      // four c-groups of [128 k][32 c] (16 KB apart); 8 k rows = 1024 B per k-step
-              bhi = make_desc_mn(sFhi + (kb * 4 + ks) * 1024, 16384);
-              blo = make_desc_mn(sFlo + (kb * 4 + ks) * 1024, 16384);
-            }
-            const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-            if (p.passes == 3) {
-              tc_mma_tf32_ts(d_tmem, alo + ks * 8, bhi, idesc, first);
-              tc_mma_tf32_ts(d_tmem, ahi + ks * 8, blo, idesc, 1u);
-              tc_mma_tf32_ts(d_tmem, ahi + ks * 8, bhi, idesc, 1u);
-            } else {
-              tc_mma_tf32_ts(d_tmem, ahi + ks * 8, bhi, idesc, first);
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {
+            if (ks < ksteps) {
+              const uint64_t bhi = bhi0 + (uint64_t)(kb * KB_INC + ks * KS_INC);
+              const uint64_t blo = blo0 + (uint64_t)(kb * KB_INC + ks * KS_INC);
+              const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+              if (p.passes == 3) {
+                tc_mma_tf32_ts(d_tmem, alo + ks * 8, bhi, idesc, first);
+                tc_mma_tf32_ts(d_tmem, ahi + ks * 8, blo, idesc, 1u);
+                tc_mma_tf32_ts(d_tmem, ahi + ks * 8, bhi, idesc, 1u);
+              } else {
+                tc_mma_tf32_ts(d_tmem, ahi + ks * 8, bhi, idesc, first);
+              }
             }
           }
           tc_commit(a_free + 8 * at);                 // TMEM A stage reusable once these MMAs retire
           if (kb == nkb - 1) tc_commit(tmem_full + 8 * a);
-          if (++at == ASTAGES) { at = 0; aph ^= 1; }
         }
+        __syncwarp();
+        if (++at == ASTAGES) { at = 0; aph ^= 1; }
       }
     }
   } else if (warp >= 4 && warp < 4 + 4 * NSG) {
