@@ -16,8 +16,8 @@
 //
 // The split X operand is handed to the tensor core through TENSOR MEMORY (tcgen05.mma with the A operand in
 // TMEM, written by tcgen05.st), not through shared memory: shared memory then only holds the resident factor
-// (128 KB) and a 6-deep ring of raw 16 KB X tiles whose slots are released as soon as the splitters have read
-// them -- a deep TMA prefetch queue, which is what an HBM-bound kernel needs.  (A first version kept hi/lo in
+// (128 KB), a 4-deep ring of raw 16 KB X tiles whose slots are released as soon as the splitters have read
+// them, and 16 KB of staging for the bulk tensor stores of the epilogue.  (A first version kept hi/lo in
 // shared memory: 3 stages only, latency-bound at 45 % of HBM; profiles/r01_ncu_tf32_v1_summary.txt.)
 //
 // TMEM map (512 columns): [0,128) accumulator 0, [128,256) accumulator 1, [256,512) four A stages of
@@ -35,14 +35,19 @@ namespace tf32 {
 constexpr int TM = 128;                 // rows of X per tile = UMMA M = TMEM lanes
 constexpr int BK = 32;                  // k per stage (128 bytes)
 constexpr int MAXF = 128;               // factor extents supported (m, n <= 128)
-constexpr int RSTAGES = 6;              // raw X tiles in flight (shared memory ring)
+constexpr int RSTAGES = 4;              // raw X tiles in flight (shared memory ring)
 constexpr int ASTAGES = 4;              // split A tiles in flight (tensor memory ring)
 constexpr int XT_BYTES = TM * BK * 4;   // 16 KB: one raw X tile
 constexpr int F_BYTES = MAXF * MAXF * 4;  // 64 KB each for F_hi and F_lo
 constexpr int NBAR = 2 * RSTAGES + 2 * ASTAGES + 4 + 1;
-constexpr int SMEM_BYTES = 1024 + 2 * F_BYTES + RSTAGES * XT_BYTES + 8 * NBAR + 16;
+constexpr int EPI_STAGE_BYTES = 4096;   // one 32 x 32 FP32 block per epilogue warp, staged for the TMA store
+constexpr int SMEM_BYTES = 1024 + 2 * F_BYTES + RSTAGES * XT_BYTES + 4 * EPI_STAGE_BYTES + 8 * NBAR + 16;
 constexpr int NSG = 2;                  // splitter groups (4 warps each) alternating over k-blocks
-constexpr int NEG = 2;                  // epilogue groups (4 warps each), group e owns accumulator e
+constexpr int NEG = 1;                  // epilogue groups (4 warps each)
+// A ring slot must always be served by the SAME splitter group: a group that never waited on phase j of a
+// barrier can pass a parity wait for phase j+1 spuriously while the barrier is still in phase j (parity waits
+// only distinguish "one ahead" from "one behind").  RSTAGES = 5 with two groups faulted exactly like that.
+static_assert(RSTAGES % NSG == 0 && ASTAGES % NSG == 0, "ring depths must be multiples of the splitter group count");
 constexpr int THREADS = 32 * (4 + 4 * NSG + 4 * NEG);   // warps 0 producer, 1 MMA, 2-3 idle, then the groups
 constexpr int TMEM_COLS = 512;          // 2 x 128 accumulator columns + 4 x 64 A-operand columns
 constexpr int TMEM_A0 = 256;
@@ -59,6 +64,7 @@ struct Params {
   int vec_ok;            // d_cs == 1 and 16-byte alignment holds: float4 stores along c
   int x_batched;
   int passes;            // 3: lo*Fhi + hi*Flo + hi*Fhi (FP32-grade);  1: hi*Fhi only (plain TF32, opt-in)
+  int tma_store;         // beta == 0 and D is TMA-addressable: epilogue goes TMEM -> smem -> bulk tensor store
 };
 
 // ---- tcgen05 wrappers -----------------------------------------------------------------------------------
@@ -148,12 +154,14 @@ __device__ __forceinline__ void split4(float4 x, float4& hi, float4& lo) {
 // X_MN: X is MN-major (r contiguous); else K-major (k contiguous).  F_K: factor is K-major (transposed factor).
 template <bool X_MN, bool F_K>
 __global__ void __launch_bounds__(THREADS, 1)
-    gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmF, const Params p) {
+    gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmF,
+                       const __grid_constant__ CUtensorMap tmD, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));  // generic pointer to the aligned base
   const uint32_t sFhi = smem, sFlo = smem + F_BYTES, sX = smem + 2 * F_BYTES;
-  const uint32_t bars = sX + RSTAGES * XT_BYTES;
+  const uint32_t sEpi = sX + RSTAGES * XT_BYTES;          // 4 x 4 KB staging blocks (1024-byte aligned)
+  const uint32_t bars = sEpi + 4 * EPI_STAGE_BYTES;
   const uint32_t raw_full = bars, raw_free = raw_full + 8 * RSTAGES;
   const uint32_t a_full = raw_free + 8 * RSTAGES, a_free = a_full + 8 * ASTAGES;
   const uint32_t tmem_full = a_free + 8 * ASTAGES, tmem_empty = tmem_full + 16, f_full = tmem_empty + 16;
@@ -335,16 +343,17 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
   } else if (warp >= 4 + 4 * NSG) {
-    // ===================== epilogue: TMEM -> registers -> global (alpha, beta fused) =====================
-    const int grp = (warp - 4 - 4 * NSG) >> 2;      // group e drains accumulator e (tiles with it % 2 == e)
+    // ===================== epilogue: TMEM -> registers -> (smem -> TMA store | global), alpha/beta fused =====
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const uint32_t stage_s = sEpi + quarter * EPI_STAGE_BYTES;
+    uint8_t* stage_g = smem_gen + (stage_s - smem);
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
       const int a = it & 1;
-      if (a != grp) continue;
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
       const int b = (int)(tile / p.tiles_r);
-      const long long r = (tile - (long long)b * p.tiles_r) * TM + quarter * 32 + lane;
+      const int rw = (int)(tile - (long long)b * p.tiles_r) * TM + quarter * 32;   // first row of this warp
+      const long long r = rw + lane;
       mbar_wait(tmem_full + 8 * a, aphase);
       tc_fence_after();
       float* drow = p.D + (long long)b * p.d_bs + r * p.d_rs;
@@ -353,7 +362,33 @@ __global__ void __launch_bounds__(THREADS, 1)
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * 128 + c0, v);
         tc_wait_ld();
-        if (row_ok) {
+        if (p.tma_store) {
+          // stage the 32 x 32 block in shared memory in the order the output wants, then one bulk tensor store:
+          // full 128-byte lines, clipped at the matrix edge, no LSU pressure on this warp
+          if (lane == 0) tma_store_wait_read();     // previous block of this warp has been read out
+          __syncwarp();
+          if (X_MN) {
+            // output is contiguous along r (the lanes): smem [c][32 r]
+#pragma unroll
+            for (int c = 0; c < 32; c++)
+              *reinterpret_cast<float*>(stage_g + c * 128 + lane * 4) = p.alpha * __uint_as_float(v[c]);
+          } else {
+            // output is contiguous along c: smem [r][32 c], 16-byte chunks XOR (r & 7) (SWIZZLE_128B)
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+              *reinterpret_cast<float4*>(stage_g + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                  make_float4(p.alpha * __uint_as_float(v[4 * q]), p.alpha * __uint_as_float(v[4 * q + 1]),
+                              p.alpha * __uint_as_float(v[4 * q + 2]), p.alpha * __uint_as_float(v[4 * q + 3]));
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {   // bulk groups are per thread: the same lane issues, commits and later waits
+            if (X_MN) tma_store_3d(&tmD, stage_s, rw, c0, b);
+            else tma_store_3d(&tmD, stage_s, c0, rw, 0);
+            tma_store_commit();
+          }
+          __syncwarp();
+        } else if (row_ok) {
           if (p.vec_ok && c0 + 32 <= p.m) {
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
@@ -383,6 +418,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + 8 * a);
     }
+    if (lane == 0) tma_store_wait_all();   // this lane's bulk stores are complete before the CTA exits
   }
 
   // ---- teardown ----

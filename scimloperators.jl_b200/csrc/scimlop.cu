@@ -208,7 +208,8 @@ int gemm_dispatch<double>(scimlop_context* c, int precision, bool transA, bool t
 
 // ---- tcgen05 TF32 launcher (Float32, streamed operand x resident factor) ----------------------------------
 int make_map_f32(scimlop_context* c, CUtensorMap* map, const float* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2,
-                 cuuint64_t s1_bytes, cuuint64_t s2_bytes, cuuint32_t b0, cuuint32_t b1, bool mn_major) {
+                 cuuint64_t s1_bytes, cuuint64_t s2_bytes, cuuint32_t b0, cuuint32_t b1, bool mn_major,
+                 bool swizzle = true) {
   cuuint64_t gdim[3] = {d0, d1, d2};
   cuuint64_t gstr[2] = {s1_bytes, d2 > 1 ? s2_bytes : s1_bytes * d1};
   cuuint32_t box[3] = {b0, b1, 1};
@@ -216,7 +217,8 @@ int make_map_f32(scimlop_context* c, CUtensorMap* map, const float* base, cuuint
   CUresult r = c->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE,
                                // 32-bit MN-major UMMA operands need the 32-byte-atom flavour of the 128B swizzle
-                               mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                               !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                        : (mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return scimlop_fail(c, SCIMLOP_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed (CUresult %d): dims {%llu,%llu,%llu}",
@@ -229,7 +231,7 @@ int make_map_f32(scimlop_context* c, CUtensorMap* map, const float* base, cuuint
 int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, int n, long long batch, const float* X,
                 long long ldx, long long xbs, const float* F, long long ldf, float* D, long long d_rs, long long d_cs,
                 long long d_bs, float alpha, float beta, int passes, cudaStream_t st) {
-  CUtensorMap tmX, tmF;
+  CUtensorMap tmX, tmF, tmD;
   const bool xb = batch > 1 && xbs != 0;
   int rc;
   if (x_mn) rc = make_map_f32(c, &tmX, X, rows, n, xb ? batch : 1, ldx * 4, xbs * 4, 32, 32, true);
@@ -248,11 +250,17 @@ int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, 
   p.vec_ok = (d_cs == 1) && aligned16(D) && (d_rs % 4 == 0) && (d_bs % 4 == 0);
   p.x_batched = xb;
   p.passes = passes;
+  // epilogue through a bulk tensor store when W is overwritten (beta == 0) and D is TMA-addressable
+  p.tma_store = (beta == 0.f) && aligned16(D) && (x_mn ? (d_cs % 4 == 0 && (batch == 1 || d_bs % 4 == 0)) : (d_rs % 4 == 0));
+  if (x_mn) rc = make_map_f32(c, &tmD, D, rows, m, batch, d_cs * 4, d_bs * 4, 32, 32, false, /*swizzle=*/false);
+  else rc = make_map_f32(c, &tmD, D, m, rows, 1, d_rs * 4, 0, 32, 32, false, /*swizzle=*/true);
+  if (!p.tma_store) tmD = tmX;   // unused by the kernel
+  else if (rc) return rc;
   const int grid = (int)std::min<long long>(p.total_tiles, c->sm_count);
-  if (x_mn && f_k) tf32::gemm_tf32x3_kernel<true, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, p);
-  else if (x_mn) tf32::gemm_tf32x3_kernel<true, false><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, p);
-  else if (f_k) tf32::gemm_tf32x3_kernel<false, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, p);
-  else tf32::gemm_tf32x3_kernel<false, false><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, p);
+  if (x_mn && f_k) tf32::gemm_tf32x3_kernel<true, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmD, p);
+  else if (x_mn) tf32::gemm_tf32x3_kernel<true, false><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmD, p);
+  else if (f_k) tf32::gemm_tf32x3_kernel<false, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmD, p);
+  else tf32::gemm_tf32x3_kernel<false, false><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmD, p);
   c->launches++;
   SCIMLOP_CUDA(c, cudaGetLastError());
   return SCIMLOP_OK;

@@ -132,6 +132,36 @@ def test_gemm_f32_tensor_core_paths(sb, case, precision, tol):
         assert err <= tol, f"{case} precision={precision} alpha={a}: rel err {err:.3e}"
 
 
+def test_gemm_f32_tensor_core_large_repeated(sb):
+    """Many tiles per CTA, launched repeatedly: the mbarrier rings of the tcgen05 kernel must stay in phase (a
+    ring depth that is not a multiple of the splitter-group count faulted here).  At this size the check is a
+    size-independent property: the tensor-core path and the exact-FP32 FFMA path (itself oracle-checked above)
+    agree to 1e-5, and a sampled block agrees with the Float64 oracle product."""
+    import torch
+    h = sb.handle(0)
+    M, N, K = 128, 524288, 128
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.rand(M * K, device="cuda", generator=g)
+    B = torch.rand(K * N, device="cuda", generator=g)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    outs = {}
+    for prec, reps in ((3, 1), (0, 4)):
+        for rep in range(reps):
+            Cc = torch.full((M * N,), float("nan"), device="cuda")
+            rc = h.lib.scimlop_gemm_strided_batched(h.ptr, 1, prec, 0, 0, M, N, K, None, C.c_void_p(A.data_ptr()), M, 0,
+                                                    C.c_void_p(B.data_ptr()), K, 0, None, C.c_void_p(Cc.data_ptr()), M, 0, 1, st)
+            h.check(rc, "gemm f32 large")
+            torch.cuda.synchronize()
+            outs[(prec, rep)] = Cc
+    ref = outs[(3, 0)]
+    for rep in range(4):
+        err = float((outs[(0, rep)] - ref).norm() / ref.norm())
+        assert err <= 1e-5, f"rep {rep}: tensor-core vs FFMA rel err {err:.3e}"
+    Ah = A.cpu().numpy().reshape((M, K), order="F").astype(np.float64)
+    Bh = B[: K * 64].cpu().numpy().reshape((K, 64), order="F").astype(np.float64)
+    check(outs[(0, 3)][: M * 64].cpu().numpy().reshape((M, 64), order="F"), Ah @ Bh, np.float32, "sampled block vs oracle")
+
+
 def test_gemm_shared_operand_and_odd_ld(sb):
     """stride 0 = shared operand; odd leading dimensions / unaligned bases take the shape-agnostic kernel."""
     rng = np.random.default_rng(5)
