@@ -27,6 +27,11 @@ import sys
 import threading
 import time
 
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # the CPU arm uses every host thread it can, also under torchrun (which exports OMP_NUM_THREADS=1)
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -37,6 +42,10 @@ KCOLS = 256                      # columns per GPU
 FLOPS_PER_COL = 2.0 * MI * NI * NO + 2.0 * MO * NO * MI      # stage 1 + stage 2
 METRIC = "kron(A,B)*V mul! throughput (512x512 (x) 512x512 Float64, 262144x256 batch per GPU)"
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool: tools/peaks.cu -> profiles/r01_peaks_microbench.json
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm_dmma_kernel on this workload, from the
+# `ncu --set full` capture summarised in profiles/r01_ncu_dmma_v3_summary.txt (539.1 + 492.6 MB stage 1,
+# 539.9 + 495.1 MB stage 2): the algorithmic 537 MB in + 537 MB out, i.e. no re-reads.
+NCU_DRAM_BYTES_PER_LAUNCH = 0.5 * ((539.069184 + 492.583680) + (539.915520 + 495.123200)) * 1e6
 REF_SAMPLE_COLS = 32             # --impl reference / cpu_baseline: columns per CPU step (bounded sample)
 
 
@@ -272,13 +281,23 @@ def run_gpu(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- CPU baseline on this box's host cores (rank 0, bounded sample) -------------------------------
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only, bounded sample) ---------------------
     ks = REF_SAMPLE_COLS
     vs = np.asfortranarray(Vh.numpy()[: n * ks].reshape((n, ks), order="F"))
-    t_std = cpu_time_one("stdlib", A, B, vs, reps=3)
-    t_lv = cpu_time_one("lv", A, B, vs[:, :4].copy(order="F"), reps=2) * (ks / 4.0)
-    cpu_best = min(t_std, t_lv)
-    cpu_tflops = FLOPS_PER_COL * ks / cpu_best / 1e12
+    cpu_line = None
+    if world == 1:
+        try:
+            from threadpoolctl import threadpool_limits
+            limiter = threadpool_limits(limits=os.cpu_count())
+        except Exception:
+            limiter = None
+        t_std = cpu_time_one("stdlib", A, B, vs, reps=3)
+        t_lv = cpu_time_one("lv", A, B, vs[:, :4].copy(order="F"), reps=2) * (ks / 4.0)
+        cpu_best = min(t_std, t_lv)
+        cpu_line = {"value": FLOPS_PER_COL * ks / cpu_best / 1e12, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port",
+                    "sample": f"{ks} of {KCOLS} columns (LV variant timed on 4 columns and scaled)",
+                    "stdlib_path_s": t_std, "lv_path_s": t_lv,
+                    "note": "CPU restatement of the reference algorithm (oracle/), not the Julia reference itself"}
     # parity spot check of the timed GPU result against the same CPU restatement
     from oracle import ref_numpy as R
     err = R.rel_err(W.cols(0, 2).numpy(), R.kron_apply([A, B], vs[:, :2]))
@@ -302,15 +321,14 @@ def run_gpu(args):
                 "api": "scimlop_kron_mul_host (pinned host V/W, chunked H2D | kernels | D2H overlap)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                     "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                     "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                     "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, profiles/r01_ncu_dmma_v3_summary.txt); "
+                                     "algorithmic bytes per launch = 1.076e9",
                      "kernel": "scimlop::dmma::gemm_dmma_kernel (2 launches per step: stage 1 B*U, stage 2 batched C1_j*A^T)",
                      "peak_source": "FP64 DMMA.8x8x4 issue-rate microbenchmark on this pool (profiles/r01_peaks_microbench.json); "
                                     "MEASURED_PEAKS.json holds no FP64 figure (cuBLAS DGEMM 8192^3 reaches 35.5)",
                      "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": launch_ms},
-        "cpu_baseline": {"value": cpu_tflops, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{ks} of {KCOLS} columns (LV variant timed on 4 columns and scaled)",
-                         "stdlib_path_s": t_std, "lv_path_s": t_lv,
-                         "note": "CPU restatement of the reference algorithm (oracle/), not the Julia reference itself"},
+        "cpu_baseline": cpu_line,
     }
     print(json.dumps(line))
     if world > 1:

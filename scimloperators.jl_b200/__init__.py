@@ -9,7 +9,7 @@ from ._lib import Handle, ScimlopError, handle, load
 from .array import DeviceArray
 from .operators import (AbstractSciMLOperator, AddedOperator, BatchedDiagonalOperator, ComposedOperator,
                         DiagonalOperator, IdentityOperator, MatrixOperator, NullOperator, ScalarOperator,
-                        ScaledOperator, TensorProductOperator, TensorSumOperator, cache_operator, iscached, kron,
+                        ScaledOperator, TensorProductOperator, TensorSumOperator, adapt, cache_operator, iscached, kron,
                         kronsum, mul_, update_coefficients_)
 from .distributed import ColumnShard, allgather_cols, shard_columns
 

@@ -18,7 +18,7 @@
 namespace scimlop {
 namespace elt {
 
-constexpr int MAX_TERMS = 6, MAX_FAC = 4, THREADS = 256, UNROLL = 4;
+constexpr int MAX_TERMS = 4, MAX_FAC = 4, THREADS = 256, UNROLL = 4;
 
 template <typename T>
 struct Factor {

@@ -878,6 +878,37 @@ def cache_operator(L, v):
     return L.cache_operator(v)
 
 
+def adapt(L, device=None, to=None):
+    """`Adapt.adapt(to, L)` (src/adapt.jl:12-115): rebuild the operator tree with every stored array re-homed
+    by `to` (default: a copy on CUDA device `device`).  Structure, update functions and ScalarOperators are
+    kept; caches are dropped (call `cache_operator` again), exactly what replicating the factors onto another
+    GPU needs.  `to` may be any callable DeviceArray -> DeviceArray (test/adapt.jl's fake
+    backend pattern)."""
+    if to is None:
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        to = lambda a: DeviceArray(a.t.to(dev, copy=True), a.shape)
+    if isinstance(L, MatrixOperator):
+        return MatrixOperator(to(L.A), L.trans, L.update_func)
+    if isinstance(L, _VectorDiagonalOperator):
+        return _VectorDiagonalOperator(to(L.diag), L.update_func)
+    if isinstance(L, BatchedDiagonalOperator):
+        return BatchedDiagonalOperator(to(L.diag), L.update_func)
+    if isinstance(L, (IdentityOperator, NullOperator)):
+        return type(L)(L.len)
+    if isinstance(L, ScaledOperator):
+        return ScaledOperator(L.lam, adapt(L.L, to=to))
+    if isinstance(L, AddedOperator):
+        return AddedOperator(*[adapt(op, to=to) for op in L.ops])
+    if isinstance(L, ComposedOperator):
+        return ComposedOperator(*[adapt(op, to=to) for op in L.ops])
+    if isinstance(L, TensorProductOperator):
+        return TensorProductOperator(*[adapt(op, to=to) for op in L.ops])
+    if isinstance(L, TensorSumOperator):
+        return TensorSumOperator(*[adapt(op, to=to) for op in L.ops])
+    raise TypeError(f"adapt: {type(L).__name__} is outside the B200 hot path")
+
+
 def iscached(L):
     return L.iscached()
 

@@ -406,6 +406,10 @@ def test_operator_trees(sb, dtype, N, K):
                                         np.diag(f(d1)) @ f(A).T + 2 * f(A) + I),
         "D1*D2 + 3I - D1": (sb.DiagonalOperator(d1) * sb.DiagonalOperator(d2) + 3.0 * sb.IdentityOperator(N)
                             - sb.DiagonalOperator(d1), np.diag(f(d1) * f(d2)) + 3 * I - np.diag(f(d1))),
+        "six diagonal terms (two elementwise passes)": (
+            sb.DiagonalOperator(d1) + sb.DiagonalOperator(d2) + 2.0 * sb.DiagonalOperator(d1) * sb.DiagonalOperator(d2)
+            + sb.IdentityOperator(N) - 0.5 * sb.DiagonalOperator(d2) + 3.0 * sb.IdentityOperator(N),
+            np.diag(f(d1) + f(d2) + 2 * f(d1) * f(d2) - 0.5 * f(d2)) + 4 * I),
         "0*A + B": (0.0 * M(A) + M(B), f(B)),
         "A + Null": (M(A) + sb.NullOperator(N), f(A)),
         "Null*A": (sb.NullOperator(N) * M(A), np.zeros((N, N))),
@@ -462,6 +466,34 @@ def test_update_coefficients(sb):
     for (p, t) in ((2.0, 3.0), (0.5, -1.0)):
         got = L(w, dv, None, p, t).numpy()
         check(got, (p * t * A + np.diag(d * t)) @ v, np.float64, f"p={p} t={t}")
+
+
+def test_adapt_rehomes_every_array(sb):
+    """test/adapt.jl:19-30,73-192: a storage-mapping function reaches every array of every operator type, the
+    structure is preserved, and the adapted operator computes the same thing."""
+    rng = np.random.default_rng(11)
+    N, K = 12, 5
+    A, d, Dk = rnd(rng, N, N), rnd(rng, N), rnd(rng, N, K)
+    seen = []
+
+    def to(a):
+        seen.append(a.shape)
+        return sb.DeviceArray(a.t.clone(), a.shape)
+
+    L = (sb.DiagonalOperator(d) * sb.MatrixOperator(A).adjoint() + 2.0 * sb.MatrixOperator(A) + sb.IdentityOperator(N)
+         + sb.DiagonalOperator(Dk) + sb.NullOperator(N))
+    L2 = sb.adapt(L, to=to)
+    assert sorted(seen) == sorted([(N,), (N, N), (N, N), (N, K)])
+    assert type(L2) is type(L) and [type(o) for o in L2.ops] == [type(o) for o in L.ops]
+    v = dev(sb, rnd(rng, N, K))
+    check((sb.cache_operator(L2, v) * v).numpy(), (sb.cache_operator(L, v) * v).numpy(), np.float64, "adapted tree")
+    seen.clear()
+    T = sb.kron(sb.MatrixOperator(A), sb.kron(sb.IdentityOperator(3), sb.DiagonalOperator(d)))
+    T2 = sb.adapt(T, to=to)
+    assert sorted(seen) == sorted([(N, N), (N,)]) and T2.size() == T.size()
+    vt = dev(sb, rnd(rng, T.size()[1], 3))
+    check((sb.cache_operator(T2, vt) * vt).numpy(), (sb.cache_operator(T, vt) * vt).numpy(), np.float64, "adapted TPO")
+    assert not sb.adapt(sb.cache_operator(sb.kron(A, A), dev(sb, rnd(rng, N * N, 2)))).iscached()   # caches are dropped
 
 
 # ---- configuration shapes (BASELINE.json configs) ---------------------------------------------------------
