@@ -39,9 +39,9 @@ constexpr int RSTAGES = 4;              // raw X tiles in flight (shared memory 
 constexpr int ASTAGES = 4;              // split A tiles in flight (tensor memory ring)
 constexpr int XT_BYTES = TM * BK * 4;   // 16 KB: one raw X tile
 constexpr int F_BYTES = MAXF * MAXF * 4;  // 64 KB each for F_hi and F_lo
-constexpr int NBAR = 2 * RSTAGES + 2 * ASTAGES + 4 + 1;
-constexpr int EPI_STAGE_BYTES = 4096;   // one 32 x 32 FP32 block per epilogue warp, staged for the TMA store
-constexpr int SMEM_BYTES = 1024 + 2 * F_BYTES + RSTAGES * XT_BYTES + 4 * EPI_STAGE_BYTES + 8 * NBAR + 16;
+constexpr int NBAR = 2 * RSTAGES + 2 * ASTAGES + 4 + 1 + 8;
+constexpr int EPI_STAGE_BYTES = 4096;   // one 32 x 32 FP32 block; two per epilogue warp (double-buffered)
+constexpr int SMEM_BYTES = 1024 + 2 * F_BYTES + RSTAGES * XT_BYTES + 8 * EPI_STAGE_BYTES + 8 * NBAR + 16;
 constexpr int NSG = 2;                  // splitter groups (4 warps each) alternating over k-blocks
 constexpr int NEG = 1;                  // epilogue groups (4 warps each)
 // A ring slot must always be served by the SAME splitter group: a group that never waited on phase j of a
@@ -64,7 +64,7 @@ struct Params {
   int vec_ok;            // d_cs == 1 and 16-byte alignment holds: float4 stores along c
   int x_batched;
   int passes;            // 3: lo*Fhi + hi*Flo + hi*Fhi (FP32-grade);  1: hi*Fhi only (plain TF32, opt-in)
-  int tma_store;         // beta == 0 and D is TMA-addressable: epilogue goes TMEM -> smem -> bulk tensor store
+  int tma_store;         // D is TMA-addressable: epilogue goes TMEM -> smem (-> + beta * old block, TMA-loaded) -> bulk store
 };
 
 // ---- tcgen05 wrappers -----------------------------------------------------------------------------------
@@ -160,12 +160,13 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));  // generic pointer to the aligned base
   const uint32_t sFhi = smem, sFlo = smem + F_BYTES, sX = smem + 2 * F_BYTES;
-  const uint32_t sEpi = sX + RSTAGES * XT_BYTES;          // 4 x 4 KB staging blocks (1024-byte aligned)
-  const uint32_t bars = sEpi + 4 * EPI_STAGE_BYTES;
+  const uint32_t sEpi = sX + RSTAGES * XT_BYTES;          // 4 warps x 2 x 4 KB staging blocks (1024-byte aligned)
+  const uint32_t bars = sEpi + 8 * EPI_STAGE_BYTES;
   const uint32_t raw_full = bars, raw_free = raw_full + 8 * RSTAGES;
   const uint32_t a_full = raw_free + 8 * RSTAGES, a_free = a_full + 8 * ASTAGES;
   const uint32_t tmem_full = a_free + 8 * ASTAGES, tmem_empty = tmem_full + 16, f_full = tmem_empty + 16;
-  const uint32_t tmem_slot = f_full + 8;
+  const uint32_t epi_bar = f_full + 8;                     // [4 warps][2 buffers]: old-D block has landed
+  const uint32_t tmem_slot = epi_bar + 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       mbar_init(tmem_empty + 8 * a, 4);   // one arrival per epilogue warp
     }
     mbar_init(f_full, 1);
+    for (int q = 0; q < 8; q++) mbar_init(epi_bar + 8 * q, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -345,8 +347,12 @@ __global__ void __launch_bounds__(THREADS, 1)
   } else if (warp >= 4 + 4 * NSG) {
     // ===================== epilogue: TMEM -> registers -> (smem -> TMA store | global), alpha/beta fused =====
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
-    const uint32_t stage_s = sEpi + quarter * EPI_STAGE_BYTES;
+    const uint32_t stage_s = sEpi + quarter * 2 * EPI_STAGE_BYTES;     // two buffers of this warp
     uint8_t* stage_g = smem_gen + (stage_s - smem);
+    const uint32_t ebar = epi_bar + 16 * quarter;
+    uint32_t eph0 = 0, eph1 = 0;                    // phases of the two "old block landed" barriers
+    const bool readw = (p.beta != 0.f);
+    const int nblk = (p.m + 31) / 32;
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
       const int a = it & 1;
@@ -354,37 +360,66 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int b = (int)(tile / p.tiles_r);
       const int rw = (int)(tile - (long long)b * p.tiles_r) * TM + quarter * 32;   // first row of this warp
       const long long r = rw + lane;
+      // beta != 0: the old 32 x 32 block of D is TMA-loaded into the staging buffer it will be stored from
+      auto load_old = [&](int blk) {
+        if (lane == 0) {
+          const int buf = blk & 1;
+          tma_store_wait_read();      // the store that last used this buffer has been read out
+          mbar_arrive_expect_tx(ebar + 8 * buf, EPI_STAGE_BYTES);
+          if (X_MN) tma_load_3d(stage_s + buf * EPI_STAGE_BYTES, &tmD, ebar + 8 * buf, rw, blk * 32, b);
+          else tma_load_3d(stage_s + buf * EPI_STAGE_BYTES, &tmD, ebar + 8 * buf, blk * 32, rw, 0);
+        }
+      };
+      if (p.tma_store && readw) load_old(0);        // overlaps the wait for the accumulator
       mbar_wait(tmem_full + 8 * a, aphase);
       tc_fence_after();
       float* drow = p.D + (long long)b * p.d_bs + r * p.d_rs;
       const bool row_ok = r < p.rows;
-      for (int c0 = 0; c0 < p.m; c0 += 32) {
+      for (int blk = 0; blk < nblk; blk++) {
+        const int c0 = blk * 32;
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * 128 + c0, v);
         tc_wait_ld();
         if (p.tma_store) {
-          // stage the 32 x 32 block in shared memory in the order the output wants, then one bulk tensor store:
-          // full 128-byte lines, clipped at the matrix edge, no LSU pressure on this warp
-          if (lane == 0) tma_store_wait_read();     // previous block of this warp has been read out
-          __syncwarp();
+          // stage the block in shared memory in the order the output wants, then ONE bulk tensor store: full
+          // 128-byte lines, clipped at the matrix edge, no LSU pressure on this warp
+          const int buf = blk & 1;
+          uint8_t* sg = stage_g + buf * EPI_STAGE_BYTES;
+          if (readw) {
+            if (blk + 1 < nblk) load_old(blk + 1);  // prefetch the next old block into the other buffer
+            if (buf == 0) { mbar_wait(ebar, eph0); eph0 ^= 1; } else { mbar_wait(ebar + 8, eph1); eph1 ^= 1; }
+          } else {
+            if (lane == 0) tma_store_wait_read1();  // the store issued two blocks ago has been read out
+            __syncwarp();
+          }
           if (X_MN) {
             // output is contiguous along r (the lanes): smem [c][32 r]
 #pragma unroll
-            for (int c = 0; c < 32; c++)
-              *reinterpret_cast<float*>(stage_g + c * 128 + lane * 4) = p.alpha * __uint_as_float(v[c]);
+            for (int c = 0; c < 32; c++) {
+              float* q = reinterpret_cast<float*>(sg + c * 128 + lane * 4);
+              float o = p.alpha * __uint_as_float(v[c]);
+              if (readw) o += p.beta * *q;
+              *q = o;
+            }
           } else {
             // output is contiguous along c: smem [r][32 c], 16-byte chunks XOR (r & 7) (SWIZZLE_128B)
 #pragma unroll
-            for (int q = 0; q < 8; q++)
-              *reinterpret_cast<float4*>(stage_g + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                  make_float4(p.alpha * __uint_as_float(v[4 * q]), p.alpha * __uint_as_float(v[4 * q + 1]),
-                              p.alpha * __uint_as_float(v[4 * q + 2]), p.alpha * __uint_as_float(v[4 * q + 3]));
+            for (int q = 0; q < 8; q++) {
+              float4* dst = reinterpret_cast<float4*>(sg + lane * 128 + ((q ^ (lane & 7)) << 4));
+              float4 o = make_float4(p.alpha * __uint_as_float(v[4 * q]), p.alpha * __uint_as_float(v[4 * q + 1]),
+                                     p.alpha * __uint_as_float(v[4 * q + 2]), p.alpha * __uint_as_float(v[4 * q + 3]));
+              if (readw) {
+                const float4 old = *dst;
+                o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+              }
+              *dst = o;
+            }
           }
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {   // bulk groups are per thread: the same lane issues, commits and later waits
-            if (X_MN) tma_store_3d(&tmD, stage_s, rw, c0, b);
-            else tma_store_3d(&tmD, stage_s, c0, rw, 0);
+            if (X_MN) tma_store_3d(&tmD, stage_s + buf * EPI_STAGE_BYTES, rw, c0, b);
+            else tma_store_3d(&tmD, stage_s + buf * EPI_STAGE_BYTES, c0, rw, 0);
             tma_store_commit();
           }
           __syncwarp();

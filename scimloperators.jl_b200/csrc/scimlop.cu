@@ -250,8 +250,8 @@ int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, 
   p.vec_ok = (d_cs == 1) && aligned16(D) && (d_rs % 4 == 0) && (d_bs % 4 == 0);
   p.x_batched = xb;
   p.passes = passes;
-  // epilogue through a bulk tensor store when W is overwritten (beta == 0) and D is TMA-addressable
-  p.tma_store = (beta == 0.f) && aligned16(D) && (x_mn ? (d_cs % 4 == 0 && (batch == 1 || d_bs % 4 == 0)) : (d_rs % 4 == 0));
+  // epilogue through shared-memory staging + bulk tensor loads/stores when D is TMA-addressable
+  p.tma_store = aligned16(D) && (x_mn ? (d_cs % 4 == 0 && (batch == 1 || d_bs % 4 == 0)) : (d_rs % 4 == 0));
   if (x_mn) rc = make_map_f32(c, &tmD, D, rows, m, batch, d_cs * 4, d_bs * 4, 32, 32, false, /*swizzle=*/false);
   else rc = make_map_f32(c, &tmD, D, m, rows, 1, d_rs * 4, 0, 32, 32, false, /*swizzle=*/true);
   if (!p.tma_store) tmD = tmX;   // unused by the kernel

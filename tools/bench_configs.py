@@ -94,7 +94,12 @@ def c3(reps, k=512):
     W = sb.DeviceArray.empty((n, k), np.float32)
     L = sb.cache_operator(sb.TensorProductOperator(*[sb.MatrixOperator(f) for f in F]), V)
     t = timeit(lambda: sb.mul_(W, L, V), max(2, reps // 3), warm=1)
-    report(f"c3 128^3 three-factor f32 k={k} 3arg", 3 * 2 * 128.0 * n * k, 2.0 * n * k * 4, *t, "f32")
+    report(f"c3 128^3 three-factor f32 k={k} 3arg", 3 * 2 * 128.0 * n * k, 2.0 * n * k * 4, *t, "f32",
+           {"hbm_frac_3_passes": 3 * 2.0 * n * k * 4 / (t[1] * 1e-3) / 1e9 / PEAKS["hbm_gbs"]})
+    W.t.fill_(0.5)
+    t = timeit(lambda: sb.mul_(W, L, V, 0.7, 0.3), max(2, reps // 3), warm=1)
+    report(f"c3 128^3 three-factor f32 k={k} 5arg", 3 * 2 * 128.0 * n * k, 3.0 * n * k * 4, *t, "f32",
+           {"hbm_frac_3_passes": (3 * 2.0 + 1.0) * n * k * 4 / (t[1] * 1e-3) / 1e9 / PEAKS["hbm_gbs"]})
 
 
 def c4elt(reps):
