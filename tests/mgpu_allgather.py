@@ -1,0 +1,51 @@
+"""Multi-GPU check (run under torchrun on >= 2 GPUs; driven by tests/test_multigpu.py on a multi-GPU box):
+column-sharded kron mul! with replicated factors, then the OPTIONAL in-place NCCL all-gather of W
+(scimlop_allgather_cols) -- every rank must end up with the full, correct W."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import scimlop_b200 as sb
+    from scimlop_b200 import distributed as sd
+    from oracle import ref_numpy as R
+    h = sb.handle(local)
+    rng = np.random.default_rng(0)                       # same seed everywhere: replicated factors and global V
+    A, B = np.asfortranarray(rng.random((48, 40))), np.asfortranarray(rng.random((32, 24)))
+    kper = 6
+    k = kper * world
+    V = np.asfortranarray(rng.random((40 * 24, k)))
+    sh = sb.ColumnShard(k, world, rank)
+    assert (sh.first, sh.count) == (rank * kper, kper)
+    # NCCL communicator of the library (unique id travels through torch.distributed)
+    def bcast(b):
+        obj = [b]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+    sd.init_comm(h, world, rank, bcast)
+    Wfull = sb.DeviceArray.full((48 * 32, k), float("nan"), np.float64)
+    v_loc = sb.DeviceArray.from_numpy(sh.take(V))
+    L = sb.cache_operator(sb.kron(A, B), v_loc)
+    sb.mul_(Wfull.cols(sh.first, sh.first + sh.count), L, v_loc)     # this rank's slab, in place in the full W
+    sd.allgather_cols(h, Wfull, kper)
+    torch.cuda.synchronize()
+    err = R.rel_err(Wfull.numpy(), np.kron(A, B) @ V)
+    ok = torch.tensor([1.0 if err < 1e-12 else 0.0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("ALLGATHER_OK" if ok.item() == 1.0 else f"ALLGATHER_FAILED err={err:.3e}")
+    dist.destroy_process_group()
+    return 0 if ok.item() == 1.0 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -561,6 +561,29 @@ def test_config3_shapes_reduced_batch(sb):
     check(got, R.kron_apply([A, B, Cm], v), np.float32, "config3 3-arg")
 
 
+def test_config3_full_size_properties(sb):
+    """configs[2] at full size (2097152 x 512 Float32, 4.3 GB per array, tcgen05 path): sampled columns against
+    the Float64 oracle, and the alpha/beta identity W <- 2 L V - W == W."""
+    import torch
+    rng0 = np.random.default_rng(0)
+    F = [rnd(rng0, 128, 128, dtype=np.float32) for _ in range(3)]
+    n, k = 128 ** 3, 512
+    g = torch.Generator(device="cuda").manual_seed(1)
+    V = sb.DeviceArray(torch.rand(n * k, dtype=torch.float32, device="cuda", generator=g), (n, k))
+    L = sb.cache_operator(sb.TensorProductOperator(*F), V)
+    W = sb.DeviceArray.full((n, k), float("nan"), np.float32)
+    sb.mul_(W, L, V)
+    assert torch.isfinite(W.t).all()
+    for j in (0, 511):
+        check(W.cols(j, j + 1).numpy(), R.kron_apply(F, V.cols(j, j + 1).numpy()), np.float32, f"column {j}")
+    W2 = W.copy()
+    sb.mul_(W2, L, V, 2.0, -1.0)
+    err = float((W2.t - W.t).norm() / W.t.norm())
+    assert err <= 1e-5, f"alpha/beta identity violated: {err:.3e}"
+    del W2, W, V, L
+    torch.cuda.empty_cache()
+
+
 def test_config4_shapes_reduced(sb):
     """configs[3]: α(D*M' + 2M + I)v + βw, N = 2^12 (dense part), and the all-diagonal variant at N = 2^16."""
     rng = np.random.default_rng(4)
