@@ -186,6 +186,20 @@ int scimlop_kron_mul_host(scimlop_handle_t h, int dtype, int precision, int nfac
                           const int32_t* kinds, const void* V, int64_t ldv, void* W, int64_t ldw,
                           int64_t k, const void* alpha, const void* beta, int64_t chunk_cols);
 
+/* ---- solver-loop vector kernels (the caller side of the matvec) ------------------- */
+/* Column-wise dot products: out[j] = sum_i X[i,j] * Y[i,j], j < k; `out` is a DEVICE vector of k scalars.
+ * (Y == X gives squared column norms.)  Everything stays on the stream: graph-capturable. */
+int scimlop_col_dot(scimlop_handle_t h, int dtype, int64_t n, int64_t k, const void* X, int64_t ldx,
+                    const void* Y, int64_t ldy, void* out_dev, void* stream);
+
+/* W[:,j] = a_j * X[:,j] + b_j * W[:,j] with per-column coefficients held in DEVICE memory:
+ * a_j = sa * an[j] / ad[j], b_j = sb * bn[j] / bd[j] (an, ad, bn, bd: device vectors of k scalars or NULL = 1;
+ * sa, sb: host doubles).  sb == 0 with bn == NULL never reads W.  If `dot_dev` is not NULL it receives
+ * dot[j] = sum_i W_new[i,j]^2 in the same pass (e.g. the new squared residual norm of a CG step). */
+int scimlop_col_axpby_dot(scimlop_handle_t h, int dtype, int64_t n, int64_t k, const void* X, int64_t ldx,
+                          double sa, const void* an_dev, const void* ad_dev, void* W, int64_t ldw, double sb,
+                          const void* bn_dev, const void* bd_dev, void* dot_dev, void* stream);
+
 /* ---- multi-GPU: column sharding ---------------------------------------------------- */
 /* Columns [first, first+count) of a k-column batch owned by `rank` of `nranks` (contiguous slabs). */
 int scimlop_shard_columns(int64_t k, int nranks, int rank, int64_t* first, int64_t* count);

@@ -12,5 +12,6 @@ from .operators import (AbstractSciMLOperator, AddedOperator, BatchedDiagonalOpe
                         ScaledOperator, TensorProductOperator, TensorSumOperator, adapt, cache_operator, iscached, kron,
                         kronsum, mul_, update_coefficients_)
 from .distributed import ColumnShard, allgather_cols, shard_columns
+from . import krylov
 
 __all__ = [n for n in dir() if not n.startswith("_")]

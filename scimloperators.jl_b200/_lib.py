@@ -58,6 +58,8 @@ SIGNATURES = {
     "scimlop_tree_mul": [_P, _INT, _INT, C.POINTER(Term), _INT, _P, _I64, _P, _I64, _I64, _P, _P, _P, _SZ, _P],
     "scimlop_kron_mul_host": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _I64, _P, _I64, _I64,
                               _P, _P, _I64],
+    "scimlop_col_dot": [_P, _INT, _I64, _I64, _P, _I64, _P, _I64, _P, _P],
+    "scimlop_col_axpby_dot": [_P, _INT, _I64, _I64, _P, _I64, C.c_double, _P, _P, _P, _I64, C.c_double, _P, _P, _P, _P],
     "scimlop_shard_columns": [_I64, _INT, _INT, _I64P, _I64P],
     "scimlop_comm_unique_id": [_P],
     "scimlop_comm_init": [_P, _INT, _INT, _P],

@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "context.h"
+#include "krylov.cuh"
 
 namespace {
 
@@ -232,4 +233,87 @@ extern "C" int scimlop_destroy(scimlop_handle_t h) {
   h->magic = 0;
   delete h;
   return SCIMLOP_OK;
+}
+
+// ================================================================================================
+// solver-loop vector kernels
+// ================================================================================================
+namespace {
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+int col_dot_t(scimlop_context* h, int64_t n, int64_t k, const T* X, int64_t ldx, const T* Y, int64_t ldy, T* out,
+              cudaStream_t st) {
+  constexpr int NV = scimlop::kry::V16<T>::N;
+  const bool vec = (n % NV == 0) && (ldx % NV == 0) && (ldy % NV == 0) && al16(X) && al16(Y);
+  const long long chunk = (long long)scimlop::kry::THREADS * (vec ? NV : 1) * scimlop::kry::U;
+  long long bx = std::max<long long>(1, std::min<long long>((n + chunk - 1) / chunk, (long long)h->sm_count * 8 / std::max<int64_t>(1, std::min<int64_t>(k, 8))));
+  SCIMLOP_CUDA(h, cudaMemsetAsync(out, 0, (size_t)k * sizeof(T), st));
+  for (int64_t j0 = 0; j0 < k; j0 += 65535) {
+    const unsigned ky = (unsigned)std::min<int64_t>(65535, k - j0);
+    dim3 grid((unsigned)bx, ky);
+    if (vec) scimlop::kry::col_dot_kernel<T, true><<<grid, scimlop::kry::THREADS, 0, st>>>(n, X + j0 * ldx, ldx, Y + j0 * ldy, ldy, out + j0);
+    else scimlop::kry::col_dot_kernel<T, false><<<grid, scimlop::kry::THREADS, 0, st>>>(n, X + j0 * ldx, ldx, Y + j0 * ldy, ldy, out + j0);
+    h->launches++;
+  }
+  SCIMLOP_CUDA(h, cudaGetLastError());
+  return SCIMLOP_OK;
+}
+
+template <typename T>
+int col_axpby_t(scimlop_context* h, int64_t n, int64_t k, const T* X, int64_t ldx, double sa, const T* an, const T* ad,
+                T* W, int64_t ldw, double sb, const T* bn, const T* bd, T* dot, cudaStream_t st) {
+  constexpr int NV = scimlop::kry::V16<T>::N;
+  const bool vec = (n % NV == 0) && (ldx % NV == 0) && (ldw % NV == 0) && al16(X) && al16(W);
+  const long long chunk = (long long)scimlop::kry::THREADS * (vec ? NV : 1) * scimlop::kry::U;
+  long long bx = std::max<long long>(1, std::min<long long>((n + chunk - 1) / chunk, (long long)h->sm_count * 8 / std::max<int64_t>(1, std::min<int64_t>(k, 8))));
+  if (dot) SCIMLOP_CUDA(h, cudaMemsetAsync(dot, 0, (size_t)k * sizeof(T), st));
+  for (int64_t j0 = 0; j0 < k; j0 += 65535) {
+    const unsigned ky = (unsigned)std::min<int64_t>(65535, k - j0);
+    scimlop::kry::AxpbyParams<T> p;
+    p.n = n; p.X = X + j0 * ldx; p.ldx = ldx; p.W = W + j0 * ldw; p.ldw = ldw;
+    p.sa = (T)sa; p.sb = (T)sb;
+    p.an = an ? an + j0 : nullptr; p.ad = ad ? ad + j0 : nullptr; p.bn = bn ? bn + j0 : nullptr; p.bd = bd ? bd + j0 : nullptr;
+    p.dot = dot ? dot + j0 : nullptr;
+    p.read_w = !(sb == 0.0 && !bn && !bd);
+    dim3 grid((unsigned)bx, ky);
+    if (vec) scimlop::kry::col_axpby_dot_kernel<T, true><<<grid, scimlop::kry::THREADS, 0, st>>>(p);
+    else scimlop::kry::col_axpby_dot_kernel<T, false><<<grid, scimlop::kry::THREADS, 0, st>>>(p);
+    h->launches++;
+  }
+  SCIMLOP_CUDA(h, cudaGetLastError());
+  return SCIMLOP_OK;
+}
+}  // namespace
+
+extern "C" int scimlop_col_dot(scimlop_handle_t h, int dtype, int64_t n, int64_t k, const void* X, int64_t ldx,
+                               const void* Y, int64_t ldy, void* out_dev, void* stream) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (dtype != SCIMLOP_F64 && dtype != SCIMLOP_F32) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "unsupported dtype %d", dtype);
+  if (n < 0 || k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "col_dot: negative size");
+  if (k == 0) return SCIMLOP_OK;
+  if (!out_dev || (n > 0 && (!X || !Y))) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "col_dot: null operand");
+  if (n > 0 && (ldx < n || ldy < n)) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "col_dot: leading dimension smaller than n");
+  scimlop_device_guard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SCIMLOP_F64) return col_dot_t<double>(h, n, k, (const double*)X, ldx, (const double*)Y, ldy, (double*)out_dev, st);
+  return col_dot_t<float>(h, n, k, (const float*)X, ldx, (const float*)Y, ldy, (float*)out_dev, st);
+}
+
+extern "C" int scimlop_col_axpby_dot(scimlop_handle_t h, int dtype, int64_t n, int64_t k, const void* X, int64_t ldx,
+                                     double sa, const void* an_dev, const void* ad_dev, void* W, int64_t ldw, double sb,
+                                     const void* bn_dev, const void* bd_dev, void* dot_dev, void* stream) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (dtype != SCIMLOP_F64 && dtype != SCIMLOP_F32) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "unsupported dtype %d", dtype);
+  if (n < 0 || k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "col_axpby: negative size");
+  if (n == 0 || k == 0) return SCIMLOP_OK;
+  if (!X || !W) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "col_axpby: null operand");
+  if (ldx < n || ldw < n) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "col_axpby: leading dimension smaller than n");
+  scimlop_device_guard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SCIMLOP_F64)
+    return col_axpby_t<double>(h, n, k, (const double*)X, ldx, sa, (const double*)an_dev, (const double*)ad_dev, (double*)W,
+                               ldw, sb, (const double*)bn_dev, (const double*)bd_dev, (double*)dot_dev, st);
+  return col_axpby_t<float>(h, n, k, (const float*)X, ldx, sa, (const float*)an_dev, (const float*)ad_dev, (float*)W, ldw,
+                            sb, (const float*)bn_dev, (const float*)bd_dev, (float*)dot_dev, st);
 }

@@ -164,7 +164,36 @@ def c5(reps, k=8):
            2.0 * n * n * k * 8 + 2.0 * n * n * 8, t[0] / R, t[1] / R, "f64")
 
 
-ALL = {"c1": c1, "c2": c2, "c3": c3, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
+def krylov(reps, k=8):
+    """Solver-loop kernels at config-5 size (16.7M x 8) and a graph-captured batched CG iteration on the
+    4096^2-grid Kronecker sum (SPD factors)."""
+    n = 4096
+    N = n * n
+    X, Y, W = dev_rand((N, k), np.float64, 1), dev_rand((N, k), np.float64, 2), dev_rand((N, k), np.float64, 3)
+    out = sb.DeviceArray.zeros((k,), np.float64)
+    nb = N * k * 8
+    t = timeit(lambda: sb.krylov.col_dot(X, Y, out), reps)
+    report(f"col_dot {N}x{k} f64", 2.0 * N * k, 2.0 * nb, *t, "hbm")
+    t = timeit(lambda: sb.krylov.col_axpby(X, W, sa=0.5, an=out, ad=out, sb=1.0), reps)
+    report(f"col_axpby (device coefficients) {N}x{k} f64", 2.0 * N * k, 3.0 * nb, *t, "hbm")
+    t = timeit(lambda: sb.krylov.col_axpby(X, W, sa=0.5, sb=1.0, dot=out), reps)
+    report(f"col_axpby + fused |w|^2 {N}x{k} f64", 4.0 * N * k, 3.0 * nb, *t, "hbm")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    def spd():
+        Q = torch.rand(n, n, dtype=torch.float64, device="cuda", generator=g)
+        M = Q @ Q.T / n + torch.eye(n, dtype=torch.float64, device="cuda")
+        return sb.DeviceArray(M.T.contiguous().reshape(-1), (n, n))
+    L = sb.kronsum(sb.MatrixOperator(spd()), sb.MatrixOperator(spd()))
+    Bm = dev_rand((N, k), np.float64, 4)
+    Xs = sb.DeviceArray.zeros((N, k), np.float64)
+    _, _, st = sb.krylov.cg(L, Bm, Xs, 8, use_graph=True, iters_per_graph=8)      # builds the graph
+    t = timeit(lambda: st.graph.replay(), 3, warm=1)
+    flops_it = 2 * 2.0 * n ** 3 * k
+    report(f"batched CG iteration (graph of 8) on kronsum 4096^2 grid k={k}: per iteration", flops_it,
+           11.0 * nb + 3.0 * nb, t[0] / 8, t[1] / 8, "f64", {"note": "matvec = 2 DMMA launches; 4 vector kernels per iteration"})
+
+
+ALL = {"krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
