@@ -61,7 +61,10 @@ enum {
   SCIMLOP_IDENTITY = 1, /* IdentityOperator                              src/basic.jl:28-30           */
   SCIMLOP_DIAG = 2,     /* DiagonalOperator(::Vector): data = n entries  src/matrix.jl:438-459        */
   SCIMLOP_BDIAG = 3,    /* BatchedDiagonalOperator: data = n x k, ld     src/batch.jl:11-28           */
-  SCIMLOP_NULL = 4      /* NullOperator                                  src/basic.jl:185-188         */
+  SCIMLOP_NULL = 4,     /* NullOperator                                  src/basic.jl:185-188         */
+  SCIMLOP_BANDED = 5    /* MatrixOperator over a banded (tridiagonal, ...) n x n matrix, kron factors only:
+                           data = n x (2b+1) column-major, diagonal d in column d+b aligned by row
+                           (data[i + n*(d+b)] = A[i, i+d]); lds[f] carries the half-bandwidth b (<= 4)  */
 };
 /* OR-ed into a kron factor kind: the factor is the lazy adjoint/transpose of the stored matrix
  * (`adjoint(::MatrixOperator)` wraps the array, src/matrix.jl:174-175; TPO adjoint maps over factors,
@@ -145,6 +148,13 @@ int scimlop_kronsum_mul(scimlop_handle_t h, int dtype, int precision, const void
                         int64_t mo, const void* B, int64_t ldb, int64_t mi, const void* V, int64_t ldv,
                         void* W, int64_t ldw, int64_t k, const void* alpha, const void* beta,
                         void* stream);
+
+/* Kronecker sum of two BANDED matrices (finite-difference Laplacian, the HBM-bound flavour of config 5):
+ *   W_j(mi x mo) = alpha * (By * V_j + V_j * Bx^T) + beta * W_j  in ONE pass over V and W.
+ * Bx: mo x (2bx+1) bands of the outer factor, By: mi x (2by+1) bands of the inner factor (SCIMLOP_BANDED layout). */
+int scimlop_kronsum_banded_mul(scimlop_handle_t h, int dtype, const void* Bx, int bx, int64_t mo, const void* By,
+                               int by, int64_t mi, const void* V, int64_t ldv, void* W, int64_t ldw, int64_t k,
+                               const void* alpha, const void* beta, void* stream);
 
 /* ---- operator trees --------------------------------------------------------------------------------- */
 /* A tree is handed over flattened (the host does what src/basic.jl:619-635 does for sums and :936-939

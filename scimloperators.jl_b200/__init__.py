@@ -7,7 +7,7 @@ through the `scimlop_b200` shim at the repo root (`import scimlop_b200 as sb`)."
 from . import _lib
 from ._lib import Handle, ScimlopError, handle, load
 from .array import DeviceArray
-from .operators import (AbstractSciMLOperator, AddedOperator, BatchedDiagonalOperator, ComposedOperator,
+from .operators import (AbstractSciMLOperator, AddedOperator, BandedMatrix, BatchedDiagonalOperator, ComposedOperator,
                         DiagonalOperator, IdentityOperator, MatrixOperator, NullOperator, ScalarOperator,
                         ScaledOperator, TensorProductOperator, TensorSumOperator, adapt, cache_operator, iscached, kron,
                         kronsum, mul_, update_coefficients_)

@@ -14,7 +14,7 @@ OK = 0
 ERR_NULL_POINTER, ERR_BAD_SHAPE, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_BAD_HANDLE, ERR_NO_DEVICE = range(1, 9)
 F64, F32 = 0, 1
 PREC_DEFAULT, PREC_TF32X3, PREC_TF32, PREC_FP32_EXACT = 0, 1, 2, 3
-DENSE, IDENTITY, DIAG, BDIAG, NULL = 0, 1, 2, 3, 4
+DENSE, IDENTITY, DIAG, BDIAG, NULL, BANDED = 0, 1, 2, 3, 4, 5
 TRANS = 0x100
 
 
@@ -54,6 +54,7 @@ SIGNATURES = {
                          _P, _P, _SZ, _P],
     "scimlop_outer_mul_fast": [_P, _INT, _INT, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P],
     "scimlop_kronsum_mul": [_P, _INT, _INT, _P, _I64, _I64, _P, _I64, _I64, _P, _I64, _P, _I64, _I64, _P, _P, _P],
+    "scimlop_kronsum_banded_mul": [_P, _INT, _P, _INT, _I64, _P, _INT, _I64, _P, _I64, _P, _I64, _I64, _P, _P, _P],
     "scimlop_tree_workspace_bytes": [_INT, C.POINTER(Term), _INT, _I64, C.POINTER(_SZ)],
     "scimlop_tree_mul": [_P, _INT, _INT, C.POINTER(Term), _INT, _P, _I64, _P, _I64, _I64, _P, _P, _P, _SZ, _P],
     "scimlop_kron_mul_host": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _I64, _P, _I64, _I64,

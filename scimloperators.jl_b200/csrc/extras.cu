@@ -71,6 +71,10 @@ extern "C" int scimlop_kron_mul_host(scimlop_handle_t h, int dtype, int precisio
     } else if (kinds[f] == SCIMLOP_DIAG) {
       if (!factors[f]) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_mul_host: null diagonal factor %d", f);
       off += align_up((size_t)dims[2 * f] * es, 256);
+    } else if (kinds[f] == SCIMLOP_BANDED) {
+      if (!factors[f]) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_mul_host: null banded factor %d", f);
+      if (lds[f] < 0 || lds[f] > 4) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "kron_mul_host: bad half-bandwidth");
+      off += align_up((size_t)dims[2 * f] * (size_t)(2 * lds[f] + 1) * es, 256);
     }
   }
   const size_t vslot = align_up((size_t)cols * cc * es, 256), wslot = align_up((size_t)rows * cc * es, 256);
@@ -94,6 +98,7 @@ extern "C" int scimlop_kron_mul_host(scimlop_handle_t h, int dtype, int precisio
     if ((kinds[f] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE)
       bytes = (size_t)lds[f] * (size_t)((kinds[f] & SCIMLOP_TRANS) ? dims[2 * f] : dims[2 * f + 1]) * es;
     else if (kinds[f] == SCIMLOP_DIAG) bytes = (size_t)dims[2 * f] * es;
+    else if (kinds[f] == SCIMLOP_BANDED) bytes = (size_t)dims[2 * f] * (size_t)(2 * lds[f] + 1) * es;
     if (bytes) {
       dfac[f] = base + fac_off[f];
       SCIMLOP_CUDA(h, cudaMemcpyAsync(base + fac_off[f], factors[f], bytes, cudaMemcpyHostToDevice, h->s_h2d));

@@ -8,6 +8,7 @@
 #include <new>
 
 #include "context.h"
+#include "banded.cuh"
 #include "eltwise.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_simt.cuh"
@@ -491,8 +492,8 @@ int kron_plan(scimlop_context* c, int nfactors, const int64_t* dims, const int32
   for (int f = 0; f < nfactors; f++) {
     const int64_t m = dims[2 * f], n = dims[2 * f + 1];
     if (m < 0 || n < 0) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "kron: negative factor size");
-    if (kinds[f] == SCIMLOP_IDENTITY || kinds[f] == SCIMLOP_DIAG) {
-      if (m != n) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "kron: identity/diagonal factor %d must be square", f);
+    if (kinds[f] == SCIMLOP_IDENTITY || kinds[f] == SCIMLOP_DIAG || kinds[f] == SCIMLOP_BANDED) {
+      if (m != n) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "kron: identity/diagonal/banded factor %d must be square", f);
     } else if ((kinds[f] & ~SCIMLOP_TRANS) != SCIMLOP_DENSE) {
       return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "kron: factor kind %d not supported inside a tensor product", kinds[f]);
     }
@@ -538,7 +539,17 @@ int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* cons
     const T a = last ? alpha : T(1), bt = last ? beta : T(0);
     const bool tr = (kinds[p] & SCIMLOP_TRANS) != 0;
     int rc;
-    if (kinds[p] == SCIMLOP_DIAG) {
+    if (kinds[p] == SCIMLOP_BANDED) {
+      // mode product with a banded matrix: a 1-D stencil along index (i / L) % n      [HBM-bound]
+      const long long total = L * n * R;
+      const int b = (int)lds[p];
+      if (b < 0 || b > band::MAXB) return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "kron: half-bandwidth %d not in 0..%d", b, band::MAXB);
+      const long long blocks = std::min<long long>((total + band::THREADS - 1) / band::THREADS, (long long)c->sm_count * 32);
+      band::band_mode_kernel<T><<<(unsigned)std::max<long long>(1, blocks), band::THREADS, 0, st>>>(
+          total, L, n, b, static_cast<const T*>(factors[p]), cur, out, a, bt);
+      c->launches++;
+      rc = (cudaGetLastError() == cudaSuccess) ? SCIMLOP_OK : scimlop_fail(c, SCIMLOP_ERR_CUDA, "band_mode_kernel launch failed");
+    } else if (kinds[p] == SCIMLOP_DIAG) {
       // mode product with a diagonal: scale along index (i / L) % n of every column of the L*n x R view
       elt::Params<T> ep;
       memset(&ep, 0, sizeof(ep));
@@ -675,6 +686,38 @@ extern "C" int scimlop_kronsum_mul(scimlop_handle_t h, int dtype, int precision,
                              (double*)W, k, scalar_or<double>(alpha, 1.0), scalar_or<double>(beta, 0.0), st);
   return kronsum_t<float>(h, precision, (const float*)A, lda, mo, (const float*)B, ldb, mi, (const float*)V, (float*)W,
                           k, scalar_or<float>(alpha, 1.f), scalar_or<float>(beta, 0.f), st);
+}
+
+template <typename T>
+static int kronsum_banded_t(scimlop_context* h, const T* Bx, int bx, int64_t mo, const T* By, int by, int64_t mi, const T* V,
+                            T* W, int64_t k, T alpha, T beta, cudaStream_t st) {
+  dim3 grid((unsigned)((mi + 63) / 64), (unsigned)((mo + 3) / 4), (unsigned)std::min<int64_t>(k, 64));
+  if (grid.y > 65535u) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kronsum_banded: outer extent too large");
+  band::band_kronsum_kernel<T><<<grid, band::THREADS, 0, st>>>(mi, mo, k, bx, by, Bx, By, V, W, alpha, beta);
+  h->launches++;
+  SCIMLOP_CUDA(h, cudaGetLastError());
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_kronsum_banded_mul(scimlop_handle_t h, int dtype, const void* Bx, int bx, int64_t mo,
+                                          const void* By, int by, int64_t mi, const void* V, int64_t ldv, void* W,
+                                          int64_t ldw, int64_t k, const void* alpha, const void* beta, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_dtype(h, dtype)) return rc;
+  if (mo < 0 || mi < 0 || k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kronsum_banded: negative size");
+  if (bx < 0 || by < 0 || bx > band::MAXB || by > band::MAXB)
+    return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "kronsum_banded: half-bandwidth must be in 0..%d", band::MAXB);
+  if (mo == 0 || mi == 0 || k == 0) return SCIMLOP_OK;
+  if (!Bx || !By || !V || !W) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kronsum_banded: null operand");
+  if (ldv != mi * mo || ldw != mi * mo)
+    return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kronsum_banded: V and W must be contiguous (ld == mi*mo)");
+  scimlop_device_guard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SCIMLOP_F64)
+    return kronsum_banded_t<double>(h, (const double*)Bx, bx, mo, (const double*)By, by, mi, (const double*)V, (double*)W,
+                                    k, scalar_or<double>(alpha, 1.0), scalar_or<double>(beta, 0.0), st);
+  return kronsum_banded_t<float>(h, (const float*)Bx, bx, mo, (const float*)By, by, mi, (const float*)V, (float*)W, k,
+                                 scalar_or<float>(alpha, 1.f), scalar_or<float>(beta, 0.f), st);
 }
 
 // ================================================================================================

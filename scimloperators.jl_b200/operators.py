@@ -71,6 +71,36 @@ def _check_vw(L, w, v):
         raise AssertionError("mul!: w and v must not alias")
 
 
+class BandedMatrix:
+    """Device storage of a banded n x n matrix (Tridiagonal, pentadiagonal, ...: what a finite-difference
+    `MatrixOperator` holds).  `bands` is n x (2b+1): diagonal d in column d+b, aligned by row
+    (bands[i, d+b] = A[i, i+d]) -- the SCIMLOP_BANDED layout of the C ABI."""
+
+    def __init__(self, bands, b):
+        self.bands = _as_device(bands)
+        self.b = int(b)
+        if self.bands.ndim != 2 or self.bands.shape[1] != 2 * self.b + 1:
+            raise ValueError("BandedMatrix: bands must be n x (2b+1)")
+
+    @staticmethod
+    def from_dense(A, b):
+        A = np.asarray(A)
+        n = A.shape[0]
+        bands = np.zeros((n, 2 * b + 1), dtype=A.dtype, order="F")
+        for d in range(-b, b + 1):
+            i = np.arange(max(0, -d), min(n, n - d))
+            bands[i, d + b] = A[i, i + d]
+        return BandedMatrix(bands, b)
+
+    @property
+    def shape(self):
+        return (self.bands.shape[0], self.bands.shape[0])
+
+    @property
+    def dtype(self):
+        return self.bands.dtype
+
+
 class ScalarOperator:
     """src/scalar.jl:124-127 -- mutable scalar; `update_func(old, u, p, t)` gives the new value (:267-270)."""
 
@@ -206,9 +236,12 @@ class MatrixOperator(AbstractSciMLOperator):
     device matrix in place (:257-271)."""
 
     def __init__(self, A, trans=False, update_func=None):
-        self.A = _as_device(A)
-        if self.A.ndim != 2:
+        self.banded = isinstance(A, BandedMatrix)
+        self.A = A if self.banded else _as_device(A)
+        if not self.banded and self.A.ndim != 2:
             raise ValueError("MatrixOperator needs a matrix")
+        if self.banded and trans:
+            raise NotImplementedError("adjoint of a banded MatrixOperator: transpose the bands on the host")
         self.trans = bool(trans)
         self.update_func = update_func
 
@@ -219,6 +252,7 @@ class MatrixOperator(AbstractSciMLOperator):
     def size(self):
         m, n = self.A.shape
         return (n, m) if self.trans else (m, n)
+
 
     def adjoint(self):
         if self.update_func is not None:
@@ -237,6 +271,15 @@ class MatrixOperator(AbstractSciMLOperator):
         _check_vw(self, w, v)
         h = _lib.handle(w.device_index)
         m, n = self.size()
+        if self.banded:   # a one-factor "Kronecker product": the banded mode-product kernel
+            nb = self.A.shape[0]
+            dims, lds = (C.c_int64 * 2)(nb, nb), (C.c_int64 * 1)(self.A.b)
+            kinds, ptrs = (C.c_int32 * 1)(_lib.BANDED), (C.c_void_p * 1)(self.A.bands.ptr)
+            h.check(h.lib.scimlop_kron_mul(h.ptr, _DT[w.dtype], self.precision, 1, ptrs, dims, lds, kinds,
+                                           C.c_void_p(v.ptr), nb, C.c_void_p(w.ptr), nb, _ncols(v),
+                                           _scalar(w.dtype, alpha), _scalar(w.dtype, beta), None, 0, _stream()),
+                    "scimlop_kron_mul")
+            return w
         h.check(h.lib.scimlop_matmul(h.ptr, _DT[w.dtype], self.precision, int(self.trans), m, n, _ncols(v),
                                      C.c_void_p(self.A.ptr), self.A.ld, C.c_void_p(v.ptr), v.ld,
                                      C.c_void_p(w.ptr), w.ld, _scalar(w.dtype, alpha), _scalar(w.dtype, beta),
@@ -451,6 +494,8 @@ def _scale_getter(scalars):
 
 def _terms_with_scalars(L, scalars=()):
     """Flatten like src/basic.jl:619-635 (sums) and :936-939 (products); returns [(scalars, leaves)] or None."""
+    if isinstance(L, MatrixOperator) and L.banded:
+        return None    # banded leaves are applied by their own kernel, not by scimlop_tree_mul
     if isinstance(L, _LEAVES):
         return [(tuple(scalars), [L])]
     if isinstance(L, ScaledOperator):
@@ -649,6 +694,8 @@ class ComposedOperator(_TreeMixin, AbstractSciMLOperator):
 # ====================================================================================================
 def _kron_leaf(op):
     """(kind, data_ptr, ld) if `op` can be a native Kronecker factor, else None."""
+    if isinstance(op, MatrixOperator) and op.banded:
+        return (_lib.BANDED, op.A.bands.ptr, op.A.b)      # lds[] carries the half-bandwidth for banded factors
     if isinstance(op, MatrixOperator):
         return (_lib.DENSE | (_lib.TRANS if op.trans else 0), op.A.ptr, op.A.ld)
     if isinstance(op, IdentityOperator):
@@ -786,7 +833,7 @@ class TensorProductOperator(AbstractSciMLOperator):
         while isinstance(outer, ScaledOperator):                                   # :755-759 / :800-804 (intended)
             lam *= outer.lam.convert()
             outer = outer.L
-        if not isinstance(outer, MatrixOperator):
+        if not isinstance(outer, MatrixOperator) or outer.banded:
             raise NotImplementedError(f"outer factor {type(outer).__name__} is not supported by the B200 backend "
                                       "(the Julia wrapper keeps the generic path for it)")
         a = alpha if lam == 1.0 else lam * (1.0 if alpha is None else float(alpha))
@@ -815,8 +862,9 @@ class TensorSumOperator(AbstractSciMLOperator):
             if m != n:
                 raise AssertionError("TensorSumOperator needs square factors")
         self.ops = (outer, inner)
-        self._native = (isinstance(outer, MatrixOperator) and isinstance(inner, MatrixOperator)
-                        and not outer.trans and not inner.trans)
+        both = isinstance(outer, MatrixOperator) and isinstance(inner, MatrixOperator)
+        self._banded = both and outer.banded and inner.banded
+        self._native = both and not outer.trans and not inner.trans and (self._banded or not (outer.banded or inner.banded))
         self.products = None
         if not self._native:
             self.products = (TensorProductOperator(outer, IdentityOperator(inner.size()[0])),
@@ -854,6 +902,12 @@ class TensorSumOperator(AbstractSciMLOperator):
         A, B = self.ops[0].A, self.ops[1].A
         mo, mi = A.shape[0], B.shape[0]
         n = mo * mi
+        if self._banded:   # finite-difference Laplacian: ONE HBM-bound pass
+            h.check(h.lib.scimlop_kronsum_banded_mul(h.ptr, _DT[w.dtype], C.c_void_p(A.bands.ptr), A.b, mo,
+                                                     C.c_void_p(B.bands.ptr), B.b, mi, C.c_void_p(v.ptr), n,
+                                                     C.c_void_p(w.ptr), n, _ncols(v), _scalar(w.dtype, alpha),
+                                                     _scalar(w.dtype, beta), _stream()), "scimlop_kronsum_banded_mul")
+            return w
         h.check(h.lib.scimlop_kronsum_mul(h.ptr, _DT[w.dtype], self.precision, C.c_void_p(A.ptr), A.ld, mo,
                                           C.c_void_p(B.ptr), B.ld, mi, C.c_void_p(v.ptr), n, C.c_void_p(w.ptr), n,
                                           _ncols(v), _scalar(w.dtype, alpha), _scalar(w.dtype, beta), _stream()),

@@ -193,7 +193,26 @@ def krylov(reps, k=8):
            11.0 * nb + 3.0 * nb, t[0] / 8, t[1] / 8, "f64", {"note": "matvec = 2 DMMA launches; 4 vector kernels per iteration"})
 
 
-ALL = {"krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
+def c5fd(reps, k=8):
+    """Finite-difference flavour of config 5: tridiagonal Dxx, Dyy on the 4096^2 grid -- one HBM-bound pass."""
+    n = 4096
+    N = n * n
+    def tri(seed):
+        b = dev_rand((n, 3), np.float64, seed)
+        return sb.MatrixOperator(sb.BandedMatrix(b, 1))
+    V, W = dev_rand((N, k), np.float64, 1), dev_rand((N, k), np.float64, 2)
+    L = sb.cache_operator(sb.kronsum(tri(7), tri(8)), V)
+    nb = N * k * 8
+    t = timeit(lambda: sb.mul_(W, L, V), reps)
+    report(f"c5-fd kronsum(tridiag, tridiag) 4096^2 grid f64 k={k} 3-arg", 10.0 * N * k, 2.0 * nb, *t, "hbm")
+    t = timeit(lambda: sb.mul_(W, L, V, 0.7, 0.3), reps)
+    report(f"c5-fd kronsum(tridiag, tridiag) 4096^2 grid f64 k={k} 5-arg", 12.0 * N * k, 3.0 * nb, *t, "hbm")
+    L2 = sb.cache_operator(sb.kron(tri(7), sb.IdentityOperator(n)) + sb.kron(sb.IdentityOperator(n), tri(8)), V)
+    t = timeit(lambda: sb.mul_(W, L2, V), reps)
+    report(f"c5-fd as AddedOperator of two banded TPOs (two passes) k={k}", 10.0 * N * k, 5.0 * nb, *t, "hbm")
+
+
+ALL = {"c5fd": c5fd, "krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
