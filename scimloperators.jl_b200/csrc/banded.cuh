@@ -73,5 +73,84 @@ __global__ void __launch_bounds__(THREADS) band_kronsum_kernel(long long mi, lon
   }
 }
 
+// Tridiagonal x tridiagonal (the 5-point finite-difference Laplacian), the case that has to run at HBM speed:
+// a block owns 256 consecutive i and sweeps a chunk of o with a sliding window of three grid lines held in
+// registers, so every element of V is loaded once per thread (the i-neighbours come from L1), with the line
+// two steps ahead already in flight.  Requires mi even and 16-byte aligned V / W.
+template <typename T> struct V2;
+template <> struct V2<double> { using type = double2; };
+template <> struct V2<float> { using type = float2; };
+
+template <typename T>
+__global__ void __launch_bounds__(128) band_kronsum_tri_kernel(long long mi, long long mo, int ochunk,
+                                                               const T* __restrict__ Bx, const T* __restrict__ By,
+                                                               const T* __restrict__ V, T* W, T alpha, T beta) {
+  using P = typename V2<T>::type;
+  const long long i0 = ((long long)blockIdx.x * 128 + threadIdx.x) * 2;
+  // (a thread past the edge keeps running with clamped rows so that the warp shuffles stay converged)
+  const bool active = i0 < mi;
+  const long long i0c = active ? i0 : mi - 2;
+  const long long o_begin = (long long)blockIdx.y * ochunk;
+  const long long o_end = min(mo, o_begin + (long long)ochunk);
+  const long long plane = mi * mo;
+  const T* v = V + (long long)blockIdx.z * plane + i0c;
+  T* w = W + (long long)blockIdx.z * plane + i0c;
+  // rows i0, i0+1 of By: sub-, main, super-diagonal
+  const T a0 = __ldg(By + i0c), b0 = __ldg(By + i0c + mi), c0 = __ldg(By + i0c + 2 * mi);
+  const T a1 = __ldg(By + i0c + 1), b1 = __ldg(By + i0c + 1 + mi), c1 = __ldg(By + i0c + 1 + 2 * mi);
+  const bool has_left = i0c > 0, has_right = i0c + 2 < mi;
+  const int lane = threadIdx.x & 31;
+  auto line = [&](long long o) -> P {
+    if (o < 0 || o >= mo) return P{T(0), T(0)};
+    return __ldcs(reinterpret_cast<const P*>(v + o * mi));
+  };
+  // i-neighbours of the pair come from the neighbouring lanes by shuffle; only the two edge lanes of a warp
+  // load a scalar (lane 0: v[i0-1], lane 31: v[i0+2]), and they do so PF lines ahead like the main loads
+  auto edge = [&](long long o) -> T {
+    if (o < 0 || o >= mo) return T(0);
+    if (lane == 0) return has_left ? v[o * mi - 1] : T(0);
+    if (lane == 31) return has_right ? v[o * mi + 2] : T(0);
+    return T(0);
+  };
+  constexpr int PF = 4;                     // lines in flight ahead of the one being computed
+  P q[PF + 2];                              // q[0] = line o-1, q[1] = line o, q[2..PF+1] = lines o+1 .. o+PF
+  T e[PF + 1];                              // e[0] = edge scalar of line o, e[1..PF] of lines o+1 .. o+PF
+#pragma unroll
+  for (int u = 0; u < PF + 2; u++) q[u] = line(o_begin - 1 + u);
+#pragma unroll
+  for (int u = 0; u < PF + 1; u++) e[u] = edge(o_begin + u);
+  for (long long o = o_begin; o < o_end; o++) {
+    const P far = line(o + PF + 1);
+    const T efar = edge(o + PF + 1);
+    const P prev = q[0], cur = q[1], nxt = q[2];
+    T left = __shfl_up_sync(0xffffffffu, cur.y, 1);
+    T right = __shfl_down_sync(0xffffffffu, cur.x, 1);
+    if (lane == 0) left = e[0];
+    if (lane == 31) right = e[0];
+    if (!has_left) left = T(0);      // outside the grid: never let a neighbour lane's value (or a NaN) in
+    if (!has_right) right = T(0);
+    const T xs = __ldg(Bx + o), xm = __ldg(Bx + o + mo), xp = __ldg(Bx + o + 2 * mo);   // row o of Bx (block-uniform)
+    T r0 = fma(a0, left, fma(b0, cur.x, c0 * cur.y));
+    T r1 = fma(a1, cur.x, fma(b1, cur.y, c1 * right));
+    r0 = fma(xs, prev.x, fma(xm, cur.x, fma(xp, nxt.x, r0)));
+    r1 = fma(xs, prev.y, fma(xm, cur.y, fma(xp, nxt.y, r1)));
+    r0 *= alpha;
+    r1 *= alpha;
+    P* dst = reinterpret_cast<P*>(w + o * mi);
+    if (beta != T(0)) {
+      const P old = *dst;
+      r0 = fma(beta, old.x, r0);
+      r1 = fma(beta, old.y, r1);
+    }
+    if (active) __stcs(dst, P{r0, r1});
+#pragma unroll
+    for (int u = 0; u < PF + 1; u++) q[u] = q[u + 1];
+    q[PF + 1] = far;
+#pragma unroll
+    for (int u = 0; u < PF; u++) e[u] = e[u + 1];
+    e[PF] = efar;
+  }
+}
+
 }  // namespace band
 }  // namespace scimlop

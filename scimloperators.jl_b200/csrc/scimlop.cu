@@ -691,6 +691,17 @@ extern "C" int scimlop_kronsum_mul(scimlop_handle_t h, int dtype, int precision,
 template <typename T>
 static int kronsum_banded_t(scimlop_context* h, const T* Bx, int bx, int64_t mo, const T* By, int by, int64_t mi, const T* V,
                             T* W, int64_t k, T alpha, T beta, cudaStream_t st) {
+  if (bx == 1 && by == 1 && mi % 2 == 0 && aligned16(V) && aligned16(W) && k <= 65535) {
+    // 5-point stencil fast path: sliding window over o, 256 i per block
+    const int ochunk = 128;
+    dim3 g((unsigned)((mi / 2 + 127) / 128), (unsigned)((mo + ochunk - 1) / ochunk), (unsigned)k);
+    if (g.y <= 65535u) {
+      band::band_kronsum_tri_kernel<T><<<g, 128, 0, st>>>(mi, mo, ochunk, Bx, By, V, W, alpha, beta);
+      h->launches++;
+      SCIMLOP_CUDA(h, cudaGetLastError());
+      return SCIMLOP_OK;
+    }
+  }
   dim3 grid((unsigned)((mi + 63) / 64), (unsigned)((mo + 3) / 4), (unsigned)std::min<int64_t>(k, 64));
   if (grid.y > 65535u) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kronsum_banded: outer extent too large");
   band::band_kronsum_kernel<T><<<grid, band::THREADS, 0, st>>>(mi, mo, k, bx, by, Bx, By, V, W, alpha, beta);
