@@ -146,16 +146,145 @@ function mul!(w::DevMat{T}, L::BatchedDiagonalOperator, v::DevMat{T}, α::Number
 end
 
 # ---- trees: AddedOperator / ComposedOperator / ScaledOperator -> one scimlop_tree_mul call -----------------
-# The flattening (sum of products of leaves) mirrors `_terms_with_scalars` of the Python twin; the C structs
-# are `scimlop_factor_t` / `scimlop_term_t` of include/scimlop_b200.h.
+# A tree over native leaves is handed over flattened: a sum of terms, each term = (product of ScalarOperator
+# values) * leaf_1 * leaf_2 * ... (what src/basic.jl:619-635 does for sums and :936-939 for products).
+# The C structs are `scimlop_factor_t` / `scimlop_term_t` of include/scimlop_b200.h.
 struct CFactor
     kind::Cint; trans::Cint; data::Ptr{Cvoid}; ld::Int64; rows::Int64; cols::Int64
 end
 struct CTerm
     scale::Cdouble; nfactors::Cint; factors::Ptr{CFactor}
 end
-# (construction of the CFactor/CTerm arrays at `cache_operator` time and the `mul!` methods for
-#  AddedOperator / ComposedOperator / ScaledOperator follow the same pattern as the TPO methods above:
-#  build once, refresh `scale` from the ScalarOperators per call, `ccall((:scimlop_tree_mul, LIB), ...)`.)
+
+# leaf -> CFactor, or nothing if the leaf is not native
+function cfactor(op, T)
+    m, n = size(op)
+    if op isa IdentityOperator
+        return CFactor(IDENTITY, 0, C_NULL, 0, m, n)
+    elseif op isa SciMLOperators.NullOperator
+        return CFactor(NULLOP, 0, C_NULL, 0, m, n)
+    elseif op isa BatchedDiagonalOperator && op.diag isa CuArray{T}
+        return CFactor(BDIAG, 0, dptr(op.diag), size(op.diag, 1), m, n)
+    elseif op isa MatrixOperator
+        A = op.A
+        A isa CuMatrix{T} && return CFactor(DENSE, 0, dptr(A), stride(A, 2), m, n)
+        A isa Union{Adjoint{T, <:CuMatrix{T}}, Transpose{T, <:CuMatrix{T}}} &&
+            return CFactor(DENSE, 1, dptr(parent(A)), stride(parent(A), 2), m, n)
+        A isa Diagonal{T, <:CuVector{T}} && return CFactor(DIAG, 0, dptr(A.diag), 0, m, n)
+    end
+    return nothing
+end
+
+# [(scalars::Vector, leaves::Vector{CFactor})] or nothing; a sum inside a product is not distributed
+function flatten_tree(L, T, scalars = Any[])
+    if L isa ScaledOperator
+        return flatten_tree(L.L, T, vcat(scalars, Any[L.λ]))
+    elseif L isa AddedOperator
+        out = Tuple{Vector{Any}, Vector{CFactor}}[]
+        for op in L.ops
+            t = flatten_tree(op, T, scalars)
+            t === nothing && return nothing
+            append!(out, t)
+        end
+        return out
+    elseif L isa ComposedOperator
+        sc = copy(scalars); leaves = CFactor[]
+        for op in L.ops
+            t = flatten_tree(op, T, Any[])
+            (t === nothing || length(t) != 1) && return nothing
+            append!(sc, t[1][1]); append!(leaves, t[1][2])
+        end
+        return [(sc, leaves)]
+    else
+        f = cfactor(L, T)
+        return f === nothing ? nothing : [(copy(scalars), CFactor[f])]
+    end
+end
+
+# The plan lives next to the operator's own cache (a WeakKeyDict keeps `copy`/`adapt` semantics untouched):
+# factor arrays, the term array and the device workspace are built once in `cache_operator`; `mul!` only
+# refreshes the scales (ScalarOperators may have been updated, src/scalar.jl:267-270) and ccalls.
+mutable struct TreePlan{T}
+    terms::Vector{CTerm}
+    keep::Vector{Vector{CFactor}}
+    scalars::Vector{Vector{Any}}
+    ws::CuVector{UInt8}
+    k::Int
+end
+const PLANS = WeakKeyDict{Any, Any}()
+const TreeOp = Union{AddedOperator, ComposedOperator, ScaledOperator}
+
+function build_plan(L::TreeOp, v::DevMat{T}) where {T <: F}
+    fl = flatten_tree(L, T)
+    fl === nothing && return nothing
+    keep = [t[2] for t in fl]
+    terms = [CTerm(1.0, length(f), pointer(f)) for f in keep]
+    nbytes = Ref{Csize_t}(0)
+    rc = ccall((:scimlop_tree_workspace_bytes, LIB), Cint, (Cint, Ptr{CTerm}, Cint, Int64, Ref{Csize_t}),
+               dtype(T), terms, length(terms), size(v, 2), nbytes)
+    rc == 0 || error("scimlop_tree_workspace_bytes: status $rc")
+    TreePlan{T}(terms, keep, [t[1] for t in fl], CUDA.zeros(UInt8, max(nbytes[], 1)), size(v, 2))
+end
+
+function SciMLOperators.cache_operator(L::TreeOp, v::DevMat{T}) where {T <: F}
+    Lc = invoke(SciMLOperators.cache_operator, Tuple{SciMLOperators.AbstractSciMLOperator, AbstractVecOrMat}, L, v)
+    plan = build_plan(Lc, v)
+    plan === nothing || (PLANS[Lc] = plan)
+    Lc
+end
+
+function tree_mul!(w::DevMat{T}, L::TreeOp, plan::TreePlan{T}, v::DevMat{T}, a, b) where {T <: F}
+    for (i, sc) in enumerate(plan.scalars)      # refresh λ's: allocation-free (isbits CTerm, in-place setindex!)
+        λ = 1.0
+        for s in sc; λ *= Float64(convert(Number, s)); end
+        plan.terms[i] = CTerm(λ, plan.terms[i].nfactors, plan.terms[i].factors)
+    end
+    GC.@preserve plan begin
+        check(ccall((:scimlop_tree_mul, LIB), Cint,
+                    (Ptr{Cvoid}, Cint, Cint, Ptr{CTerm}, Cint, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Ptr{T}, Ptr{T},
+                     Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                    handle(), dtype(T), 0, plan.terms, length(plan.terms), dptr(v), size(v, 1), dptr(w), size(w, 1),
+                    size(v, 2), a, b, dptr(plan.ws), sizeof(plan.ws), stream_ptr()), "scimlop_tree_mul")
+    end
+    w
+end
+
+for Op in (:AddedOperator, :ComposedOperator, :ScaledOperator)
+    @eval function mul!(w::DevMat{T}, L::$Op, v::DevMat{T}) where {T <: F}
+        plan = get(PLANS, L, nothing)
+        (plan === nothing || plan.k != size(v, 2)) &&
+            return invoke(mul!, Tuple{AbstractVecOrMat, $Op, AbstractVecOrMat}, w, L, v)   # generic src/basic.jl path
+        tree_mul!(w, L, plan, v, C_NULL, C_NULL)
+    end
+    @eval function mul!(w::DevMat{T}, L::$Op, v::DevMat{T}, α, β) where {T <: F}
+        plan = get(PLANS, L, nothing)
+        (plan === nothing || plan.k != size(v, 2)) &&
+            return invoke(mul!, Tuple{AbstractVecOrMat, $Op, AbstractVecOrMat, Any, Any}, w, L, v, α, β)
+        tree_mul!(w, L, plan, v, Ref(T(α)), Ref(T(β)))
+    end
+end
+
+# ---- TensorSumOperator (src/tensor.jl:387-403) ----------------------------------------------------------------
+function mul!(w::DevMat{T}, L::SciMLOperators.TensorSumOperator, v::DevMat{T}, α, β) where {T <: F}
+    outer, inner = L.ops
+    (outer isa MatrixOperator && inner isa MatrixOperator && outer.A isa CuMatrix{T} && inner.A isa CuMatrix{T}) ||
+        return invoke(mul!, Tuple{AbstractVecOrMat, SciMLOperators.TensorSumOperator, AbstractVecOrMat, Any, Any}, w, L, v, α, β)
+    check(ccall((:scimlop_kronsum_mul, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64,
+                 Int64, Ref{T}, Ref{T}, Ptr{Cvoid}),
+                handle(), dtype(T), 0, dptr(outer.A), stride(outer.A, 2), size(outer.A, 1), dptr(inner.A), stride(inner.A, 2),
+                size(inner.A, 1), dptr(v), size(v, 1), dptr(w), size(w, 1), size(v, 2), T(α), T(β), stream_ptr()),
+          "scimlop_kronsum_mul")
+    w
+end
+
+# ---- solver-loop kernels (device-resident per-column scalars), for Krylov callers -----------------------------
+function col_dot!(out::CuVector{T}, x::CuMatrix{T}, y::CuMatrix{T}) where {T <: F}
+    check(ccall((:scimlop_col_dot, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+                handle(), dtype(T), size(x, 1), size(x, 2), dptr(x), stride(x, 2), dptr(y), stride(y, 2), dptr(out),
+                stream_ptr()), "scimlop_col_dot")
+    out
+end
 
 end # module

@@ -162,6 +162,55 @@ def test_gemm_f32_tensor_core_large_repeated(sb):
     check(outs[(0, 3)][: M * 64].cpu().numpy().reshape((M, 64), order="F"), Ah @ Bh, np.float32, "sampled block vs oracle")
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_gemm_dispatch_fuzz(sb, dtype):
+    """Seeded fuzz over the GEMM dispatcher: random extents (including 1 and non-multiples of every tile),
+    padded leading dimensions (even/odd), offset base pointers, shared or batched operands, all transposes,
+    alpha/beta on or off -- whatever kernel the dispatcher picks must agree with the Float64 product."""
+    import torch
+    h = sb.handle(0)
+    rng = np.random.default_rng(1234 if dtype == np.float64 else 4321)
+    es = np.dtype(dtype).itemsize
+    ct = C.c_double if dtype == np.float64 else C.c_float
+    dt = 0 if dtype == np.float64 else 1
+    sizes = [1, 2, 5, 16, 31, 32, 33, 64, 100, 128, 129, 200, 256, 300]
+    for trial in range(40):
+        M, N, K = (int(rng.choice(sizes)) for _ in range(3))
+        if trial % 5 == 0:
+            N = int(rng.choice([1024, 2048, 4100]))      # long streamed side: tensor-core eligible shapes
+        batch = int(rng.choice([1, 1, 2, 5]))
+        ta, tb = int(rng.integers(2)), int(rng.integers(2))
+        ar, ac = (K, M) if ta else (M, K)
+        br, bc = (N, K) if tb else (K, N)
+        lda, ldb, ldc = ar + int(rng.choice([0, 0, 1, 2, 4])), br + int(rng.choice([0, 0, 1, 2, 4])), M + int(rng.choice([0, 0, 1, 4]))
+        offa, offb = int(rng.choice([0, 0, 1, 2, 4])), int(rng.choice([0, 0, 1, 2, 4]))
+        shared_b = bool(rng.integers(2)) and batch > 1
+        sA, sB, sC = lda * ac, (0 if shared_b else ldb * bc), ldc * N
+        Abuf = rnd(rng, offa + sA * batch, dtype=dtype)
+        Bbuf = rnd(rng, offb + max(sB, ldb * bc) * (1 if shared_b else batch), dtype=dtype)
+        C0 = rnd(rng, sC * batch, dtype=dtype)
+        use_ab = bool(rng.integers(2))
+        a, b = (float(rng.random()) + 0.5, float(rng.choice([0.0, 0.3]))) if use_ab else (None, None)
+        dA, dB = dev(sb, Abuf), dev(sb, Bbuf)
+        dC = dev(sb, C0 if b else np.where(np.arange(C0.size) % 3 == 0, np.nan, C0).astype(dtype))
+        rc = h.lib.scimlop_gemm_strided_batched(
+            h.ptr, dt, 0, ta, tb, M, N, K, C.byref(ct(a)) if use_ab else None, C.c_void_p(dA.ptr + es * offa), lda, sA,
+            C.c_void_p(dB.ptr + es * offb), ldb, sB, C.byref(ct(b)) if use_ab else None, C.c_void_p(dC.ptr), ldc, sC, batch,
+            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        h.check(rc, "gemm fuzz")
+        got = dC.numpy()
+        for i in range(batch):
+            Am = Abuf[offa + i * sA: offa + (i + 1) * sA].reshape((lda, ac), order="F")[:ar].astype(np.float64)
+            bo = offb + (0 if shared_b else i * sB)
+            Bm = Bbuf[bo: bo + ldb * bc].reshape((ldb, bc), order="F")[:br].astype(np.float64)
+            Cm0 = C0[i * sC:(i + 1) * sC].reshape((ldc, N), order="F")[:M].astype(np.float64)
+            want = (1.0 if a is None else a) * ((Am.T if ta else Am) @ (Bm.T if tb else Bm)) + (b * Cm0 if b else 0.0)
+            gi = got[i * sC:(i + 1) * sC].reshape((ldc, N), order="F")
+            check(gi[:M], want, dtype, f"trial {trial}: M{M} N{N} K{K} b{batch} t{ta}{tb} ld{lda},{ldb},{ldc} off{offa},{offb} ab={a},{b}")
+            if ldc > M and b:   # padding rows of C are never touched
+                assert (gi[M:] == C0[i * sC:(i + 1) * sC].reshape((ldc, N), order="F")[M:]).all()
+
+
 def test_gemm_shared_operand_and_odd_ld(sb):
     """stride 0 = shared operand; odd leading dimensions / unaligned bases take the shape-agnostic kernel."""
     rng = np.random.default_rng(5)
