@@ -223,6 +223,20 @@ int scimlop_comm_destroy(scimlop_handle_t h);
 int scimlop_allgather_cols(scimlop_handle_t h, int dtype, void* W_full, int64_t rows,
                            int64_t cols_per_rank, void* stream);
 
+/* Column-sharded kron mul! whose result is wanted REPLICATED on every rank, with the all-gather overlapped
+ * with the compute: this rank's `cols_per_rank` columns are processed in chunks of `chunk_cols` (0 = library
+ * default); as soon as a chunk of W is done on the compute stream, the matching chunks of all ranks are
+ * exchanged on a second stream (one grouped NCCL broadcast per rank over NVLink), while the next chunk computes.
+ * V is this rank's slab (prod cols x cols_per_rank); W_full is prod rows x (cols_per_rank * nranks), contiguous,
+ * rank r's columns at [r*cols_per_rank, (r+1)*cols_per_rank).  `workspace` must cover `chunk_cols` columns
+ * (scimlop_kron_workspace_bytes with k = chunk_cols, or simply with k = cols_per_rank).  Returns after
+ * enqueueing; `stream` is ordered after both the compute and the exchange. */
+int scimlop_kron_mul_allgather(scimlop_handle_t h, int dtype, int precision, int nfactors,
+                               const void* const* factors, const int64_t* dims, const int64_t* lds,
+                               const int32_t* kinds, const void* V, void* W_full, int64_t cols_per_rank,
+                               const void* alpha, int64_t chunk_cols, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

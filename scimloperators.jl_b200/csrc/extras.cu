@@ -149,6 +149,8 @@ typedef int (*nccl_get_unique_id_fn)(nccl_unique_id*);
 typedef int (*nccl_comm_init_rank_fn)(void**, int, nccl_unique_id, int);
 typedef int (*nccl_comm_destroy_fn)(void*);
 typedef int (*nccl_all_gather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*nccl_broadcast_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_group_fn)(void);
 typedef const char* (*nccl_get_error_string_fn)(int);
 constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8;  // ncclDataType_t (nccl.h)
 
@@ -220,6 +222,59 @@ extern "C" int scimlop_allgather_cols(scimlop_handle_t h, int dtype, void* W_ful
     auto es2 = reinterpret_cast<nccl_get_error_string_fn>(nccl_sym("ncclGetErrorString"));
     return scimlop_fail(h, SCIMLOP_ERR_NCCL, "ncclAllGather failed: %s", es2 ? es2(r) : "?");
   }
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_kron_mul_allgather(scimlop_handle_t h, int dtype, int precision, int nfactors,
+                                          const void* const* factors, const int64_t* dims, const int64_t* lds,
+                                          const int32_t* kinds, const void* V, void* W_full, int64_t cols_per_rank,
+                                          const void* alpha, int64_t chunk_cols, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (!h->nccl_comm) return scimlop_fail(h, SCIMLOP_ERR_NCCL, "kron_mul_allgather: call scimlop_comm_init first");
+  if (dtype != SCIMLOP_F64 && dtype != SCIMLOP_F32) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "unsupported dtype %d", dtype);
+  if (nfactors < 1 || nfactors > 8 || !dims || !kinds) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_mul_allgather: bad factor description");
+  if (cols_per_rank < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kron_mul_allgather: negative column count");
+  if (cols_per_rank == 0) return SCIMLOP_OK;
+  if (!V || !W_full) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_mul_allgather: V/W null");
+  auto bcast = reinterpret_cast<nccl_broadcast_fn>(nccl_sym("ncclBroadcast"));
+  auto gstart = reinterpret_cast<nccl_group_fn>(nccl_sym("ncclGroupStart"));
+  auto gend = reinterpret_cast<nccl_group_fn>(nccl_sym("ncclGroupEnd"));
+  if (!bcast || !gstart || !gend) return scimlop_fail(h, SCIMLOP_ERR_NCCL, "NCCL symbols not found");
+  scimlop_device_guard guard(h->device);
+  if (int rc = ensure_host_streams(h)) return rc;   // s_comp = compute, s_d2h = exchange
+  const size_t es = dtype == SCIMLOP_F64 ? 8 : 4;
+  long long rows = 1, cols = 1;
+  for (int f = 0; f < nfactors; f++) { rows *= dims[2 * f]; cols *= dims[2 * f + 1]; }
+  long long cc = chunk_cols > 0 ? chunk_cols : std::max<long long>(1, (cols_per_rank + 3) / 4);
+  cc = std::min<long long>(cc, cols_per_rank);
+  cudaStream_t user = static_cast<cudaStream_t>(stream), comp = h->s_comp, comm = h->s_d2h;
+  // both internal streams start after whatever the caller has enqueued
+  SCIMLOP_CUDA(h, cudaEventRecord(h->ev_h2d[0], user));
+  SCIMLOP_CUDA(h, cudaStreamWaitEvent(comp, h->ev_h2d[0], 0));
+  SCIMLOP_CUDA(h, cudaStreamWaitEvent(comm, h->ev_h2d[0], 0));
+  const int ncclType = dtype == SCIMLOP_F64 ? NCCL_FLOAT64 : NCCL_FLOAT32;
+  char* Wb = static_cast<char*>(W_full);
+  for (long long c0 = 0; c0 < cols_per_rank; c0 += cc) {
+    const long long nc = std::min<long long>(cc, cols_per_rank - c0);
+    char* mine = Wb + ((size_t)h->rank * cols_per_rank + c0) * rows * es;
+    int rc = scimlop_kron_mul_impl(h, dtype, precision, nfactors, factors, dims, lds, kinds,
+                                   static_cast<const char*>(V) + (size_t)c0 * cols * es, cols, mine, rows, nc, alpha,
+                                   nullptr, workspace, workspace_bytes, comp);
+    if (rc) return rc;
+    SCIMLOP_CUDA(h, cudaEventRecord(h->ev_comp[0], comp));
+    SCIMLOP_CUDA(h, cudaStreamWaitEvent(comm, h->ev_comp[0], 0));
+    if (gstart() != 0) return scimlop_fail(h, SCIMLOP_ERR_NCCL, "ncclGroupStart failed");
+    for (int r = 0; r < h->nranks; r++) {
+      char* slab = Wb + ((size_t)r * cols_per_rank + c0) * rows * es;
+      int nr = bcast(slab, slab, (size_t)nc * rows, ncclType, r, h->nccl_comm, comm);
+      if (nr != 0) { gend(); return scimlop_fail(h, SCIMLOP_ERR_NCCL, "ncclBroadcast failed (%d)", nr); }
+    }
+    if (gend() != 0) return scimlop_fail(h, SCIMLOP_ERR_NCCL, "ncclGroupEnd failed");
+  }
+  // the caller's stream continues after the last exchange (which is ordered after the last compute)
+  SCIMLOP_CUDA(h, cudaEventRecord(h->ev_d2h[0], comm));
+  SCIMLOP_CUDA(h, cudaStreamWaitEvent(user, h->ev_d2h[0], 0));
   return SCIMLOP_OK;
 }
 

@@ -59,3 +59,22 @@ def allgather_cols(handle, W_full, cols_per_rank, stream=None):
                                                    C.c_void_p(W_full.ptr), rows, int(cols_per_rank), st),
                  "scimlop_allgather_cols")
     return W_full
+
+
+def kron_mul_allgather(handle, L, V_local, W_full, cols_per_rank, alpha=None, chunk_cols=0, stream=None):
+    """Column-sharded `mul!` of a cached, natively flattened TensorProductOperator with the all-gather of W
+    overlapped chunk by chunk (scimlop_kron_mul_allgather).  W_full ends up replicated on every rank."""
+    import torch
+    from .operators import _DT, _scalar
+    nat = L._native
+    if nat is None:
+        raise TypeError("kron_mul_allgather needs a TensorProductOperator of native factors (cache_operator it first)")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+    a = alpha
+    for s in nat["scalars"]:
+        a = s.convert() * (1.0 if a is None else float(a))
+    handle.check(handle.lib.scimlop_kron_mul_allgather(
+        handle.ptr, _DT[V_local.dtype], L.precision, nat["nf"], nat["ptrs"], nat["dims"], nat["lds"], nat["kinds"],
+        C.c_void_p(V_local.ptr), C.c_void_p(W_full.ptr), int(cols_per_rank), _scalar(V_local.dtype, a), int(chunk_cols),
+        C.c_void_p(nat["ws"].data_ptr()), nat["ws_bytes"], st), "scimlop_kron_mul_allgather")
+    return W_full

@@ -39,6 +39,11 @@ def main():
     sd.allgather_cols(h, Wfull, kper)
     torch.cuda.synchronize()
     err = R.rel_err(Wfull.numpy(), np.kron(A, B) @ V)
+    # the overlapped form: compute chunk i+1 while chunk i is exchanged
+    W2 = sb.DeviceArray.full((48 * 32, k), float("nan"), np.float64)
+    sd.kron_mul_allgather(h, L, v_loc, W2, kper, alpha=0.5, chunk_cols=2)
+    torch.cuda.synchronize()
+    err = max(err, R.rel_err(W2.numpy(), 0.5 * (np.kron(A, B) @ V)))
     ok = torch.tensor([1.0 if err < 1e-12 else 0.0], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:

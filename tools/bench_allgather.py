@@ -1,0 +1,50 @@
+"""Strong-scaled config 2 with a replicated result (run under torchrun): 256 columns split over the ranks,
+kron mul! per rank, then W all-gathered -- sequentially (kernels, then ncclAllGather) and overlapped
+(scimlop_kron_mul_allgather).  Rank 0 prints one JSON line."""
+import json, os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+def main():
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import scimlop_b200 as sb
+    from scimlop_b200 import distributed as sd
+    h = sb.handle(local)
+    def bcast(b):
+        o = [b]; dist.broadcast_object_list(o, src=0); return o[0]
+    sd.init_comm(h, world, rank, bcast)
+    n, k = 512 * 512, 256
+    kper = k // world
+    rng = np.random.default_rng(0)
+    A, B = np.asfortranarray(rng.random((512, 512))), np.asfortranarray(rng.random((512, 512)))
+    g = torch.Generator(device="cuda").manual_seed(rank)
+    V = sb.DeviceArray(torch.rand(n * kper, dtype=torch.float64, device="cuda", generator=g), (n, kper))
+    W = sb.DeviceArray.zeros((n, k), np.float64)
+    L = sb.cache_operator(sb.kron(A, B), V)
+    mine = W.cols(rank * kper, (rank + 1) * kper)
+    def timed(fn, reps=10):
+        for _ in range(3): fn()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps): fn()
+        e1.record(); e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    t_comp = timed(lambda: sb.mul_(mine, L, V))
+    t_seq = timed(lambda: (sb.mul_(mine, L, V), sd.allgather_cols(h, W, kper)))
+    res = {}
+    for chunk in (max(1, kper // 8), max(1, kper // 4), max(1, kper // 2)):
+        res[f"overlapped_chunk{chunk}_ms"] = timed(lambda: sd.kron_mul_allgather(h, L, V, W, kper, chunk_cols=chunk))
+    if rank == 0:
+        print(json.dumps({"workload": "config 2 strong-scaled, W replicated", "n_gpus": world, "cols_per_rank": kper,
+                          "compute_only_ms": t_comp, "compute_then_allgather_ms": t_seq, **res,
+                          "gathered_bytes_per_rank": (world - 1) * n * kper * 8}))
+    dist.destroy_process_group()
+
+if __name__ == "__main__":
+    main()
