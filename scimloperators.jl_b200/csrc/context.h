@@ -20,6 +20,7 @@ struct scimlop_context {
   uint32_t magic;
   int device;
   int sm_count;
+  int sm_reserve;  // SMs left free by the persistent GEMM kernels (for concurrently running NCCL kernels)
   scimlop_encode_tiled_fn encode_tiled;
   char last_error[512];
   int64_t launches;

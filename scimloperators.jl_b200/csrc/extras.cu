@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "context.h"
 #include "krylov.cuh"
@@ -255,6 +256,11 @@ extern "C" int scimlop_kron_mul_allgather(scimlop_handle_t h, int dtype, int pre
   SCIMLOP_CUDA(h, cudaStreamWaitEvent(comm, h->ev_h2d[0], 0));
   const int ncclType = dtype == SCIMLOP_F64 ? NCCL_FLOAT64 : NCCL_FLOAT32;
   char* Wb = static_cast<char*>(W_full);
+  // The GEMM kernels are persistent (one CTA per SM, most of its shared memory): leave a few SMs free so the
+  // NCCL kernels of the exchange can actually run next to them instead of waiting for a kernel boundary.
+  const char* rs = getenv("SCIMLOP_GATHER_SM_RESERVE");
+  struct Reserve { scimlop_context* c; int old; ~Reserve() { c->sm_reserve = old; } } reserve{h, h->sm_reserve};
+  h->sm_reserve = (h->nranks > 1 && rs) ? atoi(rs) : 0;   // measured on 2 GPUs: reserving SMs does not help
   for (long long c0 = 0; c0 < cols_per_rank; c0 += cc) {
     const long long nc = std::min<long long>(cc, cols_per_rank - c0);
     char* mine = Wb + ((size_t)h->rank * cols_per_rank + c0) * rows * es;

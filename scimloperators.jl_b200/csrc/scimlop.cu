@@ -149,7 +149,7 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
   for (int q = 0; q < nscale; q++) { p.scale[q].ptr = static_cast<const double*>(scales[q].ptr); p.scale[q].ld = scales[q].ld; }
   p.vec_ok = aligned16(C) && !(ldc & 1) && (batch == 1 || !(sC & 1));
   p.a_batched = a_batched; p.b_batched = b_batched;
-  const int grid = (int)std::min<long long>(p.total_tiles, c->sm_count);
+  const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
   if (!transA && !transB) dmma::gemm_dmma_kernel<false, false><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
   else if (!transA && transB) dmma::gemm_dmma_kernel<false, true><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
   else if (transA && !transB) dmma::gemm_dmma_kernel<true, false><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
@@ -257,7 +257,7 @@ int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, 
   else rc = make_map_f32(c, &tmD, D, m, rows, 1, d_rs * 4, 0, 32, 32, false, /*swizzle=*/true);
   if (!p.tma_store) tmD = tmX;   // unused by the kernel
   else if (rc) return rc;
-  const int grid = (int)std::min<long long>(p.total_tiles, c->sm_count);
+  const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
   if (x_mn && f_k) tf32::gemm_tf32x3_kernel<true, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmD, p);
   else if (x_mn) tf32::gemm_tf32x3_kernel<true, false><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmD, p);
   else if (f_k) tf32::gemm_tf32x3_kernel<false, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmD, p);

@@ -38,8 +38,10 @@ def main():
     t_comp = timed(lambda: sb.mul_(mine, L, V))
     t_seq = timed(lambda: (sb.mul_(mine, L, V), sd.allgather_cols(h, W, kper)))
     res = {}
-    for chunk in (max(1, kper // 8), max(1, kper // 4), max(1, kper // 2)):
-        res[f"overlapped_chunk{chunk}_ms"] = timed(lambda: sd.kron_mul_allgather(h, L, V, W, kper, chunk_cols=chunk))
+    for reserve in (0, 8, 16, 32):
+        os.environ["SCIMLOP_GATHER_SM_RESERVE"] = str(reserve)
+        for chunk in (max(1, kper // 8), max(1, kper // 4)):
+            res[f"overlapped_reserve{reserve}_chunk{chunk}_ms"] = timed(lambda: sd.kron_mul_allgather(h, L, V, W, kper, chunk_cols=chunk))
     if rank == 0:
         print(json.dumps({"workload": "config 2 strong-scaled, W replicated", "n_gpus": world, "cols_per_rank": kper,
                           "compute_only_ms": t_comp, "compute_then_allgather_ms": t_seq, **res,
