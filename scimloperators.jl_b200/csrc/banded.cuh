@@ -9,6 +9,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "ptx.cuh"
+
 namespace scimlop {
 namespace band {
 
@@ -149,6 +151,117 @@ __global__ void __launch_bounds__(128) band_kronsum_tri_kernel(long long mi, lon
 #pragma unroll
     for (int u = 0; u < PF; u++) e[u] = e[u + 1];
     e[PF] = efar;
+  }
+}
+
+// TMA-tiled 5-point stencil (the version that streams at HBM speed): a persistent CTA walks tiles of
+// 254 x 16 grid points; a producer warp keeps TSTAGES halo tiles (256 x 18, zero-filled outside the grid by TMA)
+// in flight through a full/empty mbarrier ring, eight consumer warps read their five neighbours from shared
+// memory and write W with coalesced stores.  Bytes in flight per SM come from the bulk copies (3 x 36 KB), not
+// from registers, which is what the register-window version above lacked (ncu: 89 % long-scoreboard stalls).
+// The innermost TMA coordinate must keep the box start 16-byte aligned (an odd FP64 coordinate is an illegal
+// instruction, tools/tma_probe.cu), so the left halo is 16 bytes wide (2 doubles / 4 floats) and so is the
+// unused strip on the right: interior = 256 - 2*HL points per tile row.
+constexpr int TTI = 256, TTO = 18, TO_IN = TTO - 2, TSTAGES = 3, TTHREADS = 288;
+template <typename T> struct Tri { static constexpr int HL = 16 / (int)sizeof(T); static constexpr int IN = TTI - 2 * HL; };
+template <typename T>
+constexpr int tri_smem_bytes() { return TSTAGES * TTI * TTO * (int)sizeof(T) + 1024 + 64; }
+
+struct TriParams {
+  long long mi, mo, k;
+  int tiles_i, tiles_o;
+  long long total_tiles;   // tiles_i * tiles_o * k
+};
+
+template <typename T, bool READW>
+__global__ void __launch_bounds__(TTHREADS, 1)
+    band_kronsum_tri_tma_kernel(const __grid_constant__ CUtensorMap tmV, const TriParams p, const T* __restrict__ Bx,
+                                const T* __restrict__ By, T* W, T alpha, T beta) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
+  const T* tiles = reinterpret_cast<const T*>(smem_raw + (smem - smem_u32(smem_raw)));
+  constexpr uint32_t TILE_BYTES = TTI * TTO * sizeof(T);
+  constexpr int HL = Tri<T>::HL, TI_IN = Tri<T>::IN;
+  const uint32_t full_bar = smem + TSTAGES * TILE_BYTES, empty_bar = full_bar + 8 * TSTAGES;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TSTAGES; s++) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 8); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const long long per_col = (long long)p.tiles_i * p.tiles_o;
+  if (warp == 8) {
+    // ---- producer ----
+    int stage = 0; uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int j = (int)(tile / per_col);
+      const long long rem = tile - (long long)j * per_col;
+      const int to = (int)(rem / p.tiles_i), ti = (int)(rem - (long long)to * p.tiles_i);
+      mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(full_bar + 8 * stage, TILE_BYTES);
+        tma_load_3d(smem + stage * TILE_BYTES, &tmV, full_bar + 8 * stage, ti * TI_IN - HL, to * TO_IN - 1, j);
+      }
+      __syncwarp();
+      if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
+    }
+    return;
+  }
+  // ---- consumers: thread t <-> tile column t (grid index i = ti*TI_IN - HL + t), interior t = HL .. HL+TI_IN-1 ----
+  const int t = threadIdx.x;   // 0..255
+  int stage = 0; uint32_t phase = 0;
+  const long long plane = p.mi * p.mo;
+  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int j = (int)(tile / per_col);
+    const long long rem = tile - (long long)j * per_col;
+    const int to = (int)(rem / p.tiles_i), ti = (int)(rem - (long long)to * p.tiles_i);
+    const long long i = (long long)ti * TI_IN - HL + t;
+    const bool interior = (t >= HL) && (t < HL + TI_IN) && (i < p.mi);
+    T a = T(0), b = T(0), c = T(0);
+    if (interior) { a = __ldg(By + i); b = __ldg(By + i + p.mi); c = __ldg(By + i + 2 * p.mi); }
+    const long long o0 = (long long)to * TO_IN;
+    T* wcol = W + (long long)j * plane + i;
+    if (!READW) {
+      mbar_wait(full_bar + 8 * stage, phase);
+      const T* s = tiles + (size_t)stage * TTI * TTO;
+      if (interior) {
+#pragma unroll 4
+        for (int r = 1; r <= TO_IN; r++) {
+          const long long o = o0 + r - 1;
+          if (o >= p.mo) break;
+          const T xs = __ldg(Bx + o), xm = __ldg(Bx + o + p.mo), xp = __ldg(Bx + o + 2 * p.mo);
+          const T* row = s + r * TTI + t;
+          T v = fma(a, row[-1], fma(b, row[0], c * row[1]));
+          v = fma(xs, row[-TTI], fma(xm, row[0], fma(xp, row[TTI], v)));
+          __stcs(wcol + o * p.mi, alpha * v);
+        }
+      }
+    } else {
+      // fetch the old W values of this thread's 16 points while the halo tile is still in flight
+      T old[TO_IN];
+      if (interior) {
+#pragma unroll
+        for (int r = 0; r < TO_IN; r++) old[r] = (o0 + r < p.mo) ? __ldcs(wcol + (o0 + r) * p.mi) : T(0);
+      }
+      mbar_wait(full_bar + 8 * stage, phase);
+      const T* s = tiles + (size_t)stage * TTI * TTO;
+      if (interior) {
+#pragma unroll
+        for (int r = 1; r <= TO_IN; r++) {
+          const long long o = o0 + r - 1;
+          if (o < p.mo) {
+            const T xs = __ldg(Bx + o), xm = __ldg(Bx + o + p.mo), xp = __ldg(Bx + o + 2 * p.mo);
+            const T* row = s + r * TTI + t;
+            T v = fma(a, row[-1], fma(b, row[0], c * row[1]));
+            v = fma(xs, row[-TTI], fma(xm, row[0], fma(xp, row[TTI], v)));
+            __stcs(wcol + o * p.mi, fma(beta, old[r - 1], alpha * v));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(empty_bar + 8 * stage);
+    if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
   }
 }
 

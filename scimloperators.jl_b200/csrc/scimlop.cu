@@ -366,6 +366,10 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   optin2((const void*)tf32::gemm_tf32x3_kernel<false, true>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<true, false>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<true, true>);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<double>());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<double>());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<float>());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<float>());
   if (e != cudaSuccess) {
     delete c;
     return SCIMLOP_ERR_CUDA;
@@ -691,6 +695,34 @@ extern "C" int scimlop_kronsum_mul(scimlop_handle_t h, int dtype, int precision,
 template <typename T>
 static int kronsum_banded_t(scimlop_context* h, const T* Bx, int bx, int64_t mo, const T* By, int by, int64_t mi, const T* V,
                             T* W, int64_t k, T alpha, T beta, cudaStream_t st) {
+  if (bx == 1 && by == 1 && aligned16(V) && (mi * sizeof(T)) % 16 == 0 && mi >= 64 && mo >= 16 &&
+      mi < 2147483647LL && mo < 2147483647LL && k < 2147483647LL) {
+    // TMA-tiled 5-point stencil: halo tiles stream through a 3-deep bulk-copy ring
+    CUtensorMap tmV;
+    cuuint64_t gdim[3] = {(cuuint64_t)mi, (cuuint64_t)mo, (cuuint64_t)k};
+    cuuint64_t gstr[2] = {(cuuint64_t)mi * sizeof(T), (cuuint64_t)mi * (cuuint64_t)mo * sizeof(T)};
+    cuuint32_t box[3] = {band::TTI, band::TTO, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = h->encode_tiled(&tmV, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                                 const_cast<T*>(V), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) {
+      band::TriParams p;
+      p.mi = mi; p.mo = mo; p.k = k;
+      p.tiles_i = (int)((mi + band::Tri<T>::IN - 1) / band::Tri<T>::IN);
+      p.tiles_o = (int)((mo + band::TO_IN - 1) / band::TO_IN);
+      p.total_tiles = (long long)p.tiles_i * p.tiles_o * k;
+      const int grid = (int)std::min<long long>(p.total_tiles, (long long)h->sm_count * 2);
+      if (beta == T(0))
+        band::band_kronsum_tri_tma_kernel<T, false><<<grid, band::TTHREADS, band::tri_smem_bytes<T>(), st>>>(tmV, p, Bx, By, W, alpha, beta);
+      else
+        band::band_kronsum_tri_tma_kernel<T, true><<<grid, band::TTHREADS, band::tri_smem_bytes<T>(), st>>>(tmV, p, Bx, By, W, alpha, beta);
+      h->launches++;
+      SCIMLOP_CUDA(h, cudaGetLastError());
+      return SCIMLOP_OK;
+    }
+  }
   if (bx == 1 && by == 1 && mi % 2 == 0 && aligned16(V) && aligned16(W) && k <= 65535) {
     // 5-point stencil fast path: sliding window over o, 256 i per block
     const int ochunk = 128;

@@ -732,7 +732,8 @@ def test_banded_factors(sb, dtype):
         return A
 
     f = lambda a: np.asarray(a, dtype=np.float64)
-    for (mo, bo, mi, bi, k) in ((9, 1, 13, 1, 5), (64, 2, 37, 1, 3), (5, 4, 6, 3, 2), (300, 1, 257, 1, 2)):
+    for (mo, bo, mi, bi, k) in ((9, 1, 13, 1, 5), (64, 2, 37, 1, 3), (5, 4, 6, 3, 2), (300, 1, 257, 1, 2), (40, 1, 300, 1, 3),
+                                (600, 1, 520, 1, 2)):
         A, B = banded(mo, bo), banded(mi, bi)
         opA, opB = sb.MatrixOperator(sb.BandedMatrix.from_dense(A, bo)), sb.MatrixOperator(sb.BandedMatrix.from_dense(B, bi))
         v, w0 = rnd(rng, mo * mi, k, dtype=dtype), rnd(rng, mo * mi, k, dtype=dtype)
