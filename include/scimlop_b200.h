@@ -237,6 +237,24 @@ int scimlop_kron_mul_allgather(scimlop_handle_t h, int dtype, int precision, int
                                const void* alpha, int64_t chunk_cols, void* workspace, size_t workspace_bytes,
                                void* stream);
 
+/* ---- fused compute + all-gather over peer memory (NVLink stores from the GEMM epilogue) ------------------------
+ * One process per GPU; each rank exports its W_full allocation (scimlop_peer_export: a 64-byte CUDA IPC handle
+ * plus the offset of the pointer inside its allocation), the handles travel through the caller's rendezvous,
+ * and every rank maps the others' buffers (scimlop_peer_open).  scimlop_kron_mul_peers then computes this rank's
+ * column slab ONCE and stores every output tile into its own W_full AND into the same columns of every peer's
+ * W_full from the stage-2 epilogue, tile by tile while the tensor pipe works on the next tile -- no separate
+ * collective.  scimlop_comm_barrier (a one-word NCCL all-reduce on the stream) tells every rank that all slabs
+ * have landed.  Float64, outermost factor dense, beta == 0 (the result is overwritten). */
+int scimlop_peer_export(scimlop_handle_t h, const void* dev_ptr, void* ipc_handle_64B, int64_t* offset);
+int scimlop_peer_open(scimlop_handle_t h, const void* ipc_handle_64B, int64_t offset, void** peer_ptr);
+int scimlop_peer_close(scimlop_handle_t h, void* peer_ptr, int64_t offset);
+int scimlop_kron_mul_peers(scimlop_handle_t h, int dtype, int precision, int nfactors,
+                           const void* const* factors, const int64_t* dims, const int64_t* lds,
+                           const int32_t* kinds, const void* V, int64_t k, void* W_local,
+                           void* const* peer_targets, int npeers, const void* alpha, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int scimlop_comm_barrier(scimlop_handle_t h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,12 @@ SIGNATURES = {
     "scimlop_comm_init": [_P, _INT, _INT, _P],
     "scimlop_comm_destroy": [_P],
     "scimlop_allgather_cols": [_P, _INT, _P, _I64, _I64, _P],
+    "scimlop_peer_export": [_P, _P, _P, _I64P],
+    "scimlop_peer_open": [_P, _P, _I64, C.POINTER(_P)],
+    "scimlop_peer_close": [_P, _P, _I64],
+    "scimlop_kron_mul_peers": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _I64, _P, C.POINTER(_P), _INT,
+                               _P, _P, _SZ, _P],
+    "scimlop_comm_barrier": [_P, _P],
     "scimlop_kron_mul_allgather": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _P, _I64, _P, _I64, _P, _SZ, _P],
 }
 

@@ -36,6 +36,7 @@ struct scimlop_context {
   void* nccl_lib;
   void* nccl_comm;
   int nranks, rank;
+  void* comm_scratch;  // one word on the device for scimlop_comm_barrier
 };
 
 constexpr uint32_t SCIMLOP_MAGIC = 0x5C1B200u;

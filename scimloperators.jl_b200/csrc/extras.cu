@@ -152,6 +152,7 @@ typedef int (*nccl_comm_destroy_fn)(void*);
 typedef int (*nccl_all_gather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*nccl_broadcast_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*nccl_group_fn)(void);
+typedef int (*nccl_all_reduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef const char* (*nccl_get_error_string_fn)(int);
 constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8;  // ncclDataType_t (nccl.h)
 
@@ -284,6 +285,59 @@ extern "C" int scimlop_kron_mul_allgather(scimlop_handle_t h, int dtype, int pre
   return SCIMLOP_OK;
 }
 
+// ---- peer memory (CUDA IPC) + stream barrier ---------------------------------------------------------------------
+extern "C" int scimlop_peer_export(scimlop_handle_t h, const void* dev_ptr, void* handle64, int64_t* offset) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (!dev_ptr || !handle64 || !offset) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "peer_export: null argument");
+  scimlop_device_guard guard(h->device);
+  // IPC handles name whole allocations: find the base of the allocation this pointer lives in
+  typedef CUresult (*get_range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+    return scimlop_fail(h, SCIMLOP_ERR_CUDA, "cuMemGetAddressRange not available");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (reinterpret_cast<get_range_fn>(fn)(&base, &size, (CUdeviceptr)dev_ptr) != CUDA_SUCCESS)
+    return scimlop_fail(h, SCIMLOP_ERR_CUDA, "cuMemGetAddressRange failed");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  SCIMLOP_CUDA(h, cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle64), (void*)base));
+  *offset = (int64_t)((CUdeviceptr)dev_ptr - base);
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_peer_open(scimlop_handle_t h, const void* handle64, int64_t offset, void** peer_ptr) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (!handle64 || !peer_ptr) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "peer_open: null argument");
+  scimlop_device_guard guard(h->device);
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, sizeof(hd));
+  void* base = nullptr;
+  SCIMLOP_CUDA(h, cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+  *peer_ptr = static_cast<char*>(base) + offset;
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_peer_close(scimlop_handle_t h, void* peer_ptr, int64_t offset) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (!peer_ptr) return SCIMLOP_OK;
+  scimlop_device_guard guard(h->device);
+  SCIMLOP_CUDA(h, cudaIpcCloseMemHandle(static_cast<char*>(peer_ptr) - offset));
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_comm_barrier(scimlop_handle_t h, void* stream) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (!h->nccl_comm) return scimlop_fail(h, SCIMLOP_ERR_NCCL, "comm_barrier: call scimlop_comm_init first");
+  auto ar = reinterpret_cast<nccl_all_reduce_fn>(nccl_sym("ncclAllReduce"));
+  if (!ar) return scimlop_fail(h, SCIMLOP_ERR_NCCL, "ncclAllReduce not found");
+  scimlop_device_guard guard(h->device);
+  if (!h->comm_scratch) SCIMLOP_CUDA(h, cudaMalloc(&h->comm_scratch, 256));
+  int r = ar(h->comm_scratch, h->comm_scratch, 1, NCCL_FLOAT32, /*ncclSum*/ 0, h->nccl_comm, static_cast<cudaStream_t>(stream));
+  if (r != 0) return scimlop_fail(h, SCIMLOP_ERR_NCCL, "ncclAllReduce (barrier) failed (%d)", r);
+  return SCIMLOP_OK;
+}
+
 extern "C" int scimlop_destroy(scimlop_handle_t h) {
   if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
   scimlop_device_guard guard(h->device);
@@ -296,6 +350,7 @@ extern "C" int scimlop_destroy(scimlop_handle_t h) {
     cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_comp); cudaStreamDestroy(h->s_d2h);
   }
   if (h->stage) cudaFree(h->stage);
+  if (h->comm_scratch) cudaFree(h->comm_scratch);
   h->magic = 0;
   delete h;
   return SCIMLOP_OK;

@@ -43,6 +43,11 @@ struct Params {
   Scale scale[MAX_SCALES];
   int vec_ok;  // C base, ldc, strideC allow 16-byte stores
   int a_batched, b_batched;
+  // Fused "compute + all-gather": every output tile is ALSO stored into the same place of up to 7 peer GPUs'
+  // copies of C (peer-mapped pointers, NVLink stores from the epilogue), so a replicated result needs no
+  // separate collective.  Only with beta == 0.
+  int npeer;
+  double* peerC[7];
 };
 
 // k index used by lane t in MMA step s of a BK=16 block.  The permutation makes the 64-bit fragment
@@ -233,6 +238,20 @@ __global__ void __launch_bounds__(THREADS, 1)
           for (int i = 0; i < 8; i++)
             *reinterpret_cast<double2*>(col + 8 * i) = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
         }
+        if (p.npeer > 0) {
+          // the same tile into every peer's C (peer-mapped memory: these stores travel over NVLink)
+          const long long off = Cb - p.C;
+          for (int q = 0; q < p.npeer; q++) {
+            double* Pb = p.peerC[q] + off;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              double* col = Pb + (long long)(8 * j) * p.ldc;
+#pragma unroll
+              for (int i = 0; i < 8; i++)
+                *reinterpret_cast<double2*>(col + 8 * i) = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+            }
+          }
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -281,6 +300,11 @@ __global__ void __launch_bounds__(THREADS, 1)
             }
             dst[0] = v0;
             if (pair) dst[1] = v1;
+          }
+          for (int q = 0; q < p.npeer; q++) {   // (beta == 0 is enforced on the host when peers are given)
+            double* pd = p.peerC[q] + (dst - p.C);
+            pd[0] = v0;
+            if (pair) pd[1] = v1;
           }
         }
       }

@@ -33,6 +33,12 @@ struct ScaleArg {
   const void* ptr;
   long long ld;
 };
+// peer destinations of a fused compute + all-gather launch (thread-local: set around the last kron stage)
+struct PeerArg {
+  int n = 0;
+  void* ptr[7] = {};
+};
+thread_local PeerArg g_peers;
 
 // ---- elementwise launcher -------------------------------------------------------------------------
 template <typename T>
@@ -149,6 +155,12 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
   for (int q = 0; q < nscale; q++) { p.scale[q].ptr = static_cast<const double*>(scales[q].ptr); p.scale[q].ld = scales[q].ld; }
   p.vec_ok = aligned16(C) && !(ldc & 1) && (batch == 1 || !(sC & 1));
   p.a_batched = a_batched; p.b_batched = b_batched;
+  p.npeer = g_peers.n;
+  for (int q = 0; q < g_peers.n; q++) {
+    p.peerC[q] = static_cast<double*>(g_peers.ptr[q]);
+    p.vec_ok = p.vec_ok && aligned16(g_peers.ptr[q]);
+  }
+  if (g_peers.n > 0 && beta != 0.0) return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "peer targets need beta == 0");
   const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
   if (!transA && !transB) dmma::gemm_dmma_kernel<false, false><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
   else if (!transA && transB) dmma::gemm_dmma_kernel<false, true><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
@@ -200,6 +212,8 @@ int gemm_dispatch<double>(scimlop_context* c, int precision, bool transA, bool t
   if (precision != SCIMLOP_PREC_DEFAULT)
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "Float64 only supports SCIMLOP_PREC_DEFAULT (got %d)", precision);
   if (M <= 0 || N <= 0 || batch <= 0) return SCIMLOP_OK;
+  if (g_peers.n > 0 && !dmma_eligible(M, N, K, A, lda, sA, B, ldb, sB, batch))
+    return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "peer targets need a DMMA-eligible (aligned Float64) last stage");
   if (dmma_eligible(M, N, K, A, lda, sA, B, ldb, sB, batch))
     return launch_dmma(c, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, nscale,
                        scales, st);
@@ -561,6 +575,16 @@ int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* cons
       ep.nterms = 1; ep.coef[0] = T(1); ep.nvec[0] = 1; ep.nfac[0] = 1;
       ep.fac[0][0].ptr = static_cast<const T*>(factors[p]); ep.fac[0][0].ld = 0; ep.fac[0][0].div = L; ep.fac[0][0].mod = n;
       rc = launch_eltwise(c, ep, st);
+    } else if (g_peers.n > 0 && !last) {
+      PeerArg saved = g_peers;      // intermediates stay local: only the stage that writes W goes to the peers
+      g_peers.n = 0;
+      if (L == 1)
+        rc = gemm_dispatch<T>(c, precision, tr, false, m, R, n, a, static_cast<const T*>(factors[p]), lds[p], 0, cur, n, 0,
+                              bt, out, m, 0, 1, 0, nullptr, st);
+      else
+        rc = gemm_dispatch<T>(c, precision, false, !tr, L, m, n, a, cur, L, L * n, static_cast<const T*>(factors[p]),
+                              lds[p], 0, bt, out, L, L * m, R, 0, nullptr, st);
+      g_peers = saved;
     } else if (L == 1) {
       // innermost applied mode: out(m x R) = op(F)(m x n) * cur(n x R)    [src/tensor.jl:568,603]
       rc = gemm_dispatch<T>(c, precision, tr, false, m, R, n, a, static_cast<const T*>(factors[p]), lds[p], 0, cur,
@@ -636,6 +660,30 @@ extern "C" int scimlop_kron_mul(scimlop_handle_t h, int dtype, int precision, in
   scimlop_device_guard guard(h->device);
   return scimlop_kron_mul_impl(h, dtype, precision, nfactors, factors, dims, lds, kinds, V, ldv, W, ldw, k, alpha,
                                beta, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int scimlop_kron_mul_peers(scimlop_handle_t h, int dtype, int precision, int nfactors,
+                                      const void* const* factors, const int64_t* dims, const int64_t* lds,
+                                      const int32_t* kinds, const void* V, int64_t k, void* W_local,
+                                      void* const* peer_targets, int npeers, const void* alpha, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (dtype != SCIMLOP_F64) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "kron_mul_peers: Float64 only");
+  if (npeers < 0 || npeers > 7) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kron_mul_peers: 0..7 peers");
+  if (npeers > 0 && !peer_targets) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_mul_peers: peer_targets null");
+  if (!dims || !kinds || nfactors < 1 || nfactors > 8) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_mul_peers: bad factors");
+  if (kinds[0] != SCIMLOP_DENSE && kinds[0] != (SCIMLOP_DENSE | SCIMLOP_TRANS))
+    // the stage that writes W is the outermost factor's mode product; it must be a GEMM to carry the peer stores
+    return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "kron_mul_peers: the outermost factor must be dense");
+  long long rows = 1, cols = 1;
+  for (int f = 0; f < nfactors; f++) { rows *= dims[2 * f]; cols *= dims[2 * f + 1]; }
+  scimlop_device_guard guard(h->device);
+  g_peers.n = npeers;
+  for (int q = 0; q < npeers; q++) g_peers.ptr[q] = peer_targets[q];
+  int rc = scimlop_kron_mul_impl(h, dtype, precision, nfactors, factors, dims, lds, kinds, V, cols, W_local, rows, k, alpha,
+                                 nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  g_peers.n = 0;
+  return rc;
 }
 
 extern "C" int scimlop_outer_mul_fast(scimlop_handle_t h, int dtype, int precision, void* W, const void* A,

@@ -78,3 +78,55 @@ def kron_mul_allgather(handle, L, V_local, W_full, cols_per_rank, alpha=None, ch
         C.c_void_p(V_local.ptr), C.c_void_p(W_full.ptr), int(cols_per_rank), _scalar(V_local.dtype, a), int(chunk_cols),
         C.c_void_p(nat["ws"].data_ptr()), nat["ws_bytes"], st), "scimlop_kron_mul_allgather")
     return W_full
+
+
+class PeerWindow:
+    """Every rank's W_full mapped into this process (CUDA IPC): what the fused compute + all-gather epilogue
+    stores into.  `all_gather_object(obj) -> [obj of rank 0, ...]` is the caller's rendezvous
+    (e.g. torch.distributed.all_gather_object)."""
+
+    def __init__(self, handle, W_full, rank, world, all_gather_object):
+        self.h, self.rank, self.world, self.W = handle, int(rank), int(world), W_full
+        buf, off = C.create_string_buffer(64), C.c_int64(0)
+        handle.check(handle.lib.scimlop_peer_export(handle.ptr, C.c_void_p(W_full.ptr), buf, C.byref(off)), "scimlop_peer_export")
+        everyone = all_gather_object((bytes(buf.raw), off.value))
+        self.base, self._opened = [None] * world, []
+        for r, (hb, o) in enumerate(everyone):
+            if r == rank:
+                self.base[r] = W_full.ptr
+                continue
+            p = C.c_void_p()
+            handle.check(handle.lib.scimlop_peer_open(handle.ptr, C.create_string_buffer(hb, 64), o, C.byref(p)), "scimlop_peer_open")
+            self.base[r] = p.value
+            self._opened.append((p.value, o))
+
+    def close(self):
+        for p, o in self._opened:
+            self.h.lib.scimlop_peer_close(self.h.ptr, C.c_void_p(p), o)
+        self._opened = []
+
+
+def kron_mul_peers(handle, L, V_local, window, cols_per_rank, alpha=None, stream=None, barrier=True):
+    """This rank's column slab of W = (kron factors) V, stored by the stage-2 GEMM epilogue into EVERY rank's
+    W_full (peer stores over NVLink), then a one-word stream barrier.  Float64, replicated result."""
+    import torch
+    from .operators import _DT, _scalar
+    nat = L._native
+    if nat is None:
+        raise TypeError("kron_mul_peers needs a TensorProductOperator of native factors (cache_operator it first)")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+    rows = window.W.shape[0]
+    es = 8
+    slab = window.rank * int(cols_per_rank) * rows * es
+    peers = [window.base[r] + slab for r in range(window.world) if r != window.rank]
+    arr = (C.c_void_p * max(1, len(peers)))(*peers)
+    a = alpha
+    for s in nat["scalars"]:
+        a = s.convert() * (1.0 if a is None else float(a))
+    handle.check(handle.lib.scimlop_kron_mul_peers(
+        handle.ptr, _DT[V_local.dtype], L.precision, nat["nf"], nat["ptrs"], nat["dims"], nat["lds"], nat["kinds"],
+        C.c_void_p(V_local.ptr), int(cols_per_rank), C.c_void_p(window.base[window.rank] + slab), arr, len(peers),
+        _scalar(V_local.dtype, a), C.c_void_p(nat["ws"].data_ptr()), nat["ws_bytes"], st), "scimlop_kron_mul_peers")
+    if barrier:
+        handle.check(handle.lib.scimlop_comm_barrier(handle.ptr, st), "scimlop_comm_barrier")
+    return window.W

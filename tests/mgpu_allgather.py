@@ -44,6 +44,25 @@ def main():
     sd.kron_mul_allgather(h, L, v_loc, W2, kper, alpha=0.5, chunk_cols=2)
     torch.cuda.synchronize()
     err = max(err, R.rel_err(W2.numpy(), 0.5 * (np.kron(A, B) @ V)))
+    # the fused form: stage-2 epilogue stores every tile into all ranks' W (peer memory), no collective
+    def gather_obj(o):
+        out = [None] * world
+        dist.all_gather_object(out, o)
+        return out
+    Ab, Bb = np.asfortranarray(rng.random((128, 96))), np.asfortranarray(rng.random((64, 80)))
+    Vb = np.asfortranarray(rng.random((96 * 80, k)))
+    W3 = sb.DeviceArray.full((128 * 64, k), float("nan"), np.float64)
+    win = sd.PeerWindow(h, W3, rank, world, gather_obj)
+    vb_loc = sb.DeviceArray.from_numpy(sh.take(Vb))
+    Lb = sb.cache_operator(sb.kron(Ab, Bb), vb_loc)
+    for rep in range(3):
+        W3.t.fill_(float("nan"))
+        torch.cuda.synchronize(); dist.barrier()
+        sd.kron_mul_peers(h, Lb, vb_loc, win, kper, alpha=0.5)
+        torch.cuda.synchronize()
+        err = max(err, R.rel_err(W3.numpy(), 0.5 * (np.kron(Ab, Bb) @ Vb)))
+        dist.barrier()
+    win.close()
     ok = torch.tensor([1.0 if err < 1e-12 else 0.0], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -38,10 +38,23 @@ def main():
     t_comp = timed(lambda: sb.mul_(mine, L, V))
     t_seq = timed(lambda: (sb.mul_(mine, L, V), sd.allgather_cols(h, W, kper)))
     res = {}
-    for reserve in (0, 8, 16, 32):
-        os.environ["SCIMLOP_GATHER_SM_RESERVE"] = str(reserve)
-        for chunk in (max(1, kper // 8), max(1, kper // 4)):
-            res[f"overlapped_reserve{reserve}_chunk{chunk}_ms"] = timed(lambda: sd.kron_mul_allgather(h, L, V, W, kper, chunk_cols=chunk))
+    for chunk in (max(1, kper // 8), max(1, kper // 4)):
+        res[f"nccl_overlapped_chunk{chunk}_ms"] = timed(lambda: sd.kron_mul_allgather(h, L, V, W, kper, chunk_cols=chunk))
+    def gather_obj(o):
+        out = [None] * world
+        dist.all_gather_object(out, o)
+        return out
+    win = sd.PeerWindow(h, W, rank, world, gather_obj)
+    res["fused_peer_store_epilogue_ms"] = timed(lambda: sd.kron_mul_peers(h, L, V, win, kper))
+    res["fused_peer_store_no_barrier_ms"] = timed(lambda: sd.kron_mul_peers(h, L, V, win, kper, barrier=False))
+    # correctness of the replicated result against the local-only computation of this rank's slab
+    ref = sb.DeviceArray.zeros((n, kper), np.float64)
+    sb.mul_(ref, L, V)
+    W.t.zero_(); torch.cuda.synchronize(); dist.barrier()
+    sd.kron_mul_peers(h, L, V, win, kper); torch.cuda.synchronize(); dist.barrier()
+    res["fused_slab_max_abs_diff"] = float((W.cols(rank * kper, (rank + 1) * kper).t - ref.t).abs().max())
+    res["fused_all_slabs_nonzero"] = bool((W.t != 0).all())
+    win.close()
     if rank == 0:
         print(json.dumps({"workload": "config 2 strong-scaled, W replicated", "n_gpus": world, "cols_per_rank": kper,
                           "compute_only_ms": t_comp, "compute_then_allgather_ms": t_seq, **res,
