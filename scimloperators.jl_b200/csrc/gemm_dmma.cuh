@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t full_bar = smem + STAGES * STAGE_BYTES;  // STAGES x 8 B
   const uint32_t empty_bar = full_bar + STAGES * 8;
+  const uint32_t scratch = full_bar + 128;  // one word per consumer warp (mbar_arrive_after_loads)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -208,9 +209,17 @@ __global__ void __launch_bounds__(THREADS, 1)
       SCIMLOP_MMA_STEP(a1, b1);
       SCIMLOP_LOAD_FRAGS(a1, b1, so, 3);
       SCIMLOP_MMA_STEP(a0, b0);
-      // all of this stage's fragments are in registers: hand the slot back to the producer
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
+      // hand the slot back to the producer once all of this stage's fragments have ARRIVED in registers
+      // (see mbar_arrive_after_loads)
+      {
+        uint32_t digest = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) digest ^= fold_bits(a0[i]) ^ fold_bits(a1[i]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) digest ^= fold_bits(b0[j]) ^ fold_bits(b1[j]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_after_loads(empty_bar + 8 * stage, scratch + 4 * warp, digest);
+      }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
       // prefetch step 0 of the next stage (next k-block, or the first k-block of this CTA's next tile)
       if (!(last_tile && kb == nk - 1)) {

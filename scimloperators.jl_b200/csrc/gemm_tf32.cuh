@@ -41,7 +41,7 @@ constexpr int XT_BYTES = TM * BK * 4;   // 16 KB: one raw X tile
 constexpr int F_BYTES = MAXF * MAXF * 4;  // 64 KB each for F_hi and F_lo
 constexpr int NBAR = 2 * RSTAGES + 2 * ASTAGES + 4 + 1 + 8;
 constexpr int EPI_STAGE_BYTES = 4096;   // one 32 x 32 FP32 block; two per epilogue warp (double-buffered)
-constexpr int SMEM_BYTES = 1024 + 2 * F_BYTES + RSTAGES * XT_BYTES + 8 * EPI_STAGE_BYTES + 8 * NBAR + 16;
+constexpr int SMEM_BYTES = 1024 + 2 * F_BYTES + RSTAGES * XT_BYTES + 8 * EPI_STAGE_BYTES + 8 * NBAR + 16 + 64;
 constexpr int NSG = 2;                  // splitter groups (4 warps each) alternating over k-blocks
 constexpr int NEG = 1;                  // epilogue groups (4 warps each)
 // A ring slot must always be served by the SAME splitter group: a group that never waited on phase j of a
@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t tmem_full = a_free + 8 * ASTAGES, tmem_empty = tmem_full + 16, f_full = tmem_empty + 16;
   const uint32_t epi_bar = f_full + 8;                     // [4 warps][2 buffers]: old-D block has landed
   const uint32_t tmem_slot = epi_bar + 64;
+  const uint32_t scratch = tmem_slot + 16;                 // one word per warp (mbar_arrive_after_loads)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -329,9 +330,12 @@ __global__ void __launch_bounds__(THREADS, 1)
             lo[4 * cidx + 2] = __float_as_uint(l.z); lo[4 * cidx + 3] = __float_as_uint(l.w);
           }
         }
-        // the raw slot is free as soon as every lane holds its values in registers
+        // the raw slot is free as soon as every lane holds its values in registers (lo depends on every load)
+        uint32_t digest = 0;
+#pragma unroll
+        for (int k = 0; k < 32; k++) digest ^= lo[k];
         __syncwarp();
-        if (lane == 0) mbar_arrive(raw_free + 8 * rs);
+        if (lane == 0) mbar_arrive_after_loads(raw_free + 8 * rs, scratch + 4 * warp, digest);
         // hand hi / lo to the tensor core through TMEM
         mbar_wait(a_free + 8 * at, aph ^ 1);
         tc_fence_after();

@@ -25,6 +25,21 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Releasing a TMA slot that was read with ld.shared: the arrive must not take effect before the loads have
+// returned.  ptxas orders the two only through registers, and loads still queued in the LSU (behind
+// back-pressured global / NVLink stores) when the arrive lands let the producer's next TMA write overtake them
+// -- seen on 2 GPUs as one k-block of stale operands in one warp.  `digest` is any value
+// computed from EVERY loaded register: storing it to a scratch word first makes the arrive wait for the data.
+__device__ __forceinline__ void mbar_arrive_after_loads(uint32_t bar, uint32_t scratch, uint32_t digest) {
+  asm volatile(
+      "st.shared.u32 [%1], %2;\n\t"
+      "mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar), "r"(scratch), "r"(digest)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t fold_bits(double x) {
+  const long long b = __double_as_longlong(x);
+  return (uint32_t)b ^ (uint32_t)(b >> 32);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
