@@ -41,7 +41,8 @@ enum {
   SCIMLOP_ERR_CUDA = 5,          /* a CUDA runtime/driver call failed; see scimlop_last_error */
   SCIMLOP_ERR_NCCL = 6,          /* NCCL missing or a collective failed */
   SCIMLOP_ERR_BAD_HANDLE = 7,
-  SCIMLOP_ERR_NO_DEVICE = 8      /* no usable sm_100 device: there is NO CPU fallback */
+  SCIMLOP_ERR_NO_DEVICE = 8,     /* no usable sm_100 device: there is NO CPU fallback */
+  SCIMLOP_ERR_SINGULAR = 9       /* scimlop_invert met an exactly zero pivot (LAPACK's info > 0 / SingularException) */
 };
 
 /* ---- element types & precision modes ------------------------------------------------------------- */
@@ -114,6 +115,22 @@ int scimlop_diag_mul(scimlop_handle_t h, int dtype, int64_t n, int64_t k, const 
  * NullOperator form W = beta * W with a strong zero for beta == 0 (src/basic.jl:248-264). */
 int scimlop_axpby(scimlop_handle_t h, int dtype, int64_t n, int64_t k, const void* V, int64_t ldv,
                   void* W, int64_t ldw, const void* alpha, const void* beta, void* stream);
+
+/* ---- ldiv! (the solve side) --------------------------------------------------- */
+/* Diagonal / batched-diagonal ldiv!: W(n x k) = V ./ d, ldd as for scimlop_diag_mul; W may alias V (the
+ * two-argument form).  src/batch.jl:181-200; stdlib `ldiv!(::Diagonal, v)` behind src/matrix.jl:363-366. */
+int scimlop_diag_div(scimlop_handle_t h, int dtype, int64_t n, int64_t k, const void* d, int64_t ldd,
+                     const void* V, int64_t ldv, void* W, int64_t ldw, void* stream);
+
+/* The cached object behind `ldiv!` of a square dense factor: Ainv = inv(A), formed on the device by
+ * Gauss-Jordan elimination with partial pivoting (Ainv may alias A).  It replaces the LAPACK factorisation of
+ * `factorize(L)` (src/matrix.jl:513-516; per Kronecker factor: src/tensor.jl:227): with the inverse factors
+ * cached, `ldiv!(w, L::TensorProductOperator, v)` (src/tensor.jl:612-642 + outer_div! :864-899) is
+ * scimlop_kron_mul on them -- the same tensor-core mode products as mul!.  Setup work: synchronises `stream`
+ * and returns SCIMLOP_ERR_SINGULAR for an exactly zero pivot.  Workspace size from the query. */
+int scimlop_invert_workspace_bytes(int dtype, int64_t n, size_t* bytes);
+int scimlop_invert(scimlop_handle_t h, int dtype, int64_t n, const void* A, int64_t lda, void* Ainv,
+                   int64_t ldinv, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- TensorProductOperator ------------------------------------------------------------------------- */
 /* Scratch needed by scimlop_kron_mul for these factors and k columns (replaces the 7-slot cache tuple of

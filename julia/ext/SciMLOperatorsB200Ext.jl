@@ -278,6 +278,56 @@ function mul!(w::DevMat{T}, L::SciMLOperators.TensorSumOperator, v::DevMat{T}, Î
     w
 end
 
+# ---- the solve side: factorize / ldiv! (src/matrix.jl:513-516, src/tensor.jl:227, :612-673) ---------------------
+# `factorize(::MatrixOperator)` over device storage caches the explicit inverse, formed on the device by
+# scimlop_invert; it is wrapped as the `F` of an InvertibleOperator, whose `ldiv!(w, L.F, v)` (src/matrix.jl:632-639)
+# then dispatches to the `mul!` above.  A factorised TensorProductOperator therefore solves with scimlop_kron_mul
+# on the inverse factors -- the same two tensor-core mode products as `mul!`.
+struct DeviceInverse{T} <: AbstractMatrix{T}      # what `F` holds: inv(A), applied by multiplication
+    inv::CuMatrix{T}
+end
+Base.size(F::DeviceInverse) = size(F.inv)
+SciMLOperators.has_ldiv(::DeviceInverse) = true
+SciMLOperators.has_ldiv!(::DeviceInverse) = true
+LinearAlgebra.ldiv!(w::DevMat{T}, F::DeviceInverse{T}, v::DevMat{T}) where {T <: F} = mul!(w, F.inv, v, true, false)
+
+function LinearAlgebra.factorize(L::MatrixOperator{T, <:CuMatrix{T}}) where {T <: F}
+    n = LinearAlgebra.checksquare(L.A)
+    Ainv = similar(L.A)
+    nbytes = Ref{Csize_t}(0)
+    ccall((:scimlop_invert_workspace_bytes, LIB), Cint, (Cint, Int64, Ref{Csize_t}), dtype(T), n, nbytes)
+    ws = CUDA.zeros(UInt8, nbytes[])
+    check(ccall((:scimlop_invert, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                handle(), dtype(T), n, dptr(L.A), stride(L.A, 2), dptr(Ainv), stride(Ainv, 2), dptr(ws), sizeof(ws),
+                stream_ptr()), "scimlop_invert")           # status 9 (singular) -> error, like SingularException
+    SciMLOperators.InvertibleOperator(L, DeviceInverse{T}(Ainv))
+end
+
+# flatten_inverse(L, T): like flatten, with every InvertibleOperator leaf replaced by pointer(L.F.inv) and Î» by 1/Î»
+function LinearAlgebra.ldiv!(w::DevMat{T}, L::TensorProductOperator, v::DevMat{T}) where {T <: F}
+    @assert iscached(L)                                                            # src/tensor.jl:617
+    fl = flatten_inverse(L, T)
+    fl === nothing && return invoke(ldiv!, Tuple{AbstractVecOrMat, TensorProductOperator, AbstractVecOrMat}, w, L, v)
+    kinds, ptrs, dims, lds, Î»inv = fl
+    ws = L.cache[1]
+    check(ccall((:scimlop_kron_mul, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}, Ptr{Cint}, Ptr{Cvoid}, Int64,
+                 Ptr{Cvoid}, Int64, Int64, Ptr{T}, Ptr{T}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                handle(), dtype(T), 0, length(kinds), ptrs, dims, lds, kinds, dptr(v), size(v, 1), dptr(w),
+                size(w, 1), size(v, 2), Ref(T(Î»inv)), C_NULL, dptr(ws), sizeof(ws), stream_ptr()), "scimlop_kron_mul")
+    w
+end
+LinearAlgebra.ldiv!(L::TensorProductOperator, v::DevMat{T}) where {T <: F} = ldiv!(v, L, v)   # W may alias V when >= 2 stages
+
+function LinearAlgebra.ldiv!(w::DevMat{T}, L::BatchedDiagonalOperator, v::DevMat{T}) where {T <: F}   # src/batch.jl:181-193
+    check(ccall((:scimlop_diag_div, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
+                handle(), dtype(T), size(v, 1), size(v, 2), dptr(L.diag), stride(L.diag, 2), dptr(v), stride(v, 2),
+                dptr(w), stride(w, 2), stream_ptr()), "scimlop_diag_div")
+    w
+end
+
 # ---- solver-loop kernels (device-resident per-column scalars), for Krylov callers -----------------------------
 function col_dot!(out::CuVector{T}, x::CuMatrix{T}, y::CuMatrix{T}) where {T <: F}
     check(ccall((:scimlop_col_dot, LIB), Cint,

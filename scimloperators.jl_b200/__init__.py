@@ -10,7 +10,8 @@ from .array import DeviceArray
 from .operators import (AbstractSciMLOperator, AddedOperator, BandedMatrix, BatchedDiagonalOperator, ComposedOperator,
                         DiagonalOperator, IdentityOperator, MatrixOperator, NullOperator, ScalarOperator,
                         ScaledOperator, TensorProductOperator, TensorSumOperator, adapt, cache_operator, iscached, kron,
-                        kronsum, mul_, update_coefficients_)
+                        kronsum, mul_, update_coefficients_, InvertibleOperator, InvertedOperator, factorize, has_ldiv,
+                        inv, invert_matrix, ldiv_)
 from .distributed import ColumnShard, allgather_cols, shard_columns
 from . import krylov
 

@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libscimlop_b200.so")
 
 # enums of include/scimlop_b200.h
 OK = 0
-ERR_NULL_POINTER, ERR_BAD_SHAPE, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_BAD_HANDLE, ERR_NO_DEVICE = range(1, 9)
+(ERR_NULL_POINTER, ERR_BAD_SHAPE, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_BAD_HANDLE, ERR_NO_DEVICE,
+ ERR_SINGULAR) = range(1, 10)
 F64, F32 = 0, 1
 PREC_DEFAULT, PREC_TF32X3, PREC_TF32, PREC_FP32_EXACT = 0, 1, 2, 3
 DENSE, IDENTITY, DIAG, BDIAG, NULL, BANDED = 0, 1, 2, 3, 4, 5
@@ -49,6 +50,9 @@ SIGNATURES = {
                                      _I64, _P, _P, _I64, _I64, _I64, _P],
     "scimlop_diag_mul": [_P, _INT, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P],
     "scimlop_axpby": [_P, _INT, _I64, _I64, _P, _I64, _P, _I64, _P, _P, _P],
+    "scimlop_diag_div": [_P, _INT, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P],
+    "scimlop_invert_workspace_bytes": [_INT, _I64, C.POINTER(_SZ)],
+    "scimlop_invert": [_P, _INT, _I64, _P, _I64, _P, _I64, _P, _SZ, _P],
     "scimlop_kron_workspace_bytes": [_INT, _INT, _I64P, _I32P, _I64, C.POINTER(_SZ)],
     "scimlop_kron_mul": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _I64, _P, _I64, _I64, _P,
                          _P, _P, _SZ, _P],

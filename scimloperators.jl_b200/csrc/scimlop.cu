@@ -335,6 +335,7 @@ extern "C" const char* scimlop_status_string(int s) {
     case SCIMLOP_ERR_NCCL: return "NCCL error";
     case SCIMLOP_ERR_BAD_HANDLE: return "bad handle";
     case SCIMLOP_ERR_NO_DEVICE: return "no sm_100 device (there is no CPU fallback)";
+    case SCIMLOP_ERR_SINGULAR: return "singular matrix";
     default: return "unknown status";
   }
 }

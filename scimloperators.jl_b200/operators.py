@@ -18,6 +18,9 @@ libscimlop_b200.so.  Names follow the reference (`!` becomes a trailing undersco
   ComposedOperator          src/basic.jl:909-939        ComposedOperator
   TensorProductOperator     src/tensor.jl:88-142        TensorProductOperator, kron
   TensorSumOperator         src/tensor.jl:269-298       TensorSumOperator, kronsum
+  InvertibleOperator        src/matrix.jl:501-511       InvertibleOperator, factorize
+  InvertedOperator          src/basic.jl:1316-1336      InvertedOperator, inv
+  ldiv!(w, L, v) / ldiv!(L, v)  src/tensor.jl:612-673   ldiv_(w, L, v) / ldiv_(L, v)
   cache_operator            src/interface.jl:245-252    cache_operator
   update_coefficients!      src/interface.jl:150-154    update_coefficients_
   mul!(w, L, v[, α, β])                                 mul_(w, L, v[, alpha, beta])
@@ -69,6 +72,24 @@ def _check_vw(L, w, v):
                         "(SURVEY.md §8 pitfalls); the Julia wrapper falls back to the generic path here")
     if w.t.data_ptr() == v.t.data_ptr() and w.t.numel() > 0:
         raise AssertionError("mul!: w and v must not alias")
+
+
+def _check_ldiv(L, w, v):
+    m, n = L.size()
+    if v.shape[0] != m or w.shape[0] != n or _ncols(v) != _ncols(w):
+        raise AssertionError(f"DimensionMismatch: ldiv! with operator {m}x{n}, v {v.shape}, w {w.shape}")
+    if v.dtype != w.dtype or (L.dtype is not None and L.dtype != v.dtype):
+        raise TypeError("ldiv!: operator, v and w must have one element type")
+
+
+def _diag_div(diag, ldd, w, v, scale):
+    h = _lib.handle(w.device_index)
+    n, k = v.shape[0], _ncols(v)
+    h.check(h.lib.scimlop_diag_div(h.ptr, _DT[w.dtype], n, k, C.c_void_p(diag.ptr), ldd, C.c_void_p(v.ptr), v.ld,
+                                   C.c_void_p(w.ptr), w.ld, _stream()), "scimlop_diag_div")
+    if scale is not None and float(scale) != 1.0:
+        _lmul(w, float(scale), h)
+    return w
 
 
 class BandedMatrix:
@@ -144,6 +165,26 @@ class AbstractSciMLOperator:
     def _flat_terms(self):
         """[(scale, [leaf, ...]), ...] if this operator is a sum of products of native leaves, else None."""
         return None
+
+    # ---- the solve side: has_ldiv / ldiv! (src/interface.jl has_ldiv, has_ldiv!) ---------------------------
+    def has_ldiv(self):
+        return False
+
+    def _ldiv(self, w, v, scale=None):
+        """w = scale * (L \\ v); w may be v itself for the two-argument form."""
+        raise TypeError(f"{type(self).__name__} has no ldiv!: factorize(L) first (has_ldiv(L) is false)")
+
+    def ldiv_(self, *args):
+        """`ldiv!(w, L, v)` as L.ldiv_(w, v); `ldiv!(L, v)` as L.ldiv_(v).  Returns the destination."""
+        if len(args) == 1:
+            (v,) = args
+            _check_ldiv(self, v, v)
+            return self._ldiv(v, v)
+        w, v = args
+        _check_ldiv(self, w, v)
+        if w.t.data_ptr() == v.t.data_ptr() and w.t.numel() > 0:
+            raise AssertionError("ldiv!(w, L, v): w and v must not alias (use the two-argument form)")
+        return self._ldiv(w, v)
 
     # ---- call forms: src/interface.jl:161-171 --------------------------------------------------------
     def __call__(self, *args):
@@ -315,6 +356,12 @@ class _VectorDiagonalOperator(AbstractSciMLOperator):
     def _flat_terms(self):
         return [(1.0, [self])]
 
+    def has_ldiv(self):
+        return True
+
+    def _ldiv(self, w, v, scale=None):  # stdlib ldiv!(::Diagonal, v) behind src/matrix.jl:363-366
+        return _diag_div(self.diag, 0, w, v, scale)
+
     def mul_(self, w, v, alpha=None, beta=None):
         _check_vw(self, w, v)
         h = _lib.handle(w.device_index)
@@ -354,6 +401,14 @@ class BatchedDiagonalOperator(AbstractSciMLOperator):
     def _flat_terms(self):
         return [(1.0, [self])]
 
+    def has_ldiv(self):
+        return True
+
+    def _ldiv(self, w, v, scale=None):  # src/batch.jl:181-200
+        if tuple(v.shape) != tuple(self.diag.shape):
+            raise AssertionError(f"BatchedDiagonalOperator: v {v.shape} must match diag {self.diag.shape}")
+        return _diag_div(self.diag, self.diag.ld, w, v, scale)
+
     def mul_(self, w, v, alpha=None, beta=None):
         _check_vw(self, w, v)
         if tuple(v.shape) != tuple(self.diag.shape):
@@ -389,6 +444,17 @@ class IdentityOperator(AbstractSciMLOperator):
 
     def _flat_terms(self):
         return [(1.0, [self])]
+
+    def has_ldiv(self):
+        return True
+
+    def _ldiv(self, w, v, scale=None):  # src/basic.jl:92-99: a copy (nothing at all in place)
+        h = _lib.handle(w.device_index)
+        if w.t.data_ptr() == v.t.data_ptr():
+            return w if scale is None or float(scale) == 1.0 else _lmul(w, float(scale), h)
+        h.check(h.lib.scimlop_axpby(h.ptr, _DT[w.dtype], self.len, _ncols(v), C.c_void_p(v.ptr), v.ld,
+                                    C.c_void_p(w.ptr), w.ld, _scalar(w.dtype, scale), None, _stream()), "scimlop_axpby")
+        return w
 
     def mul_(self, w, v, alpha=None, beta=None):
         _check_vw(self, w, v)
@@ -494,6 +560,8 @@ def _scale_getter(scalars):
 
 def _terms_with_scalars(L, scalars=()):
     """Flatten like src/basic.jl:619-635 (sums) and :936-939 (products); returns [(scalars, leaves)] or None."""
+    if isinstance(L, InvertibleOperator):
+        return _terms_with_scalars(L.L, scalars)      # mul! of an InvertibleOperator is mul! of L.L
     if isinstance(L, MatrixOperator) and L.banded:
         return None    # banded leaves are applied by their own kernel, not by scimlop_tree_mul
     if isinstance(L, _LEAVES):
@@ -534,6 +602,192 @@ class _TreeMixin:
 
 
 # ====================================================================================================
+# the solve side: InvertibleOperator / factorize / ldiv!   
+# ====================================================================================================
+class InvertibleOperator(AbstractSciMLOperator):
+    """src/matrix.jl:501-511: `L` answers mul!, `F` answers ldiv! (:632-639).  In the reference `F` is a LAPACK
+    factorisation; here it is an operator that APPLIES the inverse (for a dense factor: the explicit inverse
+    formed once on the device by scimlop_invert), so that ldiv! runs on the same tensor-core path as mul!.
+    `refresh` re-forms F after `update_coefficients!` changed L (the reference updates both, :575-579)."""
+
+    def __init__(self, L, F, refresh=None):
+        if L.size() != F.size()[::-1]:
+            raise AssertionError(f"InvertibleOperator: L is {L.size()}, F is {F.size()}")
+        self.L, self.F, self._refresh = L, F, refresh
+        self._stash = None
+
+    @property
+    def dtype(self):
+        return self.L.dtype
+
+    def size(self):
+        return self.L.size()
+
+    def getops(self):
+        return (self.L, self.F)
+
+    def adjoint(self):   # src/matrix.jl:565
+        return InvertibleOperator(self.L.adjoint(), self.F.adjoint())
+
+    def iscached(self):
+        return self.L.iscached() and self.F.iscached()
+
+    def cache_operator(self, v):   # src/matrix.jl:610-615
+        self.L = self.L.cache_operator(v)
+        self.F = self.F.cache_operator(v)
+        return self
+
+    def update_coefficients_(self, u=None, p=None, t=None):
+        self.L.update_coefficients_(u, p, t)
+        if self._refresh is not None:
+            self._refresh()
+        else:
+            self.F.update_coefficients_(u, p, t)
+        return self
+
+    def _flat_terms(self):
+        return self.L._flat_terms()
+
+    def mul_(self, w, v, alpha=None, beta=None):   # src/matrix.jl:619-631
+        return self.L.mul_(w, v, alpha, beta)
+
+    def has_ldiv(self):
+        return True
+
+    def _ldiv(self, w, v, scale=None):
+        src = v
+        if w.t.data_ptr() == v.t.data_ptr():
+            if self._stash is None or self._stash.shape != tuple(v.shape) or self._stash.dtype != v.dtype:
+                self._stash = DeviceArray.empty(tuple(v.shape), v.dtype, v.device_index)
+            self._stash.t.copy_(v.t)
+            src = self._stash
+        return self.F.mul_(w, src, scale, None if scale is None else False)
+
+
+class InvertedOperator(AbstractSciMLOperator):
+    """src/basic.jl:1316-1336: lazy inverse; `mul!` is the wrapped operator's ldiv! (:1420-1442) and vice versa."""
+
+    def __init__(self, L):
+        if not L.has_ldiv():
+            raise AssertionError("InvertedOperator: the operator has no ldiv! (factorize it first)")
+        self.L = L
+        self._tmp = None
+
+    @property
+    def dtype(self):
+        return self.L.dtype
+
+    def size(self):
+        return self.L.size()[::-1]
+
+    def getops(self):
+        return (self.L,)
+
+    def iscached(self):
+        return self.L.iscached()
+
+    def cache_operator(self, v):
+        m = self.L.size()[1]
+        self.L = self.L.cache_operator(DeviceArray.zeros((m,) + tuple(v.shape[1:]), v.dtype, v.device_index))
+        return self
+
+    def has_ldiv(self):
+        return True
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        _check_vw(self, w, v)
+        if alpha is None:
+            return self.L._ldiv(w, v)
+        if _beta_is_zero(beta):
+            return self.L._ldiv(w, v, alpha)
+        # 5-arg: w = α (L \\ v) + β w through one scratch (the reference's copy!/axpby!, src/basic.jl:1428-1442)
+        if self._tmp is None or self._tmp.shape != tuple(w.shape) or self._tmp.dtype != w.dtype:
+            self._tmp = DeviceArray.empty(tuple(w.shape), w.dtype, w.device_index)
+        self.L._ldiv(self._tmp, v)
+        h = _lib.handle(w.device_index)
+        h.check(h.lib.scimlop_axpby(h.ptr, _DT[w.dtype], w.shape[0], _ncols(w), C.c_void_p(self._tmp.ptr), self._tmp.ld,
+                                    C.c_void_p(w.ptr), w.ld, _scalar(w.dtype, alpha), _scalar(w.dtype, beta), _stream()),
+                "scimlop_axpby")
+        return w
+
+    def _ldiv(self, w, v, scale=None):   # src/basic.jl:1444-1450
+        if w.t.data_ptr() == v.t.data_ptr():
+            raise NotImplementedError("two-argument ldiv! of an InvertedOperator (a mul! in place)")
+        return self.L.mul_(w, v, scale, None if scale is None else False)
+
+
+def invert_matrix(A):
+    """inv(A) of a square device matrix via scimlop_invert (Gauss-Jordan, partial pivoting, on the device)."""
+    A = _as_device(A)
+    n, n2 = A.shape
+    if n != n2:
+        raise AssertionError("factorize: only square factors have an ldiv! on this path (test/matrix.jl:646)")
+    out = DeviceArray.empty((n, n), A.dtype, A.device_index)
+    _invert_into(A, out)
+    return out
+
+
+def _invert_into(A, out):
+    h = _lib.handle(A.device_index)
+    n = A.shape[0]
+    nbytes = C.c_size_t(0)
+    h.check(h.lib.scimlop_invert_workspace_bytes(_DT[A.dtype], n, C.byref(nbytes)), "scimlop_invert_workspace_bytes")
+    ws = torch.empty(max(1, nbytes.value), dtype=torch.uint8, device=A.t.device)
+    h.check(h.lib.scimlop_invert(h.ptr, _DT[A.dtype], n, C.c_void_p(A.ptr), A.ld, C.c_void_p(out.ptr), out.ld,
+                                 C.c_void_p(ws.data_ptr()), nbytes.value, _stream()), "scimlop_invert")
+    return out
+
+
+def factorize(L):
+    """`LinearAlgebra.factorize(L)`: src/matrix.jl:513-516 (leaf), src/basic.jl:500 (Scaled), :1056 (Composed),
+    src/tensor.jl:227 (every Kronecker factor).  Singular factors raise ScimlopError(ERR_SINGULAR)."""
+    if isinstance(L, InvertibleOperator):
+        return L
+    if isinstance(L, MatrixOperator):
+        if L.banded:
+            raise NotImplementedError("factorize of a banded MatrixOperator (a banded solve) is not on this path")
+        inv = invert_matrix(L.A)
+        refresh = (lambda: _invert_into(L.A, inv)) if L.update_func is not None else None
+        return InvertibleOperator(L, MatrixOperator(inv, L.trans), refresh)
+    if isinstance(L, _VectorDiagonalOperator):
+        rec = DeviceArray.empty(L.diag.shape, L.diag.dtype, L.diag.device_index)
+        ones = DeviceArray.full(L.diag.shape, 1.0, L.diag.dtype, L.diag.device_index)
+        fill = lambda: _diag_div(L.diag, 0, rec.reshape(rec.shape[0], 1), ones.reshape(ones.shape[0], 1), None)
+        fill()
+        return InvertibleOperator(L, _VectorDiagonalOperator(rec), fill if L.update_func is not None else None)
+    if isinstance(L, (BatchedDiagonalOperator, IdentityOperator)):
+        return L                                   # they answer ldiv! themselves
+    if isinstance(L, ScaledOperator):
+        return ScaledOperator(L.lam, factorize(L.L))
+    if isinstance(L, ComposedOperator):
+        return ComposedOperator(*[factorize(op) for op in L.ops])
+    if isinstance(L, TensorProductOperator):
+        return TensorProductOperator(*[factorize(op) for op in L.ops])
+    raise TypeError(f"factorize: {type(L).__name__} cannot be factorised on this path "
+                    "(the reference converts to a dense matrix, src/matrix.jl:513-516)")
+
+
+def inv(L):
+    """`inv(L)`: lazy InvertedOperator (src/basic.jl:1316-1336)."""
+    return L.L if isinstance(L, InvertedOperator) else InvertedOperator(L)
+
+
+def has_ldiv(L):
+    return L.has_ldiv()
+
+
+def ldiv_(*args):
+    """`ldiv!(w, L, v)` or `ldiv!(L, v)`; returns the destination."""
+    if len(args) == 3:
+        w, L, v = args
+        return L.ldiv_(w, v)
+    if len(args) == 2:
+        L, v = args
+        return L.ldiv_(v)
+    raise TypeError("ldiv!: ldiv_(w, L, v) or ldiv_(L, v)")
+
+
+# ====================================================================================================
 # lazy algebra
 # ====================================================================================================
 class ScaledOperator(_TreeMixin, AbstractSciMLOperator):
@@ -563,6 +817,12 @@ class ScaledOperator(_TreeMixin, AbstractSciMLOperator):
         self.L = self.L.cache_operator(v)
         self._try_plan(v)
         return self
+
+    def has_ldiv(self):
+        return self.L.has_ldiv() and self.lam.convert() != 0
+
+    def _ldiv(self, w, v, scale=None):  # src/basic.jl:538-546: ldiv!(w, L.L, v); ldiv!(λ, w) -- folded into one pass
+        return self.L._ldiv(w, v, (1.0 if scale is None else float(scale)) / self.lam.convert())
 
     def mul_(self, w, v, alpha=None, beta=None):
         _check_vw(self, w, v)
@@ -669,6 +929,26 @@ class ComposedOperator(_TreeMixin, AbstractSciMLOperator):
         self.ops = tuple(self.ops[i].cache_operator(inputs[i]) for i in range(n))
         return self
 
+    def has_ldiv(self):
+        return all(op.has_ldiv() for op in self.ops)
+
+    def _ldiv(self, w, v, scale=None):
+        """src/basic.jl:1209-1256: (A∘B∘C) \\ v = C \\ (B \\ (A \\ v)); intermediates ping-pong through two scratch
+        arrays (all factors must be square here, as `factorize` requires)."""
+        n = len(self.ops)
+        if n == 1:
+            return self.ops[0]._ldiv(w, v, scale)
+        if getattr(self, "_ldiv_scratch", None) is None or self._ldiv_scratch[0].shape != tuple(v.shape) \
+                or self._ldiv_scratch[0].dtype != v.dtype:
+            self._ldiv_scratch = [DeviceArray.zeros(tuple(v.shape), v.dtype, v.device_index) for _ in range(2)]
+        cur = v
+        for i, op in enumerate(self.ops):
+            last = i == n - 1
+            out = w if last else self._ldiv_scratch[i & 1]
+            op._ldiv(out, cur, scale if last else None)
+            cur = out
+        return w
+
     def mul_(self, w, v, alpha=None, beta=None):
         _check_vw(self, w, v)
         if not self.iscached():
@@ -694,6 +974,8 @@ class ComposedOperator(_TreeMixin, AbstractSciMLOperator):
 # ====================================================================================================
 def _kron_leaf(op):
     """(kind, data_ptr, ld) if `op` can be a native Kronecker factor, else None."""
+    while isinstance(op, InvertibleOperator):
+        op = op.L
     if isinstance(op, MatrixOperator) and op.banded:
         return (_lib.BANDED, op.A.bands.ptr, op.A.b)      # lds[] carries the half-bandwidth for banded factors
     if isinstance(op, MatrixOperator):
@@ -717,6 +999,7 @@ class TensorProductOperator(AbstractSciMLOperator):
             ops = [ops[0], TensorProductOperator(*ops[1:])]
         self.ops = tuple(ops)
         self._native = None   # (factors..., workspace) when the whole product is native
+        self._native_inv = None   # the same for ldiv!: the inverse factors of a factorised product
         self.cache = None     # c1 of the reference when falling back to the two-stage algorithm
         self._k = None
 
@@ -797,6 +1080,85 @@ class TensorProductOperator(AbstractSciMLOperator):
         outer = outer.cache_operator(DeviceArray.zeros((no, mi * k), v.dtype, v.device_index))  # :536,:539
         self.ops = (outer, inner)
         return self
+
+    # ---- ldiv!: src/tensor.jl:612-673 + outer_div! :864-933 ---------------------------------------------
+    def _flatten_inverse(self):
+        """Like _flatten, but every leaf is replaced by the operator that applies its inverse."""
+        leaves, scalars = [], []
+
+        def walk(op):
+            if isinstance(op, ScaledOperator):
+                scalars.append(op.lam)
+                return walk(op.L)
+            if isinstance(op, TensorProductOperator):
+                return all(walk(o) for o in op.ops)
+            if isinstance(op, IdentityOperator):
+                leaves.append(op)
+                return True
+            if isinstance(op, InvertibleOperator) and _kron_leaf(op.F) is not None and not isinstance(op.F, InvertibleOperator):
+                leaves.append(op.F)
+                return True
+            return False
+
+        return (leaves, scalars) if walk(self) else None
+
+    def has_ldiv(self):
+        return self._flatten_inverse() is not None
+
+    def _ldiv(self, w, v, scale=None):
+        """(A ⊗ B) \\ v = (A⁻¹ ⊗ B⁻¹) v: with the inverse factors cached by `factorize` this is scimlop_kron_mul on
+        them -- the same two tensor-core mode products as mul!, no permutedims!, no triangular sweeps."""
+        if not self.iscached():
+            raise AssertionError("cache needs to be set up for operator of type TensorProductOperator: "
+                                 "call cache_operator(L, v) first")  # src/tensor.jl:617,653
+        k = _ncols(v)
+        if k != self._k:
+            raise AssertionError("operator was cached for a different number of columns: call cache_operator again")
+        if self._native_inv is None or self._native_inv["dtype"] != v.dtype:
+            flat = self._flatten_inverse()
+            if flat is None:
+                raise TypeError("ldiv!(::TensorProductOperator): every factor must be factorised "
+                                "(factorize(L), src/tensor.jl:227) or an identity")
+            leaves, scalars = flat
+            nf = len(leaves)
+            dims, lds = (C.c_int64 * (2 * nf))(), (C.c_int64 * nf)()
+            kinds, ptrs = (C.c_int32 * nf)(), (C.c_void_p * nf)()
+            ndense = 0
+            for i, op in enumerate(leaves):
+                m, n = op.size()
+                if m != n:
+                    raise AssertionError("ldiv!(::TensorProductOperator) needs square factors")
+                dims[2 * i], dims[2 * i + 1] = m, n
+                kinds[i], ptrs[i], lds[i] = _kron_leaf(op)
+                ndense += (kinds[i] & 0xFF) in (_lib.DENSE, _lib.BANDED)
+            nbytes = C.c_size_t(0)
+            rc = _lib.load().scimlop_kron_workspace_bytes(_DT[v.dtype], nf, dims, kinds, k, C.byref(nbytes))
+            if rc != _lib.OK:
+                raise _lib.ScimlopError(rc, "scimlop_kron_workspace_bytes")
+            fwd = self._native
+            ws = fwd["ws"] if fwd is not None and fwd["ws_bytes"] >= nbytes.value else \
+                torch.empty(max(1, nbytes.value), dtype=torch.uint8, device=v.t.device)
+            self._native_inv = dict(nf=nf, dims=dims, lds=lds, kinds=kinds, ptrs=ptrs, ws=ws, ws_bytes=nbytes.value,
+                                    scalars=scalars, dtype=v.dtype, nstages=sum(1 for i in range(nf) if kinds[i] != _lib.IDENTITY),
+                                    ndense=ndense, stash=None)
+        nat = self._native_inv
+        a = scale
+        for s in nat["scalars"]:
+            a = (1.0 if a is None else float(a)) / s.convert()
+        src = v
+        if w.t.data_ptr() == v.t.data_ptr() and nat["nstages"] == 1 and nat["ndense"] == 1:
+            # two-argument form with a single GEMM stage: a GEMM cannot run in place, stage v once
+            if nat["stash"] is None or nat["stash"].shape != tuple(v.shape):
+                nat["stash"] = DeviceArray.empty(tuple(v.shape), v.dtype, v.device_index)
+            nat["stash"].t.copy_(v.t)
+            src = nat["stash"]
+        h = _lib.handle(w.device_index)
+        n = self.size()[1]
+        h.check(h.lib.scimlop_kron_mul(h.ptr, _DT[w.dtype], self.precision, nat["nf"], nat["ptrs"], nat["dims"],
+                                       nat["lds"], nat["kinds"], C.c_void_p(src.ptr), n, C.c_void_p(w.ptr), n, k,
+                                       _scalar(w.dtype, a), None, C.c_void_p(nat["ws"].data_ptr()), nat["ws_bytes"],
+                                       _stream()), "scimlop_kron_mul")
+        return w
 
     def mul_(self, w, v, alpha=None, beta=None):
         _check_vw(self, w, v)
@@ -950,6 +1312,8 @@ def adapt(L, device=None, to=None):
         return BatchedDiagonalOperator(to(L.diag), L.update_func)
     if isinstance(L, (IdentityOperator, NullOperator)):
         return type(L)(L.len)
+    if isinstance(L, InvertibleOperator):
+        return InvertibleOperator(adapt(L.L, to=to), adapt(L.F, to=to))
     if isinstance(L, ScaledOperator):
         return ScaledOperator(L.lam, adapt(L.L, to=to))
     if isinstance(L, AddedOperator):

@@ -199,3 +199,21 @@ def test_c_oracle(oracle_c, dtype, tol):
     w = np.full_like(w0, np.nan)
     oracle_c.diag_mul(w, bd, v, 0.7, 0.0)
     assert R.rel_err(w, 0.7 * bd * v) < tol
+
+
+@pytest.mark.parametrize("vector_input", [False, True])
+def test_tpo_ldiv_restatement_matches_dense_solve(vector_input):
+    """test/matrix.jl:646-671, :801-806: `ldiv!(w, factorize(opAB), v) ≈ AB \\ v` for the square shapes."""
+    rng = np.random.default_rng(5)
+    for n1, n2, n3 in [(3, 5, 7), (7, 4, 2)]:
+        A, B, Cm = (np.asfortranarray(rng.random((n, n)) + np.eye(n)) for n in (n1, n2, n3))
+        K = 1 if vector_input else 19
+        v = rng.random(n1 * n2) if vector_input else np.asfortranarray(rng.random((n1 * n2, K)))
+        want = np.linalg.solve(np.kron(A, B), v)
+        assert R.rel_err(R.tpo_ldiv(A, B, v), want) < 1e-12
+        assert R.rel_err(R.kron_solve([A, B], v), want) < 1e-12
+        v3 = rng.random(n1 * n2 * n3) if vector_input else np.asfortranarray(rng.random((n1 * n2 * n3, K)))
+        want3 = np.linalg.solve(np.kron(A, np.kron(B, Cm)), v3)
+        assert R.rel_err(R.kron_solve([A, B, Cm], v3), want3) < 1e-11
+        # nested like the reference's A ⊗ (B ⊗ C): the inner solve is itself a TPO ldiv!
+        assert R.rel_err(R.tpo_ldiv(A, np.kron(B, Cm), v3), want3) < 1e-11
