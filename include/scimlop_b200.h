@@ -203,6 +203,14 @@ int scimlop_tree_mul(scimlop_handle_t h, int dtype, int precision, const scimlop
                      const void* alpha, const void* beta, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* BlockDiagonalOperator mul! (src/block.jl:145-179): block b (rows_b x cols_b; DENSE with .trans, DIAG, BDIAG with
+ * .ld, IDENTITY or NULL) maps rows [sum cols_<b, +cols_b) of V to rows [sum rows_<b, +rows_b) of W,
+ * W_b = alpha * op_b * V_b + beta * W_b.  Equal dense blocks stored at a uniform stride run as ONE strided-batched
+ * GEMM (row slices of the column-major V / W are batch strides); otherwise one launch per block. */
+int scimlop_blockdiag_mul(scimlop_handle_t h, int dtype, int precision, int nblocks,
+                          const scimlop_factor_t* blocks, const void* V, int64_t ldv, void* W, int64_t ldw,
+                          int64_t k, const void* alpha, const void* beta, void* stream);
+
 /* ---- host-buffer entry (end-to-end path) ------------------------------------------------------------- */
 /* Same as scimlop_kron_mul but V, W and the factors live in (ideally pinned) HOST memory: columns are
  * streamed through the device in chunks of `chunk_cols` (0 = library default) with H2D copy, compute and

@@ -61,6 +61,7 @@ SIGNATURES = {
     "scimlop_kronsum_banded_mul": [_P, _INT, _P, _INT, _I64, _P, _INT, _I64, _P, _I64, _P, _I64, _I64, _P, _P, _P],
     "scimlop_tree_workspace_bytes": [_INT, C.POINTER(Term), _INT, _I64, C.POINTER(_SZ)],
     "scimlop_tree_mul": [_P, _INT, _INT, C.POINTER(Term), _INT, _P, _I64, _P, _I64, _I64, _P, _P, _P, _SZ, _P],
+    "scimlop_blockdiag_mul": [_P, _INT, _INT, _INT, C.POINTER(Factor), _P, _I64, _P, _I64, _I64, _P, _P, _P],
     "scimlop_kron_mul_host": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _I64, _P, _I64, _I64,
                               _P, _P, _I64],
     "scimlop_col_dot": [_P, _INT, _I64, _I64, _P, _I64, _P, _I64, _P, _P],

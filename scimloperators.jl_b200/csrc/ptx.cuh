@@ -36,6 +36,7 @@ __device__ __forceinline__ void mbar_arrive_after_loads(uint32_t bar, uint32_t s
       "mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar), "r"(scratch), "r"(digest)
       : "memory");
 }
+__device__ __forceinline__ uint32_t fold_bits(float x) { return __float_as_uint(x); }
 __device__ __forceinline__ uint32_t fold_bits(double x) {
   const long long b = __double_as_longlong(x);
   return (uint32_t)b ^ (uint32_t)(b >> 32);

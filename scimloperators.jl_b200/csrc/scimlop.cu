@@ -12,6 +12,7 @@
 #include "eltwise.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_skinny.cuh"
 #include "gemm_tf32.cuh"
 
 using namespace scimlop;
@@ -197,6 +198,96 @@ int launch_simt(scimlop_context* c, bool transA, bool transB, long long M, long 
   return SCIMLOP_OK;
 }
 
+// ---- few-column products (k < 16): TMA-streamed, cluster-split, HBM-bound (gemm_skinny.cuh) ------------------
+template <typename T>
+bool skinny_eligible(scimlop_context* c, bool transB, long long M, long long N, long long K, const T* A, long long lda,
+                     const T* B, long long ldb, long long batch, int nscale) {
+  // up to 48 (Float64) / 64 (Float32) columns in passes of 8: measured cheaper than a 128-wide GEMM tile that is
+  // mostly padding (16384^2 Float64: 0.30 ms per pass vs 2.3 ms for the DMMA kernel at any N <= 128)
+  if (batch != 1 || transB || nscale != 0 || N < 1 || N > (sizeof(T) == 8 ? 48 : 64)) return false;
+  if (M < 16 || K < 64 || M * K < (1LL << 16)) return false;           // tiny products: the generic path is fine
+  const long long per16 = 16 / (long long)sizeof(T);
+  if (!aligned16(A) || !aligned16(B) || lda % per16 || (N > 1 && ldb % per16)) return false;
+  if (M > (1LL << 31) - 1 || K > (1LL << 31) - 1 || lda > (1LL << 36) || ldb > (1LL << 36)) return false;
+  return c->encode_tiled != nullptr;
+}
+
+template <typename T, bool TRANS, int KC>
+int launch_skinny_k(scimlop_context* c, const CUtensorMap& tmA, const CUtensorMap& tmX, const skinny::Params& p, dim3 grid,
+                    cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(skinny::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = skinny::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = grid.x;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  auto kern = skinny::gemm_skinny_kernel<T, TRANS, KC>;
+  static bool optin = false;   // per instantiation
+  if (!optin) {
+    SCIMLOP_CUDA(c, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, skinny::SMEM_BYTES));
+    optin = true;
+  }
+  SCIMLOP_CUDA(c, cudaLaunchKernelEx(&cfg, kern, tmA, tmX, p));
+  c->launches++;
+  return SCIMLOP_OK;
+}
+
+template <typename T>
+int launch_skinny(scimlop_context* c, bool transA, long long M, long long N, long long K, T alpha, const T* A, long long lda,
+                  const T* B, long long ldb, T beta, T* C, long long ldc, cudaStream_t st) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  constexpr int TC = 128 * VEC;
+  const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const int kc = N == 1 ? 1 : (N == 2 ? 2 : (N <= 4 ? 4 : 8));
+  CUtensorMap tmA, tmX;
+  cuuint32_t estr[2] = {1, 1};
+  {
+    // stored matrix: contiguous extent first (NT: M rows; T: the reduction index)
+    cuuint64_t gdim[2] = {(cuuint64_t)(transA ? K : M), (cuuint64_t)(transA ? M : K)};
+    cuuint64_t gstr[1] = {(cuuint64_t)lda * sizeof(T)};
+    cuuint32_t box[2] = {256, skinny::TO};
+    CUresult r = c->encode_tiled(&tmA, dt, 2, const_cast<T*>(A), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return scimlop_fail(c, SCIMLOP_ERR_CUDA, "cuTensorMapEncodeTiled(skinny A) failed (CUresult %d)", (int)r);
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t gstr[1] = {(cuuint64_t)(N > 1 ? ldb : ((K * (long long)sizeof(T) + 15) / 16 * 16 / (long long)sizeof(T))) * sizeof(T)};
+    cuuint32_t box[2] = {(cuuint32_t)(transA ? 256 : skinny::TO), (cuuint32_t)kc};
+    CUresult r = c->encode_tiled(&tmX, dt, 2, const_cast<T*>(B), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return scimlop_fail(c, SCIMLOP_ERR_CUDA, "cuTensorMapEncodeTiled(skinny X) failed (CUresult %d)", (int)r);
+  }
+  skinny::Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = K; p.k = (int)N; p.ldy = ldc; p.Y = C; p.alpha = (double)alpha; p.beta = (double)beta;
+  const long long otiles = transA ? (M + skinny::TO - 1) / skinny::TO : (M + TC - 1) / TC;
+  p.tiles_red = (int)(transA ? (K + TC - 1) / TC : (K + skinny::TO - 1) / skinny::TO);
+  const int passes = (int)((N + skinny::MAXC - 1) / skinny::MAXC);
+  if (otiles > 65535) return -1;   // caller falls back
+  long long s = c->sm_count / std::max<long long>(1, otiles * passes);
+  s = std::min<long long>(s, std::max(1, p.tiles_red / 8));
+  s = std::max<long long>(1, std::min<long long>(8, s));
+  p.splits = (int)s;
+  dim3 grid((unsigned)s, (unsigned)otiles, (unsigned)passes);
+#define SCIMLOP_SKINNY(KC_)                                                                         \
+  (transA ? launch_skinny_k<T, true, KC_>(c, tmA, tmX, p, grid, st) : launch_skinny_k<T, false, KC_>(c, tmA, tmX, p, grid, st))
+  switch (kc) {
+    case 1: return SCIMLOP_SKINNY(1);
+    case 2: return SCIMLOP_SKINNY(2);
+    case 4: return SCIMLOP_SKINNY(4);
+    default: return SCIMLOP_SKINNY(8);
+  }
+#undef SCIMLOP_SKINNY
+}
+
 // C_b = alpha * rowscale .* (op(A_b) op(B_b)) + beta * C_b
 template <typename T>
 int gemm_dispatch(scimlop_context* c, int precision, bool transA, bool transB, long long M, long long N,
@@ -212,6 +303,10 @@ int gemm_dispatch<double>(scimlop_context* c, int precision, bool transA, bool t
   if (precision != SCIMLOP_PREC_DEFAULT)
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "Float64 only supports SCIMLOP_PREC_DEFAULT (got %d)", precision);
   if (M <= 0 || N <= 0 || batch <= 0) return SCIMLOP_OK;
+  if (g_peers.n == 0 && skinny_eligible<double>(c, transB, M, N, K, A, lda, B, ldb, batch, nscale)) {
+    const int rc = launch_skinny<double>(c, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, st);
+    if (rc >= 0) return rc;
+  }
   if (g_peers.n > 0 && !dmma_eligible(M, N, K, A, lda, sA, B, ldb, sB, batch))
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "peer targets need a DMMA-eligible (aligned Float64) last stage");
   if (dmma_eligible(M, N, K, A, lda, sA, B, ldb, sB, batch))
@@ -302,6 +397,10 @@ int gemm_dispatch<float>(scimlop_context* c, int precision, bool transA, bool tr
         aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0 && sA % 4 == 0)
       return launch_tf32(c, /*x_mn=*/true, /*f_k=*/!transB, M, (int)N, (int)K, batch, A, lda, sA, B, ldb, C, 1, ldc, sC,
                          alpha, beta, passes, st);
+  }
+  if (precision != SCIMLOP_PREC_TF32 && skinny_eligible<float>(c, transB, M, N, K, A, lda, B, ldb, batch, nscale)) {
+    const int rc = launch_skinny<float>(c, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, st);
+    if (rc >= 0) return rc;
   }
   if (precision == SCIMLOP_PREC_TF32)
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED,
@@ -487,6 +586,97 @@ extern "C" int scimlop_axpby(scimlop_handle_t h, int dtype, int64_t n, int64_t k
                                  scalar_or<double>(beta, 0.0), st);
   return eltwise_axpby<float>(h, n, k, (const float*)V, ldv, (float*)W, ldw, scalar_or<float>(alpha, 1.f),
                               scalar_or<float>(beta, 0.f), st);
+}
+
+// ================================================================================================
+// BlockDiagonalOperator (src/block.jl:145-179)
+// ================================================================================================
+namespace {
+
+template <typename T>
+int blockdiag_t(scimlop_context* h, int precision, int nblocks, const scimlop_factor_t* blk, const T* V, int64_t ldv,
+                T* W, int64_t ldw, int64_t k, T alpha, T beta, cudaStream_t st) {
+  // equal dense blocks at a uniform stride: ONE strided-batched GEMM, block b reads rows [b*n, (b+1)*n) of V and
+  // writes rows [b*m, (b+1)*m) of W (row offsets are just batch strides of the column-major views)
+  bool uniform = nblocks > 1 && (blk[0].kind & 0xFF) == SCIMLOP_DENSE;
+  long long stride = 0;
+  for (int b = 1; uniform && b < nblocks; b++) {
+    uniform = blk[b].kind == blk[0].kind && blk[b].trans == blk[0].trans && blk[b].rows == blk[0].rows &&
+              blk[b].cols == blk[0].cols && blk[b].ld == blk[0].ld;
+    const long long d = static_cast<const char*>(blk[b].data) - static_cast<const char*>(blk[b - 1].data);
+    if (b == 1) stride = d;
+    uniform = uniform && d == stride && d > 0 && d % (long long)sizeof(T) == 0;
+  }
+  if (uniform) {
+    const bool tr = blk[0].trans != 0;
+    return gemm_dispatch<T>(h, precision, tr, false, blk[0].rows, k, blk[0].cols, alpha, static_cast<const T*>(blk[0].data),
+                            blk[0].ld, stride / (long long)sizeof(T), V, ldv, blk[0].cols, beta, W, ldw, blk[0].rows,
+                            nblocks, 0, nullptr, st);
+  }
+  long long r0 = 0, c0 = 0;
+  for (int b = 0; b < nblocks; b++) {
+    const long long m = blk[b].rows, n = blk[b].cols;
+    const T* v = V + c0;
+    T* w = W + r0;
+    int rc = SCIMLOP_OK;
+    switch (blk[b].kind & 0xFF) {
+      case SCIMLOP_DENSE:
+        rc = gemm_dispatch<T>(h, precision, blk[b].trans != 0, false, m, k, n, alpha, static_cast<const T*>(blk[b].data),
+                              blk[b].ld, 0, v, ldv, 0, beta, w, ldw, 0, 1, 0, nullptr, st);
+        break;
+      case SCIMLOP_DIAG:
+      case SCIMLOP_BDIAG:
+        rc = diag_mul_t<T>(h, m, k, blk[b].data, (blk[b].kind & 0xFF) == SCIMLOP_DIAG ? 0 : blk[b].ld, v, ldv, w, ldw, &alpha,
+                           &beta, st);
+        break;
+      case SCIMLOP_IDENTITY:
+        rc = eltwise_axpby<T>(h, m, k, v, ldv, w, ldw, alpha, beta, st);
+        break;
+      case SCIMLOP_NULL:
+        rc = eltwise_axpby<T>(h, m, k, nullptr, 0, w, ldw, T(0), beta, st);
+        break;
+      default:
+        rc = scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "blockdiag: block %d has unsupported kind %d", b, blk[b].kind);
+    }
+    if (rc) return rc;
+    r0 += m;
+    c0 += n;
+  }
+  return SCIMLOP_OK;
+}
+
+}  // namespace
+
+extern "C" int scimlop_blockdiag_mul(scimlop_handle_t h, int dtype, int precision, int nblocks,
+                                     const scimlop_factor_t* blocks, const void* V, int64_t ldv, void* W, int64_t ldw,
+                                     int64_t k, const void* alpha, const void* beta, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_dtype(h, dtype)) return rc;
+  if (nblocks < 1 || !blocks) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "blockdiag: no blocks");
+  if (k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "blockdiag: negative k");
+  long long rows = 0, cols = 0;
+  for (int b = 0; b < nblocks; b++) {
+    const int kind = blocks[b].kind & 0xFF;
+    if (blocks[b].rows < 0 || blocks[b].cols < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "blockdiag: negative block size");
+    if (kind != SCIMLOP_DENSE && blocks[b].rows != blocks[b].cols)
+      return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "blockdiag: block %d is elementwise but not square", b);
+    if ((kind == SCIMLOP_DENSE || kind == SCIMLOP_DIAG || kind == SCIMLOP_BDIAG) && !blocks[b].data)
+      return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "blockdiag: block %d has no data", b);
+    if (kind == SCIMLOP_DENSE && blocks[b].ld < (blocks[b].trans ? blocks[b].cols : blocks[b].rows))
+      return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "blockdiag: block %d leading dimension too small", b);
+    rows += blocks[b].rows;
+    cols += blocks[b].cols;
+  }
+  if (k == 0 || rows == 0) return SCIMLOP_OK;
+  if (!V || !W) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "blockdiag: V/W null");
+  if (ldv < cols || ldw < rows) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "blockdiag: leading dimension smaller than the operator");
+  scimlop_device_guard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SCIMLOP_F64)
+    return blockdiag_t<double>(h, precision, nblocks, blocks, (const double*)V, ldv, (double*)W, ldw, k,
+                               scalar_or<double>(alpha, 1.0), scalar_or<double>(beta, 0.0), st);
+  return blockdiag_t<float>(h, precision, nblocks, blocks, (const float*)V, ldv, (float*)W, ldw, k,
+                            scalar_or<float>(alpha, 1.f), scalar_or<float>(beta, 0.f), st);
 }
 
 // ================================================================================================

@@ -21,6 +21,8 @@ libscimlop_b200.so.  Names follow the reference (`!` becomes a trailing undersco
   InvertibleOperator        src/matrix.jl:501-511       InvertibleOperator, factorize
   InvertedOperator          src/basic.jl:1316-1336      InvertedOperator, inv
   ldiv!(w, L, v) / ldiv!(L, v)  src/tensor.jl:612-673   ldiv_(w, L, v) / ldiv_(L, v)
+  BlockDiagonalOperator     src/block.jl:37-50          BlockDiagonalOperator
+  WOperator                 src/woperator.jl:176-230    WOperator
   cache_operator            src/interface.jl:245-252    cache_operator
   update_coefficients!      src/interface.jl:150-154    update_coefficients_
   mul!(w, L, v[, α, β])                                 mul_(w, L, v[, alpha, beta])
@@ -599,6 +601,170 @@ class _TreeMixin:
             return False
         self._plan = _TreePlan(self, [(_scale_getter(sc), leaves) for sc, leaves in terms], v)
         return True
+
+
+# ====================================================================================================
+# BlockDiagonalOperator and WOperator   
+# ====================================================================================================
+class BlockDiagonalOperator(AbstractSciMLOperator):
+    """src/block.jl:37-50: block b maps its slice of v to its slice of w; `mul!` :145-179 loops over the blocks with
+    row views.  Here the whole operator is ONE call (scimlop_blockdiag_mul): equal dense blocks run as a single
+    strided-batched GEMM (a row slice of the column-major v / w is a batch stride), ragged blocks as one launch
+    each.  `cache_operator` re-homes equal dense constant blocks into one contiguous allocation so that the batched
+    form applies (the analogue of `cache_internals`, :110-119)."""
+
+    def __init__(self, *ops):
+        if len(ops) == 1 and isinstance(ops[0], (tuple, list)):
+            ops = tuple(ops[0])
+        if not ops:
+            raise AssertionError("BlockDiagonalOperator needs at least one block")   # src/block.jl:45
+        self.ops = tuple(op if isinstance(op, AbstractSciMLOperator) else MatrixOperator(op) for op in ops)
+        for op in self.ops:
+            if not isinstance(op, _LEAVES) or (isinstance(op, MatrixOperator) and op.banded):
+                raise NotImplementedError(f"BlockDiagonalOperator block {type(op).__name__}: the B200 backend takes "
+                                          "Matrix / Diagonal / BatchedDiagonal / Identity / Null blocks "
+                                          "(the Julia wrapper keeps the generic loop for anything else)")
+        self._blocks = None
+        self._packed = None
+
+    @property
+    def dtype(self):
+        for op in self.ops:
+            if op.dtype is not None:
+                return op.dtype
+        return None
+
+    def size(self):   # src/block.jl:66-69
+        return (sum(op.size()[0] for op in self.ops), sum(op.size()[1] for op in self.ops))
+
+    def getops(self):
+        return self.ops
+
+    def adjoint(self):   # src/block.jl:77-80
+        return BlockDiagonalOperator(*[op.adjoint() for op in self.ops])
+
+    def iscached(self):
+        return self._blocks is not None
+
+    def cache_operator(self, v):
+        if v.shape[0] != self.size()[1]:
+            raise AssertionError(f"cache_operator: v has {v.shape[0]} rows, operator has {self.size()[1]} columns")
+        ops = self.ops
+        dense = [op for op in ops if isinstance(op, MatrixOperator)]
+        if len(ops) > 1 and len(dense) == len(ops) and all(
+                op.update_func is None and op.A.shape == ops[0].A.shape and op.trans == ops[0].trans
+                and op.A.dtype == ops[0].A.dtype for op in ops):
+            r, c = ops[0].A.shape
+            packed = DeviceArray.empty((r, c * len(ops)), ops[0].A.dtype, v.device_index)
+            for b, op in enumerate(ops):
+                packed.cols(b * c, (b + 1) * c).t.copy_(op.A.t)
+            self._packed = packed
+            self.ops = tuple(MatrixOperator(packed.cols(b * c, (b + 1) * c), op.trans) for b, op in enumerate(ops))
+        k = _ncols(v)
+        arr = (_lib.Factor * len(self.ops))()
+        for b, op in enumerate(self.ops):
+            f = arr[b]
+            f.rows, f.cols = op.size()
+            f.trans, f.data, f.ld = 0, None, 0
+            if isinstance(op, MatrixOperator):
+                f.kind, f.trans, f.data, f.ld = _lib.DENSE, int(op.trans), op.A.ptr, op.A.ld
+            elif isinstance(op, _VectorDiagonalOperator):
+                f.kind, f.data = _lib.DIAG, op.diag.ptr
+            elif isinstance(op, BatchedDiagonalOperator):
+                if op.diag.shape[1] != k:
+                    raise AssertionError(f"BatchedDiagonalOperator block: diag {op.diag.shape} does not match k={k}")
+                f.kind, f.data, f.ld = _lib.BDIAG, op.diag.ptr, op.diag.ld
+            elif isinstance(op, IdentityOperator):
+                f.kind = _lib.IDENTITY
+            else:
+                f.kind = _lib.NULL
+            if op.dtype is not None and op.dtype != v.dtype:
+                raise TypeError(f"block eltype {op.dtype} != array eltype {v.dtype}")
+        self._blocks = arr
+        return self
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        _check_vw(self, w, v)
+        if self._blocks is None:
+            self.cache_operator(v)
+        h = _lib.handle(w.device_index)
+        h.check(h.lib.scimlop_blockdiag_mul(h.ptr, _DT[w.dtype], self.precision, len(self.ops), self._blocks,
+                                            C.c_void_p(v.ptr), v.ld, C.c_void_p(w.ptr), w.ld, _ncols(v),
+                                            _scalar(w.dtype, alpha), _scalar(w.dtype, beta), _stream()),
+                "scimlop_blockdiag_mul")
+        return w
+
+
+class _NegInvGamma(ScalarOperator):
+    """The -1/γ (or -λ/γ for a UniformScaling mass matrix) of a WOperator, read at every mul!."""
+
+    def __init__(self, owner, lam=1.0):
+        self.owner, self.lam = owner, float(lam)
+        self.update_func = None
+
+    @property
+    def val(self):
+        return -self.lam / float(self.owner.gamma)
+
+    @val.setter
+    def val(self, x):
+        pass
+
+    def convert(self):
+        return self.val
+
+
+class WOperator(AbstractSciMLOperator):
+    """src/woperator.jl:176-230: `W = J - M/γ`.  The reference's `mul!` (:447-481) is `mul!(Y, M, B)`, `lmul!(-1/γ, Y)`,
+    `mul!(cache, J, B)`, `Y .+= cache`; here it is one tree call: the J product writes Y, the M product accumulates with
+    α = -1/γ in its epilogue (a scalar mass matrix λI rides in the elementwise pass).  `gamma` is mutable, as in the
+    reference (`update_coefficients!(W, u, p, t; gamma)`, :372-388)."""
+
+    def __init__(self, mass_matrix, gamma, J):
+        self.J = J if isinstance(J, AbstractSciMLOperator) else MatrixOperator(J)
+        n = self.J.size()[0]
+        if np.isscalar(mass_matrix):                       # UniformScaling λ*I
+            self.mass_matrix = IdentityOperator(n)
+            self._neg = _NegInvGamma(self, mass_matrix)
+        else:
+            self.mass_matrix = mass_matrix if isinstance(mass_matrix, AbstractSciMLOperator) else MatrixOperator(mass_matrix)
+            self._neg = _NegInvGamma(self)
+        if self.mass_matrix.size() != self.J.size():
+            raise AssertionError(f"WOperator: mass matrix {self.mass_matrix.size()} vs J {self.J.size()}")
+        self.gamma = gamma
+        self._sum = AddedOperator(self.J, ScaledOperator(self._neg, self.mass_matrix))
+
+    @property
+    def dtype(self):
+        return self.J.dtype
+
+    def size(self):
+        return self.J.size()
+
+    def getops(self):
+        return (self.J, self.mass_matrix)
+
+    def iscached(self):
+        return self._sum.iscached()
+
+    def cache_operator(self, v):
+        self._sum = self._sum.cache_operator(v)
+        return self
+
+    def update_coefficients_(self, u=None, p=None, t=None, gamma=None):
+        self.J.update_coefficients_(u, p, t)
+        self.mass_matrix.update_coefficients_(u, p, t)
+        if gamma is not None:
+            self.gamma = gamma
+        return self
+
+    def _flat_terms(self):
+        return self._sum._flat_terms()
+
+    def mul_(self, w, v, alpha=None, beta=None):
+        if not self._sum.iscached():
+            self._sum = self._sum.cache_operator(v)
+        return self._sum.mul_(w, v, alpha, beta)
 
 
 # ====================================================================================================
@@ -1314,6 +1480,12 @@ def adapt(L, device=None, to=None):
         return type(L)(L.len)
     if isinstance(L, InvertibleOperator):
         return InvertibleOperator(adapt(L.L, to=to), adapt(L.F, to=to))
+    if isinstance(L, BlockDiagonalOperator):
+        return BlockDiagonalOperator(*[adapt(op, to=to) for op in L.ops])
+    if isinstance(L, WOperator):
+        lam = L._neg.lam
+        return WOperator(lam if isinstance(L.mass_matrix, IdentityOperator) and lam != 1.0 else adapt(L.mass_matrix, to=to),
+                         L.gamma, adapt(L.J, to=to))
     if isinstance(L, ScaledOperator):
         return ScaledOperator(L.lam, adapt(L.L, to=to))
     if isinstance(L, AddedOperator):

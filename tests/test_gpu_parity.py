@@ -826,3 +826,45 @@ def test_error_statuses(sb):
     e = sb.DeviceArray.zeros((16, 0), np.float64)
     L = sb.cache_operator(sb.kron(np.eye(4), np.eye(4)), e)
     assert sb.mul_(sb.DeviceArray.zeros((16, 0), np.float64), L, e).shape == (16, 0)
+
+
+# ---- few-column products (gemm_skinny.cuh): vector / thin-matrix mul! of a MatrixOperator ---------------------
+SKINNY_CASES = [
+    # M (rows of op(A)), N (reduction), k
+    (256, 64, 1), (512, 256, 1), (300, 1000, 1), (4096, 4096, 1), (4100, 4104, 2), (1000, 77 * 2, 3), (2048, 3000, 5),
+    (777 * 2, 1234, 8), (640, 5000, 9), (1026, 2050, 15), (64, 65536, 1), (48, 40000, 4), (16, 70000, 7),
+    (10000, 128, 1), (20000, 64, 6), (2048, 2048, 16), (1500, 3000, 33), (520, 4000, 48),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("trans", [False, True])
+@pytest.mark.parametrize("case", SKINNY_CASES)
+def test_matrix_operator_few_columns(sb, case, trans, dtype):
+    """`mul!(w, L::MatrixOperator, v)` with a vector or a thin matrix (test/matrix.jl:72-80 uses K = 12 columns and
+    vectors): the TMA-streamed, cluster-split path, 3-arg into NaN-filled w and 5-arg."""
+    M, N, k = case
+    rng = np.random.default_rng(M * 31 + N * 7 + k)
+    A = rnd(rng, *((N, M) if trans else (M, N)), dtype=dtype) - dtype(0.5)
+    v = rnd(rng, N, k, dtype=dtype) - dtype(0.5)
+    w0 = rnd(rng, M, k, dtype=dtype)
+    L = sb.MatrixOperator(A, trans=trans)
+    opA = (A.T if trans else A).astype(np.float64)
+    want = opA @ v.astype(np.float64)
+    # summation error of a length-N Float32 dot product grows like sqrt(N) eps; the bound is the north_star's at N <= 4096
+    tol = TOL[np.dtype(dtype)] * (max(1.0, np.sqrt(N / 4096.0)) if dtype == np.float32 else 1.0)
+    w = sb.DeviceArray.full((M, k), float("nan"), dtype)
+    sb.mul_(w, L, dev(sb, v))
+    got = w.numpy()
+    assert np.isfinite(got).all()
+    # cancellation-free error measure: entries are sums of +-0.25-sized terms, compare against the norm of |A||v|
+    scale = np.linalg.norm(np.abs(opA) @ np.abs(v.astype(np.float64)))
+    assert np.linalg.norm(got - want) <= tol * scale, f"3-arg err {np.linalg.norm(got - want) / scale:.3e}"
+    w = dev(sb, w0)
+    sb.mul_(w, L, dev(sb, v), 0.7, 0.3)
+    want5 = 0.7 * want + 0.3 * w0.astype(np.float64)
+    assert np.linalg.norm(w.numpy() - want5) <= tol * (scale + np.linalg.norm(w0)), "5-arg"
+    if k == 1:   # a true Vector input (ndim == 1)
+        wv = sb.DeviceArray.full((M,), float("nan"), dtype)
+        sb.mul_(wv, L, dev(sb, v[:, 0].copy()))
+        assert np.linalg.norm(wv.numpy() - want[:, 0]) <= tol * scale

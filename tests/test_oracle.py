@@ -217,3 +217,21 @@ def test_tpo_ldiv_restatement_matches_dense_solve(vector_input):
         assert R.rel_err(R.kron_solve([A, B, Cm], v3), want3) < 1e-11
         # nested like the reference's A ⊗ (B ⊗ C): the inner solve is itself a TPO ldiv!
         assert R.rel_err(R.tpo_ldiv(A, np.kron(B, Cm), v3), want3) < 1e-11
+
+
+def test_block_diagonal_and_woperator_restatements():
+    """src/block.jl:145-179 and src/woperator.jl:447-481 against their dense definitions
+    (test/block.jl: `L * v ≈ Matrix(L) * v`; test/woperator.jl: `W * v ≈ (J - M/γ) * v`)."""
+    import scipy.linalg as sla
+    rng = np.random.default_rng(9)
+    blocks = [rnd(rng, 3, 5), np.diag(rng.random(4)), rnd(rng, 6, 2), np.eye(3)]
+    dense = sla.block_diag(*blocks)
+    v = rnd(rng, dense.shape[1], 7)
+    w0 = rnd(rng, dense.shape[0], 7)
+    assert R.rel_err(R.block_diag_mul(np.full_like(w0, np.nan), blocks, v), dense @ v) < RTOL
+    assert R.rel_err(R.block_diag_mul(w0.copy(), blocks, v, 0.7, 0.3), 0.7 * dense @ v + 0.3 * w0) < RTOL
+    n = 9
+    J, M, gamma = rnd(rng, n, n), rnd(rng, n, n), 0.37
+    b = rng.random(n)
+    assert R.rel_err(R.woperator_mul(np.empty(n), M, gamma, J, b), (J - M / gamma) @ b) < RTOL
+    assert R.rel_err(R.woperator_mul(np.empty(n), 2.0, gamma, J, b), (J - 2.0 * np.eye(n) / gamma) @ b) < RTOL
