@@ -235,18 +235,27 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   }
 
-  // ---- combine the splits through distributed shared memory (rank order), then alpha / beta and the store ----
+  // ---- combine the splits through distributed shared memory, then alpha / beta and the store.  Every rank sums
+  //      (in rank order, so the result does not depend on who adds) and stores its own 1/nsplit of the outputs. ----
   cluster_sync_all();
-  if (cluster_rank() == 0 && warp < CONSUMERS / 32) {
+  if (warp < CONSUMERS / 32) {
     T* Y = static_cast<T*>(p.Y);
     const T alpha = (T)p.alpha, beta = (T)p.beta;
     constexpr int ROWS = TRANS ? TO : TC;      // outputs of this CTA
-    for (int e = threadIdx.x; e < ROWS * KC; e += CONSUMERS) {
+    const int total = ROWS * KC;
+    const int chunk = (total + nsplit - 1) / nsplit;
+    const int e0 = (int)cluster_rank() * chunk, e1 = min(total, e0 + chunk);
+    for (int e = e0 + threadIdx.x; e < e1; e += CONSUMERS) {
       const int c = e / ROWS, r = e - c * ROWS;
       const long long row = (long long)otile * ROWS + r;
       if (row >= p.M || c0 + c >= p.k) continue;
-      T v = red_gen[c * ROWS + r];
-      for (int s = 1; s < nsplit; s++) v += ld_cluster<T>(map_to_rank(red + (uint32_t)(c * ROWS + r) * sizeof(T), s));
+      T part[8];
+#pragma unroll
+      for (int s = 0; s < 8; s++)
+        part[s] = s < nsplit ? ld_cluster<T>(map_to_rank(red + (uint32_t)e * sizeof(T), s)) : T(0);
+      T v = part[0];
+#pragma unroll
+      for (int s = 1; s < 8; s++) v += part[s];
       T* dst = Y + row + (long long)(c0 + c) * p.ldy;
       *dst = (beta == T(0)) ? alpha * v : fma(alpha, v, beta * *dst);
     }
