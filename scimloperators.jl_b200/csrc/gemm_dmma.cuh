@@ -209,24 +209,26 @@ __global__ void __launch_bounds__(THREADS, 1)
       SCIMLOP_MMA_STEP(a1, b1);
       SCIMLOP_LOAD_FRAGS(a1, b1, so, 3);
       SCIMLOP_MMA_STEP(a0, b0);
-      // hand the slot back to the producer once all of this stage's fragments have ARRIVED in registers
-      // (see mbar_arrive_after_loads)
-      {
-        uint32_t digest = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) digest ^= fold_bits(a0[i]) ^ fold_bits(a1[i]);
-#pragma unroll
-        for (int j = 0; j < 4; j++) digest ^= fold_bits(b0[j]) ^ fold_bits(b1[j]);
-        __syncwarp();
-        if (lane == 0) mbar_arrive_after_loads(empty_bar + 8 * stage, scratch + 4 * warp, digest);
-      }
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
       // prefetch step 0 of the next stage (next k-block, or the first k-block of this CTA's next tile)
+      const uint32_t done_bar = empty_bar + 8 * stage;
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
       if (!(last_tile && kb == nk - 1)) {
         mbar_wait(full_bar + 8 * stage, phase);
         SCIMLOP_LOAD_FRAGS(a0, b0, stage * STAGE_BYTES, 0);
       }
       SCIMLOP_MMA_STEP(a1, b1);
+      // hand the finished slot back to the producer once its fragments have ARRIVED in registers (see
+      // mbar_arrive_after_loads).  Steps 1-2 were consumed before a0/b0 and a1/b1 were overwritten above; the
+      // digest covers step 3.  Placed after the last MMA step so that waiting for the data costs no issue slots.
+      {
+        uint32_t digest = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) digest ^= fold_bits(a1[i]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) digest ^= fold_bits(b1[j]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_after_loads(done_bar, scratch + 4 * warp, digest);
+      }
     }
 #undef SCIMLOP_LOAD_FRAGS
 #undef SCIMLOP_MMA_STEP
