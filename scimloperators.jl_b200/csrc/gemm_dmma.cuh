@@ -75,7 +75,15 @@ __device__ __forceinline__ uint32_t tile_off(int o, int k) {
 // setmaxnreg.dec and the consumers grow to CONSUMER_REGS with setmaxnreg.inc (2*232 + 40 <= 512), which is
 // what lets a 64x32 FP64 warp tile (128 accumulator registers) plus double-buffered fragments live in
 // registers without spilling.
-template <bool A_KC, bool B_OC>
+//
+// SPLIT = true is the few-tiles form (a vector-input Kronecker product, a small MatrixOperator): one tile per
+// thread-block CLUSTER, the K range divided over the cluster's CTAs, partial tiles summed through distributed
+// shared memory in rank order (each rank reduces and stores 1/size of the tile).  Launched with
+// grid = cluster size x tiles.
+constexpr int PART_PITCH = BM + 8;   // doubles per column of the partial tile in shared memory (conflict-free stores)
+static_assert(PART_PITCH * BN * 8 <= STAGES * STAGE_BYTES, "partial tile must fit in the (idle) operand ring");
+
+template <bool A_KC, bool B_OC, bool SPLIT = false>
 __global__ void __launch_bounds__(THREADS, 1)
     gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const Params p) {
@@ -98,8 +106,14 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
   __syncthreads();
 
-  const int nk = (p.K + BK - 1) / BK;
+  const int nk_all = (p.K + BK - 1) / BK;
   const int ntiles = (int)p.total_tiles;
+  // SPLIT: this CTA's share of the k-blocks of its cluster's single tile
+  const int crank = SPLIT ? (int)cluster_rank() : 0, csize = SPLIT ? (int)cluster_size() : 1;
+  const int kb_first = SPLIT ? (int)((long long)nk_all * crank / csize) : 0;
+  const int nk = SPLIT ? (int)((long long)nk_all * (crank + 1) / csize) - kb_first : nk_all;
+  const int tile_first = SPLIT ? (int)(blockIdx.x / csize) : (int)blockIdx.x;
+  const int tile_step = SPLIT ? ntiles : (int)gridDim.x;   // SPLIT: exactly one tile per cluster
 
   if (warp >= CONSUMER_WARPS) {
     // ================= TMA producer warpgroup =================
@@ -110,14 +124,14 @@ __global__ void __launch_bounds__(THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       const int tiles_mn = p.tiles_m * p.tiles_n;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < ntiles; tile += tile_step) {
         const int b = tile / tiles_mn;
         const int rem = tile - b * tiles_mn;
         const int nt = rem / p.tiles_m;
         const int mt = rem - nt * p.tiles_m;
         const int m0 = mt * BM, n0 = nt * BN;
         const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
-        for (int kb = 0; kb < nk; kb++) {
+        for (int kb = kb_first; kb < kb_first + nk; kb++) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t sA = smem + stage * STAGE_BYTES;
           const uint32_t sB = sA + TILE_BYTES;
@@ -139,6 +153,11 @@ __global__ void __launch_bounds__(THREADS, 1)
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+    }
+    if (SPLIT) {   // the whole CTA takes part in the cluster barriers of the reduction
+      __syncwarp();
+      cluster_sync_all();
+      cluster_sync_all();
     }
     return;
   }
@@ -182,18 +201,18 @@ __global__ void __launch_bounds__(THREADS, 1)
   double a0[8], b0[4], a1[8], b1[4];  // double-buffered fragments: step s computes while step s+1 loads
 
   // prime the software pipeline with the first fragments of this CTA's first stage
-  if ((int)blockIdx.x < ntiles && nk > 0) {
+  if (tile_first < ntiles && nk > 0) {
     mbar_wait(full_bar, 0);
     SCIMLOP_LOAD_FRAGS(a0, b0, 0u, 0);
   }
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = tile_first; tile < ntiles; tile += tile_step) {
     const int tiles_mn = p.tiles_m * p.tiles_n;
     const int b = tile / tiles_mn;
     const int rem = tile - b * tiles_mn;
     const int nt = rem / p.tiles_m;
     const int mt = rem - nt * p.tiles_m;
-    const bool last_tile = tile + (int)gridDim.x >= ntiles;
+    const bool last_tile = tile + tile_step >= ntiles;
 
     double acc[8][4][2];
 #pragma unroll
@@ -233,6 +252,63 @@ __global__ void __launch_bounds__(THREADS, 1)
 #undef SCIMLOP_LOAD_FRAGS
 #undef SCIMLOP_MMA_STEP
 
+    if (SPLIT) {
+      // ---- split-K epilogue: partial tile -> shared memory (the operand ring is idle now), cluster barrier,
+      //      every rank sums its share of the columns over all ranks (rank order) and runs the fused epilogue ----
+      asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");   // all consumer warps are done reading the ring
+      {
+        const uint32_t pbase = smem + (uint32_t)(((wn * 32 + g) * PART_PITCH + wm * 64 + 2 * t) * 8);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(pbase + (uint32_t)((8 * j * PART_PITCH + 8 * i) * 8)),
+                         "d"(acc[i][j][0]), "d"(acc[i][j][1])
+                         : "memory");
+      }
+      cluster_sync_all();
+      // rank r owns tile columns [r*ncols, ...): two rows (16 bytes) per thread and step, remote loads of all ranks
+      // issued before the first use
+      const int ncols = (BN + csize - 1) / csize;
+      const int n_lo = crank * ncols, n_hi = min(BN, n_lo + ncols);
+      for (int e = (int)threadIdx.x; e < (n_hi - n_lo) * (BM / 2); e += CONSUMER_WARPS * 32) {
+        const int nl = n_lo + e / (BM / 2), ml = 2 * (e % (BM / 2));
+        const int m = mt * BM + ml, n = nt * BN + nl;
+        if (m >= p.M || n >= p.N) continue;
+        const uint32_t off = smem + (uint32_t)((nl * PART_PITCH + ml) * 8);
+        double p0[8], p1[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+          p0[s] = p1[s] = 0.0;
+          if (s < csize)
+            asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(p0[s]), "=d"(p1[s]) : "r"(map_to_rank(off, s)));
+        }
+        double v0 = p0[0], v1 = p1[0];
+#pragma unroll
+        for (int s = 1; s < 8; s++) { v0 += p0[s]; v1 += p1[s]; }
+        const bool pair = m + 1 < p.M;
+        for (int q = 0; q < p.nscale; q++) {
+          const double* sp = p.scale[q].ptr + (p.scale[q].ld ? (long long)n * p.scale[q].ld : 0) + m;
+          v0 *= sp[0];
+          if (pair) v1 *= sp[1];
+        }
+        double* dst = p.C + (long long)b * p.strideC + (long long)n * p.ldc + m;
+        if (pair && p.vec_ok) {
+          double2 o = make_double2(p.alpha * v0, p.alpha * v1);
+          if (p.beta != 0.0) {
+            const double2 old = *reinterpret_cast<const double2*>(dst);
+            o.x = fma(p.beta, old.x, o.x);
+            o.y = fma(p.beta, old.y, o.y);
+          }
+          *reinterpret_cast<double2*>(dst) = o;
+        } else {
+          dst[0] = (p.beta == 0.0) ? p.alpha * v0 : fma(p.alpha, v0, p.beta * dst[0]);
+          if (pair) dst[1] = (p.beta == 0.0) ? p.alpha * v1 : fma(p.alpha, v1, p.beta * dst[1]);
+        }
+      }
+      cluster_sync_all();   // nobody leaves while a peer may still read its partial tile
+      return;
+    }
     // ---- fused epilogue: rowscale, alpha, beta, store (the next tile's first stages are already in flight) ----
     const int mbase = mt * BM + wm * 64 + 2 * t;
     const int nbase = nt * BN + wn * 32 + g;

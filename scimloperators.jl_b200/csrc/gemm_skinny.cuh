@@ -48,34 +48,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-template <typename T>
-__device__ __forceinline__ T ld_cluster(uint32_t addr);
-template <>
-__device__ __forceinline__ double ld_cluster<double>(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-template <>
-__device__ __forceinline__ float ld_cluster<float>(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
-
 template <typename T> struct Vec;
 template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
 template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };

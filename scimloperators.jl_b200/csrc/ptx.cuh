@@ -112,6 +112,41 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   return v;
 }
 
+// ---- thread-block clusters / distributed shared memory ---------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ T ld_cluster(uint32_t addr);
+template <>
+__device__ __forceinline__ double ld_cluster<double>(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+template <>
+__device__ __forceinline__ float ld_cluster<float>(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
 // ---- DMMA: D(8x8) += A(8x4,row) * B(4x8,col), FP64 ------------------------------------------------------
 // lane = 4*g + t supplies A[g][t] and B[t][g] and owns D[g][2t], D[g][2t+1].
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {

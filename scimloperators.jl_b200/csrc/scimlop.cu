@@ -162,6 +162,43 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
     p.vec_ok = p.vec_ok && aligned16(g_peers.ptr[q]);
   }
   if (g_peers.n > 0 && beta != 0.0) return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "peer targets need beta == 0");
+  // few tiles (vector-input Kronecker products, small operators): split K over a thread-block cluster.  Pick the
+  // cluster size with the smallest modelled time: waves x (k-blocks per CTA x 2.2 us + reduction); the number of
+  // co-resident clusters comes from the occupancy query at handle creation (8-CTA clusters do not tile all SMs).
+  const long long nk_all = (K + dmma::BK - 1) / dmma::BK;
+  long long ks = 1;
+  if (g_peers.n == 0 && p.total_tiles < c->sm_count) {
+    double best = (double)((p.total_tiles + c->sm_count - 1) / c->sm_count) * (nk_all * 2.2 + 2.0);
+    for (long long cand = 2; cand <= 8; cand *= 2) {
+      const long long maxc = c->dmma_max_clusters[cand];
+      if (maxc <= 0 || nk_all < 2 * cand) continue;
+      const double t = (double)((p.total_tiles + maxc - 1) / maxc) * ((double)((nk_all + cand - 1) / cand) * 2.2 + 6.0);
+      if (t < best) { best = t; ks = cand; }
+    }
+  }
+  if (g_peers.n == 0 && ks >= 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(ks * p.total_tiles), 1, 1);
+    cfg.blockDim = dim3(dmma::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = dmma::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ks;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    if (!transA && !transB) e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<false, false, true>, tmA, tmB, p);
+    else if (!transA && transB) e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<false, true, true>, tmA, tmB, p);
+    else if (transA && !transB) e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<true, false, true>, tmA, tmB, p);
+    else e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<true, true, true>, tmA, tmB, p);
+    c->launches++;
+    SCIMLOP_CUDA(c, e);
+    return SCIMLOP_OK;
+  }
   const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
   if (!transA && !transB) dmma::gemm_dmma_kernel<false, false><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
   else if (!transA && transB) dmma::gemm_dmma_kernel<false, true><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
@@ -229,11 +266,6 @@ int launch_skinny_k(scimlop_context* c, const CUtensorMap& tmA, const CUtensorMa
   cfg.attrs = at;
   cfg.numAttrs = 1;
   auto kern = skinny::gemm_skinny_kernel<T, TRANS, KC>;
-  static bool optin = false;   // per instantiation
-  if (!optin) {
-    SCIMLOP_CUDA(c, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, skinny::SMEM_BYTES));
-    optin = true;
-  }
   SCIMLOP_CUDA(c, cudaLaunchKernelEx(&cfg, kern, tmA, tmX, p));
   c->launches++;
   return SCIMLOP_OK;
@@ -473,6 +505,27 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   optin((const void*)dmma::gemm_dmma_kernel<false, true>);
   optin((const void*)dmma::gemm_dmma_kernel<true, false>);
   optin((const void*)dmma::gemm_dmma_kernel<true, true>);
+  optin((const void*)dmma::gemm_dmma_kernel<false, false, true>);
+  optin((const void*)dmma::gemm_dmma_kernel<false, true, true>);
+  optin((const void*)dmma::gemm_dmma_kernel<true, false, true>);
+  optin((const void*)dmma::gemm_dmma_kernel<true, true, true>);
+  for (int cs = 2; cs <= 8 && e == cudaSuccess; cs *= 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(cs * 64, 1, 1);
+    cfg.blockDim = dim3(dmma::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = dmma::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, dmma::gemm_dmma_kernel<false, false, true>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      nclusters = 0;
+    }
+    c->dmma_max_clusters[cs] = nclusters;
+  }
   auto optin2 = [&](const void* f) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, tf32::SMEM_BYTES);
   };
@@ -480,6 +533,15 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   optin2((const void*)tf32::gemm_tf32x3_kernel<false, true>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<true, false>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<true, true>);
+  auto optin3 = [&](const void* f) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, skinny::SMEM_BYTES);
+  };
+#define SCIMLOP_SKINNY_OPTIN(T_, KC_)                                      \
+  optin3((const void*)skinny::gemm_skinny_kernel<T_, false, KC_>);        \
+  optin3((const void*)skinny::gemm_skinny_kernel<T_, true, KC_>);
+  SCIMLOP_SKINNY_OPTIN(double, 1) SCIMLOP_SKINNY_OPTIN(double, 2) SCIMLOP_SKINNY_OPTIN(double, 4) SCIMLOP_SKINNY_OPTIN(double, 8)
+  SCIMLOP_SKINNY_OPTIN(float, 1) SCIMLOP_SKINNY_OPTIN(float, 2) SCIMLOP_SKINNY_OPTIN(float, 4) SCIMLOP_SKINNY_OPTIN(float, 8)
+#undef SCIMLOP_SKINNY_OPTIN
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<double>());
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<double>());
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<float>());
