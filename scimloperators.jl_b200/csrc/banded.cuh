@@ -164,8 +164,11 @@ __global__ void __launch_bounds__(128) band_kronsum_tri_kernel(long long mi, lon
 // unused strip on the right: interior = 256 - 2*HL points per tile row.
 constexpr int TTI = 256, TTO = 18, TO_IN = TTO - 2, TSTAGES = 3, TTHREADS = 288;
 template <typename T> struct Tri { static constexpr int HL = 16 / (int)sizeof(T); static constexpr int IN = TTI - 2 * HL; };
-template <typename T>
-constexpr int tri_smem_bytes() { return TSTAGES * TTI * TTO * (int)sizeof(T) + 1024 + 64; }
+// READW (5-arg, beta != 0): the old W tile (IN x 16) rides in the same ring stage, also by TMA
+template <typename T, bool READW>
+struct TriStage { static constexpr int BYTES = TTI * TTO * (int)sizeof(T) + (READW ? TTI * TO_IN * (int)sizeof(T) : 0); };
+template <typename T, bool READW = false>
+constexpr int tri_smem_bytes() { return TSTAGES * TriStage<T, READW>::BYTES + 1024 + 64; }
 
 struct TriParams {
   long long mi, mo, k;
@@ -175,14 +178,17 @@ struct TriParams {
 
 template <typename T, bool READW>
 __global__ void __launch_bounds__(TTHREADS, 1)
-    band_kronsum_tri_tma_kernel(const __grid_constant__ CUtensorMap tmV, const TriParams p, const T* __restrict__ Bx,
-                                const T* __restrict__ By, T* W, T alpha, T beta) {
+    band_kronsum_tri_tma_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmW,
+                                const TriParams p, const T* __restrict__ Bx, const T* __restrict__ By, T* W, T alpha,
+                                T beta) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
   const T* tiles = reinterpret_cast<const T*>(smem_raw + (smem - smem_u32(smem_raw)));
   constexpr uint32_t TILE_BYTES = TTI * TTO * sizeof(T);
+  constexpr uint32_t STAGE_BYTES = TriStage<T, READW>::BYTES;
   constexpr int HL = Tri<T>::HL, TI_IN = Tri<T>::IN;
-  const uint32_t full_bar = smem + TSTAGES * TILE_BYTES, empty_bar = full_bar + 8 * TSTAGES;
+  constexpr uint32_t WTILE_BYTES = TI_IN * TO_IN * sizeof(T);   // what the W box delivers (box {IN, 16})
+  const uint32_t full_bar = smem + TSTAGES * STAGE_BYTES, empty_bar = full_bar + 8 * TSTAGES;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int s = 0; s < TSTAGES; s++) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 8); }
@@ -199,8 +205,9 @@ __global__ void __launch_bounds__(TTHREADS, 1)
       const int to = (int)(rem / p.tiles_i), ti = (int)(rem - (long long)to * p.tiles_i);
       mbar_wait(empty_bar + 8 * stage, phase ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(full_bar + 8 * stage, TILE_BYTES);
-        tma_load_3d(smem + stage * TILE_BYTES, &tmV, full_bar + 8 * stage, ti * TI_IN - HL, to * TO_IN - 1, j);
+        mbar_arrive_expect_tx(full_bar + 8 * stage, TILE_BYTES + (READW ? WTILE_BYTES : 0u));
+        tma_load_3d(smem + stage * STAGE_BYTES, &tmV, full_bar + 8 * stage, ti * TI_IN - HL, to * TO_IN - 1, j);
+        if (READW) tma_load_3d(smem + stage * STAGE_BYTES + TILE_BYTES, &tmW, full_bar + 8 * stage, ti * TI_IN, to * TO_IN, j);
       }
       __syncwarp();
       if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     T* wcol = W + (long long)j * plane + i;
     if (!READW) {
       mbar_wait(full_bar + 8 * stage, phase);
-      const T* s = tiles + (size_t)stage * TTI * TTO;
+      const T* s = reinterpret_cast<const T*>(reinterpret_cast<const uint8_t*>(tiles) + (size_t)stage * STAGE_BYTES);
       if (interior) {
 #pragma unroll 4
         for (int r = 1; r <= TO_IN; r++) {
@@ -237,25 +244,20 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         }
       }
     } else {
-      // fetch the old W values of this thread's 16 points while the halo tile is still in flight
-      T old[TO_IN];
-      if (interior) {
-#pragma unroll
-        for (int r = 0; r < TO_IN; r++) old[r] = (o0 + r < p.mo) ? __ldcs(wcol + (o0 + r) * p.mi) : T(0);
-      }
+      // the old W values of this tile arrived with the halo tile (box {IN, 16}: row r-1, column t - HL)
       mbar_wait(full_bar + 8 * stage, phase);
-      const T* s = tiles + (size_t)stage * TTI * TTO;
+      const T* s = reinterpret_cast<const T*>(reinterpret_cast<const uint8_t*>(tiles) + (size_t)stage * STAGE_BYTES);
+      const T* wold = reinterpret_cast<const T*>(reinterpret_cast<const uint8_t*>(s) + TILE_BYTES) + (t - HL);
       if (interior) {
-#pragma unroll
+#pragma unroll 4
         for (int r = 1; r <= TO_IN; r++) {
           const long long o = o0 + r - 1;
-          if (o < p.mo) {
-            const T xs = __ldg(Bx + o), xm = __ldg(Bx + o + p.mo), xp = __ldg(Bx + o + 2 * p.mo);
-            const T* row = s + r * TTI + t;
-            T v = fma(a, row[-1], fma(b, row[0], c * row[1]));
-            v = fma(xs, row[-TTI], fma(xm, row[0], fma(xp, row[TTI], v)));
-            __stcs(wcol + o * p.mi, fma(beta, old[r - 1], alpha * v));
-          }
+          if (o >= p.mo) break;
+          const T xs = __ldg(Bx + o), xm = __ldg(Bx + o + p.mo), xp = __ldg(Bx + o + 2 * p.mo);
+          const T* row = s + r * TTI + t;
+          T v = fma(a, row[-1], fma(b, row[0], c * row[1]));
+          v = fma(xs, row[-TTI], fma(xm, row[0], fma(xp, row[TTI], v)));
+          __stcs(wcol + o * p.mi, fma(beta, wold[(r - 1) * TI_IN], alpha * v));
         }
       }
     }

@@ -543,9 +543,9 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   SCIMLOP_SKINNY_OPTIN(float, 1) SCIMLOP_SKINNY_OPTIN(float, 2) SCIMLOP_SKINNY_OPTIN(float, 4) SCIMLOP_SKINNY_OPTIN(float, 8)
 #undef SCIMLOP_SKINNY_OPTIN
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<double>());
-  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<double>());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<double, true>());
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<float>());
-  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<float>());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)band::band_kronsum_tri_tma_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, band::tri_smem_bytes<float, true>());
   if (e != cudaSuccess) {
     delete c;
     return SCIMLOP_ERR_CUDA;
@@ -1008,17 +1008,29 @@ static int kronsum_banded_t(scimlop_context* h, const T* Bx, int bx, int64_t mo,
                                  const_cast<T*>(V), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUtensorMap tmW = tmV;
+    const bool readw = beta != T(0);
+    if (r == CUDA_SUCCESS && readw) {
+      // the old W tile travels by TMA too (needs the same alignment of W as of V; else the other stencil paths)
+      if (!aligned16(W)) r = CUDA_ERROR_INVALID_VALUE;
+      else {
+        cuuint32_t wbox[3] = {(cuuint32_t)band::Tri<T>::IN, band::TO_IN, 1};
+        r = h->encode_tiled(&tmW, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, W, gdim,
+                            gstr, wbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+    }
     if (r == CUDA_SUCCESS) {
       band::TriParams p;
       p.mi = mi; p.mo = mo; p.k = k;
       p.tiles_i = (int)((mi + band::Tri<T>::IN - 1) / band::Tri<T>::IN);
       p.tiles_o = (int)((mo + band::TO_IN - 1) / band::TO_IN);
       p.total_tiles = (long long)p.tiles_i * p.tiles_o * k;
-      const int grid = (int)std::min<long long>(p.total_tiles, (long long)h->sm_count * 2);
-      if (beta == T(0))
-        band::band_kronsum_tri_tma_kernel<T, false><<<grid, band::TTHREADS, band::tri_smem_bytes<T>(), st>>>(tmV, p, Bx, By, W, alpha, beta);
+      const int grid = (int)std::min<long long>(p.total_tiles, (long long)h->sm_count * (readw ? 1 : 2));
+      if (!readw)
+        band::band_kronsum_tri_tma_kernel<T, false><<<grid, band::TTHREADS, band::tri_smem_bytes<T>(), st>>>(tmV, tmW, p, Bx, By, W, alpha, beta);
       else
-        band::band_kronsum_tri_tma_kernel<T, true><<<grid, band::TTHREADS, band::tri_smem_bytes<T>(), st>>>(tmV, p, Bx, By, W, alpha, beta);
+        band::band_kronsum_tri_tma_kernel<T, true><<<grid, band::TTHREADS, band::tri_smem_bytes<T, true>(), st>>>(tmV, tmW, p, Bx, By, W, alpha, beta);
       h->launches++;
       SCIMLOP_CUDA(h, cudaGetLastError());
       return SCIMLOP_OK;

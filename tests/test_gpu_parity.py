@@ -426,7 +426,7 @@ def test_leaves(sb, dtype, N, K):
 
 # ---- trees: test/basic.jl:258-318 (Scaled), :320-427 (Added), :516-608 (Composed), README.md:69-73 --------
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("N,K", [(8, 12), (96, 5), (257, 3)])
+@pytest.mark.parametrize("N,K", [(8, 12), (96, 5), (257, 3), (300, 40), (1000, 24)])   # the last two: split-K DMMA tiles with diagonal epilogues
 def test_operator_trees(sb, dtype, N, K):
     rng = np.random.default_rng(N + K)
     A, B, Cm = (rnd(rng, N, N, dtype=dtype) for _ in range(3))
