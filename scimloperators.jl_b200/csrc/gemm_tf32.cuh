@@ -57,7 +57,8 @@ struct Params {
   int m, n;              // factor extents (output columns, contraction length)
   int batch;
   int tiles_r;           // ceil(rows / 128)
-  long long total_tiles; // tiles_r * batch
+  int tiles_c;           // STREAM_F: ceil(m / 128) column tiles; 1 otherwise
+  long long total_tiles; // tiles_r * tiles_c * batch
   float* D;
   long long d_rs, d_cs, d_bs;  // D(r, c, b) at r*d_rs + c*d_cs + b*d_bs
   float alpha, beta;
@@ -152,15 +153,24 @@ __device__ __forceinline__ void split4(float4 x, float4& hi, float4& lo) {
 }
 
 // X_MN: X is MN-major (r contiguous); else K-major (k contiguous).  F_K: factor is K-major (transposed factor).
-template <bool X_MN, bool F_K>
+//
+// STREAM_F = true is the general GEMM (any contraction length, any number of output columns): the second operand
+// is no longer a small resident factor but streams through the SAME ring as X, as 128-column x 32-k tiles of its
+// PRE-SPLIT halves F_hi / F_lo (tmF / tmF2; split once per call by split_hilo_kernel, so that the B operand needs no
+// in-kernel shared->shared pass).  A ring stage is then X | F_hi | F_lo (3 x 16 KB) and is released by the four
+// splitter warps AND by the tcgen05.commit of the MMAs that read it.  The output is r-contiguous (column-major C).
+template <bool X_MN, bool F_K, bool STREAM_F = false>
 __global__ void __launch_bounds__(THREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmF,
-                       const __grid_constant__ CUtensorMap tmD, const Params p) {
+                       const __grid_constant__ CUtensorMap tmF2, const __grid_constant__ CUtensorMap tmD, const Params p) {
+  static_assert(!STREAM_F || RSTAGES == ASTAGES, "streamed-F mode indexes both rings with one counter");
+  constexpr bool OUT_R = STREAM_F ? true : X_MN;          // output contiguous along r (the TMEM lanes)
+  constexpr uint32_t XSTRIDE = STREAM_F ? 3 * XT_BYTES : XT_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));  // generic pointer to the aligned base
-  const uint32_t sFhi = smem, sFlo = smem + F_BYTES, sX = smem + 2 * F_BYTES;
-  const uint32_t sEpi = sX + RSTAGES * XT_BYTES;          // 4 warps x 2 x 4 KB staging blocks (1024-byte aligned)
+  const uint32_t sFhi = smem, sFlo = smem + F_BYTES, sX = STREAM_F ? smem : smem + 2 * F_BYTES;
+  const uint32_t sEpi = sX + RSTAGES * XSTRIDE;           // 4 warps x 2 x 4 KB staging blocks (1024-byte aligned)
   const uint32_t bars = sEpi + 8 * EPI_STAGE_BYTES;
   const uint32_t raw_full = bars, raw_free = raw_full + 8 * RSTAGES;
   const uint32_t a_full = raw_free + 8 * RSTAGES, a_free = a_full + 8 * ASTAGES;
@@ -174,7 +184,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < RSTAGES; s++) {
       mbar_init(raw_full + 8 * s, 1);   // TMA transaction bytes
-      mbar_init(raw_free + 8 * s, 4);   // one arrival per splitter warp
+      mbar_init(raw_free + 8 * s, STREAM_F ? 5 : 4);   // one arrival per splitter warp (+ the MMAs' commit)
     }
     for (int s = 0; s < ASTAGES; s++) {
       mbar_init(a_full + 8 * s, 4);     // one arrival per splitter warp
@@ -202,6 +212,10 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmF);
+    if (STREAM_F) tma_prefetch_desc(&tmF2);
+  }
+  if (!STREAM_F) {
+  if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(f_full, F_BYTES);
     // four 16 KB boxes: F_K: {32 k, 128 c} per k-block; else {32 c, 128 k} per c-group
     for (int q = 0; q < 4; q++) tma_load_3d(sFhi + q * 16384, &tmF, f_full, 32 * q, 0, 0);
@@ -218,10 +232,12 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
   }
   fence_async_smem();
+  }
   __syncthreads();
 
   const int nkb = (p.n + BK - 1) / BK;                 // k-blocks of 32
-  const int n_mma = ((p.m + 15) / 16) * 16;            // UMMA N
+  const int n_mma = STREAM_F ? 128 : ((p.m + 15) / 16) * 16;   // UMMA N (streamed tiles are zero-filled past the edge)
+  const long long tiles_rc = (long long)p.tiles_r * p.tiles_c;
   const uint32_t idesc = make_idesc(false, !F_K, n_mma);   // A comes from TMEM (row = lane, k = column)
 
   if (warp == 0) {
@@ -229,15 +245,30 @@ __global__ void __launch_bounds__(THREADS, 1)
     int stage = 0;
     uint32_t phase = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int b = (int)(tile / p.tiles_r);
-      const int r0 = (int)(tile - (long long)b * p.tiles_r) * TM;
+      const int b = (int)(tile / tiles_rc);
+      const int rem = (int)(tile - (long long)b * tiles_rc);
+      const int ct = rem / p.tiles_r;
+      const int r0 = (rem - ct * p.tiles_r) * TM;
       const int bx = p.x_batched ? b : 0;
       for (int kb = 0; kb < nkb; kb++) {
         mbar_wait(raw_free + 8 * stage, phase ^ 1);
         if (elect_one()) {
-          const uint32_t dst = sX + stage * XT_BYTES;
+          const uint32_t dst = sX + stage * XSTRIDE;
           const uint32_t bar = raw_full + 8 * stage;
-          mbar_arrive_expect_tx(bar, XT_BYTES);
+          mbar_arrive_expect_tx(bar, XSTRIDE);
+          if (STREAM_F) {
+            // the pre-split operand tiles of this k-block: F_K {32 k, 128 c}; else four boxes {32 c, 32 k}
+            if (F_K) {
+              tma_load_3d(dst + XT_BYTES, &tmF, bar, kb * BK, ct * 128, 0);
+              tma_load_3d(dst + 2 * XT_BYTES, &tmF2, bar, kb * BK, ct * 128, 0);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                tma_load_3d(dst + XT_BYTES + q * 4096, &tmF, bar, ct * 128 + 32 * q, kb * BK, 0);
+                tma_load_3d(dst + 2 * XT_BYTES + q * 4096, &tmF2, bar, ct * 128 + 32 * q, kb * BK, 0);
+              }
+            }
+          }
           if (X_MN) {
 #pragma unroll
             for (int q = 0; q < 4; q++) tma_load_3d(dst + q * 4096, &tmX, bar, r0 + 32 * q, kb * BK, bx);
@@ -266,16 +297,20 @@ __global__ void __launch_bounds__(THREADS, 1)
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + a * 128;
       for (int kb = 0; kb < nkb; kb++) {
+        if (STREAM_F) mbar_wait(raw_full + 8 * at, aph);   // the F_hi / F_lo tiles of this stage have landed
         mbar_wait(a_full + 8 * at, aph);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t ahi = tmem_base + TMEM_A0 + at * 64, alo = ahi + 32;
           const int ksteps = min(4, (p.n - kb * BK + 7) / 8);
+          const uint32_t sF = sX + at * XSTRIDE + XT_BYTES;   // STREAM_F: this stage's F_hi tile, F_lo follows
+          const uint64_t shi = F_K ? make_desc_k(sF) : make_desc_mn(sF, 4096);
+          const uint64_t slo = F_K ? make_desc_k(sF + XT_BYTES) : make_desc_mn(sF + XT_BYTES, 4096);
 #pragma unroll
           for (int ks = 0; ks < 4; ks++) {
             if (ks < ksteps) {
-              const uint64_t bhi = bhi0 + (uint64_t)(kb * KB_INC + ks * KS_INC);
-              const uint64_t blo = blo0 + (uint64_t)(kb * KB_INC + ks * KS_INC);
+              const uint64_t bhi = STREAM_F ? shi + (uint64_t)(ks * KS_INC) : bhi0 + (uint64_t)(kb * KB_INC + ks * KS_INC);
+              const uint64_t blo = STREAM_F ? slo + (uint64_t)(ks * KS_INC) : blo0 + (uint64_t)(kb * KB_INC + ks * KS_INC);
               const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
               if (p.passes == 3) {
                 tc_mma_tf32_ts(d_tmem, alo + ks * 8, bhi, idesc, first);
@@ -287,6 +322,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             }
           }
           tc_commit(a_free + 8 * at);                 // TMEM A stage reusable once these MMAs retire
+          if (STREAM_F) tc_commit(raw_free + 8 * at);   // ... and so are the F tiles of the shared-memory stage
           if (kb == nkb - 1) tc_commit(tmem_full + 8 * a);
         }
         __syncwarp();
@@ -305,7 +341,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         const int rs = (int)(kbg % RSTAGES), at = (int)(kbg % ASTAGES);
         const uint32_t rph = (uint32_t)((kbg / RSTAGES) & 1), aph = (uint32_t)((kbg / ASTAGES) & 1);
         mbar_wait(raw_full + 8 * rs, rph);
-        const uint8_t* src = smem_gen + 2 * F_BYTES + rs * XT_BYTES;
+        const uint8_t* src = smem_gen + (sX - smem) + rs * XSTRIDE;
         uint32_t hi[32], lo[32];
         if (X_MN) {
           // [4 r-groups][32 k rows][128 B of 32 r], 32-byte chunks XOR (k & 3): lane reads its r for every k
@@ -356,13 +392,16 @@ __global__ void __launch_bounds__(THREADS, 1)
     const uint32_t ebar = epi_bar + 16 * quarter;
     uint32_t eph0 = 0, eph1 = 0;                    // phases of the two "old block landed" barriers
     const bool readw = (p.beta != 0.f);
-    const int nblk = (p.m + 31) / 32;
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
       const int a = it & 1;
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-      const int b = (int)(tile / p.tiles_r);
-      const int rw = (int)(tile - (long long)b * p.tiles_r) * TM + quarter * 32;   // first row of this warp
+      const int b = (int)(tile / tiles_rc);
+      const int rem = (int)(tile - (long long)b * tiles_rc);
+      const int ct = rem / p.tiles_r;
+      const int cbase = ct * 128;                                   // first output column of this tile
+      const int nblk = (min(128, p.m - cbase) + 31) / 32;
+      const int rw = (rem - ct * p.tiles_r) * TM + quarter * 32;   // first row of this warp
       const long long r = rw + lane;
       // beta != 0: the old 32 x 32 block of D is TMA-loaded into the staging buffer it will be stored from
       auto load_old = [&](int blk) {
@@ -370,7 +409,7 @@ __global__ void __launch_bounds__(THREADS, 1)
           const int buf = blk & 1;
           tma_store_wait_read();      // the store that last used this buffer has been read out
           mbar_arrive_expect_tx(ebar + 8 * buf, EPI_STAGE_BYTES);
-          if (X_MN) tma_load_3d(stage_s + buf * EPI_STAGE_BYTES, &tmD, ebar + 8 * buf, rw, blk * 32, b);
+          if (OUT_R) tma_load_3d(stage_s + buf * EPI_STAGE_BYTES, &tmD, ebar + 8 * buf, rw, cbase + blk * 32, b);
           else tma_load_3d(stage_s + buf * EPI_STAGE_BYTES, &tmD, ebar + 8 * buf, blk * 32, rw, 0);
         }
       };
@@ -380,9 +419,9 @@ __global__ void __launch_bounds__(THREADS, 1)
       float* drow = p.D + (long long)b * p.d_bs + r * p.d_rs;
       const bool row_ok = r < p.rows;
       for (int blk = 0; blk < nblk; blk++) {
-        const int c0 = blk * 32;
+        const int c0 = cbase + blk * 32;
         uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * 128 + c0, v);
+        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * 128 + blk * 32, v);
         tc_wait_ld();
         if (p.tma_store) {
           // stage the block in shared memory in the order the output wants, then ONE bulk tensor store: full
@@ -396,7 +435,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             if (lane == 0) tma_store_wait_read1();  // the store issued two blocks ago has been read out
             __syncwarp();
           }
-          if (X_MN) {
+          if (OUT_R) {
             // output is contiguous along r (the lanes): smem [c][32 r]
 #pragma unroll
             for (int c = 0; c < 32; c++) {
@@ -422,7 +461,7 @@ __global__ void __launch_bounds__(THREADS, 1)
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {   // bulk groups are per thread: the same lane issues, commits and later waits
-            if (X_MN) tma_store_3d(&tmD, stage_s + buf * EPI_STAGE_BYTES, rw, c0, b);
+            if (OUT_R) tma_store_3d(&tmD, stage_s + buf * EPI_STAGE_BYTES, rw, c0, b);
             else tma_store_3d(&tmD, stage_s + buf * EPI_STAGE_BYTES, c0, rw, 0);
             tma_store_commit();
           }
@@ -465,6 +504,19 @@ __global__ void __launch_bounds__(THREADS, 1)
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// hi / lo halves of an FP32 matrix region (cols columns of ld floats each; the padding rows travel along)
+__global__ void split_hilo_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, long long n4) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* h4 = reinterpret_cast<float4*>(hi);
+  float4* l4 = reinterpret_cast<float4*>(lo);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 h, l;
+    split4(__ldcs(s4 + i), h, l);
+    h4[i] = h;
+    l4[i] = l;
   }
 }
 

@@ -386,6 +386,7 @@ int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, 
   memset(&p, 0, sizeof(p));
   p.rows = rows; p.m = m; p.n = n; p.batch = (int)batch;
   p.tiles_r = (int)((rows + tf32::TM - 1) / tf32::TM);
+  p.tiles_c = 1;
   p.total_tiles = (long long)p.tiles_r * batch;
   p.D = D; p.d_rs = d_rs; p.d_cs = d_cs; p.d_bs = d_bs;
   p.alpha = alpha; p.beta = beta;
@@ -399,13 +400,71 @@ int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, 
   if (!p.tma_store) tmD = tmX;   // unused by the kernel
   else if (rc) return rc;
   const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
-  if (x_mn && f_k) tf32::gemm_tf32x3_kernel<true, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmD, p);
-  else if (x_mn) tf32::gemm_tf32x3_kernel<true, false><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmD, p);
-  else if (f_k) tf32::gemm_tf32x3_kernel<false, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmD, p);
-  else tf32::gemm_tf32x3_kernel<false, false><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmD, p);
+  if (x_mn && f_k) tf32::gemm_tf32x3_kernel<true, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmF, tmD, p);
+  else if (x_mn) tf32::gemm_tf32x3_kernel<true, false><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmF, tmD, p);
+  else if (f_k) tf32::gemm_tf32x3_kernel<false, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmF, tmD, p);
+  else tf32::gemm_tf32x3_kernel<false, false><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmF, tmD, p);
   c->launches++;
   SCIMLOP_CUDA(c, cudaGetLastError());
   return SCIMLOP_OK;
+}
+
+// General Float32 GEMM on tcgen05 (3xTF32): C(M x N) = alpha * op(A)(M x K) * op(B)(K x N) + beta * C, any K and N.
+// X = op(A) streams through TMEM (split by the splitter warps), B is split ONCE into hi / lo halves (stream-ordered
+// scratch from cudaMallocAsync: 2 x the size of B) and streams through the same ring as 128-column tiles.
+int launch_tf32_stream(scimlop_context* c, bool transA, bool transB, long long M, long long N, long long K, float alpha,
+                       const float* A, long long lda, const float* B, long long ldb, float beta, float* C, long long ldc,
+                       int passes, cudaStream_t st) {
+  const long long bcols = transB ? K : N;              // stored columns of B (ldb floats each)
+  const size_t half = (size_t)ldb * (size_t)bcols * sizeof(float);
+  float* scratch = nullptr;
+  SCIMLOP_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&scratch), 2 * half, st));
+  float* Bhi = scratch;
+  float* Blo = scratch + (size_t)ldb * (size_t)bcols;
+  {
+    const long long n4 = (long long)(half / 16);
+    const int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)c->sm_count * 8);
+    tf32::split_hilo_kernel<<<grid, 256, 0, st>>>(B, Bhi, Blo, n4);
+    c->launches++;
+  }
+  CUtensorMap tmX, tmFhi, tmFlo, tmD;
+  int rc;
+  // X = op(A): transA ? K-major (k contiguous, rows r = M at stride lda) : MN-major (r contiguous)
+  if (!transA) rc = make_map_f32(c, &tmX, A, M, K, 1, lda * 4, 0, 32, 32, true);
+  else rc = make_map_f32(c, &tmX, A, K, M, 1, lda * 4, 0, 32, 128, false);
+  // F = op(B)(c = n, k): !transB: B stored K x N, k contiguous -> K-major; transB: stored N x K, c contiguous -> MN-major
+  for (int h = 0; h < 2 && !rc; h++) {
+    const float* base = h ? Blo : Bhi;
+    CUtensorMap* tm = h ? &tmFlo : &tmFhi;
+    if (!transB) rc = make_map_f32(c, tm, base, K, N, 1, ldb * 4, 0, 32, 128, false);
+    else rc = make_map_f32(c, tm, base, N, K, 1, ldb * 4, 0, 32, 32, true);
+  }
+  tf32::Params p;
+  memset(&p, 0, sizeof(p));
+  if (!rc) {
+    p.rows = M; p.m = (int)N; p.n = (int)K; p.batch = 1;
+    p.tiles_r = (int)((M + tf32::TM - 1) / tf32::TM);
+    p.tiles_c = (int)((N + 127) / 128);
+    p.total_tiles = (long long)p.tiles_r * p.tiles_c;
+    p.D = C; p.d_rs = 1; p.d_cs = ldc; p.d_bs = 0;
+    p.alpha = alpha; p.beta = beta;
+    p.vec_ok = 0;
+    p.passes = passes;
+    p.tma_store = aligned16(C) && ldc % 4 == 0;
+    if (p.tma_store) rc = make_map_f32(c, &tmD, C, M, N, 1, ldc * 4, 0, 32, 32, false, /*swizzle=*/false);
+    else tmD = tmX;
+  }
+  if (!rc) {
+    const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
+    if (!transA && !transB) tf32::gemm_tf32x3_kernel<true, true, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmFhi, tmFlo, tmD, p);
+    else if (!transA) tf32::gemm_tf32x3_kernel<true, false, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmFhi, tmFlo, tmD, p);
+    else if (!transB) tf32::gemm_tf32x3_kernel<false, true, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmFhi, tmFlo, tmD, p);
+    else tf32::gemm_tf32x3_kernel<false, false, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmFhi, tmFlo, tmD, p);
+    c->launches++;
+    if (cudaGetLastError() != cudaSuccess) rc = scimlop_fail(c, SCIMLOP_ERR_CUDA, "gemm_tf32x3_kernel<stream> launch failed");
+  }
+  cudaFreeAsync(scratch, st);
+  return rc;
 }
 
 template <>
@@ -434,6 +493,12 @@ int gemm_dispatch<float>(scimlop_context* c, int precision, bool transA, bool tr
     const int rc = launch_skinny<float>(c, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, st);
     if (rc >= 0) return rc;
   }
+  // large Float32 products: the streamed-operand tcgen05 kernel (the FFMA kernel below peaks at ~27 TFLOP/s)
+  if (precision != SCIMLOP_PREC_FP32_EXACT && nscale == 0 && batch == 1 && M >= 128 && N >= 16 && K >= 32 &&
+      2.0 * (double)M * (double)N * (double)K >= 1e8 && M < 2147483647LL && N < 2147483647LL && K < 2147483647LL &&
+      aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0)
+    return launch_tf32_stream(c, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc,
+                              precision == SCIMLOP_PREC_TF32 ? 1 : 3, st);
   if (precision == SCIMLOP_PREC_TF32)
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED,
                         "single-pass TF32 was requested but this shape is not eligible for the tcgen05 path");
@@ -532,6 +597,10 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   optin2((const void*)tf32::gemm_tf32x3_kernel<false, false>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<false, true>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<true, false>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<true, true, true>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<true, false, true>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<false, true, true>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<false, false, true>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<true, true>);
   auto optin3 = [&](const void* f) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, skinny::SMEM_BYTES);

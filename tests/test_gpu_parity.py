@@ -868,3 +868,44 @@ def test_matrix_operator_few_columns(sb, case, trans, dtype):
         wv = sb.DeviceArray.full((M,), float("nan"), dtype)
         sb.mul_(wv, L, dev(sb, v[:, 0].copy()))
         assert np.linalg.norm(wv.numpy() - want[:, 0]) <= tol * scale
+
+
+# ---- general Float32 GEMM on tcgen05 (streamed pre-split operand): large MatrixOperator products ---------------
+TF32_STREAM_CASES = [
+    # M, N, K, transA, transB
+    (512, 256, 512, 0, 0), (512, 256, 512, 1, 0), (512, 256, 512, 0, 1), (512, 256, 512, 1, 1),
+    (1000, 200, 1000, 0, 0), (300, 260, 700, 0, 0), (300, 260, 700, 1, 0), (2048, 16, 2048, 0, 0),
+    (132, 1032, 380, 0, 1), (4096, 1024, 4096, 0, 0), (4096, 1024, 4096, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", TF32_STREAM_CASES)
+@pytest.mark.parametrize("precision,tol", [(0, 1e-5), (3, 1e-5), (2, 3e-3)])
+def test_gemm_f32_streamed_tensor_core(sb, case, precision, tol):
+    """`mul!(w, L::MatrixOperator{Float32}, v)` with a big matrix and many columns (config 4's dense part in
+    Float32): arbitrary M, N, K on the tcgen05 3xTF32 kernel with the pre-split second operand streamed."""
+    import torch
+    M, N, K, ta, tb = case
+    rng = np.random.default_rng(M + 3 * N + 7 * K + ta + 2 * tb)
+    A = rnd(rng, *((K, M) if ta else (M, K)), dtype=np.float32) - np.float32(0.5)
+    B = rnd(rng, *((N, K) if tb else (K, N)), dtype=np.float32) - np.float32(0.5)
+    C0 = rnd(rng, M, N, dtype=np.float32)
+    opA = (A.T if ta else A).astype(np.float64)
+    opB = (B.T if tb else B).astype(np.float64)
+    prod = opA @ opB
+    scale = np.linalg.norm(np.abs(opA) @ np.abs(opB))      # cancellation-free reference magnitude
+    h = sb.handle(0)
+    for (a, b) in ((0.7, 0.3), (None, None)):
+        dA, dB = dev(sb, A), dev(sb, B)
+        dC = dev(sb, C0 if b else np.full_like(C0, np.nan))
+        pa = C.byref(C.c_float(a)) if a is not None else None
+        pb = C.byref(C.c_float(b)) if b is not None else None
+        rc = h.lib.scimlop_gemm_strided_batched(
+            h.ptr, 1, precision, ta, tb, M, N, K, pa, C.c_void_p(dA.ptr), A.shape[0], 0, C.c_void_p(dB.ptr), B.shape[0], 0,
+            pb, C.c_void_p(dC.ptr), M, 0, 1, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        h.check(rc, "gemm f32 stream")
+        got = dC.numpy().astype(np.float64)
+        want = (1.0 if a is None else a) * prod + (b * C0 if b else 0.0)
+        assert np.isfinite(got).all()
+        err = np.linalg.norm(got - want) / (scale + (np.linalg.norm(C0) if b else 0.0))
+        assert err <= tol, f"{case} precision={precision} alpha={a}: err {err:.3e}"
