@@ -158,13 +158,13 @@ __device__ __forceinline__ void split4(float4 x, float4& hi, float4& lo) {
 // is no longer a small resident factor but streams through the SAME ring as X, as 128-column x 32-k tiles of its
 // PRE-SPLIT halves F_hi / F_lo (tmF / tmF2; split once per call by split_hilo_kernel, so that the B operand needs no
 // in-kernel shared->shared pass).  A ring stage is then X | F_hi | F_lo (3 x 16 KB) and is released by the four
-// splitter warps AND by the tcgen05.commit of the MMAs that read it.  The output is r-contiguous (column-major C).
-template <bool X_MN, bool F_K, bool STREAM_F = false>
+// splitter warps AND by the tcgen05.commit of the MMAs that read it.
+template <bool X_MN, bool F_K, bool STREAM_F = false, bool OUT_R = X_MN>
 __global__ void __launch_bounds__(THREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmF,
                        const __grid_constant__ CUtensorMap tmF2, const __grid_constant__ CUtensorMap tmD, const Params p) {
   static_assert(!STREAM_F || RSTAGES == ASTAGES, "streamed-F mode indexes both rings with one counter");
-  constexpr bool OUT_R = STREAM_F ? true : X_MN;          // output contiguous along r (the TMEM lanes)
+  // OUT_R: the output is contiguous along r (the TMEM lanes); else along c.  Resident-factor mode: OUT_R == X_MN.
   constexpr uint32_t XSTRIDE = STREAM_F ? 3 * XT_BYTES : XT_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(THREADS, 1)
           tma_store_wait_read();      // the store that last used this buffer has been read out
           mbar_arrive_expect_tx(ebar + 8 * buf, EPI_STAGE_BYTES);
           if (OUT_R) tma_load_3d(stage_s + buf * EPI_STAGE_BYTES, &tmD, ebar + 8 * buf, rw, cbase + blk * 32, b);
-          else tma_load_3d(stage_s + buf * EPI_STAGE_BYTES, &tmD, ebar + 8 * buf, blk * 32, rw, 0);
+          else tma_load_3d(stage_s + buf * EPI_STAGE_BYTES, &tmD, ebar + 8 * buf, cbase + blk * 32, rw, 0);
         }
       };
       if (p.tma_store && readw) load_old(0);        // overlaps the wait for the accumulator

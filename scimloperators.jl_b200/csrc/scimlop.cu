@@ -409,57 +409,81 @@ int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, 
   return SCIMLOP_OK;
 }
 
-// General Float32 GEMM on tcgen05 (3xTF32): C(M x N) = alpha * op(A)(M x K) * op(B)(K x N) + beta * C, any K and N.
-// X = op(A) streams through TMEM (split by the splitter warps), B is split ONCE into hi / lo halves (stream-ordered
-// scratch from cudaMallocAsync: 2 x the size of B) and streams through the same ring as 128-column tiles.
-int launch_tf32_stream(scimlop_context* c, bool transA, bool transB, long long M, long long N, long long K, float alpha,
-                       const float* A, long long lda, const float* B, long long ldb, float beta, float* C, long long ldc,
-                       int passes, cudaStream_t st) {
-  const long long bcols = transB ? K : N;              // stored columns of B (ldb floats each)
-  const size_t half = (size_t)ldb * (size_t)bcols * sizeof(float);
+// General Float32 GEMM on tcgen05 (3xTF32): C_b(M x N) = alpha * op(A_b)(M x K) * op(B)(K x N) + beta * C_b, any K, N.
+// One operand ("X") streams through the splitter warps into TMEM, the other ("F") is split ONCE into hi / lo halves
+// (stream-ordered scratch from cudaMallocAsync: 2 x its size) and streams through the same ring as 128-column tiles.
+// F is the SMALLER operand: `f_is_a == false`: X = op(A), F = op(B), rows = M (output contiguous along r; batches of
+// A / C with one shared B allowed); `f_is_a == true`: X = op(B)^T, F = op(A), rows = N (output contiguous along c).
+int launch_tf32_stream(scimlop_context* c, bool f_is_a, bool transA, bool transB, long long M, long long N, long long K,
+                       float alpha, const float* A, long long lda, long long sA, const float* B, long long ldb, float beta,
+                       float* C, long long ldc, long long sC, long long batch, int passes, cudaStream_t st) {
+  const float* Fsrc = f_is_a ? A : B;
+  const long long ldf = f_is_a ? lda : ldb;
+  const long long fcols = f_is_a ? (transA ? M : K) : (transB ? K : N);   // stored columns of F (ldf floats each)
+  const size_t half = (size_t)ldf * (size_t)fcols * sizeof(float);
   float* scratch = nullptr;
   SCIMLOP_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&scratch), 2 * half, st));
-  float* Bhi = scratch;
-  float* Blo = scratch + (size_t)ldb * (size_t)bcols;
+  float* Fhi = scratch;
+  float* Flo = scratch + (size_t)ldf * (size_t)fcols;
   {
     const long long n4 = (long long)(half / 16);
     const int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)c->sm_count * 8);
-    tf32::split_hilo_kernel<<<grid, 256, 0, st>>>(B, Bhi, Blo, n4);
+    tf32::split_hilo_kernel<<<grid, 256, 0, st>>>(Fsrc, Fhi, Flo, n4);
     c->launches++;
   }
+  // roles
+  const long long rows = f_is_a ? N : M, mcols = f_is_a ? M : N;
+  const float* X = f_is_a ? B : A;
+  const long long ldx = f_is_a ? ldb : lda;
+  // X(r, k): !f_is_a: A(m, k): transA ? K-major : MN-major;  f_is_a: B(k, n): transB (stored N x K) ? MN-major : K-major
+  const bool x_mn = f_is_a ? transB : !transA;
+  // F(c, k): !f_is_a: B(k, n): transB ? MN-major : K-major;   f_is_a: A(m, k): transA (stored K x M) ? K-major : MN-major
+  const bool f_k = f_is_a ? transA : !transB;
+  const bool xb = !f_is_a && batch > 1 && sA != 0;
   CUtensorMap tmX, tmFhi, tmFlo, tmD;
   int rc;
-  // X = op(A): transA ? K-major (k contiguous, rows r = M at stride lda) : MN-major (r contiguous)
-  if (!transA) rc = make_map_f32(c, &tmX, A, M, K, 1, lda * 4, 0, 32, 32, true);
-  else rc = make_map_f32(c, &tmX, A, K, M, 1, lda * 4, 0, 32, 128, false);
-  // F = op(B)(c = n, k): !transB: B stored K x N, k contiguous -> K-major; transB: stored N x K, c contiguous -> MN-major
+  if (x_mn) rc = make_map_f32(c, &tmX, X, rows, K, xb ? batch : 1, ldx * 4, sA * 4, 32, 32, true);
+  else rc = make_map_f32(c, &tmX, X, K, rows, xb ? batch : 1, ldx * 4, sA * 4, 32, 128, false);
   for (int h = 0; h < 2 && !rc; h++) {
-    const float* base = h ? Blo : Bhi;
+    const float* base = h ? Flo : Fhi;
     CUtensorMap* tm = h ? &tmFlo : &tmFhi;
-    if (!transB) rc = make_map_f32(c, tm, base, K, N, 1, ldb * 4, 0, 32, 128, false);
-    else rc = make_map_f32(c, tm, base, N, K, 1, ldb * 4, 0, 32, 32, true);
+    if (f_k) rc = make_map_f32(c, tm, base, K, mcols, 1, ldf * 4, 0, 32, 128, false);
+    else rc = make_map_f32(c, tm, base, mcols, K, 1, ldf * 4, 0, 32, 32, true);
   }
   tf32::Params p;
   memset(&p, 0, sizeof(p));
   if (!rc) {
-    p.rows = M; p.m = (int)N; p.n = (int)K; p.batch = 1;
-    p.tiles_r = (int)((M + tf32::TM - 1) / tf32::TM);
-    p.tiles_c = (int)((N + 127) / 128);
-    p.total_tiles = (long long)p.tiles_r * p.tiles_c;
-    p.D = C; p.d_rs = 1; p.d_cs = ldc; p.d_bs = 0;
+    p.rows = rows; p.m = (int)mcols; p.n = (int)K; p.batch = (int)batch;
+    p.tiles_r = (int)((rows + tf32::TM - 1) / tf32::TM);
+    p.tiles_c = (int)((mcols + 127) / 128);
+    p.total_tiles = (long long)p.tiles_r * p.tiles_c * batch;
+    p.D = C;
+    p.d_rs = f_is_a ? ldc : 1; p.d_cs = f_is_a ? 1 : ldc; p.d_bs = sC;
     p.alpha = alpha; p.beta = beta;
-    p.vec_ok = 0;
+    p.vec_ok = f_is_a && aligned16(C) && ldc % 4 == 0;
+    p.x_batched = xb;
     p.passes = passes;
-    p.tma_store = aligned16(C) && ldc % 4 == 0;
-    if (p.tma_store) rc = make_map_f32(c, &tmD, C, M, N, 1, ldc * 4, 0, 32, 32, false, /*swizzle=*/false);
-    else tmD = tmX;
+    p.tma_store = aligned16(C) && ldc % 4 == 0 && (batch == 1 || sC % 4 == 0);
+    if (!p.tma_store) tmD = tmX;
+    else if (!f_is_a) rc = make_map_f32(c, &tmD, C, M, N, batch, ldc * 4, sC * 4, 32, 32, false, /*swizzle=*/false);
+    else rc = make_map_f32(c, &tmD, C, M, N, 1, ldc * 4, 0, 32, 32, false, /*swizzle=*/true);
   }
   if (!rc) {
     const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
-    if (!transA && !transB) tf32::gemm_tf32x3_kernel<true, true, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmFhi, tmFlo, tmD, p);
-    else if (!transA) tf32::gemm_tf32x3_kernel<true, false, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmFhi, tmFlo, tmD, p);
-    else if (!transB) tf32::gemm_tf32x3_kernel<false, true, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmFhi, tmFlo, tmD, p);
-    else tf32::gemm_tf32x3_kernel<false, false, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmFhi, tmFlo, tmD, p);
+#define SCIMLOP_TF32S(XM, FK, OR) \
+  tf32::gemm_tf32x3_kernel<XM, FK, true, OR><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmFhi, tmFlo, tmD, p)
+    if (!f_is_a) {
+      if (x_mn && f_k) SCIMLOP_TF32S(true, true, true);
+      else if (x_mn) SCIMLOP_TF32S(true, false, true);
+      else if (f_k) SCIMLOP_TF32S(false, true, true);
+      else SCIMLOP_TF32S(false, false, true);
+    } else {
+      if (x_mn && f_k) SCIMLOP_TF32S(true, true, false);
+      else if (x_mn) SCIMLOP_TF32S(true, false, false);
+      else if (f_k) SCIMLOP_TF32S(false, true, false);
+      else SCIMLOP_TF32S(false, false, false);
+    }
+#undef SCIMLOP_TF32S
     c->launches++;
     if (cudaGetLastError() != cudaSuccess) rc = scimlop_fail(c, SCIMLOP_ERR_CUDA, "gemm_tf32x3_kernel<stream> launch failed");
   }
@@ -493,12 +517,20 @@ int gemm_dispatch<float>(scimlop_context* c, int precision, bool transA, bool tr
     const int rc = launch_skinny<float>(c, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, st);
     if (rc >= 0) return rc;
   }
-  // large Float32 products: the streamed-operand tcgen05 kernel (the FFMA kernel below peaks at ~27 TFLOP/s)
-  if (precision != SCIMLOP_PREC_FP32_EXACT && nscale == 0 && batch == 1 && M >= 128 && N >= 16 && K >= 32 &&
-      2.0 * (double)M * (double)N * (double)K >= 1e8 && M < 2147483647LL && N < 2147483647LL && K < 2147483647LL &&
-      aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0)
-    return launch_tf32_stream(c, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc,
-                              precision == SCIMLOP_PREC_TF32 ? 1 : 3, st);
+  // large Float32 products: the streamed-operand tcgen05 kernel (the FFMA kernel below peaks at ~27 TFLOP/s).
+  // The smaller operand is the one that gets pre-split; batches need one shared B (the outer Kronecker modes).
+  if (precision != SCIMLOP_PREC_FP32_EXACT && nscale == 0 && K >= 32 && (batch == 1 || sB == 0) &&
+      2.0 * (double)M * (double)N * (double)K * (double)batch >= 1e8 && M < 2147483647LL && N < 2147483647LL &&
+      K < 2147483647LL && batch < 2147483647LL && aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0 &&
+      (batch == 1 || sA % 4 == 0)) {
+    const int passes = precision == SCIMLOP_PREC_TF32 ? 1 : 3;
+    const bool a_small = batch == 1 && (double)M * (double)K < (double)K * (double)N;
+    if (a_small && N >= 128 && M >= 16)
+      return launch_tf32_stream(c, true, transA, transB, M, N, K, alpha, A, lda, 0, B, ldb, beta, C, ldc, 0, 1, passes, st);
+    if (M * batch >= 128 && N >= 16)
+      return launch_tf32_stream(c, false, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, beta, C, ldc, sC, batch,
+                                passes, st);
+  }
   if (precision == SCIMLOP_PREC_TF32)
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED,
                         "single-pass TF32 was requested but this shape is not eligible for the tcgen05 path");
@@ -597,10 +629,14 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   optin2((const void*)tf32::gemm_tf32x3_kernel<false, false>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<false, true>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<true, false>);
-  optin2((const void*)tf32::gemm_tf32x3_kernel<true, true, true>);
-  optin2((const void*)tf32::gemm_tf32x3_kernel<true, false, true>);
-  optin2((const void*)tf32::gemm_tf32x3_kernel<false, true, true>);
-  optin2((const void*)tf32::gemm_tf32x3_kernel<false, false, true>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<true, true, true, true>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<true, false, true, true>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<false, true, true, true>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<false, false, true, true>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<true, true, true, false>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<true, false, true, false>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<false, true, true, false>);
+  optin2((const void*)tf32::gemm_tf32x3_kernel<false, false, true, false>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<true, true>);
   auto optin3 = [&](const void* f) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, skinny::SMEM_BYTES);

@@ -876,6 +876,9 @@ TF32_STREAM_CASES = [
     (512, 256, 512, 0, 0), (512, 256, 512, 1, 0), (512, 256, 512, 0, 1), (512, 256, 512, 1, 1),
     (1000, 200, 1000, 0, 0), (300, 260, 700, 0, 0), (300, 260, 700, 1, 0), (2048, 16, 2048, 0, 0),
     (132, 1032, 380, 0, 1), (4096, 1024, 4096, 0, 0), (4096, 1024, 4096, 1, 0),
+    # the FIRST operand is the small one (it is the one that gets pre-split; output contiguous along c)
+    (512, 4096, 512, 0, 0), (512, 4096, 512, 1, 0), (512, 4096, 512, 0, 1), (512, 4096, 512, 1, 1),
+    (200, 3000, 260, 0, 0), (16, 5000, 700, 1, 0),
 ]
 
 
@@ -909,3 +912,22 @@ def test_gemm_f32_streamed_tensor_core(sb, case, precision, tol):
         assert np.isfinite(got).all()
         err = np.linalg.norm(got - want) / (scale + (np.linalg.norm(C0) if b else 0.0))
         assert err <= tol, f"{case} precision={precision} alpha={a}: err {err:.3e}"
+
+
+@pytest.mark.parametrize("factor", [256, 512, 200])
+def test_tpo_float32_large_factors(sb, factor):
+    """Float32 Kronecker product with factors beyond the resident-factor limit (128): both mode products run on the
+    streamed tcgen05 kernel (stage 1 with the factor pre-split, stage 2 batched with the shared factor)."""
+    rng = np.random.default_rng(factor)
+    n, k = factor, 24
+    A, B = rnd(rng, n, n, dtype=np.float32) - np.float32(0.5), rnd(rng, n, n, dtype=np.float32) - np.float32(0.5)
+    v, w0 = rnd(rng, n * n, k, dtype=np.float32), rnd(rng, n * n, k, dtype=np.float32)
+    dv = dev(sb, v)
+    L = sb.cache_operator(sb.kron(A, B), dv)
+    want = R.kron_apply([A.astype(np.float64), B.astype(np.float64)], v.astype(np.float64))
+    scale = np.linalg.norm(R.kron_apply([np.abs(A).astype(np.float64), np.abs(B).astype(np.float64)], np.abs(v).astype(np.float64)))
+    got = sb.mul_(dev(sb, np.full_like(w0, np.nan)), L, dv).numpy()
+    assert np.isfinite(got).all()
+    assert np.linalg.norm(got - want) <= 1e-5 * scale
+    got5 = sb.mul_(dev(sb, w0), L, dv, 0.7, 0.3).numpy()
+    assert np.linalg.norm(got5 - (0.7 * want + 0.3 * w0)) <= 1e-5 * (scale + np.linalg.norm(w0))
