@@ -22,6 +22,7 @@ struct scimlop_context {
   int sm_count;
   int sm_reserve;  // SMs left free by the persistent GEMM kernels (for concurrently running NCCL kernels)
   scimlop_encode_tiled_fn encode_tiled;
+  cudaMemPool_t pool;        // stream-ordered scratch of the streamed Float32 GEMM (kept across calls: no release)
   int dmma_max_clusters[9];  // co-resident clusters of the split-K DMMA kernel per cluster size (occupancy query)
   char last_error[512];
   int64_t launches;

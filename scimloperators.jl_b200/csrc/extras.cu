@@ -351,6 +351,7 @@ extern "C" int scimlop_destroy(scimlop_handle_t h) {
   }
   if (h->stage) cudaFree(h->stage);
   if (h->comm_scratch) cudaFree(h->comm_scratch);
+  if (h->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(h->pool); }
   h->magic = 0;
   delete h;
   return SCIMLOP_OK;

@@ -58,6 +58,8 @@ struct Params {
   int batch;
   int tiles_r;           // ceil(rows / 128)
   int tiles_c;           // STREAM_F: ceil(m / 128) column tiles; 1 otherwise
+  int c_fast;            // tile order: column tiles fastest (concurrent CTAs share an X row tile through L2; right when
+                         // the pre-split operand is L2-resident), else row tiles fastest (they share an F panel)
   long long total_tiles; // tiles_r * tiles_c * batch
   float* D;
   long long d_rs, d_cs, d_bs;  // D(r, c, b) at r*d_rs + c*d_cs + b*d_bs
@@ -247,8 +249,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = (int)(tile / tiles_rc);
       const int rem = (int)(tile - (long long)b * tiles_rc);
-      const int ct = rem / p.tiles_r;
-      const int r0 = (rem - ct * p.tiles_r) * TM;
+      const int ct = p.c_fast ? rem % p.tiles_c : rem / p.tiles_r;
+      const int r0 = (p.c_fast ? rem / p.tiles_c : rem - ct * p.tiles_r) * TM;
       const int bx = p.x_batched ? b : 0;
       for (int kb = 0; kb < nkb; kb++) {
         mbar_wait(raw_free + 8 * stage, phase ^ 1);
@@ -398,10 +400,10 @@ __global__ void __launch_bounds__(THREADS, 1)
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
       const int b = (int)(tile / tiles_rc);
       const int rem = (int)(tile - (long long)b * tiles_rc);
-      const int ct = rem / p.tiles_r;
+      const int ct = p.c_fast ? rem % p.tiles_c : rem / p.tiles_r;
       const int cbase = ct * 128;                                   // first output column of this tile
       const int nblk = (min(128, p.m - cbase) + 31) / 32;
-      const int rw = (rem - ct * p.tiles_r) * TM + quarter * 32;   // first row of this warp
+      const int rw = (p.c_fast ? rem / p.tiles_c : rem - ct * p.tiles_r) * TM + quarter * 32;   // first row of this warp
       const long long r = rw + lane;
       // beta != 0: the old 32 x 32 block of D is TMA-loaded into the staging buffer it will be stored from
       auto load_old = [&](int blk) {
