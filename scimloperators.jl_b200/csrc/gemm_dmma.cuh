@@ -80,25 +80,37 @@ __device__ __forceinline__ uint32_t tile_off(int o, int k) {
 // thread-block CLUSTER, the K range divided over the cluster's CTAs, partial tiles summed through distributed
 // shared memory in rank order (each rank reduces and stores 1/size of the tile).  Launched with
 // grid = cluster size x tiles.
+// PEER = true is the fused compute + all-gather form with BULK stores: the ring shrinks to 3 stages and the freed
+// shared memory holds one finished 128 x 128 tile, which ONE thread then sends to the local C and to every peer's
+// C with a bulk tensor store each (cp.async.bulk.tensor shared -> global over NVLink: full-size packets, no LSU
+// traffic, asynchronous to the next tile's DMMAs).  Needs beta == 0, no row scalings, TMA-addressable C.
+constexpr int PEER_STAGES = 3;
+constexpr int PEER_SMEM_BYTES = PEER_STAGES * STAGE_BYTES + BM * BN * 8 + 1024 + 256;
+struct PeerMaps {
+  CUtensorMap m[8];   // [0] = local C, [1..npeer] = the peers' C (same geometry)
+};
 constexpr int PART_PITCH = BM + 8;   // doubles per column of the partial tile in shared memory (conflict-free stores)
 static_assert(PART_PITCH * BN * 8 <= STAGES * STAGE_BYTES, "partial tile must fit in the (idle) operand ring");
 
-template <bool A_KC, bool B_OC, bool SPLIT = false>
+template <bool A_KC, bool B_OC, bool SPLIT = false, bool PEER = false>
 __global__ void __launch_bounds__(THREADS, 1)
     gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const Params p) {
+                     const Params p, const __grid_constant__ PeerMaps pm) {
+  static_assert(!(SPLIT && PEER), "split-K and peer stores are separate launch modes");
+  constexpr int NSTAGE = PEER ? PEER_STAGES : STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 128B swizzle patterns repeat every 1024 B: align the tile ring (in the 32-bit shared window).
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t full_bar = smem + STAGES * STAGE_BYTES;  // STAGES x 8 B
-  const uint32_t empty_bar = full_bar + STAGES * 8;
+  const uint32_t out_tile = smem + NSTAGE * STAGE_BYTES;   // PEER: the finished tile, dense [n][128 m]
+  const uint32_t full_bar = out_tile + (PEER ? BM * BN * 8 : 0);  // NSTAGE x 8 B
+  const uint32_t empty_bar = full_bar + NSTAGE * 8;
   const uint32_t scratch = full_bar + 128;  // one word per consumer warp (mbar_arrive_after_loads)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) {
+    for (int s = 0; s < NSTAGE; s++) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, CONSUMER_WARPS);
     }
@@ -150,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
             for (int q = 0; q < 8; q++) tma_load_3d(sB + q * 2048, &tmB, bar, n0 + 16 * q, k0, bb);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       SCIMLOP_MMA_STEP(a0, b0);
       // prefetch step 0 of the next stage (next k-block, or the first k-block of this CTA's next tile)
       const uint32_t done_bar = empty_bar + 8 * stage;
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       if (!(last_tile && kb == nk - 1)) {
         mbar_wait(full_bar + 8 * stage, phase);
         SCIMLOP_LOAD_FRAGS(a0, b0, stage * STAGE_BYTES, 0);
@@ -308,6 +320,30 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       cluster_sync_all();   // nobody leaves while a peer may still read its partial tile
       return;
+    }
+    if (PEER) {
+      // ---- bulk-store epilogue: tile -> shared memory -> one bulk tensor store per destination ----
+      if (threadIdx.x == 0) tma_store_wait_read();      // the previous tile's stores have been read out of out_tile
+      asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
+      {
+        const double alpha = p.alpha;
+        const uint32_t obase = out_tile + (uint32_t)(((wn * 32 + g) * BM + wm * 64 + 2 * t) * 8);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(obase + (uint32_t)((8 * j * BM + 8 * i) * 8)),
+                         "d"(alpha * acc[i][j][0]), "d"(alpha * acc[i][j][1])
+                         : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
+      if (threadIdx.x == 0) {
+        for (int q = 0; q <= p.npeer; q++) tma_store_3d(&pm.m[q], out_tile, mt * BM, nt * BN, b);
+        tma_store_commit();
+        if (last_tile) tma_store_wait_all();              // everything has landed before the CTA retires
+      }
+      continue;
     }
     // ---- fused epilogue: rowscale, alpha, beta, store (the next tile's first stages are already in flight) ----
     const int mbase = mt * BM + wm * 64 + 2 * t;

@@ -162,6 +162,30 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
     p.vec_ok = p.vec_ok && aligned16(g_peers.ptr[q]);
   }
   if (g_peers.n > 0 && beta != 0.0) return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "peer targets need beta == 0");
+  static dmma::PeerMaps pmaps_unused;   // the non-peer kernels ignore it
+  dmma::PeerMaps& pmaps = pmaps_unused;
+  // fused all-gather with bulk stores: one 3-D {M, N, batch} map per destination, box = one output tile
+  dmma::PeerMaps peer_maps;
+  const bool peer_bulk = g_peers.n > 0 && nscale == 0 && beta == 0.0 && p.vec_ok && !transA && getenv("SCIMLOP_PEER_LSU") == nullptr;
+  if (peer_bulk) {
+    for (int q = 0; q <= g_peers.n; q++) {
+      double* base = q == 0 ? C : static_cast<double*>(g_peers.ptr[q - 1]);
+      cuuint64_t gdim[3] = {(cuuint64_t)M, (cuuint64_t)N, (cuuint64_t)batch};
+      cuuint64_t gstr[2] = {(cuuint64_t)ldc * 8, batch > 1 ? (cuuint64_t)sC * 8 : (cuuint64_t)ldc * 8 * (cuuint64_t)N};
+      cuuint32_t box[3] = {dmma::BM, dmma::BN, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = c->encode_tiled(&peer_maps.m[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return scimlop_fail(c, SCIMLOP_ERR_CUDA, "cuTensorMapEncodeTiled(peer C %d) failed (CUresult %d)", q, (int)r);
+    }
+    const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
+    if (!transB) dmma::gemm_dmma_kernel<false, false, false, true><<<grid, dmma::THREADS, dmma::PEER_SMEM_BYTES, st>>>(tmA, tmB, p, peer_maps);
+    else dmma::gemm_dmma_kernel<false, true, false, true><<<grid, dmma::THREADS, dmma::PEER_SMEM_BYTES, st>>>(tmA, tmB, p, peer_maps);
+    c->launches++;
+    SCIMLOP_CUDA(c, cudaGetLastError());
+    return SCIMLOP_OK;
+  }
   // few tiles (vector-input Kronecker products, small operators): split K over a thread-block cluster.  Pick the
   // cluster size with the smallest modelled time: waves x (k-blocks per CTA x 2.2 us + reduction); the number of
   // co-resident clusters comes from the occupancy query at handle creation (8-CTA clusters do not tile all SMs).
@@ -191,19 +215,19 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
     cfg.attrs = at;
     cfg.numAttrs = 1;
     cudaError_t e;
-    if (!transA && !transB) e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<false, false, true>, tmA, tmB, p);
-    else if (!transA && transB) e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<false, true, true>, tmA, tmB, p);
-    else if (transA && !transB) e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<true, false, true>, tmA, tmB, p);
-    else e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<true, true, true>, tmA, tmB, p);
+    if (!transA && !transB) e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<false, false, true>, tmA, tmB, p, pmaps);
+    else if (!transA && transB) e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<false, true, true>, tmA, tmB, p, pmaps);
+    else if (transA && !transB) e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<true, false, true>, tmA, tmB, p, pmaps);
+    else e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<true, true, true>, tmA, tmB, p, pmaps);
     c->launches++;
     SCIMLOP_CUDA(c, e);
     return SCIMLOP_OK;
   }
   const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
-  if (!transA && !transB) dmma::gemm_dmma_kernel<false, false><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
-  else if (!transA && transB) dmma::gemm_dmma_kernel<false, true><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
-  else if (transA && !transB) dmma::gemm_dmma_kernel<true, false><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
-  else dmma::gemm_dmma_kernel<true, true><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p);
+  if (!transA && !transB) dmma::gemm_dmma_kernel<false, false><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p, pmaps);
+  else if (!transA && transB) dmma::gemm_dmma_kernel<false, true><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p, pmaps);
+  else if (transA && !transB) dmma::gemm_dmma_kernel<true, false><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p, pmaps);
+  else dmma::gemm_dmma_kernel<true, true><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p, pmaps);
   c->launches++;
   SCIMLOP_CUDA(c, cudaGetLastError());
   return SCIMLOP_OK;
@@ -618,6 +642,8 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   optin((const void*)dmma::gemm_dmma_kernel<false, true>);
   optin((const void*)dmma::gemm_dmma_kernel<true, false>);
   optin((const void*)dmma::gemm_dmma_kernel<true, true>);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)dmma::gemm_dmma_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dmma::PEER_SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)dmma::gemm_dmma_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dmma::PEER_SMEM_BYTES);
   optin((const void*)dmma::gemm_dmma_kernel<false, false, true>);
   optin((const void*)dmma::gemm_dmma_kernel<false, true, true>);
   optin((const void*)dmma::gemm_dmma_kernel<true, false, true>);

@@ -70,3 +70,50 @@ def test_cuda_path_against_golden(dtype, tol):
     assert R.rel_err(sb.mul_(dev(G["tree_w0"]), Lb, v, ALPHA, BETA).numpy(), G["btree_out5"]) <= tol
     S = sb.cache_operator(sb.kronsum(F(G["ksum_A"].astype(dtype)), F(G["ksum_B"].astype(dtype))), dev(G["ksum_v"]))
     assert R.rel_err(sb.mul_(dev(G["ksum_w0"]), S, dev(G["ksum_v"]), ALPHA, BETA).numpy(), G["ksum_out5"]) <= tol
+
+
+# ---- ldiv!, BlockDiagonalOperator, WOperator (tests/golden/make_golden_solve.py) ----
+GS = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solve_blocks_golden.npz"))
+
+
+def test_oracle_solve_and_blocks_against_golden():
+    A, B, Cm = F(GS["ldiv_A"]), F(GS["ldiv_B"]), F(GS["ldiv_C"])
+    assert R.rel_err(R.tpo_ldiv(A, B, F(GS["ldiv2_v"])), GS["ldiv2_out"]) < 1e-12
+    assert R.rel_err(R.tpo_ldiv(A, B, GS["ldiv2_vec"]), GS["ldiv2_outvec"]) < 1e-12
+    assert R.rel_err(R.tpo_ldiv(A, np.kron(B, Cm), F(GS["ldiv3_v"])), GS["ldiv3_out"]) < 1e-12
+    assert R.rel_err(R.kron_solve([A, B, Cm], GS["ldiv3_vec"]), GS["ldiv3_outvec"]) < 1e-12
+    blocks = [GS["blk_b0"], np.diag(GS["blk_d1"]), GS["blk_b2"], np.eye(3)]
+    assert R.rel_err(R.block_diag_mul(np.full_like(GS["blk_w0"], np.nan), blocks, GS["blk_v"]), GS["blk_out3"]) < 1e-13
+    assert R.rel_err(R.block_diag_mul(GS["blk_w0"].copy(), blocks, GS["blk_v"], ALPHA, BETA), GS["blk_out5"]) < 1e-13
+    g = float(GS["w_gamma"])
+    assert R.rel_err(R.woperator_mul(np.empty(16), GS["w_M"], g, GS["w_J"], GS["w_b"]), GS["w_out"]) < 1e-13
+    assert R.rel_err(R.woperator_mul(np.empty(16), 2.0, g, GS["w_J"], GS["w_b"]), GS["w_out_uniform"]) < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+def test_cuda_solve_and_blocks_against_golden(dtype, tol):
+    import scimlop_b200 as sb
+    dev = lambda a: sb.DeviceArray.from_numpy(F(np.asarray(a, dtype=dtype)))
+    A, B, Cm = (F(GS[k].astype(dtype)) for k in ("ldiv_A", "ldiv_B", "ldiv_C"))
+    for nf, mats in ((2, (A, B)), (3, (A, B, Cm))):
+        for vk, ok in ((f"ldiv{nf}_v", f"ldiv{nf}_out"), (f"ldiv{nf}_vec", f"ldiv{nf}_outvec")):
+            v = dev(GS[vk])
+            L = sb.cache_operator(sb.factorize(sb.kron(*mats)), v)
+            w = sb.DeviceArray.full(GS[vk].shape, float("nan"), dtype)
+            assert R.rel_err(sb.ldiv_(w, L, v).numpy(), GS[ok]) <= tol, vk
+            u = dev(GS[vk])
+            assert R.rel_err(sb.ldiv_(L, u).numpy(), GS[ok]) <= tol, vk + " in place"
+    v = dev(GS["blk_v"])
+    L = sb.cache_operator(sb.BlockDiagonalOperator(F(GS["blk_b0"].astype(dtype)), sb.DiagonalOperator(GS["blk_d1"].astype(dtype)),
+                                                   F(GS["blk_b2"].astype(dtype)), sb.IdentityOperator(3)), v)
+    w = sb.DeviceArray.full(GS["blk_w0"].shape, float("nan"), dtype)
+    assert R.rel_err(sb.mul_(w, L, v).numpy(), GS["blk_out3"]) <= tol
+    assert R.rel_err(sb.mul_(dev(GS["blk_w0"]), L, v, ALPHA, BETA).numpy(), GS["blk_out5"]) <= tol
+    b = dev(GS["w_b"])
+    g = float(GS["w_gamma"])
+    y = sb.DeviceArray.full((16,), float("nan"), dtype)
+    W = sb.cache_operator(sb.WOperator(F(GS["w_M"].astype(dtype)), g, F(GS["w_J"].astype(dtype))), b)
+    assert R.rel_err(sb.mul_(y, W, b).numpy(), GS["w_out"]) <= 4 * tol
+    Wu = sb.cache_operator(sb.WOperator(2.0, g, F(GS["w_J"].astype(dtype))), b)
+    assert R.rel_err(sb.mul_(y, Wu, b).numpy(), GS["w_out_uniform"]) <= 4 * tol
