@@ -42,6 +42,13 @@ constexpr int F_BYTES = MAXF * MAXF * 4;  // 64 KB each for F_hi and F_lo
 constexpr int NBAR = 2 * RSTAGES + 2 * ASTAGES + 4 + 1 + 8;
 constexpr int EPI_STAGE_BYTES = 4096;   // one 32 x 32 FP32 block; two per epilogue warp (double-buffered)
 constexpr int SMEM_BYTES = 1024 + 2 * F_BYTES + RSTAGES * XT_BYTES + 8 * EPI_STAGE_BYTES + 8 * NBAR + 16 + 64;
+// The tensor core adds into its FP32 accumulator with round-toward-zero: on same-sign data the error of a long
+// accumulation chain grows LINEARLY (measured: 2e-8 * K relative, 1e-5 at K = 512, 1.6e-4 at K = 8192 -- tools/
+// tf32_accuracy.py).  So a TMEM accumulator only ever holds CHUNK_KB k-blocks (128 k = 48 MMAs); the epilogue warps
+// drain every chunk into FP32 registers with round-to-nearest adds while the MMAs of the next chunk fill the other
+// accumulator.  Error after that: ~1e-6 at any K.
+constexpr int CHUNK_KB = 4;             // (streamed mode only: the resident-factor mode has K <= 128 = one chunk)
+constexpr int EPI_REGS = 216, CTRL_REGS = 40;   // setmaxnreg: 128 running sums per epilogue thread (40 + 2*128 + 216 = 512)
 constexpr int NSG = 2;                  // splitter groups (4 warps each) alternating over k-blocks
 constexpr int NEG = 1;                  // epilogue groups (4 warps each)
 // A ring slot must always be served by the SAME splitter group: a group that never waited on phase j of a
@@ -242,6 +249,9 @@ __global__ void __launch_bounds__(THREADS, 1)
   const long long tiles_rc = (long long)p.tiles_r * p.tiles_c;
   const uint32_t idesc = make_idesc(false, !F_K, n_mma);   // A comes from TMEM (row = lane, k = column)
 
+  // register re-balancing (whole warpgroups): the control warpgroup gives, the epilogue warpgroup takes
+  if (warp < 4) {
+  if (STREAM_F) setmaxnreg_dec<CTRL_REGS>();
   if (warp == 0) {
     // ===================== TMA producer: raw X tiles (warp-uniform loop, one elected lane issues) =====================
     int stage = 0;
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int r0 = (p.c_fast ? rem / p.tiles_c : rem - ct * p.tiles_r) * TM;
       const int bx = p.x_batched ? b : 0;
       for (int kb = 0; kb < nkb; kb++) {
-        mbar_wait(raw_free + 8 * stage, phase ^ 1);
+        mbar_wait_relaxed(raw_free + 8 * stage, phase ^ 1);
         if (elect_one()) {
           const uint32_t dst = sX + stage * XSTRIDE;
           const uint32_t bar = raw_full + 8 * stage;
@@ -291,14 +301,18 @@ __global__ void __launch_bounds__(THREADS, 1)
     constexpr uint32_t KS_INC = F_K ? (32 >> 4) : (1024 >> 4);      // next k-step of 8
     int at = 0;
     uint32_t aph = 0;
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
-      const int a = it & 1;
-      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-      mbar_wait(tmem_empty + 8 * a, aphase ^ 1);   // epilogue drained this accumulator
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + a * 128;
+    int it = 0;      // chunk counter of this CTA: accumulator it & 1
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      uint32_t d_tmem = 0;
       for (int kb = 0; kb < nkb; kb++) {
+        const bool chunk_first = STREAM_F ? (kb % CHUNK_KB) == 0 : kb == 0;
+        const bool chunk_last = STREAM_F ? ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1) : kb == nkb - 1;
+        const int a = it & 1;
+        if (chunk_first) {
+          mbar_wait(tmem_empty + 8 * a, (uint32_t)((it >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+          tc_fence_after();
+          d_tmem = tmem_base + a * 128;
+        }
         if (STREAM_F) mbar_wait(raw_full + 8 * at, aph);   // the F_hi / F_lo tiles of this stage have landed
         mbar_wait(a_full + 8 * at, aph);
         tc_fence_after();
@@ -313,7 +327,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             if (ks < ksteps) {
               const uint64_t bhi = STREAM_F ? shi + (uint64_t)(ks * KS_INC) : bhi0 + (uint64_t)(kb * KB_INC + ks * KS_INC);
               const uint64_t blo = STREAM_F ? slo + (uint64_t)(ks * KS_INC) : blo0 + (uint64_t)(kb * KB_INC + ks * KS_INC);
-              const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+              const uint32_t first = (chunk_first && ks == 0) ? 0u : 1u;
               if (p.passes == 3) {
                 tc_mma_tf32_ts(d_tmem, alo + ks * 8, bhi, idesc, first);
                 tc_mma_tf32_ts(d_tmem, ahi + ks * 8, blo, idesc, 1u);
@@ -325,12 +339,14 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
           tc_commit(a_free + 8 * at);                 // TMEM A stage reusable once these MMAs retire
           if (STREAM_F) tc_commit(raw_free + 8 * at);   // ... and so are the F tiles of the shared-memory stage
-          if (kb == nkb - 1) tc_commit(tmem_full + 8 * a);
+          if (chunk_last) tc_commit(tmem_full + 8 * a);
         }
         __syncwarp();
+        if (chunk_last) it++;
         if (++at == ASTAGES) { at = 0; aph ^= 1; }
       }
     }
+  }
   } else if (warp >= 4 && warp < 4 + 4 * NSG) {
     // ===================== splitters: raw X tile (smem) -> hi, lo (TMEM A operand) =====================
     const int grp = (warp - 4) >> 2;         // this group handles k-blocks with (global index % NSG) == grp
@@ -387,6 +403,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
   } else if (warp >= 4 + 4 * NSG) {
+    if (STREAM_F) setmaxnreg_inc<EPI_REGS>();
     // ===================== epilogue: TMEM -> registers -> (smem -> TMA store | global), alpha/beta fused =====
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
     const uint32_t stage_s = sEpi + quarter * 2 * EPI_STAGE_BYTES;     // two buffers of this warp
@@ -394,10 +411,9 @@ __global__ void __launch_bounds__(THREADS, 1)
     const uint32_t ebar = epi_bar + 16 * quarter;
     uint32_t eph0 = 0, eph1 = 0;                    // phases of the two "old block landed" barriers
     const bool readw = (p.beta != 0.f);
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
-      const int a = it & 1;
-      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+    int it = 0;      // chunk counter, in step with the MMA warp
+    const int nchunks = STREAM_F ? (nkb + CHUNK_KB - 1) / CHUNK_KB : 1;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = (int)(tile / tiles_rc);
       const int rem = (int)(tile - (long long)b * tiles_rc);
       const int ct = p.c_fast ? rem % p.tiles_c : rem / p.tiles_r;
@@ -416,15 +432,48 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
       };
       if (p.tma_store && readw) load_old(0);        // overlaps the wait for the accumulator
-      mbar_wait(tmem_full + 8 * a, aphase);
-      tc_fence_after();
+      // streamed mode: drain the chunk accumulators into registers (round-to-nearest adds outside the tensor core);
+      // resident mode: one chunk, read block by block straight from TMEM below
+      float sum[STREAM_F ? 128 : 1];
+      int a = it & 1;
+      if (STREAM_F) {
+        for (int ch = 0; ch < nchunks; ch++, it++) {
+          a = it & 1;
+          mbar_wait_relaxed(tmem_full + 8 * a, (uint32_t)((it >> 1) & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int blk = 0; blk < 4; blk++) {
+            if (blk < nblk) {
+              uint32_t v[32];
+              tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * 128 + blk * 32, v);
+              tc_wait_ld();
+#pragma unroll
+              for (int c = 0; c < 32; c++)
+                sum[(STREAM_F ? blk * 32 + c : 0)] = (ch == 0) ? __uint_as_float(v[c]) : sum[(STREAM_F ? blk * 32 + c : 0)] + __uint_as_float(v[c]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + 8 * a);
+        }
+      } else {
+        mbar_wait_relaxed(tmem_full + 8 * a, (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+      }
       float* drow = p.D + (long long)b * p.d_bs + r * p.d_rs;
       const bool row_ok = r < p.rows;
-      for (int blk = 0; blk < nblk; blk++) {
+#pragma unroll
+      for (int blk = 0; blk < 4; blk++) {
+        if (blk >= nblk) break;
         const int c0 = cbase + blk * 32;
         uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * 128 + blk * 32, v);
-        tc_wait_ld();
+        if (STREAM_F) {
+#pragma unroll
+          for (int c = 0; c < 32; c++) v[c] = __float_as_uint(sum[(STREAM_F ? blk * 32 + c : 0)]);
+        } else {
+          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * 128 + blk * 32, v);
+          tc_wait_ld();
+        }
         if (p.tma_store) {
           // stage the block in shared memory in the order the output wants, then ONE bulk tensor store: full
           // 128-byte lines, clipped at the matrix edge, no LSU pressure on this warp
@@ -494,9 +543,12 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + 8 * a);
+      if (!STREAM_F) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + 8 * a);
+        it++;
+      }
     }
     if (lane == 0) tma_store_wait_all();   // this lane's bulk stores are complete before the CTA exits
   }

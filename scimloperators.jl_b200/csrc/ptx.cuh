@@ -56,6 +56,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for long waits of warps that share an SM sub-partition with busy warps: back off between polls
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(256);
+}
 
 // One lane of a converged warp, chosen by hardware (elect.sync).  Warp-uniform control flow around an
 // `if (elect_one())` lets the compiler keep mbarrier / TMA / tcgen05 operands in uniform registers instead of
