@@ -931,3 +931,19 @@ def test_tpo_float32_large_factors(sb, factor):
     assert np.linalg.norm(got - want) <= 1e-5 * scale
     got5 = sb.mul_(dev(sb, w0), L, dv, 0.7, 0.3).numpy()
     assert np.linalg.norm(got5 - (0.7 * want + 0.3 * w0)) <= 1e-5 * (scale + np.linalg.norm(w0))
+
+
+@pytest.mark.parametrize("K", [2048, 16384])
+def test_gemm_f32_long_contraction_same_sign_data(sb, K):
+    """Tensor-core FP32 accumulation rounds toward zero: on all-positive data an unchunked accumulator drifts by
+    2e-8 * K (1.6e-4 at K = 8192).  The streamed kernel sums 128-k chunks outside the tensor core and must hold
+    the Float32 tolerance at any contraction length."""
+    rng = np.random.default_rng(K)
+    M, N = 384, 256
+    A, B = rnd(rng, M, K, dtype=np.float32), rnd(rng, K, N, dtype=np.float32)     # uniform [0, 1): every product positive
+    L = sb.MatrixOperator(A)
+    w = sb.DeviceArray.full((M, N), float("nan"), np.float32)
+    sb.mul_(w, L, dev(sb, B))
+    want = A.astype(np.float64) @ B.astype(np.float64)
+    err = R.rel_err(w.numpy(), want)
+    assert err <= 5e-6, f"K={K}: rel err {err:.3e}"
