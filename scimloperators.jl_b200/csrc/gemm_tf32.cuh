@@ -74,6 +74,11 @@ struct Params {
   int vec_ok;            // d_cs == 1 and 16-byte alignment holds: float4 stores along c
   int x_batched;
   int passes;            // 3: lo*Fhi + hi*Flo + hi*Fhi (FP32-grade);  1: hi*Fhi only (plain TF32, opt-in)
+  // streamed mode: up to 3 row scalings of the product (left Diagonal / BatchedDiagonal factors of a tree term):
+  // value(m, n) *= scale[q][m + (ld ? n * ld : 0)], with (m, n) = (r, c) or, when rows_are_n, (c, r)
+  int nscale, rows_are_n;
+  const float* scale_ptr[3];
+  long long scale_ld[3];
   int tma_store;         // D is TMA-addressable: epilogue goes TMEM -> smem (-> + beta * old block, TMA-loaded) -> bulk store
 };
 
@@ -470,6 +475,17 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (STREAM_F) {
 #pragma unroll
           for (int c = 0; c < 32; c++) v[c] = __float_as_uint(sum[(STREAM_F ? blk * 32 + c : 0)]);
+          if (p.nscale > 0 && row_ok) {
+#pragma unroll 4
+            for (int c = 0; c < 32; c++) {
+              if (c0 + c < p.m) {
+                const long long mi = p.rows_are_n ? (long long)(c0 + c) : r, ni = p.rows_are_n ? r : (long long)(c0 + c);
+                float x = __uint_as_float(v[c]);
+                for (int q = 0; q < p.nscale; q++) x *= __ldg(p.scale_ptr[q] + mi + (p.scale_ld[q] ? ni * p.scale_ld[q] : 0));
+                v[c] = __float_as_uint(x);
+              }
+            }
+          }
         } else {
           tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * 128 + blk * 32, v);
           tc_wait_ld();

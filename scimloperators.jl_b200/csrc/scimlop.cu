@@ -440,7 +440,8 @@ int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, 
 // A / C with one shared B allowed); `f_is_a == true`: X = op(B)^T, F = op(A), rows = N (output contiguous along c).
 int launch_tf32_stream(scimlop_context* c, bool f_is_a, bool transA, bool transB, long long M, long long N, long long K,
                        float alpha, const float* A, long long lda, long long sA, const float* B, long long ldb, float beta,
-                       float* C, long long ldc, long long sC, long long batch, int passes, cudaStream_t st) {
+                       float* C, long long ldc, long long sC, long long batch, int passes, int nscale,
+                       const ScaleArg* scales, cudaStream_t st) {
   const float* Fsrc = f_is_a ? A : B;
   const long long ldf = f_is_a ? lda : ldb;
   const long long fcols = f_is_a ? (transA ? M : K) : (transB ? K : N);   // stored columns of F (ldf floats each)
@@ -503,6 +504,8 @@ int launch_tf32_stream(scimlop_context* c, bool f_is_a, bool transA, bool transB
     p.vec_ok = f_is_a && aligned16(C) && ldc % 4 == 0;
     p.x_batched = xb;
     p.passes = passes;
+    p.nscale = nscale; p.rows_are_n = f_is_a;
+    for (int q = 0; q < nscale; q++) { p.scale_ptr[q] = static_cast<const float*>(scales[q].ptr); p.scale_ld[q] = scales[q].ld; }
     p.tma_store = aligned16(C) && ldc % 4 == 0 && (batch == 1 || sC % 4 == 0);
     if (!p.tma_store) tmD = tmX;
     else if (!f_is_a) rc = make_map_f32(c, &tmD, C, M, N, batch, ldc * 4, sC * 4, 32, 32, false, /*swizzle=*/false);
@@ -559,17 +562,18 @@ int gemm_dispatch<float>(scimlop_context* c, int precision, bool transA, bool tr
   }
   // large Float32 products: the streamed-operand tcgen05 kernel (the FFMA kernel below peaks at ~27 TFLOP/s).
   // The smaller operand is the one that gets pre-split; batches need one shared B (the outer Kronecker modes).
-  if (precision != SCIMLOP_PREC_FP32_EXACT && nscale == 0 && K >= 32 && (batch == 1 || sB == 0) &&
+  if (precision != SCIMLOP_PREC_FP32_EXACT && (nscale == 0 || batch == 1) && K >= 32 && (batch == 1 || sB == 0) &&
       2.0 * (double)M * (double)N * (double)K * (double)batch >= 1e8 && M < 2147483647LL && N < 2147483647LL &&
       K < 2147483647LL && batch < 2147483647LL && aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0 &&
       (batch == 1 || sA % 4 == 0)) {
     const int passes = precision == SCIMLOP_PREC_TF32 ? 1 : 3;
     const bool a_small = batch == 1 && (double)M * (double)K < (double)K * (double)N;
     if (a_small && N >= 128 && M >= 16)
-      return launch_tf32_stream(c, true, transA, transB, M, N, K, alpha, A, lda, 0, B, ldb, beta, C, ldc, 0, 1, passes, st);
+      return launch_tf32_stream(c, true, transA, transB, M, N, K, alpha, A, lda, 0, B, ldb, beta, C, ldc, 0, 1, passes,
+                                nscale, scales, st);
     if (M * batch >= 128 && N >= 16)
       return launch_tf32_stream(c, false, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, beta, C, ldc, sC, batch,
-                                passes, st);
+                                passes, nscale, scales, st);
   }
   if (precision == SCIMLOP_PREC_TF32)
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED,

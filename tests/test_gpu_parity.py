@@ -947,3 +947,27 @@ def test_gemm_f32_long_contraction_same_sign_data(sb, K):
     want = A.astype(np.float64) @ B.astype(np.float64)
     err = R.rel_err(w.numpy(), want)
     assert err <= 5e-6, f"K={K}: rel err {err:.3e}"
+
+
+@pytest.mark.parametrize("N,K", [(1024, 64), (1536, 200)])
+def test_config4_tree_float32_on_tensor_cores(sb, N, K):
+    """configs[3] in Float32: α(D*M' + Dk*M + 2M + I)v + βw with the dense products on the streamed tcgen05 kernel and
+    the vector / batched diagonal factors applied in its epilogue."""
+    rng = np.random.default_rng(N + K)
+    f32 = np.float32
+    Mm = rnd(rng, N, N, dtype=f32) - f32(0.5)
+    d, Dk = rnd(rng, N, dtype=f32), rnd(rng, N, K, dtype=f32)
+    v, w0 = rnd(rng, N, K, dtype=f32) - f32(0.5), rnd(rng, N, K, dtype=f32)
+    dv = dev(sb, v)
+    Mop = sb.MatrixOperator(Mm)
+    L = sb.cache_operator(sb.DiagonalOperator(d) * Mop.adjoint() + sb.DiagonalOperator(Dk) * Mop + 2.0 * Mop
+                          + sb.IdentityOperator(N), dv)
+    M64, v64 = Mm.astype(np.float64), v.astype(np.float64)
+    want = 0.7 * (d[:, None] * (M64.T @ v64) + Dk * (M64 @ v64) + 2 * (M64 @ v64) + v64) + 0.3 * w0
+    scale = np.linalg.norm(np.abs(M64) @ np.abs(v64)) * 4 + np.linalg.norm(w0)
+    got = sb.mul_(dev(sb, w0), L, dv, 0.7, 0.3).numpy()
+    assert np.isfinite(got).all()
+    assert np.linalg.norm(got - want) <= 1e-5 * scale
+    want3 = d[:, None] * (M64.T @ v64) + Dk * (M64 @ v64) + 2 * (M64 @ v64) + v64
+    got3 = sb.mul_(dev(sb, np.full_like(w0, np.nan)), L, dv).numpy()
+    assert np.linalg.norm(got3 - want3) <= 1e-5 * scale
