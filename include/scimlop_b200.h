@@ -280,6 +280,27 @@ int scimlop_kron_mul_peers(scimlop_handle_t h, int dtype, int precision, int nfa
                            size_t workspace_bytes, void* stream);
 int scimlop_comm_barrier(scimlop_handle_t h, void* stream);
 
+/* ---- NVSwitch multicast windows (cuMulticast / NVLS) ------------------------------------------------------------
+ * A buffer every rank of the node holds a copy of, plus a multicast alias through which ONE store lands in all
+ * copies.  Collective set-up: scimlop_mc_open on every rank (rank 0 creates the object and returns a POSIX file
+ * descriptor in *fd_out, which the caller hands to the other ranks -- SCM_RIGHTS over a Unix socket -- as their
+ * fd_in), a barrier, scimlop_mc_bind on every rank (allocates and binds the local copy; returns the local array and
+ * the multicast alias), a barrier.  scimlop_mc_padded_bytes rounds a size up to the multicast granularity. */
+int scimlop_mc_padded_bytes(scimlop_handle_t h, size_t bytes, int nranks, size_t* padded);
+int scimlop_mc_open(scimlop_handle_t h, size_t padded_bytes, int nranks, int rank, int fd_in, int* fd_out,
+                    void** window);
+int scimlop_mc_bind(scimlop_handle_t h, void* window, void** local_ptr, void** mc_ptr);
+int scimlop_mc_free(scimlop_handle_t h, void* window);
+
+/* Fused compute + all-gather through the switch: like scimlop_kron_mul_peers, but the last mode product stores every
+ * output element once, with multimem.st, to `W_multicast` (the multicast alias of this rank's column slab); the
+ * NVSwitch replicates it into every rank's copy (this one included), so the NVLink egress per GPU is one slab
+ * instead of ranks-1 slabs.  Follow with scimlop_comm_barrier before any rank reads W. */
+int scimlop_kron_mul_mc(scimlop_handle_t h, int dtype, int precision, int nfactors, const void* const* factors,
+                        const int64_t* dims, const int64_t* lds, const int32_t* kinds, const void* V, int64_t k,
+                        void* W_local, void* W_multicast, const void* alpha, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

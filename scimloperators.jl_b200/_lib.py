@@ -77,6 +77,11 @@ SIGNATURES = {
     "scimlop_kron_mul_peers": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _I64, _P, C.POINTER(_P), _INT,
                                _P, _P, _SZ, _P],
     "scimlop_comm_barrier": [_P, _P],
+    "scimlop_mc_padded_bytes": [_P, _SZ, _INT, C.POINTER(_SZ)],
+    "scimlop_mc_open": [_P, _SZ, _INT, _INT, _INT, C.POINTER(_INT), C.POINTER(_P)],
+    "scimlop_mc_bind": [_P, _P, C.POINTER(_P), C.POINTER(_P)],
+    "scimlop_mc_free": [_P, _P],
+    "scimlop_kron_mul_mc": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _I64, _P, _P, _P, _P, _SZ, _P],
     "scimlop_kron_mul_allgather": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _P, _I64, _P, _I64, _P, _SZ, _P],
 }
 

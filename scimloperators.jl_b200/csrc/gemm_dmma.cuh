@@ -48,7 +48,20 @@ struct Params {
   // separate collective.  Only with beta == 0.
   int npeer;
   double* peerC[7];
+  // NVSwitch multicast alias of C (same geometry): when set, every output element is stored ONCE with multimem.st
+  // and the switch delivers it to every rank's copy, this one included.
+  double* mcC;
 };
+
+__device__ __forceinline__ void multimem_st16(double* addr, double a, double b) {
+  const long long x = __double_as_longlong(a), y = __double_as_longlong(b);
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(__int_as_float((int)x)),
+               "f"(__int_as_float((int)(x >> 32))), "f"(__int_as_float((int)y)), "f"(__int_as_float((int)(y >> 32)))
+               : "memory");
+}
+__device__ __forceinline__ void multimem_st8(double* addr, double a) {
+  asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(addr), "d"(a) : "memory");
+}
 
 // k index used by lane t in MMA step s of a BK=16 block.  The permutation makes the 64-bit fragment
 // loads bank-conflict-free for BOTH swizzled tile layouts (see tile_off): the four k's of a step hit
@@ -353,7 +366,15 @@ __global__ void __launch_bounds__(THREADS, 1)
     if (interior && p.nscale == 0) {
       // fast path (every tile of the headline shapes): 32 x 16-byte stores per lane, no bounds checks
       const double alpha = p.alpha, beta = p.beta;
-      if (beta == 0.0) {
+      if (beta == 0.0 && p.mcC != nullptr) {
+        double* Mb = p.mcC + (Cb - p.C);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          double* col = Mb + (long long)(8 * j) * p.ldc;
+#pragma unroll
+          for (int i = 0; i < 8; i++) multimem_st16(col + 8 * i, alpha * acc[i][j][0], alpha * acc[i][j][1]);
+        }
+      } else if (beta == 0.0) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           double* col = Cb + (long long)(8 * j) * p.ldc;
@@ -409,6 +430,12 @@ __global__ void __launch_bounds__(THREADS, 1)
           v0 *= p.alpha;
           v1 *= p.alpha;
           double* dst = col + 8 * i;
+          if (p.mcC != nullptr) {      // (beta == 0 and no scalings are enforced on the host)
+            double* md = p.mcC + (dst - p.C);
+            multimem_st8(md, v0);
+            if (pair) multimem_st8(md + 1, v1);
+            continue;
+          }
           if (pair && p.vec_ok) {
             if (p.beta != 0.0) {
               const double2 old = *reinterpret_cast<const double2*>(dst);
@@ -433,6 +460,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
   }
+  if (p.mcC != nullptr) __threadfence_system();   // multicast stores are performed before the kernel retires
 }
 
 }  // namespace dmma

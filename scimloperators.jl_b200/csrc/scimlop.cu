@@ -38,6 +38,8 @@ struct ScaleArg {
 struct PeerArg {
   int n = 0;
   void* ptr[7] = {};
+  void* mc = nullptr;   // multicast alias of the destination (scimlop_kron_mul_mc): one store reaches every rank
+  bool active() const { return n > 0 || mc != nullptr; }
 };
 thread_local PeerArg g_peers;
 
@@ -161,7 +163,11 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
     p.peerC[q] = static_cast<double*>(g_peers.ptr[q]);
     p.vec_ok = p.vec_ok && aligned16(g_peers.ptr[q]);
   }
-  if (g_peers.n > 0 && beta != 0.0) return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "peer targets need beta == 0");
+  p.mcC = static_cast<double*>(g_peers.mc);
+  if (g_peers.active() && (beta != 0.0 || nscale != 0))
+    return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "peer / multicast targets need beta == 0 and no row scalings");
+  if (g_peers.mc && (!p.vec_ok || !aligned16(g_peers.mc)))
+    return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "multicast target needs a 16-byte aligned W with even leading dimension");
   static dmma::PeerMaps pmaps_unused;   // the non-peer kernels ignore it
   dmma::PeerMaps& pmaps = pmaps_unused;
   // fused all-gather with bulk stores: one 3-D {M, N, batch} map per destination, box = one output tile
@@ -191,7 +197,7 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
   // co-resident clusters comes from the occupancy query at handle creation (8-CTA clusters do not tile all SMs).
   const long long nk_all = (K + dmma::BK - 1) / dmma::BK;
   long long ks = 1;
-  if (g_peers.n == 0 && p.total_tiles < c->sm_count) {
+  if (!g_peers.active() && p.total_tiles < c->sm_count) {
     double best = (double)((p.total_tiles + c->sm_count - 1) / c->sm_count) * (nk_all * 2.2 + 2.0);
     for (long long cand = 2; cand <= 8; cand *= 2) {
       const long long maxc = c->dmma_max_clusters[cand];
@@ -200,7 +206,7 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
       if (t < best) { best = t; ks = cand; }
     }
   }
-  if (g_peers.n == 0 && ks >= 2) {
+  if (!g_peers.active() && ks >= 2) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(ks * p.total_tiles), 1, 1);
@@ -359,11 +365,11 @@ int gemm_dispatch<double>(scimlop_context* c, int precision, bool transA, bool t
   if (precision != SCIMLOP_PREC_DEFAULT)
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "Float64 only supports SCIMLOP_PREC_DEFAULT (got %d)", precision);
   if (M <= 0 || N <= 0 || batch <= 0) return SCIMLOP_OK;
-  if (g_peers.n == 0 && skinny_eligible<double>(c, transB, M, N, K, A, lda, B, ldb, batch, nscale)) {
+  if (!g_peers.active() && skinny_eligible<double>(c, transB, M, N, K, A, lda, B, ldb, batch, nscale)) {
     const int rc = launch_skinny<double>(c, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, st);
     if (rc >= 0) return rc;
   }
-  if (g_peers.n > 0 && !dmma_eligible(M, N, K, A, lda, sA, B, ldb, sB, batch))
+  if (g_peers.active() && !dmma_eligible(M, N, K, A, lda, sA, B, ldb, sB, batch))
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "peer targets need a DMMA-eligible (aligned Float64) last stage");
   if (dmma_eligible(M, N, K, A, lda, sA, B, ldb, sB, batch))
     return launch_dmma(c, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, nscale,
@@ -979,9 +985,10 @@ int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* cons
       ep.nterms = 1; ep.coef[0] = T(1); ep.nvec[0] = 1; ep.nfac[0] = 1;
       ep.fac[0][0].ptr = static_cast<const T*>(factors[p]); ep.fac[0][0].ld = 0; ep.fac[0][0].div = L; ep.fac[0][0].mod = n;
       rc = launch_eltwise(c, ep, st);
-    } else if (g_peers.n > 0 && !last) {
+    } else if (g_peers.active() && !last) {
       PeerArg saved = g_peers;      // intermediates stay local: only the stage that writes W goes to the peers
       g_peers.n = 0;
+      g_peers.mc = nullptr;
       if (L == 1)
         rc = gemm_dispatch<T>(c, precision, tr, false, m, R, n, a, static_cast<const T*>(factors[p]), lds[p], 0, cur, n, 0,
                               bt, out, m, 0, 1, 0, nullptr, st);
@@ -1087,6 +1094,27 @@ extern "C" int scimlop_kron_mul_peers(scimlop_handle_t h, int dtype, int precisi
   int rc = scimlop_kron_mul_impl(h, dtype, precision, nfactors, factors, dims, lds, kinds, V, cols, W_local, rows, k, alpha,
                                  nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
   g_peers.n = 0;
+  return rc;
+}
+
+extern "C" int scimlop_kron_mul_mc(scimlop_handle_t h, int dtype, int precision, int nfactors,
+                                   const void* const* factors, const int64_t* dims, const int64_t* lds,
+                                   const int32_t* kinds, const void* V, int64_t k, void* W_local, void* W_multicast,
+                                   const void* alpha, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (dtype != SCIMLOP_F64) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "kron_mul_mc: Float64 only");
+  if (!W_multicast) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_mul_mc: multicast pointer null");
+  if (!dims || !kinds || nfactors < 1 || nfactors > 8) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_mul_mc: bad factors");
+  if (kinds[0] != SCIMLOP_DENSE && kinds[0] != (SCIMLOP_DENSE | SCIMLOP_TRANS))
+    return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "kron_mul_mc: the outermost factor must be dense");
+  long long rows = 1, cols = 1;
+  for (int f = 0; f < nfactors; f++) { rows *= dims[2 * f]; cols *= dims[2 * f + 1]; }
+  scimlop_device_guard guard(h->device);
+  g_peers.n = 0;
+  g_peers.mc = W_multicast;
+  int rc = scimlop_kron_mul_impl(h, dtype, precision, nfactors, factors, dims, lds, kinds, V, cols, W_local, rows, k, alpha,
+                                 nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  g_peers.mc = nullptr;
   return rc;
 }
 

@@ -130,3 +130,91 @@ def kron_mul_peers(handle, L, V_local, window, cols_per_rank, alpha=None, stream
     if barrier:
         handle.check(handle.lib.scimlop_comm_barrier(handle.ptr, st), "scimlop_comm_barrier")
     return window.W
+
+
+class _RawCuda:
+    """A device allocation that torch did not make (cuMemMap'ed), exposed through __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+
+class MulticastWindow:
+    """A replicated W on every rank of the node plus its NVSwitch multicast alias (scimlop_mc_*): one store through
+    the alias lands in every rank's copy.  Collective: construct it on all ranks at the same time.
+    `all_gather_object(obj)` and `barrier()` are the caller's rendezvous (torch.distributed's); the multicast
+    object's file descriptor travels from rank 0 to the others over a Unix socket (SCM_RIGHTS)."""
+
+    def __init__(self, handle, shape, dtype, rank, world, all_gather_object, barrier):
+        import os, socket, tempfile
+        import numpy as np
+        import torch
+        from .array import DeviceArray
+        self.h, self.rank, self.world = handle, int(rank), int(world)
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        padded = C.c_size_t(0)
+        handle.check(handle.lib.scimlop_mc_padded_bytes(handle.ptr, nbytes, world, C.byref(padded)), "scimlop_mc_padded_bytes")
+        fd_out, win = C.c_int(-1), C.c_void_p()
+        if rank == 0:
+            handle.check(handle.lib.scimlop_mc_open(handle.ptr, padded.value, world, 0, -1, C.byref(fd_out), C.byref(win)),
+                         "scimlop_mc_open")
+            path = os.path.join(tempfile.mkdtemp(prefix="scimlop_mc_"), "fd.sock")
+            srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            srv.bind(path)
+            srv.listen(world)
+            all_gather_object(path)
+            for _ in range(world - 1):
+                conn, _ = srv.accept()
+                socket.send_fds(conn, [b"fd"], [fd_out.value])
+                conn.recv(2)          # the peer has imported the descriptor
+                conn.close()
+            srv.close()
+            os.close(fd_out.value)
+            os.unlink(path)
+        else:
+            path = all_gather_object(None)[0]
+            cli = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            cli.connect(path)
+            _, fds, _, _ = socket.recv_fds(cli, 16, 1)
+            handle.check(handle.lib.scimlop_mc_open(handle.ptr, padded.value, world, rank, fds[0], C.byref(fd_out), C.byref(win)),
+                         "scimlop_mc_open")
+            cli.send(b"ok")
+            cli.close()
+            os.close(fds[0])
+        self._win = win
+        barrier()                       # every device has joined the multicast object
+        loc, mc = C.c_void_p(), C.c_void_p()
+        handle.check(handle.lib.scimlop_mc_bind(handle.ptr, win, C.byref(loc), C.byref(mc)), "scimlop_mc_bind")
+        self.local_ptr, self.mc_ptr = loc.value, mc.value
+        raw = torch.as_tensor(_RawCuda(loc.value, nbytes), device=torch.device("cuda", handle.device))
+        tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+        self.W = DeviceArray(raw.view(tdt), shape)
+        barrier()                       # every copy is bound before anyone stores through the alias
+
+    def close(self):
+        if self._win:
+            self.h.lib.scimlop_mc_free(self.h.ptr, self._win)
+            self._win = None
+
+
+def kron_mul_mc(handle, L, V_local, window, cols_per_rank, alpha=None, stream=None, barrier=True):
+    """This rank's column slab of W = (kron factors) V, stored ONCE by the last GEMM's epilogue through the NVSwitch
+    multicast alias of W (multimem.st): the switch writes it into every rank's copy.  Float64."""
+    import torch
+    from .operators import _DT, _scalar
+    nat = L._native
+    if nat is None:
+        raise TypeError("kron_mul_mc needs a TensorProductOperator of native factors (cache_operator it first)")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+    rows = window.W.shape[0]
+    slab = window.rank * int(cols_per_rank) * rows * 8
+    a = alpha
+    for s in nat["scalars"]:
+        a = s.convert() * (1.0 if a is None else float(a))
+    handle.check(handle.lib.scimlop_kron_mul_mc(
+        handle.ptr, _DT[V_local.dtype], L.precision, nat["nf"], nat["ptrs"], nat["dims"], nat["lds"], nat["kinds"],
+        C.c_void_p(V_local.ptr), int(cols_per_rank), C.c_void_p(window.local_ptr + slab), C.c_void_p(window.mc_ptr + slab),
+        _scalar(V_local.dtype, a), C.c_void_p(nat["ws"].data_ptr()), nat["ws_bytes"], st), "scimlop_kron_mul_mc")
+    if barrier:
+        handle.check(handle.lib.scimlop_comm_barrier(handle.ptr, st), "scimlop_comm_barrier")
+    return window.W

@@ -94,6 +94,27 @@ def main():
             err = max(err, 1.0)
         dist.barrier()
     win4.close()
+    # the same through the NVSwitch multicast alias (one multimem.st per element, replicated by the switch)
+    try:
+        mcw = sd.MulticastWindow(h, (512 * 512, kc * world), np.float64, rank, world, gather_obj, dist.barrier)
+    except Exception as e:   # no multicast on this node (no NVSwitch / driver support): reported, not failed
+        mcw = None
+        if rank == 0:
+            print(f"MULTICAST_UNAVAILABLE {e}", flush=True)
+    if mcw is not None:
+        for rep in range(6):
+            mcw.W.t.zero_()
+            torch.cuda.synchronize(); dist.barrier()
+            sd.kron_mul_mc(h, Lc, Vc, mcw, kc)
+            torch.cuda.synchronize(); dist.barrier()
+            d5 = float((mcw.W.t - want4).abs().max())
+            if d5 != 0.0:
+                print(f"rank {rank} rep {rep}: multicast result differs from the unfused path by {d5:.3e}", flush=True)
+                err = max(err, 1.0)
+            dist.barrier()
+        if rank == 0:
+            print("MULTICAST_OK" if err < 1e-12 else "MULTICAST_FAILED", flush=True)
+        mcw.close()
     ok = torch.tensor([1.0 if err < 1e-12 else 0.0], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -63,6 +63,25 @@ def main():
     res["fused_all_slabs_max_abs_diff"] = worst
     res["fused_all_slabs_nonzero"] = bool((W.t != 0).all())
     win.close()
+    # NVSwitch multicast: one multimem.st per element, the switch replicates into every rank's copy
+    try:
+        mcw = sd.MulticastWindow(h, (n, k), np.float64, rank, world, gather_obj, dist.barrier)
+    except Exception as e:
+        mcw = None
+        res["multicast_unavailable"] = str(e)[:200]
+    if mcw is not None:
+        res["fused_multicast_ms"] = timed(lambda: sd.kron_mul_mc(h, L, V, mcw, kper))
+        res["fused_multicast_no_barrier_ms"] = timed(lambda: sd.kron_mul_mc(h, L, V, mcw, kper, barrier=False))
+        mcw.W.t.zero_(); torch.cuda.synchronize(); dist.barrier()
+        sd.kron_mul_mc(h, L, V, mcw, kper); torch.cuda.synchronize(); dist.barrier()
+        worst = 0.0
+        for r in range(world):
+            gr = torch.Generator(device="cuda").manual_seed(r)
+            Vr = sb.DeviceArray(torch.rand(n * kper, dtype=torch.float64, device="cuda", generator=gr), (n, kper))
+            sb.mul_(ref, L, Vr)
+            worst = max(worst, float((mcw.W.cols(r * kper, (r + 1) * kper).t - ref.t).abs().max()))
+        res["multicast_all_slabs_max_abs_diff"] = worst
+        mcw.close()
     if rank == 0:
         print(json.dumps({"workload": "config 2 strong-scaled, W replicated", "n_gpus": world, "cols_per_rank": kper,
                           "compute_only_ms": t_comp, "compute_then_allgather_ms": t_seq, **res,
