@@ -117,12 +117,18 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t out_tile = smem + NSTAGE * STAGE_BYTES;   // PEER: the finished tile, dense [n][128 m]
   const uint32_t full_bar = out_tile + (PEER ? BM * BN * 8 : 0);  // NSTAGE x 8 B
   const uint32_t empty_bar = full_bar + NSTAGE * 8;
+  // PEER + multicast: out_tile hand-over between the consumers and the three copy warps of the producer warpgroup
+  const uint32_t tile_full = full_bar + 64, tile_empty = full_bar + 72;
   const uint32_t scratch = full_bar + 128;  // one word per consumer warp (mbar_arrive_after_loads)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    if (PEER) {
+      mbar_init(tile_full, 1);
+      mbar_init(tile_empty, 3);
+    }
     for (int s = 0; s < NSTAGE; s++) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, CONSUMER_WARPS);
@@ -179,6 +185,34 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
       }
     }
+    if (PEER && p.mcC != nullptr && warp > CONSUMER_WARPS) {
+      // ---- copy warps (multicast form): finished tile, shared memory -> multimem.st, off the consumers' path ----
+      const int ct = (warp - CONSUMER_WARPS - 1) * 32 + lane;      // 0..95
+      const int tiles_mn = p.tiles_m * p.tiles_n;
+      uint32_t tph = 0;
+      for (int tile = tile_first; tile < ntiles; tile += tile_step) {
+        const int b = tile / tiles_mn;
+        const int rem = tile - b * tiles_mn;
+        const int nt = rem / p.tiles_m;
+        const int mt = rem - nt * p.tiles_m;
+        double* base = p.mcC + (long long)b * p.strideC + (long long)(nt * BN) * p.ldc + mt * BM;
+        const int mlim = p.M - mt * BM, nlim = p.N - nt * BN;     // valid extent of this tile
+        mbar_wait(tile_full, tph);
+        for (int c = ct; c < BM * BN / 2; c += 96) {               // 16-byte pieces: two consecutive rows of a column
+          const int n = c / (BM / 2), m = 2 * (c % (BM / 2));
+          if (n < nlim && m < mlim) {
+            double v0, v1;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(out_tile + (uint32_t)c * 16u));
+            if (m + 1 < mlim) multimem_st16(base + (long long)n * p.ldc + m, v0, v1);
+            else multimem_st8(base + (long long)n * p.ldc + m, v0);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tile_empty);
+        tph ^= 1;
+      }
+      __threadfence_system();
+    }
     if (SPLIT) {   // the whole CTA takes part in the cluster barriers of the reduction
       __syncwarp();
       cluster_sync_all();
@@ -222,7 +256,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 
   int stage = 0;
-  uint32_t phase = 0;
+  uint32_t phase = 0, out_phase = 0;
   double a0[8], b0[4], a1[8], b1[4];  // double-buffered fragments: step s computes while step s+1 loads
 
   // prime the software pipeline with the first fragments of this CTA's first stage
@@ -336,7 +370,11 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
     if (PEER) {
       // ---- bulk-store epilogue: tile -> shared memory -> one bulk tensor store per destination ----
-      if (threadIdx.x == 0) tma_store_wait_read();      // the previous tile's stores have been read out of out_tile
+      const bool mc = p.mcC != nullptr;
+      if (threadIdx.x == 0) {                           // out_tile is free again:
+        if (mc) mbar_wait(tile_empty, out_phase ^ 1);   //   the copy warps have sent the previous tile
+        else tma_store_wait_read();                     //   the previous tile's bulk stores have been read out
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
       {
         const double alpha = p.alpha;
@@ -352,10 +390,15 @@ __global__ void __launch_bounds__(THREADS, 1)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
       if (threadIdx.x == 0) {
-        for (int q = 0; q <= p.npeer; q++) tma_store_3d(&pm.m[q], out_tile, mt * BM, nt * BN, b);
-        tma_store_commit();
-        if (last_tile) tma_store_wait_all();              // everything has landed before the CTA retires
+        if (mc) {
+          mbar_arrive(tile_full);                          // (release: the tile is complete in shared memory)
+        } else {
+          for (int q = 0; q <= p.npeer; q++) tma_store_3d(&pm.m[q], out_tile, mt * BM, nt * BN, b);
+          tma_store_commit();
+          if (last_tile) tma_store_wait_all();              // everything has landed before the CTA retires
+        }
       }
+      out_phase ^= 1;
       continue;
     }
     // ---- fused epilogue: rowscale, alpha, beta, store (the next tile's first stages are already in flight) ----

@@ -173,8 +173,9 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
   // fused all-gather with bulk stores: one 3-D {M, N, batch} map per destination, box = one output tile
   dmma::PeerMaps peer_maps;
   const bool peer_bulk = g_peers.n > 0 && nscale == 0 && beta == 0.0 && p.vec_ok && !transA && getenv("SCIMLOP_PEER_LSU") == nullptr;
-  if (peer_bulk) {
-    for (int q = 0; q <= g_peers.n; q++) {
+  const bool mc_staged = g_peers.mc != nullptr && !transA && getenv("SCIMLOP_MC_REG") == nullptr;
+  if (peer_bulk || mc_staged) {
+    for (int q = 0; peer_bulk && q <= g_peers.n; q++) {
       double* base = q == 0 ? C : static_cast<double*>(g_peers.ptr[q - 1]);
       cuuint64_t gdim[3] = {(cuuint64_t)M, (cuuint64_t)N, (cuuint64_t)batch};
       cuuint64_t gstr[2] = {(cuuint64_t)ldc * 8, batch > 1 ? (cuuint64_t)sC * 8 : (cuuint64_t)ldc * 8 * (cuuint64_t)N};
@@ -185,6 +186,7 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return scimlop_fail(c, SCIMLOP_ERR_CUDA, "cuTensorMapEncodeTiled(peer C %d) failed (CUresult %d)", q, (int)r);
     }
+    if (!peer_bulk) memset(&peer_maps, 0, sizeof(peer_maps));
     const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
     if (!transB) dmma::gemm_dmma_kernel<false, false, false, true><<<grid, dmma::THREADS, dmma::PEER_SMEM_BYTES, st>>>(tmA, tmB, p, peer_maps);
     else dmma::gemm_dmma_kernel<false, true, false, true><<<grid, dmma::THREADS, dmma::PEER_SMEM_BYTES, st>>>(tmA, tmB, p, peer_maps);
