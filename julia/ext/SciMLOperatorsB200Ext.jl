@@ -278,6 +278,21 @@ function mul!(w::DevMat{T}, L::SciMLOperators.TensorSumOperator, v::DevMat{T}, Î
     w
 end
 
+# ---- BlockDiagonalOperator (src/block.jl:145-179): the whole operator in one call ------------------------------
+function mul!(w::DevMat{T}, L::SciMLOperators.BlockDiagonalOperator, v::DevMat{T}, Î±, Î²) where {T <: F}
+    blocks = CFactor[]
+    for op in L.ops                       # only native leaves; anything else keeps the generic loop
+        f = cfactor(op, T)
+        f === nothing && return invoke(mul!, Tuple{AbstractVecOrMat, SciMLOperators.BlockDiagonalOperator, AbstractVecOrMat, Any, Any}, w, L, v, Î±, Î²)
+        push!(blocks, f)
+    end
+    check(ccall((:scimlop_blockdiag_mul, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{CFactor}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Ref{T}, Ref{T}, Ptr{Cvoid}),
+                handle(), dtype(T), 0, length(blocks), blocks, dptr(v), stride(v, 2), dptr(w), stride(w, 2), size(v, 2),
+                T(Î±), T(Î²), stream_ptr()), "scimlop_blockdiag_mul")
+    w
+end
+
 # ---- the solve side: factorize / ldiv! (src/matrix.jl:513-516, src/tensor.jl:227, :612-673) ---------------------
 # `factorize(::MatrixOperator)` over device storage caches the explicit inverse, formed on the device by
 # scimlop_invert; it is wrapped as the `F` of an InvertibleOperator, whose `ldiv!(w, L.F, v)` (src/matrix.jl:632-639)
