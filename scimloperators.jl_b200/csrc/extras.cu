@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "context.h"
 #include "krylov.cuh"
@@ -106,10 +107,24 @@ extern "C" int scimlop_kron_mul_host(scimlop_handle_t h, int dtype, int precisio
     }
   }
 
-  const long long nchunks = (k + cc - 1) / cc;
-  for (long long ci = 0; ci < nchunks; ci++) {
+  // chunk schedule: ramp up (cc/8, cc/4, cc/2), full chunks, ramp down -- the first upload and the last download are
+  // the only transfers nothing overlaps with, so they should be small (auto mode only; an explicit chunk_cols is kept)
+  std::vector<long long> sizes;
+  {
+    std::vector<long long> ramp;
+    long long used = 0;
+    if (chunk_cols <= 0)
+      for (long long sz = std::max<long long>(1, cc / 8); sz < cc && 2 * (used + sz) <= k / 2; sz *= 2) { ramp.push_back(sz); used += sz; }
+    long long mid = k - 2 * used;
+    sizes = ramp;
+    while (mid > 0) { const long long sz = std::min(cc, mid); sizes.push_back(sz); mid -= sz; }
+    for (auto it = ramp.rbegin(); it != ramp.rend(); ++it) sizes.push_back(*it);
+  }
+  const long long nchunks = (long long)sizes.size();
+  long long c0 = 0;
+  for (long long ci = 0; ci < nchunks; c0 += sizes[ci], ci++) {
     const int slot = (int)(ci % SCIMLOP_HOST_SLOTS);
-    const long long c0 = ci * cc, nc = std::min<long long>(cc, k - c0);
+    const long long nc = sizes[ci];
     char* dV = base + v_off + vslot * slot;
     char* dW = base + w_off + wslot * slot;
     if (ci >= SCIMLOP_HOST_SLOTS) {
