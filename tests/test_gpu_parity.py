@@ -971,3 +971,32 @@ def test_config4_tree_float32_on_tensor_cores(sb, N, K):
     want3 = d[:, None] * (M64.T @ v64) + Dk * (M64 @ v64) + 2 * (M64 @ v64) + v64
     got3 = sb.mul_(dev(sb, np.full_like(w0, np.nan)), L, dv).numpy()
     assert np.linalg.norm(got3 - want3) <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("dtype,M,N,K,pad", [(np.float64, 300, 5, 1000, 4), (np.float64, 4096, 1, 4096, 2), (np.float32, 512, 256, 512, 4),
+                                             (np.float32, 1000, 7, 2000, 8), (np.float64, 256, 64, 256, 6)])
+@pytest.mark.parametrize("ta", [0, 1])
+def test_gemm_padded_leading_dimensions(sb, dtype, M, N, K, pad, ta):
+    """Sub-matrices of larger allocations (lda / ldb / ldc > rows) through every fast path: the skinny TMA kernel, the
+    streamed tcgen05 kernel and the split-K DMMA kernel address operands by leading dimension only."""
+    import torch
+    rng = np.random.default_rng(M + N + K + ta)
+    ar, ac = (K, M) if ta else (M, K)
+    Abig = rnd(rng, ar + pad, ac, dtype=dtype) - dtype(0.5)
+    Bbig = rnd(rng, K + pad, N, dtype=dtype) - dtype(0.5)
+    Cbig0 = rnd(rng, M + pad, N, dtype=dtype)
+    A, B = Abig[:ar], Bbig[:K]
+    opA = (A.T if ta else A).astype(np.float64)
+    want = 0.7 * (opA @ B.astype(np.float64)) + 0.3 * Cbig0[:M]
+    scale = np.linalg.norm(np.abs(opA) @ np.abs(B.astype(np.float64))) + np.linalg.norm(Cbig0[:M])
+    h = sb.handle(0)
+    dA, dB, dC = dev(sb, Abig), dev(sb, Bbig), dev(sb, Cbig0)
+    ct = C.c_double if dtype == np.float64 else C.c_float
+    rc = h.lib.scimlop_gemm_strided_batched(
+        h.ptr, 0 if dtype == np.float64 else 1, 0, ta, 0, M, N, K, C.byref(ct(0.7)), C.c_void_p(dA.ptr), ar + pad, 0,
+        C.c_void_p(dB.ptr), K + pad, 0, C.byref(ct(0.3)), C.c_void_p(dC.ptr), M + pad, 0, 1,
+        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    h.check(rc, "gemm padded")
+    got = dC.numpy()
+    assert np.linalg.norm(got[:M] - want) <= TOL[np.dtype(dtype)] * scale
+    assert np.array_equal(got[M:], Cbig0[M:]), "rows below the sub-matrix must not be touched"
