@@ -733,6 +733,7 @@ class WOperator(AbstractSciMLOperator):
             raise AssertionError(f"WOperator: mass matrix {self.mass_matrix.size()} vs J {self.J.size()}")
         self.gamma = gamma
         self._sum = AddedOperator(self.J, ScaledOperator(self._neg, self.mass_matrix))
+        self._inv, self._inv_key, self._version = None, None, 0
 
     @property
     def dtype(self):
@@ -754,6 +755,8 @@ class WOperator(AbstractSciMLOperator):
     def update_coefficients_(self, u=None, p=None, t=None, gamma=None):
         self.J.update_coefficients_(u, p, t)
         self.mass_matrix.update_coefficients_(u, p, t)
+        if getattr(self.J, "update_func", None) is not None or getattr(self.mass_matrix, "update_func", None) is not None:
+            self._version += 1        # the cached inverse of the concrete form is stale
         if gamma is not None:
             self.gamma = gamma
         return self
@@ -765,6 +768,50 @@ class WOperator(AbstractSciMLOperator):
         if not self._sum.iscached():
             self._sum = self._sum.cache_operator(v)
         return self._sum.mul_(w, v, alpha, beta)
+
+    # ---- W \\ x: the reference converts W to a dense matrix and solves (src/woperator.jl:431-445).  Here the concrete
+    #      form J - M/γ is assembled on the device and inverted once per (J, M, γ); every solve is then a product. ----
+    def has_ldiv(self):
+        return isinstance(self.J, MatrixOperator) and not self.J.banded and \
+            isinstance(self.mass_matrix, (MatrixOperator, IdentityOperator))
+
+    def _concrete_inverse(self):
+        key = (float(self.gamma), self._version)
+        if self._inv is not None and self._inv_key == key:
+            return self._inv
+        if not self.has_ldiv():
+            raise TypeError("WOperator ldiv!: J (and a non-scalar mass matrix) must be dense MatrixOperators")
+        n = self.J.size()[0]
+        dt = self.J.dtype
+        h = _lib.handle(self.J.A.device_index)
+        dense = DeviceArray.empty((n, n), dt, self.J.A.device_index)
+        one, coef = _scalar(dt, 1.0), _scalar(dt, self._neg.convert())
+        src = self.J.A
+        if self.J.trans:            # materialise op(J): dense = J' via a product with the identity is overkill; transpose on copy
+            dense.t.copy_(src.t.view(n, n).t().contiguous().view(-1))
+        else:
+            dense.t.copy_(src.t)
+        if isinstance(self.mass_matrix, IdentityOperator):
+            ones = DeviceArray.full((n,), 1.0, dt, self.J.A.device_index)
+            # the diagonal of `dense` as a 1 x n matrix with leading dimension n + 1
+            h.check(h.lib.scimlop_axpby(h.ptr, _DT[dt], 1, n, C.c_void_p(ones.ptr), 1, C.c_void_p(dense.ptr), n + 1, coef, one,
+                                        _stream()), "scimlop_axpby")
+        else:
+            Mm = self.mass_matrix.A
+            if self.mass_matrix.trans:
+                Mm = DeviceArray(Mm.t.view(n, n).t().contiguous().view(-1), (n, n))
+            h.check(h.lib.scimlop_axpby(h.ptr, _DT[dt], n, n, C.c_void_p(Mm.ptr), n, C.c_void_p(dense.ptr), n, coef, one,
+                                        _stream()), "scimlop_axpby")
+        self._inv = MatrixOperator(_invert_into(dense, dense))
+        self._inv_key = key
+        return self._inv
+
+    def _ldiv(self, w, v, scale=None):
+        F = self._concrete_inverse()
+        src = v
+        if w.t.data_ptr() == v.t.data_ptr():
+            src = v.copy()
+        return F.mul_(w, src, scale, None if scale is None else False)
 
 
 # ====================================================================================================

@@ -118,3 +118,29 @@ def test_woperator(sb, dtype, n, K):
     sb.mul_(y, Wu, bd)
     want = R.woperator_mul(np.empty(shp), 2.0, gamma, f64(J), f64(b))
     assert np.linalg.norm(y.numpy() - want) <= tol * scale
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_woperator_solve(sb, dtype):
+    """`W \\ x` = `convert(AbstractMatrix, W) \\ x` (src/woperator.jl:431-445): the concrete form J - M/γ is assembled
+    and inverted on the device once per (J, M, γ); a new γ re-forms it."""
+    rng = np.random.default_rng(33)
+    n, K = 96, 5
+    J = np.asfortranarray((rng.random((n, n)) - 0.5).astype(dtype))
+    M = np.asfortranarray((rng.random((n, n)) + n * np.eye(n)).astype(dtype))
+    x = np.asfortranarray(rng.random((n, K)).astype(dtype))
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    for mass, Md in ((M, f64(M)), (2.0, 2.0 * np.eye(n))):
+        W = sb.WOperator(mass, 0.37, J)
+        assert sb.has_ldiv(W)
+        for gamma in (0.37, 0.05):
+            W.update_coefficients_(None, None, None, gamma=gamma)
+            dense = f64(J) - Md / gamma
+            want = np.linalg.solve(dense, f64(x))
+            tol = TOL[np.dtype(dtype)] * max(1.0, np.linalg.cond(dense) / 100.0)
+            y = sb.DeviceArray.full((n, K), float("nan"), dtype)
+            sb.ldiv_(y, W, sb.DeviceArray.from_numpy(x))
+            assert R.rel_err(y.numpy(), want) <= tol
+            u = sb.DeviceArray.from_numpy(x)
+            sb.ldiv_(W, u)
+            assert R.rel_err(u.numpy(), want) <= tol
