@@ -162,23 +162,30 @@ def test_gemm_f32_tensor_core_large_repeated(sb):
     check(outs[(0, 3)][: M * 64].cpu().numpy().reshape((M, 64), order="F"), Ah @ Bh, np.float32, "sampled block vs oracle")
 
 
+@pytest.mark.parametrize("profile", ["small", "large"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_gemm_dispatch_fuzz(sb, dtype):
+def test_gemm_dispatch_fuzz(sb, dtype, profile):
     """Seeded fuzz over the GEMM dispatcher: random extents (including 1 and non-multiples of every tile),
     padded leading dimensions (even/odd), offset base pointers, shared or batched operands, all transposes,
-    alpha/beta on or off -- whatever kernel the dispatcher picks must agree with the Float64 product."""
+    alpha/beta on or off -- whatever kernel the dispatcher picks must agree with the Float64 product.
+    "large" draws the shapes of the few-column (skinny), split-K, and streamed tcgen05 paths and their boundaries."""
     import torch
     h = sb.handle(0)
-    rng = np.random.default_rng(1234 if dtype == np.float64 else 4321)
+    rng = np.random.default_rng((1234 if dtype == np.float64 else 4321) + (7 if profile == "large" else 0))
     es = np.dtype(dtype).itemsize
     ct = C.c_double if dtype == np.float64 else C.c_float
     dt = 0 if dtype == np.float64 else 1
     sizes = [1, 2, 5, 16, 31, 32, 33, 64, 100, 128, 129, 200, 256, 300]
-    for trial in range(40):
+    for trial in range(40 if profile == "small" else 30):
         M, N, K = (int(rng.choice(sizes)) for _ in range(3))
         if trial % 5 == 0:
             N = int(rng.choice([1024, 2048, 4100]))      # long streamed side: tensor-core eligible shapes
         batch = int(rng.choice([1, 1, 2, 5]))
+        if profile == "large":
+            M = int(rng.choice([16, 64, 128, 130, 512, 700, 1024, 2048]))
+            K = int(rng.choice([32, 63, 64, 65, 128, 129, 512, 1000, 2048]))
+            N = int(rng.choice([1, 2, 3, 8, 9, 15, 16, 17, 48, 49, 64, 65, 130, 512]))
+            batch = int(rng.choice([1, 1, 1, 3]))
         ta, tb = int(rng.integers(2)), int(rng.integers(2))
         ar, ac = (K, M) if ta else (M, K)
         br, bc = (N, K) if tb else (K, N)
