@@ -1,5 +1,7 @@
-// gemm_tf32.cuh -- Float32 "streaming operand x resident factor" GEMM on the 5th-generation tensor cores:
-// tcgen05.mma (kind::tf32) with TMEM accumulators, TMA-staged operands, 3xTF32 split for FP32-grade accuracy.
+// gemm_tf32.cuh -- Float32 GEMM on the 5th-generation tensor cores: tcgen05.mma (kind::tf32) with TMEM
+// accumulators, TMA-staged operands, 3xTF32 split for FP32-grade accuracy.  Two modes of one kernel: "streaming
+// operand x resident factor" (described first; the Kronecker mode products of config 3) and, with STREAM_F, the
+// general GEMM in which the second operand streams too (see the comment above the kernel).
 //
 //   D(r, c) = alpha * sum_k X(r, k) * Fop(c, k)  +  beta * D(r, c)            r < rows, c < m, k < n
 //

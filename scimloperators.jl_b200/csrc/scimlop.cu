@@ -3,7 +3,13 @@
 //
 // Reference behaviour being replaced (SciMLOperators.jl): src/tensor.jl:543-610,750-834 (TPO mul! and
 // outer_mul!), src/matrix.jl:337-361, src/batch.jl:151-179, src/basic.jl:74-90,248-264,518-536,834-854,
-// 1160-1207.  No CPU fallback: every path ends in a CUDA kernel launch or an error status.
+// 1160-1207, src/block.jl:145-179.  No CPU fallback: every path ends in a CUDA kernel launch or an error status.
+//
+// GEMM dispatch (gemm_dispatch<T>), in order of preference:
+//   Float64: few columns -> gemm_skinny (TMA ring, cluster/DSMEM reduce, HBM-bound); aligned -> gemm_dmma (FP64
+//            DMMA; split-K over clusters when tiles < SMs; PEER variant for the fused all-gather); else gemm_simt.
+//   Float32: small resident factor -> gemm_tf32x3 (tcgen05, TMEM); few columns -> gemm_skinny; large ->
+//            gemm_tf32x3<STREAM_F> (pre-split operand streamed, chunked accumulation); else / FP32_EXACT -> gemm_simt.
 #include <algorithm>
 #include <new>
 
