@@ -43,9 +43,9 @@ FLOPS_PER_COL = 2.0 * MI * NI * NO + 2.0 * MO * NO * MI      # stage 1 + stage 2
 METRIC = "kron(A,B)*V mul! throughput (512x512 (x) 512x512 Float64, 262144x256 batch per GPU)"
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool: tools/peaks.cu -> profiles/r01_peaks_microbench.json
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm_dmma_kernel on this workload, from the
-# `ncu --set full` capture summarised in profiles/r01_ncu_dmma_v5_summary.txt (539.0 + 494.0 MB stage 1,
-# 539.3 + 497.6 MB stage 2): the algorithmic 537 MB in + 537 MB out, i.e. no re-reads.
-NCU_DRAM_BYTES_PER_LAUNCH = 0.5 * ((539.037952 + 494.045440) + (539.252224 + 497.558528)) * 1e6
+# `ncu --set full` capture summarised in profiles/r01_ncu_dmma_v6_summary.txt (539.0 + 492.1 MB stage 1,
+# 539.2 + 495.2 MB stage 2): the algorithmic 537 MB in + 537 MB out, i.e. no re-reads.
+NCU_DRAM_BYTES_PER_LAUNCH = 0.5 * ((539.041536 + 492.103936) + (539.223808 + 495.223552)) * 1e6
 REF_SAMPLE_COLS = 32             # --impl reference / cpu_baseline: columns per CPU step (bounded sample)
 
 
@@ -324,7 +324,7 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                      "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, profiles/r01_ncu_dmma_v5_summary.txt); "
+                     "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, profiles/r01_ncu_dmma_v6_summary.txt); "
                                      "algorithmic bytes per launch = 1.076e9",
                      "kernel": "scimlop::dmma::gemm_dmma_kernel (2 launches per step: stage 1 B*U, stage 2 batched C1_j*A^T)",
                      "peak_source": "FP64 DMMA.8x8x4 issue-rate microbenchmark on this pool (profiles/r01_peaks_microbench.json); "
