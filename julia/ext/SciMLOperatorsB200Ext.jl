@@ -319,7 +319,25 @@ function LinearAlgebra.factorize(L::MatrixOperator{T, <:CuMatrix{T}}) where {T <
     SciMLOperators.InvertibleOperator(L, DeviceInverse{T}(Ainv))
 end
 
-# flatten_inverse(L, T): like flatten, with every InvertibleOperator leaf replaced by pointer(L.F.inv) and λ by 1/λ
+# like `flatten`, with every factorised leaf replaced by its cached device inverse and every λ by 1/λ
+function flatten_inverse(L::TensorProductOperator, T)
+    kinds = Cint[]; ptrs = Ptr{Cvoid}[]; dims = Int64[]; lds = Int64[]; λinv = one(T)
+    function walk(op)
+        if op isa ScaledOperator
+            λinv /= convert(Number, op.λ); return walk(op.L)
+        elseif op isa TensorProductOperator
+            return all(walk, op.ops)
+        elseif op isa IdentityOperator
+            push!(kinds, IDENTITY); push!(ptrs, C_NULL); push!(lds, 0)
+        elseif op isa SciMLOperators.InvertibleOperator && op.F isa DeviceInverse{T}
+            push!(kinds, DENSE); push!(ptrs, dptr(op.F.inv)); push!(lds, stride(op.F.inv, 2))
+        else
+            return false                      # not factorised on the device: the generic ldiv! runs
+        end
+        append!(dims, size(op)); true
+    end
+    walk(L) ? (kinds, ptrs, dims, lds, λinv) : nothing
+end
 function LinearAlgebra.ldiv!(w::DevMat{T}, L::TensorProductOperator, v::DevMat{T}) where {T <: F}
     @assert iscached(L)                                                            # src/tensor.jl:617
     fl = flatten_inverse(L, T)
