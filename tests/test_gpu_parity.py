@@ -763,6 +763,12 @@ def test_banded_factors(sb, dtype):
         want = R.kron_apply([f(A), np.eye(mi)], f(v)) + R.kron_apply([np.eye(mo), f(B)], f(v))
         check(sb.mul_(dev(sb, np.full_like(w0, np.nan)), S, dv).numpy(), want, dtype, "banded kronsum 3-arg")
         check(sb.mul_(dev(sb, w0), S, dv, 0.7, 0.3).numpy(), 0.7 * want + 0.3 * f(w0), dtype, "banded kronsum 5-arg")
+        # the same operator spelled kron(A, I) + kron(I, B) (config 5's spelling) is recognised as that Kronecker sum
+        for Ladd in (sb.kron(opA, sb.IdentityOperator(mi)) + sb.kron(sb.IdentityOperator(mo), opB),
+                     sb.kron(sb.IdentityOperator(mo), opB) + sb.kron(opA, sb.IdentityOperator(mi))):
+            Ladd = sb.cache_operator(Ladd, dv)
+            assert Ladd._kronsum is not None and sb.iscached(Ladd)
+            check(sb.mul_(dev(sb, w0), Ladd, dv, 0.7, 0.3).numpy(), 0.7 * want + 0.3 * f(w0), dtype, "added-TPO spelling")
 
 
 # ---- end-to-end host entry --------------------------------------------------------------------------------
