@@ -94,3 +94,25 @@ def cg(L, B, X, iters, state=None, use_graph=True, iters_per_graph=8):
         _cg_iteration(st, X, parity)
         parity ^= 1
     return X, st.rs[parity], st
+
+
+class CapturedMul:
+    """`mul!(w, L, v[, α, β])` with fixed buffers captured once into a CUDA graph: an ODE / Krylov loop replays it
+    (`update_coefficients!` may rewrite the operator's device arrays in between -- the graph holds pointers, not
+    values; scalars α, β and ScaledOperator λ's are baked in at capture).  For small operators (config 1, vector
+    inputs) this removes the per-call host work between the launches."""
+
+    def __init__(self, L, w, v, alpha=None, beta=None):
+        self.L, self.w, self.v = L, w, v
+        self.stream = torch.cuda.Stream(device=w.t.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(self.stream):
+            L.mul_(w, v, alpha, beta)                      # warm-up outside the capture (lazy set-up happens here)
+            self.stream.synchronize()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                L.mul_(w, v, alpha, beta)
+        self.stream.synchronize()
+
+    def replay(self):
+        self.graph.replay()
+        return self.w

@@ -1013,3 +1013,4 @@ def test_gemm_padded_leading_dimensions(sb, dtype, M, N, K, pad, ta):
     got = dC.numpy()
     assert np.linalg.norm(got[:M] - want) <= TOL[np.dtype(dtype)] * scale
     assert np.array_equal(got[M:], Cbig0[M:]), "rows below the sub-matrix must not be touched"
+
