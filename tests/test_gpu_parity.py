@@ -1014,3 +1014,22 @@ def test_gemm_padded_leading_dimensions(sb, dtype, M, N, K, pad, ta):
     assert np.linalg.norm(got[:M] - want) <= TOL[np.dtype(dtype)] * scale
     assert np.array_equal(got[M:], Cbig0[M:]), "rows below the sub-matrix must not be touched"
 
+
+
+def test_captured_mul_replays_with_updated_inputs(sb):
+    """A captured mul! (CUDA graph) reads the CURRENT contents of v and of the operator's arrays at every replay."""
+    import torch
+    rng = np.random.default_rng(77)
+    A, B = rnd(rng, 12, 12), rnd(rng, 9, 9)
+    v1, v2 = rnd(rng, 108, 3), rnd(rng, 108, 3)
+    dv = dev(sb, v1)
+    w = sb.DeviceArray.full((108, 3), float("nan"), np.float64)
+    opA = sb.MatrixOperator(A)
+    L = sb.cache_operator(sb.kron(opA, B), dv)
+    cm = sb.krylov.CapturedMul(L, w, dv)
+    cm.replay(); torch.cuda.synchronize()
+    check(w.numpy(), np.kron(A, B) @ v1, np.float64, "captured mul!")
+    dv.t.copy_(dev(sb, v2).t)                                  # new input, same buffer
+    opA.A.t.mul_(2.0)                                          # update_coefficients!-style in-place change of a factor
+    cm.replay(); torch.cuda.synchronize()
+    check(w.numpy(), np.kron(2 * A, B) @ v2, np.float64, "captured mul! after updates")
