@@ -21,7 +21,7 @@ for dtype, tdt in ((np.float32, torch.float32), (np.float64, torch.float64)):
         w = sb.DeviceArray.zeros((n, k), dtype)
         for trans in (False, True):
             L = sb.MatrixOperator(A, trans=trans)
-            for prec, name in ((_lib.PREC_DEFAULT, "default"),) + (((_lib.PREC_FP32_EXACT, "fp32_exact"),) if dtype == np.float32 else ()):
+            for prec, name in ((_lib.PREC_DEFAULT, "default"),) + (((_lib.PREC_FP32_EXACT, "fp32_exact"), (_lib.PREC_TF32, "tf32_single_pass_opt_in")) if dtype == np.float32 else ()):
                 L.precision = prec
                 t = ev_time(lambda: sb.mul_(w, L, v))
                 print(json.dumps({"dtype": np.dtype(dtype).name, "n": n, "k": k, "trans": trans, "precision": name,
