@@ -10,7 +10,11 @@ first), 1 (V), 2 (W0) -- BASELINE.md §2.
 
 Multi-GPU (one process per GPU, torchrun): columns are independent units, every rank owns a full
 262144 x 256 slab (weak scaling, global batch = 256*N columns), factors replicated, NO collective on the
-data path.
+data path.  `value` stays that weak number; the same line also carries, under `config.strong`,
+the STRONG-scaled named shape (256 columns in total, 256/N per rank through scimlop_shard_columns) -- compute only,
+and with W replicated on every rank (compute -> ncclAllGather, and the fused compute + all-gather kernels over
+peer stores / NVSwitch multicast, each bit-compared with the unfused result: a mismatch fails the run) -- and,
+under `config.c5`, configs[4] (dense 4096^2 Kronecker sum, one column per GPU, R = 50 matvecs in one CUDA graph).
 
 Prints ONE JSON line (rank 0).  `value` = whole-job TFLOP/s with V, W resident in HBM; `e2e` = the same metric
 through the host-buffer C-ABI call (pinned host V/W, H2D and D2H inside the timed region); `roofline` = the
@@ -18,7 +22,8 @@ DMMA GEMM kernel against the measured FP64-DMMA issue peak; `cpu_baseline` = the
 reference algorithm (oracle/) timed on this box's host cores.
 
 `--impl reference` times the reference's own CPU algorithm (Julia is not installable here, so this is the
-oracle port: OpenBLAS GEMM + materialised permutes, src/tensor.jl:568,778-788) on a bounded sample."""
+oracle port: OpenBLAS GEMM + materialised permutes, src/tensor.jl:568,778-788) on the SAME configuration: the
+full 262144 x 256 batch per step, all host threads."""
 import argparse
 import ctypes as C
 import json
@@ -46,7 +51,10 @@ FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool: tools/peaks.cu -> prof
 # `ncu --set full` capture summarised in profiles/r01_ncu_dmma_v6_summary.txt (539.0 + 492.1 MB stage 1,
 # 539.2 + 495.2 MB stage 2): the algorithmic 537 MB in + 537 MB out, i.e. no re-reads.
 NCU_DRAM_BYTES_PER_LAUNCH = 0.5 * ((539.041536 + 492.103936) + (539.223808 + 495.223552)) * 1e6
-REF_SAMPLE_COLS = 32             # --impl reference / cpu_baseline: columns per CPU step (bounded sample)
+REF_COLS = KCOLS                 # --impl reference / cpu_baseline (stdlib variant): the full batch, as benchmarks/tensor.jl:17-24 times it
+LV_SAMPLE_COLS = 32              # cpu_baseline, LoopVectorization variant (single-thread nest): columns timed, unscaled
+C5_N = 4096                      # configs[4]: Dxx, Dyy 4096 x 4096 dense Float64
+C5_MATVECS = 50                  # matvecs captured in one CUDA graph (R >= 50)
 
 
 def make_factors():
@@ -77,6 +85,7 @@ def cpu_time_one(variant, A, B, v, reps):
             np.matmul(B, v.reshape((NI, NO * v.shape[1]), order="F"), out=c1)
             lib.lv_outer_mul(w, A, c1, MI, MO, NO, v.shape[1])
     best = float("inf")
+    fn()                                   # warm-up (page faults of the scratch, BLAS thread start-up)
     for _ in range(reps):
         t0 = time.perf_counter()
         fn()
@@ -89,7 +98,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     A, B = make_factors()
-    k = REF_SAMPLE_COLS
+    k = REF_COLS
     v = np.asfortranarray(np.random.default_rng(1).random((NO * NI, k)))
     from oracle import ref_numpy as R
     L = R.TensorProductOperator(A, B, lv=False).cache_operator(v)
@@ -102,14 +111,16 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     tflops = FLOPS_PER_COL * k / dt / 1e12
     cores = os.cpu_count()
-    sample = f"{k} of {KCOLS} columns per step (same factors, same V distribution)"
+    sample = f"all {k} of {KCOLS} columns per step (the whole configs[1] batch; nothing scaled)"
     line = {
         "impl": "reference", "metric": METRIC, "value": tflops, "unit": "TFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: kron(A,B) 512x512 (x) 512x512 Float64, mul!(w,L,v); CPU restatement of "
-                               "the reference algorithm (OpenBLAS gemm + materialised permutedims, "
-                               "src/tensor.jl:568,778-788) -- Julia is not installable in this image", "sample": sample},
+        "config": {"workload": "configs[1]: TensorProductOperator(MatrixOperator(A), MatrixOperator(B)), A,B 512x512 "
+                               "Float64, cache_operator + mul!(w,L,v) on a 262144x256 batch per GPU",
+                   "implementation": "CPU restatement of the reference algorithm (OpenBLAS gemm + materialised "
+                                     "permutedims, src/tensor.jl:568,778-788), all host threads -- Julia is not "
+                                     "installable in this image", "sample": sample},
         "cpu_baseline": {"value": tflops, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -167,6 +178,183 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.max, "reasons": sorted(self.reasons), "samples": 0}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# extra legs of the GPU arm (reported inside `config`; `value` stays the weak-scaled headline)
+# --------------------------------------------------------------------------------------------------
+def _timed_max(torch, dist, world, fn, reps, warm=3):
+    """ms per call: CUDA events on the current stream, barrier on both sides, max over ranks."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    e1.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def copy_floor_ms(torch, dist, world, Vh, Wh, Vd, Wd, reps=5):
+    """Pure pinned H2D of V concurrent with D2H of W (two streams, no kernels): the PCIe / host-memory floor of the
+    e2e step on this box at this rank count (all ranks copy at the same time)."""
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def once():
+        with torch.cuda.stream(s_up):
+            Vd.copy_(Vh, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            Wh.copy_(Wd, non_blocking=True)
+    once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) * 1e3
+
+
+def strong_legs(torch, dist, sb, h, world, rank, A, B, ms_1gpu_shape):
+    """configs[1] STRONG-scaled: 256 columns in total, columns [first, first+count) per rank.  Returns a dict for
+    `config.strong`; raises SystemExit(3) if a fused all-gather variant is not bit-identical to the unfused result."""
+    from scimlop_b200 import distributed as sd
+    n = NO * NI
+    first, kper = sd.shard_columns(KCOLS, world, rank)
+    assert kper * world == KCOLS
+
+    def slab_of(r):
+        g = torch.Generator(device="cuda").manual_seed(4242 + r)
+        return sb.DeviceArray(torch.rand(n * kper, dtype=torch.float64, device="cuda", generator=g), (n, kper))
+
+    V = slab_of(rank)
+    Wl = sb.DeviceArray.full((n, kper), float("nan"), np.float64)
+    L = sb.cache_operator(sb.kron(sb.MatrixOperator(A), sb.MatrixOperator(B)), V)
+    out = {"columns_total": KCOLS, "cols_per_rank": kper, "flops_total": FLOPS_PER_COL * KCOLS}
+    t_comp = _timed_max(torch, dist, world, lambda: sb.mul_(Wl, L, V), reps=20)
+    out["compute_only_ms"] = t_comp
+    out["compute_only_tflops"] = FLOPS_PER_COL * KCOLS / (t_comp * 1e-3) / 1e12
+    out["speedup_vs_1gpu"] = ms_1gpu_shape / t_comp if ms_1gpu_shape else None
+    if world == 1:
+        return out
+
+    # ---- W replicated on every rank ----
+    def bcast(b):
+        o = [b]
+        dist.broadcast_object_list(o, src=0)
+        return o[0]
+
+    def gather_obj(o):
+        res = [None] * world
+        dist.all_gather_object(res, o)
+        return res
+
+    sd.init_comm(h, world, rank, bcast)
+    W = sb.DeviceArray.zeros((n, KCOLS), np.float64)
+    mine = W.cols(first, first + kper)
+    out["gathered_bytes_per_rank"] = (world - 1) * n * kper * 8
+    out["replicated_nccl_ms"] = _timed_max(torch, dist, world, lambda: (sb.mul_(mine, L, V), sd.allgather_cols(h, W, kper)), reps=20)
+
+    # the unfused result of EVERY slab, recomputed locally from that rank's (seeded) V: the bit-compare reference
+    def check(Wfull, what):
+        ref = sb.DeviceArray.empty((n, kper), np.float64)
+        for r in range(world):
+            sb.mul_(ref, L, slab_of(r))
+            if not torch.equal(Wfull.cols(r * kper, (r + 1) * kper).t, ref.t):
+                d = float((Wfull.cols(r * kper, (r + 1) * kper).t - ref.t).abs().max())
+                print(json.dumps({"error": f"{what}: slab {r} on rank {rank} differs from the unfused result", "max_abs_diff": d}),
+                      file=sys.stderr, flush=True)
+                return False
+        return True
+
+    ok = True
+    try:
+        win = sd.PeerWindow(h, W, rank, world, gather_obj)
+        out["replicated_fused_peer_ms"] = _timed_max(torch, dist, world, lambda: sd.kron_mul_peers(h, L, V, win, kper), reps=20)
+        W.t.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sd.kron_mul_peers(h, L, V, win, kper)
+        torch.cuda.synchronize()
+        dist.barrier()
+        good = check(W, "fused peer-store all-gather")
+        out["replicated_fused_peer_bit_identical"] = good
+        ok = ok and good
+        torch.cuda.synchronize()
+        dist.barrier()
+        win.close()
+    except sb.ScimlopError as e:
+        out["replicated_fused_peer_unavailable"] = str(e)[:160]
+    try:
+        mcw = sd.MulticastWindow(h, (n, KCOLS), np.float64, rank, world, gather_obj, dist.barrier)
+    except Exception as e:                      # no NVSwitch multicast on this box
+        mcw = None
+        out["replicated_fused_multicast_unavailable"] = str(e)[:160]
+    if mcw is not None:
+        out["replicated_fused_multicast_ms"] = _timed_max(torch, dist, world, lambda: sd.kron_mul_mc(h, L, V, mcw, kper), reps=20)
+        mcw.W.t.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sd.kron_mul_mc(h, L, V, mcw, kper)
+        torch.cuda.synchronize()
+        dist.barrier()
+        good = check(mcw.W, "fused multicast all-gather")
+        out["replicated_fused_multicast_bit_identical"] = good
+        ok = ok and good
+        torch.cuda.synchronize()
+        dist.barrier()
+        mcw.close()
+    flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    out["all_ranks_bit_identical"] = bool(flag.item() == 0)
+    return out
+
+
+def c5_leg(torch, dist, sb, world, rank):
+    """configs[4]: kron(Dxx, I) + kron(I, Dyy) on a 4096 x 4096 grid (dense spectral-style factors, Float64), batch-
+    sharded: ONE column per GPU, C5_MATVECS dependent matvecs (w -> v ping-pong) captured in one CUDA graph."""
+    N = C5_N
+    rng = np.random.default_rng(5)
+    Dxx = np.asfortranarray(rng.random((N, N)) / N)      # spectral radius ~ 0.5: repeated application stays finite
+    Dyy = np.asfortranarray(rng.random((N, N)) / N)
+    g = torch.Generator(device="cuda").manual_seed(77 + rank)
+    v = sb.DeviceArray(torch.rand(N * N, dtype=torch.float64, device="cuda", generator=g), (N * N, 1))
+    w = sb.DeviceArray.zeros((N * N, 1), np.float64)
+    Ix = sb.IdentityOperator(N)
+    L = sb.cache_operator(sb.kron(sb.MatrixOperator(Dxx), Ix) + sb.kron(Ix, sb.MatrixOperator(Dyy)), v)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        sb.mul_(w, L, v)
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(C5_MATVECS // 2):
+                sb.mul_(w, L, v)
+                sb.mul_(v, L, w)
+    torch.cuda.current_stream().wait_stream(side)
+    ms = _timed_max(torch, dist, world, graph.replay, reps=2, warm=1)
+    flops_col = 2.0 * 2.0 * N ** 3
+    finite = bool(torch.isfinite(v.t).all().item())
+    return {"workload": "configs[4]: AddedOperator kron(Dxx,I)+kron(I,Dyy), dense 4096x4096 Float64 factors, "
+                        "N = 16777216, one column per GPU (global batch = n_gpus columns)",
+            "matvecs_per_graph": C5_MATVECS, "ms_per_matvec": ms / C5_MATVECS,
+            "tflops_aggregate": flops_col * world / (ms / C5_MATVECS * 1e-3) / 1e12,
+            "frac_of_dmma_peak_per_gpu": flops_col / (ms / C5_MATVECS * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+            "result_finite": finite}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -277,15 +465,30 @@ def run_gpu(args):
     sb.mul_(W, L, V)
     torch.cuda.synchronize()
     mism = float((W.t[: MO * MI * 4].cpu() - Wh[: MO * MI * 4]).abs().max())
+    W_head = W.cols(0, 2).numpy()          # for the parity spot check below (W is reused as a copy target next)
+
+    # pure-copy floor of the e2e step (H2D of V concurrent with D2H of W, all ranks at once)
+    floor_ms = copy_floor_ms(torch, dist, world, Vh, Wh, V.t, W.t)
+
+    # ---- strong-scaled named shape (+ replicated-W variants) and configs[4]; both inside `config` -------------
+    del L
+    strong = strong_legs(torch, dist, sb, h, world, rank, A, B, ms)
+    c5 = c5_leg(torch, dist, sb, world, rank)
+    if world > 1 and not strong.get("all_ranks_bit_identical", True):
+        if rank == 0:
+            print(json.dumps({"error": "a fused compute + all-gather variant differs from the unfused result", "strong": strong}))
+        dist.destroy_process_group()
+        return 3
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only, bounded sample) ---------------------
-    ks = REF_SAMPLE_COLS
-    vs = np.asfortranarray(Vh.numpy()[: n * ks].reshape((n, ks), order="F"))
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ----------------------------------------
+    # stdlib variant on the whole batch (same configuration as the GPU arm, ~1.3 s per mul!); the LoopVectorization
+    # variant (single-thread SIMD nest) on its own 32-column sample, reported in its own TFLOP/s -- nothing is scaled
+    vs = np.asfortranarray(Vh.numpy().reshape((n, KCOLS), order="F"))
     cpu_line = None
     if world == 1:
         try:
@@ -293,16 +496,18 @@ def run_gpu(args):
             limiter = threadpool_limits(limits=os.cpu_count())
         except Exception:
             limiter = None
-        t_std = cpu_time_one("stdlib", A, B, vs, reps=3)
-        t_lv = cpu_time_one("lv", A, B, vs[:, :4].copy(order="F"), reps=2) * (ks / 4.0)
-        cpu_best = min(t_std, t_lv)
-        cpu_line = {"value": FLOPS_PER_COL * ks / cpu_best / 1e12, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port",
-                    "sample": f"{ks} of {KCOLS} columns (LV variant timed on 4 columns and scaled)",
-                    "stdlib_path_s": t_std, "lv_path_s": t_lv,
-                    "note": "CPU restatement of the reference algorithm (oracle/), not the Julia reference itself"}
+        t_std = cpu_time_one("stdlib", A, B, vs, reps=2)
+        t_lv = cpu_time_one("lv", A, B, vs[:, :LV_SAMPLE_COLS].copy(order="F"), reps=2)
+        std_tf = FLOPS_PER_COL * KCOLS / t_std / 1e12
+        lv_tf = FLOPS_PER_COL * LV_SAMPLE_COLS / t_lv / 1e12
+        cpu_line = {"value": max(std_tf, lv_tf), "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port",
+                    "sample": f"stdlib variant: all {KCOLS} columns (min of 2 runs after one warm-up); LoopVectorization "
+                              f"variant: {LV_SAMPLE_COLS} columns, unscaled",
+                    "stdlib_path_s": t_std, "stdlib_tflops": std_tf, "lv_path_s": t_lv, "lv_tflops": lv_tf,
+                    "lv_cores": 1, "note": "CPU restatement of the reference algorithm (oracle/), not the Julia reference itself"}
     # parity spot check of the timed GPU result against the same CPU restatement
     from oracle import ref_numpy as R
-    err = R.rel_err(W.cols(0, 2).numpy(), R.kron_apply([A, B], vs[:, :2]))
+    err = R.rel_err(W_head, R.kron_apply([A, B], np.asfortranarray(vs[:, :2])))
 
     flops_per_launch = flops_step_rank / 2.0           # both launches are the same kernel and the same flop count
     launch_ms = ms / 2.0
@@ -316,10 +521,13 @@ def run_gpu(args):
                    "global_batch_columns": KCOLS * world, "parallelism": f"column-sharded x{world}, factors replicated, "
                    "no data-path collective", "l2": "inputs larger than L2: V, W and the intermediate are 537 MB "
                    "each vs 126 MB L2", "ms_per_step_5arg": ms5, "parity_rel_err_vs_oracle": err,
-                   "e2e_vs_resident_max_abs_diff": mism},
+                   "e2e_vs_resident_max_abs_diff": mism, "strong": strong, "c5": c5},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": int(Vh.numel() * 8 + Ah.nbytes + Bh.nbytes),
                 "d2h_bytes_per_step": int(Wh.numel() * 8), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                "copy_floor_ms": floor_ms, "frac_of_copy_floor": floor_ms / (e2e_s * 1e3),
+                "copy_floor": "pinned H2D of V concurrent with D2H of W on two streams, no kernels, all ranks at once "
+                              "(max over ranks); the ranks of one box share one NUMA node and its PCIe / memory paths",
                 "api": "scimlop_kron_mul_host (pinned host V/W, chunked H2D | kernels | D2H overlap)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
