@@ -8,9 +8,13 @@
  *   - `alpha`/`beta` are HOST pointers to one scalar of the operand dtype; `beta == NULL` or `*beta == 0`
  *     means "3-arg mul!": W is overwritten and never read (src/batch.jl:222-223, src/basic.jl:251,521,
  *     BLAS convention at src/matrix.jl:349); `alpha == NULL` means 1;
- *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*); nothing allocates;
- *     scratch is caller-owned (`*_workspace_bytes` says how much) -- mirrors `cache_operator`
- *     allocating once and `mul!` being allocation-free (test/Downstream/alloccheck.jl);
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*).  A `mul!` on a CACHED operator
+ *     never allocates and never re-prepares constant data: scratch is caller-owned (`*_workspace_bytes` says how
+ *     much) and the hi / lo images that the Float32 tensor-core GEMM needs of a large constant matrix are made once
+ *     (scimlop_split_attach, below) -- mirrors `cache_operator` allocating once and `mul!` being allocation-free
+ *     (test/Downstream/alloccheck.jl).  Only the two convenience forms say otherwise in their own comments:
+ *     scimlop_kron_mul_host (device staging) and a large Float32 product on an operand that was never attached
+ *     (handle-owned grow-only scratch + one extra split launch per call);
  *   - every function returns an int status (SCIMLOP_OK == 0); no exception crosses the boundary;
  *   - a handle is per device and is not thread-safe, like a cached operator's scratch
  *     (src/SciMLOperators.jl:131-132).
@@ -93,6 +97,23 @@ int scimlop_launch_count(scimlop_handle_t h, int64_t* count);
 int scimlop_matmul(scimlop_handle_t h, int dtype, int precision, int transA, int64_t m, int64_t n,
                    int64_t k, const void* A, int64_t lda, const void* V, int64_t ldv, void* W,
                    int64_t ldw, const void* alpha, const void* beta, void* stream);
+
+/* Float32 operands of the streamed tensor-core GEMM (matrices beyond the 128 x 128 resident-factor kernel: large
+ * MatrixOperators, Kronecker factors > 128, dense tree / block-diagonal leaves).  3xTF32 needs the operand as
+ * hi + lo halves; for a constant operator that is prepared ONCE: `cache_operator` allocates scimlop_split_bytes
+ * and calls scimlop_split_attach (one launch: splits now, and remembers A -> image in the handle);
+ * `update_coefficients!` of a time-dependent matrix calls scimlop_split_refresh; the finaliser calls
+ * scimlop_split_detach.  Every later product whose operand is (A, lda, rows, cols) -- through scimlop_matmul,
+ * scimlop_gemm_strided_batched, scimlop_kron_mul, scimlop_tree_mul, scimlop_blockdiag_mul -- is then ONE kernel
+ * launch with no allocation.  rows x cols is the STORED shape (before any transpose flag).  An operand that was
+ * never attached still works (uncached convenience): the smaller operand is split per call into a handle-owned
+ * scratch that grows on demand.  Replaces nothing in the reference (BLAS sgemm has no such state); it is what keeps
+ * `mul!` allocation-free here (test/Downstream/alloccheck.jl:14,100-122). */
+int scimlop_split_bytes(int64_t rows, int64_t cols, size_t* bytes);
+int scimlop_split_attach(scimlop_handle_t h, const void* A, int64_t lda, int64_t rows, int64_t cols, void* split,
+                         size_t split_bytes, void* stream);
+int scimlop_split_refresh(scimlop_handle_t h, const void* A, void* stream);
+int scimlop_split_detach(scimlop_handle_t h, const void* A);
 
 /* Strided-batched GEMM engine: C_b(M x N) = alpha * op(A_b)(M x K) * op(B_b)(K x N) + beta * C_b,
  * b = 0..batch-1, operand b at base + b*stride (elements; stride 0 = shared operand).  This is what the
@@ -269,7 +290,10 @@ int scimlop_kron_mul_allgather(scimlop_handle_t h, int dtype, int precision, int
  * column slab ONCE and stores every output tile into its own W_full AND into the same columns of every peer's
  * W_full from the stage-2 epilogue, tile by tile while the tensor pipe works on the next tile -- no separate
  * collective.  scimlop_comm_barrier (a one-word NCCL all-reduce on the stream) tells every rank that all slabs
- * have landed.  Float64, outermost factor dense, beta == 0 (the result is overwritten). */
+ * have landed.  Float64, outermost factor dense, beta == 0 (the result is overwritten).
+ * ORDERING CONTRACT: the remote stores of call i+1 may only start once every rank has finished READING the W of call
+ * i.  A caller that consumes W between calls must therefore also issue scimlop_comm_barrier BEFORE the next
+ * scimlop_kron_mul_peers / _mc (after its reads of W are enqueued), or alternate between two W buffers. */
 int scimlop_peer_export(scimlop_handle_t h, const void* dev_ptr, void* ipc_handle_64B, int64_t* offset);
 int scimlop_peer_open(scimlop_handle_t h, const void* ipc_handle_64B, int64_t offset, void** peer_ptr);
 int scimlop_peer_close(scimlop_handle_t h, void* peer_ptr, int64_t offset);

@@ -46,6 +46,10 @@ SIGNATURES = {
     "scimlop_last_error": [_P, C.c_char_p, _SZ],
     "scimlop_launch_count": [_P, _I64P],
     "scimlop_matmul": [_P, _INT, _INT, _INT, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P],
+    "scimlop_split_bytes": [_I64, _I64, C.POINTER(_SZ)],
+    "scimlop_split_attach": [_P, _P, _I64, _I64, _I64, _P, _SZ, _P],
+    "scimlop_split_refresh": [_P, _P, _P],
+    "scimlop_split_detach": [_P, _P],
     "scimlop_gemm_strided_batched": [_P, _INT, _INT, _INT, _INT, _I64, _I64, _I64, _P, _P, _I64, _I64, _P, _I64,
                                      _I64, _P, _P, _I64, _I64, _I64, _P],
     "scimlop_diag_mul": [_P, _INT, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P],

@@ -15,6 +15,17 @@ typedef CUresult (*scimlop_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, c
                                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 constexpr int SCIMLOP_HOST_SLOTS = 3;
+constexpr int SCIMLOP_MAX_SPLITS = 128;
+
+// A Float32 matrix whose hi / lo halves (3xTF32 split) the caller prepared once (scimlop_split_attach): the streamed
+// tcgen05 GEMM uses them instead of splitting the operand on every call.
+struct scimlop_split_entry {
+  const void* src;        // the matrix this is the split of (device pointer, the lookup key)
+  long long ld, rows, cols;   // its stored layout
+  float* hi;              // rows x cols, leading dimension ld_split; lo follows at hi + ld_split * cols
+  float* lo;
+  long long ld_split;
+};
 
 struct scimlop_context {
   uint32_t magic;
@@ -22,7 +33,12 @@ struct scimlop_context {
   int sm_count;
   int sm_reserve;  // SMs left free by the persistent GEMM kernels (for concurrently running NCCL kernels)
   scimlop_encode_tiled_fn encode_tiled;
-  cudaMemPool_t pool;        // stream-ordered scratch of the streamed Float32 GEMM (kept across calls: no release)
+  // Float32 streamed GEMM: hi / lo images attached by the caller (cached operators: nothing is split or allocated per
+  // call), and a grow-only scratch for the UNCACHED convenience entries (scimlop_matmul & co. on unattached operands)
+  scimlop_split_entry splits[SCIMLOP_MAX_SPLITS];
+  int nsplits;
+  void* split_scratch;
+  size_t split_scratch_bytes;
   int dmma_max_clusters[9];  // co-resident clusters of the split-K DMMA kernel per cluster size (occupancy query)
   char last_error[512];
   int64_t launches;

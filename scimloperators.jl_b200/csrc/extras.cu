@@ -97,8 +97,13 @@ extern "C" int scimlop_kron_mul_host(scimlop_handle_t h, int dtype, int precisio
   for (int f = 0; f < nfactors; f++) {
     dfac[f] = nullptr;
     size_t bytes = 0;
-    if ((kinds[f] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE)
-      bytes = (size_t)lds[f] * (size_t)((kinds[f] & SCIMLOP_TRANS) ? dims[2 * f] : dims[2 * f + 1]) * es;
+    if ((kinds[f] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE) {
+      // the logical extent only: ld * (stored cols - 1) + stored rows (a view with ld > rows may end at the end of
+      // its allocation, so the padding behind the last column must not be read)
+      const bool tr = (kinds[f] & SCIMLOP_TRANS) != 0;
+      const size_t scols = (size_t)(tr ? dims[2 * f] : dims[2 * f + 1]), srows = (size_t)(tr ? dims[2 * f + 1] : dims[2 * f]);
+      bytes = scols ? ((size_t)lds[f] * (scols - 1) + srows) * es : 0;
+    }
     else if (kinds[f] == SCIMLOP_DIAG) bytes = (size_t)dims[2 * f] * es;
     else if (kinds[f] == SCIMLOP_BANDED) bytes = (size_t)dims[2 * f] * (size_t)(2 * lds[f] + 1) * es;
     if (bytes) {
@@ -272,11 +277,8 @@ extern "C" int scimlop_kron_mul_allgather(scimlop_handle_t h, int dtype, int pre
   SCIMLOP_CUDA(h, cudaStreamWaitEvent(comm, h->ev_h2d[0], 0));
   const int ncclType = dtype == SCIMLOP_F64 ? NCCL_FLOAT64 : NCCL_FLOAT32;
   char* Wb = static_cast<char*>(W_full);
-  // The GEMM kernels are persistent (one CTA per SM, most of its shared memory): leave a few SMs free so the
-  // NCCL kernels of the exchange can actually run next to them instead of waiting for a kernel boundary.
-  const char* rs = getenv("SCIMLOP_GATHER_SM_RESERVE");
-  struct Reserve { scimlop_context* c; int old; ~Reserve() { c->sm_reserve = old; } } reserve{h, h->sm_reserve};
-  h->sm_reserve = (h->nranks > 1 && rs) ? atoi(rs) : 0;   // measured on 2 GPUs: reserving SMs does not help
+  // (Reserving SMs for the NCCL kernels next to the persistent GEMM CTAs was measured on 2 GPUs and does not help:
+  // DESIGN.md section 6 -- the GEMMs use every SM.)
   for (long long c0 = 0; c0 < cols_per_rank; c0 += cc) {
     const long long nc = std::min<long long>(cc, cols_per_rank - c0);
     char* mine = Wb + ((size_t)h->rank * cols_per_rank + c0) * rows * es;
@@ -366,7 +368,7 @@ extern "C" int scimlop_destroy(scimlop_handle_t h) {
   }
   if (h->stage) cudaFree(h->stage);
   if (h->comm_scratch) cudaFree(h->comm_scratch);
-  if (h->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(h->pool); }
+  if (h->split_scratch) { cudaDeviceSynchronize(); cudaFree(h->split_scratch); }
   h->magic = 0;
   delete h;
   return SCIMLOP_OK;

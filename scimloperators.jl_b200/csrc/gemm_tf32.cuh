@@ -579,16 +579,29 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 }
 
-// hi / lo halves of an FP32 matrix region (cols columns of ld floats each; the padding rows travel along)
-__global__ void split_hilo_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, long long n4) {
-  const float4* s4 = reinterpret_cast<const float4*>(src);
-  float4* h4 = reinterpret_cast<float4*>(hi);
-  float4* l4 = reinterpret_cast<float4*>(lo);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 h, l;
-    split4(__ldcs(s4 + i), h, l);
-    h4[i] = h;
-    l4[i] = l;
+// hi / lo halves of an FP32 matrix, column by column: only the `rows` stored entries of each column are read (a view
+// with ld > rows may end at its allocation boundary), written with leading dimension ld_out (a multiple of 4).
+// VEC: src 16-byte aligned and ld % 4 == 0 -> float4 for the full groups of 4 rows, scalars for the tail.
+template <bool VEC>
+__global__ void split_hilo_kernel(const float* __restrict__ src, long long ld, long long rows, long long cols,
+                                  float* __restrict__ hi, float* __restrict__ lo, long long ld_out) {
+  const long long r4 = VEC ? rows / 4 : 0;                  // float4 groups per column
+  const long long per_col = r4 + (rows - 4 * r4);           // work items per column: groups, then tail scalars
+  const long long total = per_col * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long c = i / per_col, q = i - c * per_col;
+    if (q < r4) {
+      float4 h, l;
+      split4(__ldcs(reinterpret_cast<const float4*>(src + c * ld) + q), h, l);
+      reinterpret_cast<float4*>(hi + c * ld_out)[q] = h;
+      reinterpret_cast<float4*>(lo + c * ld_out)[q] = l;
+    } else {
+      const long long r = 4 * r4 + (q - r4);
+      const float x = src[c * ld + r];
+      const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+      hi[c * ld_out + r] = h;
+      lo[c * ld_out + r] = __uint_as_float(__float_as_uint(x - h) & 0xFFFFE000u);
+    }
   }
 }
 

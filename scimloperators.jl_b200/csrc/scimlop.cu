@@ -40,14 +40,14 @@ struct ScaleArg {
   const void* ptr;
   long long ld;
 };
-// peer destinations of a fused compute + all-gather launch (thread-local: set around the last kron stage)
+// peer destinations of a fused compute + all-gather launch: passed explicitly down to the LAST kron stage
 struct PeerArg {
   int n = 0;
   void* ptr[7] = {};
   void* mc = nullptr;   // multicast alias of the destination (scimlop_kron_mul_mc): one store reaches every rank
   bool active() const { return n > 0 || mc != nullptr; }
 };
-thread_local PeerArg g_peers;
+const PeerArg NO_PEERS;
 
 // ---- elementwise launcher -------------------------------------------------------------------------
 template <typename T>
@@ -145,7 +145,7 @@ bool dmma_eligible(long long M, long long N, long long K, const double* A, long 
 int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long long N, long long K, double alpha,
                 const double* A, long long lda, long long sA, const double* B, long long ldb, long long sB,
                 double beta, double* C, long long ldc, long long sC, long long batch, int nscale,
-                const ScaleArg* scales, cudaStream_t st) {
+                const ScaleArg* scales, cudaStream_t st, const PeerArg& g_peers = NO_PEERS) {
   const bool a_batched = batch > 1 && sA != 0, b_batched = batch > 1 && sB != 0;
   CUtensorMap tmA, tmB;
   int rc = make_map_f64(c, &tmA, A, /*kc=*/transA, M, K, lda, sA, a_batched ? batch : 1);
@@ -178,8 +178,8 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
   dmma::PeerMaps& pmaps = pmaps_unused;
   // fused all-gather with bulk stores: one 3-D {M, N, batch} map per destination, box = one output tile
   dmma::PeerMaps peer_maps;
-  const bool peer_bulk = g_peers.n > 0 && nscale == 0 && beta == 0.0 && p.vec_ok && !transA && getenv("SCIMLOP_PEER_LSU") == nullptr;
-  const bool mc_staged = g_peers.mc != nullptr && !transA && getenv("SCIMLOP_MC_REG") == nullptr;
+  const bool peer_bulk = g_peers.n > 0 && nscale == 0 && beta == 0.0 && p.vec_ok && !transA;
+  const bool mc_staged = g_peers.mc != nullptr && !transA;
   if (peer_bulk || mc_staged) {
     for (int q = 0; peer_bulk && q <= g_peers.n; q++) {
       double* base = q == 0 ? C : static_cast<double*>(g_peers.ptr[q - 1]);
@@ -363,13 +363,14 @@ template <typename T>
 int gemm_dispatch(scimlop_context* c, int precision, bool transA, bool transB, long long M, long long N,
                   long long K, T alpha, const T* A, long long lda, long long sA, const T* B, long long ldb,
                   long long sB, T beta, T* C, long long ldc, long long sC, long long batch, int nscale,
-                  const ScaleArg* scales, cudaStream_t st);
+                  const ScaleArg* scales, cudaStream_t st, const PeerArg& peers = NO_PEERS);
 
 template <>
 int gemm_dispatch<double>(scimlop_context* c, int precision, bool transA, bool transB, long long M, long long N,
                           long long K, double alpha, const double* A, long long lda, long long sA,
                           const double* B, long long ldb, long long sB, double beta, double* C, long long ldc,
-                          long long sC, long long batch, int nscale, const ScaleArg* scales, cudaStream_t st) {
+                          long long sC, long long batch, int nscale, const ScaleArg* scales, cudaStream_t st,
+                          const PeerArg& g_peers) {
   if (precision != SCIMLOP_PREC_DEFAULT)
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "Float64 only supports SCIMLOP_PREC_DEFAULT (got %d)", precision);
   if (M <= 0 || N <= 0 || batch <= 0) return SCIMLOP_OK;
@@ -381,7 +382,7 @@ int gemm_dispatch<double>(scimlop_context* c, int precision, bool transA, bool t
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "peer targets need a DMMA-eligible (aligned Float64) last stage");
   if (dmma_eligible(M, N, K, A, lda, sA, B, ldb, sB, batch))
     return launch_dmma(c, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, nscale,
-                       scales, st);
+                       scales, st, g_peers);
   return launch_simt<double>(c, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
                              nscale, scales, st);
 }
@@ -447,42 +448,66 @@ int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, 
   return SCIMLOP_OK;
 }
 
+// ---- hi / lo images of Float32 operands (3xTF32 split) ---------------------------------------------------------
+inline long long split_ld(long long rows) { return (rows + 3) / 4 * 4; }
+inline size_t split_image_bytes(long long rows, long long cols) { return 2 * (size_t)split_ld(rows) * (size_t)cols * sizeof(float); }
+
+int launch_split(scimlop_context* c, const float* src, long long ld, long long rows, long long cols, float* hi, float* lo,
+                 cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return SCIMLOP_OK;
+  const bool vec = aligned16(src) && ld % 4 == 0;
+  const long long items = ((vec ? rows / 4 : 0) + (rows - (vec ? rows / 4 * 4 : 0))) * cols;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((items + 255) / 256, (long long)c->sm_count * 8));
+  if (vec) tf32::split_hilo_kernel<true><<<grid, 256, 0, st>>>(src, ld, rows, cols, hi, lo, split_ld(rows));
+  else tf32::split_hilo_kernel<false><<<grid, 256, 0, st>>>(src, ld, rows, cols, hi, lo, split_ld(rows));
+  c->launches++;
+  SCIMLOP_CUDA(c, cudaGetLastError());
+  return SCIMLOP_OK;
+}
+
+const scimlop_split_entry* find_split(const scimlop_context* c, const void* src, long long ld, long long rows, long long cols) {
+  for (int i = 0; i < c->nsplits; i++) {
+    const scimlop_split_entry& e = c->splits[i];
+    if (e.src == src && e.ld == ld && e.rows == rows && e.cols == cols) return &e;
+  }
+  return nullptr;
+}
+
 // General Float32 GEMM on tcgen05 (3xTF32): C_b(M x N) = alpha * op(A_b)(M x K) * op(B)(K x N) + beta * C_b, any K, N.
-// One operand ("X") streams through the splitter warps into TMEM, the other ("F") is split ONCE into hi / lo halves
-// (stream-ordered scratch from cudaMallocAsync: 2 x its size) and streams through the same ring as 128-column tiles.
-// F is the SMALLER operand: `f_is_a == false`: X = op(A), F = op(B), rows = M (output contiguous along r; batches of
-// A / C with one shared B allowed); `f_is_a == true`: X = op(B)^T, F = op(A), rows = N (output contiguous along c).
-int launch_tf32_stream(scimlop_context* c, bool f_is_a, bool transA, bool transB, long long M, long long N, long long K,
-                       float alpha, const float* A, long long lda, long long sA, const float* B, long long ldb, float beta,
-                       float* C, long long ldc, long long sC, long long batch, int passes, int nscale,
-                       const ScaleArg* scales, cudaStream_t st) {
+// One operand ("X") streams through the splitter warps into TMEM, the other ("F") streams through the same ring as
+// 128-column tiles of its hi / lo halves, which the CALLER prepared once (scimlop_split_attach at cache_operator
+// time, refreshed by update_coefficients!; `pre`), or -- for the uncached convenience entries -- which are split here
+// into the handle's grow-only scratch (one extra launch; the first call of a shape allocates).
+// `f_is_a == false`: X = op(A), F = op(B), rows = M (output contiguous along r; batches of A / C with one shared B
+// allowed); `f_is_a == true`: X = op(B)^T, F = op(A), rows = N (output contiguous along c).
+int launch_tf32_stream(scimlop_context* c, bool f_is_a, const scimlop_split_entry* pre, bool transA, bool transB,
+                       long long M, long long N, long long K, float alpha, const float* A, long long lda, long long sA,
+                       const float* B, long long ldb, float beta, float* C, long long ldc, long long sC, long long batch,
+                       int passes, int nscale, const ScaleArg* scales, cudaStream_t st) {
   const float* Fsrc = f_is_a ? A : B;
-  const long long ldf = f_is_a ? lda : ldb;
-  const long long fcols = f_is_a ? (transA ? M : K) : (transB ? K : N);   // stored columns of F (ldf floats each)
+  const long long ldsrc = f_is_a ? lda : ldb;
+  const long long frows = f_is_a ? (transA ? K : M) : (transB ? N : K);   // stored rows of F
+  const long long fcols = f_is_a ? (transA ? M : K) : (transB ? K : N);   // stored columns of F
+  const float *Fhi, *Flo;
+  long long ldf;
+  if (pre) {
+    Fhi = pre->hi; Flo = pre->lo; ldf = pre->ld_split;
+  } else {
+    const size_t need = split_image_bytes(frows, fcols);
+    if (need > c->split_scratch_bytes) {
+      // uncached entry: grow the handle-owned scratch (synchronises; cached operators never come here)
+      SCIMLOP_CUDA(c, cudaDeviceSynchronize());
+      if (c->split_scratch) { SCIMLOP_CUDA(c, cudaFree(c->split_scratch)); c->split_scratch = nullptr; c->split_scratch_bytes = 0; }
+      SCIMLOP_CUDA(c, cudaMalloc(&c->split_scratch, need));
+      c->split_scratch_bytes = need;
+    }
+    ldf = split_ld(frows);
+    float* hi = static_cast<float*>(c->split_scratch);
+    float* lo = hi + (size_t)ldf * (size_t)fcols;
+    if (int rc = launch_split(c, Fsrc, ldsrc, frows, fcols, hi, lo, st)) return rc;
+    Fhi = hi; Flo = lo;
+  }
   const size_t half = (size_t)ldf * (size_t)fcols * sizeof(float);
-  float* scratch = nullptr;
-  if (!c->pool) {
-    // the handle's own pool, never trimmed: the default pool hands memory back at every synchronisation and the
-    // next call then pays a driver allocation (seen as one 2 ms outlier among 0.7 ms calls)
-    cudaMemPoolProps props;
-    memset(&props, 0, sizeof(props));
-    props.allocType = cudaMemAllocationTypePinned;
-    props.handleTypes = cudaMemHandleTypeNone;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = c->device;
-    SCIMLOP_CUDA(c, cudaMemPoolCreate(&c->pool, &props));
-    uint64_t keep = UINT64_MAX;
-    SCIMLOP_CUDA(c, cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  }
-  SCIMLOP_CUDA(c, cudaMallocFromPoolAsync(reinterpret_cast<void**>(&scratch), 2 * half, c->pool, st));
-  float* Fhi = scratch;
-  float* Flo = scratch + (size_t)ldf * (size_t)fcols;
-  {
-    const long long n4 = (long long)(half / 16);
-    const int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)c->sm_count * 8);
-    tf32::split_hilo_kernel<<<grid, 256, 0, st>>>(Fsrc, Fhi, Flo, n4);
-    c->launches++;
-  }
   // roles
   const long long rows = f_is_a ? N : M, mcols = f_is_a ? M : N;
   const float* X = f_is_a ? B : A;
@@ -502,57 +527,55 @@ int launch_tf32_stream(scimlop_context* c, bool f_is_a, bool transA, bool transB
     if (f_k) rc = make_map_f32(c, tm, base, K, mcols, 1, ldf * 4, 0, 32, 128, false);
     else rc = make_map_f32(c, tm, base, mcols, K, 1, ldf * 4, 0, 32, 32, true);
   }
+  if (rc) return rc;
   tf32::Params p;
   memset(&p, 0, sizeof(p));
-  if (!rc) {
-    p.rows = rows; p.m = (int)mcols; p.n = (int)K; p.batch = (int)batch;
-    p.tiles_r = (int)((rows + tf32::TM - 1) / tf32::TM);
-    p.tiles_c = (int)((mcols + 127) / 128);
-    p.total_tiles = (long long)p.tiles_r * p.tiles_c * batch;
-    // a small pre-split operand (a Kronecker factor) stays in L2: then each X row tile is fetched once.  (Measured:
-    // with a 64 MB pre-split V the column-fastest order is 40 % slower than row-fastest, so the bound is tight.)
-    p.c_fast = 2 * half <= (16u << 20);
-    p.D = C;
-    p.d_rs = f_is_a ? ldc : 1; p.d_cs = f_is_a ? 1 : ldc; p.d_bs = sC;
-    p.alpha = alpha; p.beta = beta;
-    p.vec_ok = f_is_a && aligned16(C) && ldc % 4 == 0;
-    p.x_batched = xb;
-    p.passes = passes;
-    p.nscale = nscale; p.rows_are_n = f_is_a;
-    for (int q = 0; q < nscale; q++) { p.scale_ptr[q] = static_cast<const float*>(scales[q].ptr); p.scale_ld[q] = scales[q].ld; }
-    p.tma_store = aligned16(C) && ldc % 4 == 0 && (batch == 1 || sC % 4 == 0);
-    if (!p.tma_store) tmD = tmX;
-    else if (!f_is_a) rc = make_map_f32(c, &tmD, C, M, N, batch, ldc * 4, sC * 4, 32, 32, false, /*swizzle=*/false);
-    else rc = make_map_f32(c, &tmD, C, M, N, 1, ldc * 4, 0, 32, 32, false, /*swizzle=*/true);
-  }
-  if (!rc) {
-    const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
+  p.rows = rows; p.m = (int)mcols; p.n = (int)K; p.batch = (int)batch;
+  p.tiles_r = (int)((rows + tf32::TM - 1) / tf32::TM);
+  p.tiles_c = (int)((mcols + 127) / 128);
+  p.total_tiles = (long long)p.tiles_r * p.tiles_c * batch;
+  // a small pre-split operand (a Kronecker factor) stays in L2: then each X row tile is fetched once.  (Measured:
+  // with a 64 MB pre-split V the column-fastest order is 40 % slower than row-fastest, so the bound is tight.)
+  p.c_fast = 2 * half <= (16u << 20);
+  p.D = C;
+  p.d_rs = f_is_a ? ldc : 1; p.d_cs = f_is_a ? 1 : ldc; p.d_bs = sC;
+  p.alpha = alpha; p.beta = beta;
+  p.vec_ok = f_is_a && aligned16(C) && ldc % 4 == 0;
+  p.x_batched = xb;
+  p.passes = passes;
+  p.nscale = nscale; p.rows_are_n = f_is_a;
+  for (int q = 0; q < nscale; q++) { p.scale_ptr[q] = static_cast<const float*>(scales[q].ptr); p.scale_ld[q] = scales[q].ld; }
+  p.tma_store = aligned16(C) && ldc % 4 == 0 && (batch == 1 || sC % 4 == 0);
+  if (!p.tma_store) tmD = tmX;
+  else if (!f_is_a) rc = make_map_f32(c, &tmD, C, M, N, batch, ldc * 4, sC * 4, 32, 32, false, /*swizzle=*/false);
+  else rc = make_map_f32(c, &tmD, C, M, N, 1, ldc * 4, 0, 32, 32, false, /*swizzle=*/true);
+  if (rc) return rc;
+  const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
 #define SCIMLOP_TF32S(XM, FK, OR) \
   tf32::gemm_tf32x3_kernel<XM, FK, true, OR><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmFhi, tmFlo, tmD, p)
-    if (!f_is_a) {
-      if (x_mn && f_k) SCIMLOP_TF32S(true, true, true);
-      else if (x_mn) SCIMLOP_TF32S(true, false, true);
-      else if (f_k) SCIMLOP_TF32S(false, true, true);
-      else SCIMLOP_TF32S(false, false, true);
-    } else {
-      if (x_mn && f_k) SCIMLOP_TF32S(true, true, false);
-      else if (x_mn) SCIMLOP_TF32S(true, false, false);
-      else if (f_k) SCIMLOP_TF32S(false, true, false);
-      else SCIMLOP_TF32S(false, false, false);
-    }
-#undef SCIMLOP_TF32S
-    c->launches++;
-    if (cudaGetLastError() != cudaSuccess) rc = scimlop_fail(c, SCIMLOP_ERR_CUDA, "gemm_tf32x3_kernel<stream> launch failed");
+  if (!f_is_a) {
+    if (x_mn && f_k) SCIMLOP_TF32S(true, true, true);
+    else if (x_mn) SCIMLOP_TF32S(true, false, true);
+    else if (f_k) SCIMLOP_TF32S(false, true, true);
+    else SCIMLOP_TF32S(false, false, true);
+  } else {
+    if (x_mn && f_k) SCIMLOP_TF32S(true, true, false);
+    else if (x_mn) SCIMLOP_TF32S(true, false, false);
+    else if (f_k) SCIMLOP_TF32S(false, true, false);
+    else SCIMLOP_TF32S(false, false, false);
   }
-  cudaFreeAsync(scratch, st);
-  return rc;
+#undef SCIMLOP_TF32S
+  c->launches++;
+  SCIMLOP_CUDA(c, cudaGetLastError());
+  return SCIMLOP_OK;
 }
 
 template <>
 int gemm_dispatch<float>(scimlop_context* c, int precision, bool transA, bool transB, long long M, long long N,
                          long long K, float alpha, const float* A, long long lda, long long sA, const float* B,
                          long long ldb, long long sB, float beta, float* C, long long ldc, long long sC,
-                         long long batch, int nscale, const ScaleArg* scales, cudaStream_t st) {
+                         long long batch, int nscale, const ScaleArg* scales, cudaStream_t st, const PeerArg& peers) {
+  if (peers.active()) return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "peer / multicast targets are Float64 only");
   if (precision < SCIMLOP_PREC_DEFAULT || precision > SCIMLOP_PREC_FP32_EXACT)
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "unknown precision mode %d", precision);
   if (M <= 0 || N <= 0 || batch <= 0) return SCIMLOP_OK;
@@ -581,12 +604,22 @@ int gemm_dispatch<float>(scimlop_context* c, int precision, bool transA, bool tr
       K < 2147483647LL && batch < 2147483647LL && aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0 &&
       (batch == 1 || sA % 4 == 0)) {
     const int passes = precision == SCIMLOP_PREC_TF32 ? 1 : 3;
+    // an operand whose hi / lo image the caller attached (cached operators) is the pre-split one; otherwise the
+    // smaller operand is split per call (uncached entries)
+    const scimlop_split_entry* preA = batch == 1 ? find_split(c, A, lda, transA ? K : M, transA ? M : K) : nullptr;
+    const scimlop_split_entry* preB = find_split(c, B, ldb, transB ? N : K, transB ? K : N);
+    if (preA && !preB && N >= 16 && M >= 16)
+      return launch_tf32_stream(c, true, preA, transA, transB, M, N, K, alpha, A, lda, 0, B, ldb, beta, C, ldc, 0, 1, passes,
+                                nscale, scales, st);
+    if (preB && M * batch >= 16 && N >= 16)
+      return launch_tf32_stream(c, false, preB, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, beta, C, ldc, sC, batch,
+                                passes, nscale, scales, st);
     const bool a_small = batch == 1 && (double)M * (double)K < (double)K * (double)N;
     if (a_small && N >= 128 && M >= 16)
-      return launch_tf32_stream(c, true, transA, transB, M, N, K, alpha, A, lda, 0, B, ldb, beta, C, ldc, 0, 1, passes,
+      return launch_tf32_stream(c, true, preA, transA, transB, M, N, K, alpha, A, lda, 0, B, ldb, beta, C, ldc, 0, 1, passes,
                                 nscale, scales, st);
     if (M * batch >= 128 && N >= 16)
-      return launch_tf32_stream(c, false, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, beta, C, ldc, sC, batch,
+      return launch_tf32_stream(c, false, nullptr, transA, transB, M, N, K, alpha, A, lda, sA, B, ldb, beta, C, ldc, sC, batch,
                                 passes, nscale, scales, st);
   }
   if (precision == SCIMLOP_PREC_TF32)
@@ -766,6 +799,58 @@ extern "C" int scimlop_matmul(scimlop_handle_t h, int dtype, int precision, int 
                               int64_t ldw, const void* alpha, const void* beta, void* stream) {
   return scimlop_gemm_strided_batched(h, dtype, precision, transA, 0, m, k, n, alpha, A, lda, 0, V, ldv, 0, beta, W,
                                       ldw, 0, 1, stream);
+}
+
+// ---- hi / lo images of Float32 operands: prepared once per cached operator ---------------------------------------
+extern "C" int scimlop_split_bytes(int64_t rows, int64_t cols, size_t* bytes) {
+  if (!bytes) return SCIMLOP_ERR_NULL_POINTER;
+  if (rows < 0 || cols < 0) return SCIMLOP_ERR_BAD_SHAPE;
+  *bytes = split_image_bytes(rows, cols);
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_split_attach(scimlop_handle_t h, const void* A, int64_t lda, int64_t rows, int64_t cols, void* split,
+                                    size_t split_bytes, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!A || !split) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "split_attach: null pointer");
+  if (rows <= 0 || cols <= 0 || lda < rows) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "split_attach: bad shape");
+  if (split_bytes < split_image_bytes(rows, cols) || !aligned16(split))
+    return scimlop_fail(h, SCIMLOP_ERR_WORKSPACE, "split_attach: image buffer too small (%zu < %zu B) or not 16-byte aligned",
+                        split_bytes, split_image_bytes(rows, cols));
+  scimlop_split_entry* e = nullptr;
+  for (int i = 0; i < h->nsplits; i++)
+    if (h->splits[i].src == A) e = &h->splits[i];     // re-attach replaces
+  if (!e) {
+    if (h->nsplits == SCIMLOP_MAX_SPLITS) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "split_attach: more than %d attached operands", SCIMLOP_MAX_SPLITS);
+    e = &h->splits[h->nsplits++];
+  }
+  e->src = A; e->ld = lda; e->rows = rows; e->cols = cols;
+  e->ld_split = split_ld(rows);
+  e->hi = static_cast<float*>(split);
+  e->lo = e->hi + (size_t)e->ld_split * (size_t)cols;
+  scimlop_device_guard guard(h->device);
+  return launch_split(h, static_cast<const float*>(A), lda, rows, cols, e->hi, e->lo, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int scimlop_split_refresh(scimlop_handle_t h, const void* A, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  for (int i = 0; i < h->nsplits; i++) {
+    const scimlop_split_entry& e = h->splits[i];
+    if (e.src != A) continue;
+    scimlop_device_guard guard(h->device);
+    return launch_split(h, static_cast<const float*>(A), e.ld, e.rows, e.cols, e.hi, e.lo, static_cast<cudaStream_t>(stream));
+  }
+  return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "split_refresh: operand %p is not attached", A);
+}
+
+extern "C" int scimlop_split_detach(scimlop_handle_t h, const void* A) {
+  if (int rc = check_handle(h)) return rc;
+  for (int i = 0; i < h->nsplits; i++)
+    if (h->splits[i].src == A) {
+      h->splits[i] = h->splits[--h->nsplits];
+      return SCIMLOP_OK;
+    }
+  return SCIMLOP_OK;   // detaching an unknown operand is a no-op
 }
 
 template <typename T>
@@ -952,7 +1037,7 @@ int kron_plan(scimlop_context* c, int nfactors, const int64_t* dims, const int32
 template <typename T>
 int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* const* factors, const int64_t* dims,
                const int64_t* lds, const int32_t* kinds, const T* V, T* W, long long k, T alpha, T beta,
-               void* workspace, size_t ws_bytes, const KronPlan& pl, cudaStream_t st) {
+               void* workspace, size_t ws_bytes, const KronPlan& pl, cudaStream_t st, const PeerArg& g_peers) {
   if (pl.nops == 0) return eltwise_axpby<T>(c, pl.rows, k, V, pl.cols, W, pl.rows, alpha, beta, st);
   const size_t buf_bytes = align_up((size_t)pl.max_inter * sizeof(T), 256);
   const int nbuf = pl.nops >= 3 ? 2 : (pl.nops == 2 ? 1 : 0);
@@ -993,25 +1078,14 @@ int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* cons
       ep.nterms = 1; ep.coef[0] = T(1); ep.nvec[0] = 1; ep.nfac[0] = 1;
       ep.fac[0][0].ptr = static_cast<const T*>(factors[p]); ep.fac[0][0].ld = 0; ep.fac[0][0].div = L; ep.fac[0][0].mod = n;
       rc = launch_eltwise(c, ep, st);
-    } else if (g_peers.active() && !last) {
-      PeerArg saved = g_peers;      // intermediates stay local: only the stage that writes W goes to the peers
-      g_peers.n = 0;
-      g_peers.mc = nullptr;
-      if (L == 1)
-        rc = gemm_dispatch<T>(c, precision, tr, false, m, R, n, a, static_cast<const T*>(factors[p]), lds[p], 0, cur, n, 0,
-                              bt, out, m, 0, 1, 0, nullptr, st);
-      else
-        rc = gemm_dispatch<T>(c, precision, false, !tr, L, m, n, a, cur, L, L * n, static_cast<const T*>(factors[p]),
-                              lds[p], 0, bt, out, L, L * m, R, 0, nullptr, st);
-      g_peers = saved;
     } else if (L == 1) {
       // innermost applied mode: out(m x R) = op(F)(m x n) * cur(n x R)    [src/tensor.jl:568,603]
       rc = gemm_dispatch<T>(c, precision, tr, false, m, R, n, a, static_cast<const T*>(factors[p]), lds[p], 0, cur,
-                            n, 0, bt, out, m, 0, 1, 0, nullptr, st);
+                            n, 0, bt, out, m, 0, 1, 0, nullptr, st, last ? g_peers : NO_PEERS);
     } else {
       // out_r(L x m) = cur_r(L x n) * op(F)^T for every slab r           [src/tensor.jl:778-788, no permutedims]
       rc = gemm_dispatch<T>(c, precision, false, !tr, L, m, n, a, cur, L, L * n, static_cast<const T*>(factors[p]),
-                            lds[p], 0, bt, out, L, L * m, R, 0, nullptr, st);
+                            lds[p], 0, bt, out, L, L * m, R, 0, nullptr, st, last ? g_peers : NO_PEERS);
     }
     if (rc) return rc;
     cur = out;
@@ -1034,10 +1108,10 @@ extern "C" int scimlop_kron_workspace_bytes(int dtype, int nfactors, const int64
   return SCIMLOP_OK;
 }
 
-int scimlop_kron_mul_impl(scimlop_context* h, int dtype, int precision, int nfactors, const void* const* factors,
-                          const int64_t* dims, const int64_t* lds, const int32_t* kinds, const void* V, int64_t ldv,
-                          void* W, int64_t ldw, int64_t k, const void* alpha, const void* beta, void* workspace,
-                          size_t workspace_bytes, cudaStream_t st) {
+static int kron_mul_impl_peers(scimlop_context* h, int dtype, int precision, int nfactors, const void* const* factors,
+                               const int64_t* dims, const int64_t* lds, const int32_t* kinds, const void* V, int64_t ldv,
+                               void* W, int64_t ldw, int64_t k, const void* alpha, const void* beta, void* workspace,
+                               size_t workspace_bytes, cudaStream_t st, const PeerArg& peers) {
   if (int rc = check_dtype(h, dtype)) return rc;
   KronPlan pl;
   if (int rc = kron_plan(h, nfactors, dims, kinds, k, &pl)) return rc;
@@ -1064,10 +1138,18 @@ int scimlop_kron_mul_impl(scimlop_context* h, int dtype, int precision, int nfac
   if (dtype == SCIMLOP_F64)
     return kron_mul_t<double>(h, precision, nfactors, factors, dims, lds, kinds, (const double*)V, (double*)W, k,
                               scalar_or<double>(alpha, 1.0), scalar_or<double>(beta, 0.0), workspace, workspace_bytes,
-                              pl, st);
+                              pl, st, peers);
   return kron_mul_t<float>(h, precision, nfactors, factors, dims, lds, kinds, (const float*)V, (float*)W, k,
                            scalar_or<float>(alpha, 1.f), scalar_or<float>(beta, 0.f), workspace, workspace_bytes, pl,
-                           st);
+                           st, peers);
+}
+
+int scimlop_kron_mul_impl(scimlop_context* h, int dtype, int precision, int nfactors, const void* const* factors,
+                          const int64_t* dims, const int64_t* lds, const int32_t* kinds, const void* V, int64_t ldv,
+                          void* W, int64_t ldw, int64_t k, const void* alpha, const void* beta, void* workspace,
+                          size_t workspace_bytes, cudaStream_t st) {
+  return kron_mul_impl_peers(h, dtype, precision, nfactors, factors, dims, lds, kinds, V, ldv, W, ldw, k, alpha, beta,
+                             workspace, workspace_bytes, st, NO_PEERS);
 }
 
 extern "C" int scimlop_kron_mul(scimlop_handle_t h, int dtype, int precision, int nfactors,
@@ -1097,12 +1179,11 @@ extern "C" int scimlop_kron_mul_peers(scimlop_handle_t h, int dtype, int precisi
   long long rows = 1, cols = 1;
   for (int f = 0; f < nfactors; f++) { rows *= dims[2 * f]; cols *= dims[2 * f + 1]; }
   scimlop_device_guard guard(h->device);
-  g_peers.n = npeers;
-  for (int q = 0; q < npeers; q++) g_peers.ptr[q] = peer_targets[q];
-  int rc = scimlop_kron_mul_impl(h, dtype, precision, nfactors, factors, dims, lds, kinds, V, cols, W_local, rows, k, alpha,
-                                 nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
-  g_peers.n = 0;
-  return rc;
+  PeerArg peers;
+  peers.n = npeers;
+  for (int q = 0; q < npeers; q++) peers.ptr[q] = peer_targets[q];
+  return kron_mul_impl_peers(h, dtype, precision, nfactors, factors, dims, lds, kinds, V, cols, W_local, rows, k, alpha,
+                             nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), peers);
 }
 
 extern "C" int scimlop_kron_mul_mc(scimlop_handle_t h, int dtype, int precision, int nfactors,
@@ -1118,12 +1199,10 @@ extern "C" int scimlop_kron_mul_mc(scimlop_handle_t h, int dtype, int precision,
   long long rows = 1, cols = 1;
   for (int f = 0; f < nfactors; f++) { rows *= dims[2 * f]; cols *= dims[2 * f + 1]; }
   scimlop_device_guard guard(h->device);
-  g_peers.n = 0;
-  g_peers.mc = W_multicast;
-  int rc = scimlop_kron_mul_impl(h, dtype, precision, nfactors, factors, dims, lds, kinds, V, cols, W_local, rows, k, alpha,
-                                 nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
-  g_peers.mc = nullptr;
-  return rc;
+  PeerArg peers;
+  peers.mc = W_multicast;
+  return kron_mul_impl_peers(h, dtype, precision, nfactors, factors, dims, lds, kinds, V, cols, W_local, rows, k, alpha,
+                             nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), peers);
 }
 
 extern "C" int scimlop_outer_mul_fast(scimlop_handle_t h, int dtype, int precision, void* W, const void* A,

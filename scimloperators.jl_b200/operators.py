@@ -273,6 +273,9 @@ def _lmul(w, beta, h):
 # ====================================================================================================
 # leaves
 # ====================================================================================================
+_SPLIT_IMAGES = {}   # (device, ptr, ld, rows, cols) -> [image buffer, refcount]: attached Float32 hi / lo images
+
+
 class MatrixOperator(AbstractSciMLOperator):
     """src/matrix.jl:116-133; `mul!` :337-350.  `trans=True` is the lazy Adjoint wrapper produced by
     `adjoint(::MatrixOperator)` on a constant operator (:174-175).  `update_func(A, u, p, t)` mutates the
@@ -302,9 +305,58 @@ class MatrixOperator(AbstractSciMLOperator):
             raise NotImplementedError("adjoint of a time-dependent MatrixOperator builds an AdjointOperator (src/left.jl) -- out of scope")
         return MatrixOperator(self.A, not self.trans)
 
+    # ---- Float32 matrices beyond the resident-factor kernel: hi / lo image prepared once (scimlop_split_attach) ----
+    _split = None            # (key into _SPLIT_IMAGES, handle) once attached
+    SPLIT_LIMIT_BYTES = 8 << 30
+
+    def _attach_split(self):
+        """`cache_operator` side of the no-allocation contract (test/Downstream/alloccheck.jl): the 3xTF32 halves of
+        a large Float32 matrix are made once here, so that `mul!` is one launch with no scratch allocation."""
+        if self.banded or self._split is not None or self.A.dtype != np.float32:
+            return self
+        m, n = self.A.shape
+        if min(m, n) < 16 or max(m, n) <= 128:
+            return self          # SIMT / skinny / resident-factor kernels: nothing to prepare
+        lib = _lib.load()
+        nbytes = C.c_size_t(0)
+        lib.scimlop_split_bytes(m, n, C.byref(nbytes))
+        if nbytes.value > self.SPLIT_LIMIT_BYTES:
+            return self          # huge operator: its (smaller) input is split per call instead
+        h = _lib.handle(self.A.device_index)
+        key = (self.A.device_index, self.A.ptr, self.A.ld, m, n)
+        ent = _SPLIT_IMAGES.get(key)             # operators that share one array (L and L') share one image
+        if ent is None:
+            buf = torch.empty(nbytes.value, dtype=torch.uint8, device=self.A.t.device)
+            h.check(lib.scimlop_split_attach(h.ptr, C.c_void_p(self.A.ptr), self.A.ld, m, n, C.c_void_p(buf.data_ptr()),
+                                             nbytes.value, _stream()), "scimlop_split_attach")
+            ent = _SPLIT_IMAGES[key] = [buf, 0]
+        ent[1] += 1
+        self._split = (key, h)
+        return self
+
+    def cache_operator(self, v):
+        return self._attach_split()
+
+    def __del__(self):
+        sp = getattr(self, "_split", None)
+        if sp is not None:
+            try:
+                key, h = sp
+                ent = _SPLIT_IMAGES.get(key)
+                if ent is not None:
+                    ent[1] -= 1
+                    if ent[1] <= 0:
+                        h.lib.scimlop_split_detach(h.ptr, C.c_void_p(key[1]))
+                        del _SPLIT_IMAGES[key]
+            except Exception:
+                pass
+
     def update_coefficients_(self, u=None, p=None, t=None):
         if self.update_func is not None:
             self.update_func(self.A, u, p, t)
+            if self._split is not None:      # the matrix changed in place: redo its hi / lo image (one launch)
+                h = self._split[1]
+                h.check(h.lib.scimlop_split_refresh(h.ptr, C.c_void_p(self.A.ptr), _stream()), "scimlop_split_refresh")
         return self
 
     def _flat_terms(self):
@@ -509,6 +561,7 @@ class _TreePlan:
                 f = arr[j]
                 f.rows, f.cols, f.trans, f.data, f.ld = m, n, 0, None, 0
                 if isinstance(leaf, MatrixOperator):
+                    leaf._attach_split()
                     f.kind, f.trans, f.data, f.ld = _lib.DENSE, int(leaf.trans), leaf.A.ptr, leaf.A.ld
                 elif isinstance(leaf, _VectorDiagonalOperator):
                     f.kind, f.data = _lib.DIAG, leaf.diag.ptr
@@ -1301,6 +1354,8 @@ class TensorProductOperator(AbstractSciMLOperator):
                 kinds[i], ptrs[i], lds[i] = _kron_leaf(op)
                 if op.dtype is not None and op.dtype != v.dtype:
                     raise TypeError(f"factor eltype {op.dtype} != array eltype {v.dtype}")
+                if isinstance(op, MatrixOperator):
+                    op._attach_split()
             nbytes = C.c_size_t(0)
             lib = _lib.load()
             rc = lib.scimlop_kron_workspace_bytes(_DT[v.dtype], nf, dims, kinds, k, C.byref(nbytes))

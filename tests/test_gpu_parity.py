@@ -1033,3 +1033,100 @@ def test_captured_mul_replays_with_updated_inputs(sb):
     opA.A.t.mul_(2.0)                                          # update_coefficients!-style in-place change of a factor
     cm.replay(); torch.cuda.synchronize()
     check(w.numpy(), np.kron(2 * A, B) @ v2, np.float64, "captured mul! after updates")
+
+
+# ---- the no-allocation contract of the Float32 streamed path (test/Downstream/alloccheck.jl:14,100-122) ---------
+def test_float32_large_operator_mul_is_one_launch_without_allocation(sb):
+    """A cached large Float32 MatrixOperator: `cache_operator` prepares the hi / lo image once (scimlop_split_attach);
+    every `mul!` after that is exactly ONE kernel launch and no device memory is allocated or freed."""
+    import torch
+    rng = np.random.default_rng(5)
+    M, K, N = 640, 768, 512
+    A = rnd(rng, M, K, dtype=np.float32) - np.float32(0.5)
+    v = rnd(rng, K, N, dtype=np.float32)
+    dv = dev(sb, v)
+    h = sb.handle(0)
+    Lop = sb.MatrixOperator(A, update_func=lambda Adev, u, p, t: Adev.t.mul_(float(t)))
+    L = sb.cache_operator(Lop, dv)
+    w = sb.DeviceArray.full((M, N), float("nan"), np.float32)
+    sb.mul_(w, L, dv)                      # warm: lazy module loading etc.
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    n0 = h.launch_count()
+    for _ in range(5):
+        sb.mul_(w, L, dv)
+    torch.cuda.synchronize()
+    assert h.launch_count() - n0 == 5, "a cached Float32 mul! must be one launch (no per-call split)"
+    free1, _ = torch.cuda.mem_get_info()
+    assert free1 == free0, "mul! on a cached operator must not allocate device memory"
+    want = A.astype(np.float64) @ v.astype(np.float64)
+    scale = np.linalg.norm(np.abs(A).astype(np.float64) @ np.abs(v).astype(np.float64))
+    assert np.linalg.norm(w.numpy() - want) <= 1e-5 * scale
+    # update_coefficients! re-splits the changed matrix (one launch), the next mul! sees it
+    n0 = h.launch_count()
+    L.update_coefficients_(None, None, 3.0)
+    assert h.launch_count() - n0 == 1
+    sb.mul_(w, L, dv)
+    assert np.linalg.norm(w.numpy() - 3.0 * want) <= 1e-5 * 3.0 * scale
+    # the transposed operator shares the array and the image
+    Lt = sb.cache_operator(sb.MatrixOperator(L.A, trans=True), dev(sb, rnd(rng, M, N, dtype=np.float32)))
+    vt = rnd(rng, M, N, dtype=np.float32)
+    wt = sb.DeviceArray.full((K, N), float("nan"), np.float32)
+    n0 = h.launch_count()
+    sb.mul_(wt, Lt, dev(sb, vt))
+    assert h.launch_count() - n0 == 1
+    assert np.linalg.norm(wt.numpy() - 3.0 * (A.astype(np.float64).T @ vt.astype(np.float64))) <= 1e-5 * 3.0 * np.linalg.norm(
+        np.abs(A).astype(np.float64).T @ np.abs(vt).astype(np.float64))
+
+
+def test_float32_kron_large_factors_launch_count(sb):
+    """Float32 Kronecker product with 256-wide factors, cached: one launch per mode product, nothing else."""
+    rng = np.random.default_rng(6)
+    n, k = 256, 32
+    A, B = rnd(rng, n, n, dtype=np.float32) - np.float32(0.5), rnd(rng, n, n, dtype=np.float32) - np.float32(0.5)
+    v = rnd(rng, n * n, k, dtype=np.float32)
+    dv = dev(sb, v)
+    h = sb.handle(0)
+    L = sb.cache_operator(sb.kron(A, B), dv)
+    w = sb.DeviceArray.full((n * n, k), float("nan"), np.float32)
+    sb.mul_(w, L, dv)
+    n0 = h.launch_count()
+    sb.mul_(w, L, dv)
+    assert h.launch_count() - n0 == 2
+    want = R.kron_apply([A.astype(np.float64), B.astype(np.float64)], v.astype(np.float64))
+    scale = np.linalg.norm(R.kron_apply([np.abs(A).astype(np.float64), np.abs(B).astype(np.float64)], np.abs(v).astype(np.float64)))
+    assert np.linalg.norm(w.numpy() - want) <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("attach", [False, True])
+def test_float32_split_reads_only_the_logical_extent(sb, attach):
+    """A sub-matrix view (lda > rows) that ends exactly at the end of its allocation: the hi / lo split may read
+    ld * (cols - 1) + rows elements, not ld * cols (the padding behind the last column does not exist)."""
+    import torch
+    rng = np.random.default_rng(7)
+    rows, cols, lda, N = 500, 384, 512, 640          # the view's last column stops 12 rows short of a full ld; A is the smaller operand
+    Abig = rnd(rng, lda, cols, dtype=np.float32) - np.float32(0.5)
+    logical = lda * (cols - 1) + rows
+    flat = torch.from_numpy(np.ascontiguousarray(Abig.reshape(-1, order="F"))[:logical].copy()).cuda()   # exactly the logical extent
+    v = rnd(rng, cols, N, dtype=np.float32)
+    dv = dev(sb, v)
+    h = sb.handle(0)
+    w = sb.DeviceArray.full((rows, N), float("nan"), np.float32)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    img = None
+    if attach:
+        nb = C.c_size_t(0)
+        h.lib.scimlop_split_bytes(rows, cols, C.byref(nb))
+        img = torch.empty(nb.value, dtype=torch.uint8, device="cuda")
+        h.check(h.lib.scimlop_split_attach(h.ptr, C.c_void_p(flat.data_ptr()), lda, rows, cols, C.c_void_p(img.data_ptr()),
+                                           nb.value, st), "attach")
+    one = C.c_float(1.0)
+    h.check(h.lib.scimlop_matmul(h.ptr, 1, 0, 0, rows, cols, N, C.c_void_p(flat.data_ptr()), lda, C.c_void_p(dv.ptr), cols,
+                                 C.c_void_p(w.ptr), rows, C.byref(one), None, st), "matmul")
+    torch.cuda.synchronize()
+    if attach:
+        h.lib.scimlop_split_detach(h.ptr, C.c_void_p(flat.data_ptr()))
+    A = Abig[:rows]
+    want = A.astype(np.float64) @ v.astype(np.float64)
+    scale = np.linalg.norm(np.abs(A).astype(np.float64) @ np.abs(v).astype(np.float64))
+    assert np.linalg.norm(w.numpy() - want) <= 1e-5 * scale
