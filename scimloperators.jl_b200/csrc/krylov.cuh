@@ -95,10 +95,12 @@ __global__ void __launch_bounds__(THREADS) col_axpby_dot_kernel(const AxpbyParam
   constexpr int NV = VEC ? V16<T>::N : 1;
   const int j = blockIdx.y;
   T a = p.sa, b = p.sb;
+  // a zero denominator (an all-zero right-hand-side column, or a column whose residual reached exactly 0) gives the
+  // coefficient 0 instead of 0/0 = NaN: that column simply stops moving in a fixed-count / graph-replayed iteration
   if (p.an) a *= p.an[j];
-  if (p.ad) a /= p.ad[j];
+  if (p.ad) a = (p.ad[j] == T(0)) ? T(0) : a / p.ad[j];
   if (p.bn) b *= p.bn[j];
-  if (p.bd) b /= p.bd[j];
+  if (p.bd) b = (p.bd[j] == T(0)) ? T(0) : b / p.bd[j];
   const T* x = p.X + (long long)j * p.ldx;
   T* w = p.W + (long long)j * p.ldw;
   const long long chunk = (long long)THREADS * NV * U;

@@ -106,9 +106,12 @@ class PeerWindow:
         self._opened = []
 
 
-def kron_mul_peers(handle, L, V_local, window, cols_per_rank, alpha=None, stream=None, barrier=True):
+def kron_mul_peers(handle, L, V_local, window, cols_per_rank, alpha=None, stream=None, barrier=True, pre_barrier=False):
     """This rank's column slab of W = (kron factors) V, stored by the stage-2 GEMM epilogue into EVERY rank's
-    W_full (peer stores over NVLink), then a one-word stream barrier.  Float64, replicated result."""
+    W_full (peer stores over NVLink), then a one-word stream barrier.  Float64, replicated result.
+    `pre_barrier`: a caller that READS W between two calls must order "every rank has finished reading the previous
+    W" before any rank's next remote stores (include/scimlop_b200.h, ordering contract): a barrier on the stream in
+    front of the launch does that."""
     import torch
     from .operators import _DT, _scalar
     nat = L._native
@@ -123,6 +126,8 @@ def kron_mul_peers(handle, L, V_local, window, cols_per_rank, alpha=None, stream
     a = alpha
     for s in nat["scalars"]:
         a = s.convert() * (1.0 if a is None else float(a))
+    if pre_barrier:
+        handle.check(handle.lib.scimlop_comm_barrier(handle.ptr, st), "scimlop_comm_barrier")
     handle.check(handle.lib.scimlop_kron_mul_peers(
         handle.ptr, _DT[V_local.dtype], L.precision, nat["nf"], nat["ptrs"], nat["dims"], nat["lds"], nat["kinds"],
         C.c_void_p(V_local.ptr), int(cols_per_rank), C.c_void_p(window.base[window.rank] + slab), arr, len(peers),
@@ -197,9 +202,10 @@ class MulticastWindow:
             self._win = None
 
 
-def kron_mul_mc(handle, L, V_local, window, cols_per_rank, alpha=None, stream=None, barrier=True):
+def kron_mul_mc(handle, L, V_local, window, cols_per_rank, alpha=None, stream=None, barrier=True, pre_barrier=False):
     """This rank's column slab of W = (kron factors) V, stored ONCE by the last GEMM's epilogue through the NVSwitch
-    multicast alias of W (multimem.st): the switch writes it into every rank's copy.  Float64."""
+    multicast alias of W (multimem.st): the switch writes it into every rank's copy.  Float64.  `pre_barrier` as in
+    kron_mul_peers (needed when W is read between calls)."""
     import torch
     from .operators import _DT, _scalar
     nat = L._native
@@ -211,6 +217,8 @@ def kron_mul_mc(handle, L, V_local, window, cols_per_rank, alpha=None, stream=No
     a = alpha
     for s in nat["scalars"]:
         a = s.convert() * (1.0 if a is None else float(a))
+    if pre_barrier:
+        handle.check(handle.lib.scimlop_comm_barrier(handle.ptr, st), "scimlop_comm_barrier")
     handle.check(handle.lib.scimlop_kron_mul_mc(
         handle.ptr, _DT[V_local.dtype], L.precision, nat["nf"], nat["ptrs"], nat["dims"], nat["lds"], nat["kinds"],
         C.c_void_p(V_local.ptr), int(cols_per_rank), C.c_void_p(window.local_ptr + slab), C.c_void_p(window.mc_ptr + slab),

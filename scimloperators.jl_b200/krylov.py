@@ -96,23 +96,65 @@ def cg(L, B, X, iters, state=None, use_graph=True, iters_per_graph=8):
     return X, st.rs[parity], st
 
 
+def _scalar_signature(L, seen=None):
+    """Values of every ScalarOperator reachable from L (ScaledOperator λ's, WOperator γ, ...): what a captured launch
+    bakes into its kernel parameters (src/scalar.jl:267-270 updates them on the host)."""
+    from .operators import AbstractSciMLOperator, ScalarOperator
+    seen = set() if seen is None else seen
+    if id(L) in seen:
+        return ()
+    seen.add(id(L))
+    sig = []
+    for val in vars(L).values() if hasattr(L, "__dict__") else ():
+        items = val if isinstance(val, (tuple, list)) else (val,)
+        for it in items:
+            if isinstance(it, ScalarOperator):
+                sig.append(float(it.convert()))
+            elif isinstance(it, AbstractSciMLOperator):
+                sig.extend(_scalar_signature(it, seen))
+    return tuple(sig)
+
+
 class CapturedMul:
-    """`mul!(w, L, v[, α, β])` with fixed buffers captured once into a CUDA graph: an ODE / Krylov loop replays it
-    (`update_coefficients!` may rewrite the operator's device arrays in between -- the graph holds pointers, not
-    values; scalars α, β and ScaledOperator λ's are baked in at capture).  For small operators (config 1, vector
-    inputs) this removes the per-call host work between the launches."""
+    """`mul!(w, L, v[, α, β])` with fixed buffers captured once into a CUDA graph: an ODE / Krylov loop replays it.
+    `update_coefficients!` between replays is honoured: the graph holds POINTERS to the operator's device arrays, so
+    in-place updates of matrices / diagonals are seen directly; host scalars (α, β and every ScalarOperator λ, which
+    the kernels take by value) are compared at each replay and the graph is re-captured when one changed.  For small
+    operators (config 1, vector inputs) this removes the per-call host work between the launches.
+    Construction does not modify `w` (the warm-up outside the capture runs into a scratch copy when β ≠ 0)."""
 
     def __init__(self, L, w, v, alpha=None, beta=None):
-        self.L, self.w, self.v = L, w, v
+        self.L, self.w, self.v, self.alpha, self.beta = L, w, v, alpha, beta
         self.stream = torch.cuda.Stream(device=w.t.device)
+        self.captures = 0
+        self._capture(warm=True)
+
+    def _capture(self, warm):
+        L, w, v = self.L, self.w, self.v
+        self.stream.wait_stream(torch.cuda.current_stream(w.t.device))   # pending producers of v / w (ADVICE r1)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.stream(self.stream):
-            L.mul_(w, v, alpha, beta)                      # warm-up outside the capture (lazy set-up happens here)
-            self.stream.synchronize()
+            if warm:
+                # lazy set-up (module loading, handle creation) must happen outside the capture; a real mul! with
+                # beta != 0 would update w once at construction, so it runs into a scratch copy
+                from .operators import _beta_is_zero
+                target = w if _beta_is_zero(self.beta) else w.copy()
+                L.mul_(target, v, self.alpha, self.beta)
+                self.stream.synchronize()
             with torch.cuda.graph(self.graph, stream=self.stream):
-                L.mul_(w, v, alpha, beta)
+                L.mul_(w, v, self.alpha, self.beta)
         self.stream.synchronize()
+        self._sig = _scalar_signature(L)
+        self.captures += 1
 
-    def replay(self):
+    def replay(self, alpha=None, beta=None):
+        """Replays the captured mul!.  New α / β may be passed; changed scalars trigger one re-capture."""
+        changed = False
+        if alpha is not None and alpha != self.alpha:
+            self.alpha, changed = alpha, True
+        if beta is not None and beta != self.beta:
+            self.beta, changed = beta, True
+        if changed or _scalar_signature(self.L) != self._sig:
+            self._capture(warm=False)
         self.graph.replay()
         return self.w

@@ -1130,3 +1130,54 @@ def test_float32_split_reads_only_the_logical_extent(sb, attach):
     want = A.astype(np.float64) @ v.astype(np.float64)
     scale = np.linalg.norm(np.abs(A).astype(np.float64) @ np.abs(v).astype(np.float64))
     assert np.linalg.norm(w.numpy() - want) <= 1e-5 * scale
+
+
+def test_captured_mul_sees_time_dependent_scalars(sb):
+    """`update_coefficients!` of a time-dependent ScalarOperator between replays (src/scalar.jl:267-270): the kernels
+    take λ·α by value, so the captured graph is re-captured when a scalar changed -- and only then."""
+    import torch
+    rng = np.random.default_rng(78)
+    A, B = rnd(rng, 12, 12), rnd(rng, 9, 9)
+    v, w0 = rnd(rng, 108, 3), rnd(rng, 108, 3)
+    dv, w = dev(sb, v), dev(sb, w0)
+    lam = sb.ScalarOperator(2.0, update_func=lambda old, u, p, t: 1.0 + t)
+    L = sb.cache_operator(lam * sb.kron(A, B), dv)
+    cm = sb.krylov.CapturedMul(L, w, dv, 0.5, 0.25)
+    assert np.array_equal(w.numpy(), w0), "constructing a CapturedMul with beta != 0 must not modify w"
+    dense = np.kron(A, B)
+    cm.replay(); torch.cuda.synchronize()
+    want = 0.5 * 2.0 * dense @ v + 0.25 * w0
+    check(w.numpy(), want, np.float64, "captured 5-arg mul!")
+    cm.replay(); torch.cuda.synchronize()
+    want = 0.5 * 2.0 * dense @ v + 0.25 * want
+    check(w.numpy(), want, np.float64, "second replay")
+    assert cm.captures == 1
+    L.update_coefficients_(None, None, 4.0)          # λ = 5 now
+    cm.replay(); torch.cuda.synchronize()
+    want = 0.5 * 5.0 * dense @ v + 0.25 * want
+    check(w.numpy(), want, np.float64, "replay after update_coefficients! of the scalar")
+    assert cm.captures == 2
+    cm.replay(beta=0.0); torch.cuda.synchronize()     # new beta: 3-arg form, w never read
+    check(w.numpy(), 0.5 * 5.0 * dense @ v, np.float64, "replay with a new beta")
+    assert cm.captures == 3
+
+
+def test_batched_cg_zero_rhs_column_stays_finite(sb):
+    """An all-zero right-hand-side column: rs = pAp = 0, so the step lengths are 0/0 -- the vector kernels turn a zero
+    denominator into a zero coefficient (that column stays at x = 0) instead of poisoning it with NaN."""
+    rng = np.random.default_rng(23)
+    n1, n2, k = 16, 12, 4
+    Q1, Q2 = rnd(rng, n1, n1), rnd(rng, n2, n2)
+    A, B = Q1 @ Q1.T / n1 + np.eye(n1), Q2 @ Q2.T / n2 + np.eye(n2)
+    dense = np.kron(A, np.eye(n2)) + np.kron(np.eye(n1), B)
+    Bm = rnd(rng, n1 * n2, k)
+    Bm[:, 2] = 0.0
+    for use_graph in (False, True):
+        X = sb.DeviceArray.zeros(Bm.shape, np.float64)
+        dB = dev(sb, Bm)
+        L = sb.cache_operator(sb.kronsum(np.asfortranarray(A), np.asfortranarray(B)), dB)
+        X, rs, _ = sb.krylov.cg(L, dB, X, 40, use_graph=use_graph, iters_per_graph=8)
+        x = X.numpy()
+        assert np.isfinite(x).all() and np.isfinite(rs.numpy()).all(), f"graph={use_graph}"
+        assert np.array_equal(x[:, 2], np.zeros(n1 * n2))
+        assert R.rel_err(dense @ x, Bm) < 1e-8
