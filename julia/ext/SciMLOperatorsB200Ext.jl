@@ -14,7 +14,7 @@ module SciMLOperatorsB200Ext
 using SciMLOperators
 using SciMLOperators: TensorProductOperator, MatrixOperator, IdentityOperator, ScaledOperator,
                       AddedOperator, ComposedOperator, BatchedDiagonalOperator, getops, iscached
-import SciMLOperators: has_tensor_outer_mul_fast, tensor_outer_mul_fast!, cache_self
+import SciMLOperators: has_tensor_outer_mul_fast, tensor_outer_mul_fast!, cache_self, update_coefficients!
 import LinearAlgebra
 import LinearAlgebra: mul!, Diagonal, Adjoint, Transpose
 using CUDA
@@ -128,13 +128,45 @@ for (args, αβ) in (((), (:(C_NULL), :(C_NULL))), ((:α, :β), (:(Ref(T(α))), 
 end
 
 # ---- leaves over device storage (src/matrix.jl:337-350, src/batch.jl:151-179) -------------------------------
-function mul!(w::DevMat{T}, A::CuMatrix{T}, v::DevMat{T}, α::Number, β::Number) where {T <: F}
+# Methods are added for SciMLOperators' OWN types only (MatrixOperator over a CuMatrix, or over its lazy Adjoint /
+# Transpose -- `adjoint(::MatrixOperator)` of a constant operator wraps the array, src/matrix.jl:174-175).  A method on
+# the bare `mul!(::CuMatrix, ::CuMatrix, ::CuMatrix, α, β)` would be type piracy over CUDA.jl's CUBLAS method.
+const DenseDev{T} = Union{CuMatrix{T}, Adjoint{T, <:CuMatrix{T}}, Transpose{T, <:CuMatrix{T}}}
+_stored(A::CuMatrix) = (A, 0)
+_stored(A::Union{Adjoint, Transpose}) = (parent(A), 1)
+
+function mul!(w::DevMat{T}, L::MatrixOperator{T, <:DenseDev{T}}, v::DevMat{T}, α::Number, β::Number) where {T <: F}
+    A, trans = _stored(L.A)
     check(ccall((:scimlop_matmul, LIB), Cint,
                 (Ptr{Cvoid}, Cint, Cint, Cint, Int64, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64,
                  Ref{T}, Ref{T}, Ptr{Cvoid}),
-                handle(), dtype(T), 0, 0, size(A, 1), size(A, 2), size(v, 2), dptr(A), stride(A, 2), dptr(v), size(v, 1),
+                handle(), dtype(T), 0, trans, size(L, 1), size(L, 2), size(v, 2), dptr(A), stride(A, 2), dptr(v), size(v, 1),
                 dptr(w), size(w, 1), T(α), T(β), stream_ptr()), "scimlop_matmul")
     w
+end
+mul!(w::DevMat{T}, L::MatrixOperator{T, <:DenseDev{T}}, v::DevMat{T}) where {T <: F} = mul!(w, L, v, true, false)
+
+# `cache_operator` of a large Float32 MatrixOperator prepares the hi / lo image of the streamed tensor-core GEMM once
+# (include/scimlop_b200.h: scimlop_split_attach), so that mul! stays allocation-free (test/Downstream/alloccheck.jl).
+const SPLIT_IMAGES = IdDict{Any, Any}()
+function cache_self(L::MatrixOperator{Float32, <:DenseDev{Float32}}, v::DevMat{Float32})
+    A, _ = _stored(L.A)
+    (minimum(size(A)) < 16 || maximum(size(A)) <= 128 || haskey(SPLIT_IMAGES, A)) && return L
+    nbytes = Ref{Csize_t}(0)
+    ccall((:scimlop_split_bytes, LIB), Cint, (Int64, Int64, Ref{Csize_t}), size(A, 1), size(A, 2), nbytes)
+    img = CUDA.zeros(UInt8, nbytes[])
+    check(ccall((:scimlop_split_attach, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                handle(), dptr(A), stride(A, 2), size(A, 1), size(A, 2), dptr(img), nbytes[], stream_ptr()), "scimlop_split_attach")
+    SPLIT_IMAGES[A] = img
+    finalizer(a -> (ccall((:scimlop_split_detach, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), handle(), dptr(a)); delete!(SPLIT_IMAGES, a)), A)
+    L
+end
+function update_coefficients!(L::MatrixOperator{Float32, <:DenseDev{Float32}}, u, p, t; kwargs...)
+    invoke(update_coefficients!, Tuple{MatrixOperator, Any, Any, Any}, L, u, p, t; kwargs...)
+    A, _ = _stored(L.A)
+    haskey(SPLIT_IMAGES, A) && check(ccall((:scimlop_split_refresh, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                                           handle(), dptr(A), stream_ptr()), "scimlop_split_refresh")
+    L
 end
 
 function mul!(w::DevMat{T}, L::BatchedDiagonalOperator, v::DevMat{T}, α::Number, β::Number) where {T <: F}
