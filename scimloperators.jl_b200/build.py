@@ -19,14 +19,15 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, out=OUT, extra=()):
+    """`out` / `extra`: profiling variants (tools/kf16_trace.py builds a -DSCIMLOP_KF16_TRACE copy beside the library)."""
+    if not force and out == OUT and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

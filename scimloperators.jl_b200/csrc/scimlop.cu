@@ -11,6 +11,7 @@
 //   Float32: small resident factor -> gemm_tf32x3 (tcgen05, TMEM); few columns -> gemm_skinny; large ->
 //            gemm_tf32x3<STREAM_F> (pre-split operand streamed, chunked accumulation); else / FP32_EXACT -> gemm_simt.
 #include <algorithm>
+#include <type_traits>
 #include <new>
 
 #include "context.h"
@@ -20,6 +21,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_skinny.cuh"
 #include "gemm_tf32.cuh"
+#include "kron2_f16.cuh"
 
 using namespace scimlop;
 
@@ -448,6 +450,44 @@ int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, 
   return SCIMLOP_OK;
 }
 
+// ---- two fused Kronecker mode products, Float32 (kron2_f16.cuh) -----------------------------------------------------
+// out_s(m1 x m2) = alpha * F1op(m1 x n1) * X_s(n1 x n2) * F2op(m2 x n2)^T + beta * out_s for `slabs` contiguous slabs.
+// tr1 / tr2: the factor is the lazy transpose of the stored matrix (stored n x m).
+#ifdef SCIMLOP_KF16_TRACE
+long long* g_kf16_trace = nullptr;   // profiling builds only (tools/kf16_trace.py): 64 x 64 device stamps of CTA 0
+#endif
+bool kron2_f16_eligible(int precision, long long m1, long long n1, long long m2, long long n2, long long slabs,
+                        const float* X, const float* D) {
+  if (precision != SCIMLOP_PREC_DEFAULT && precision != SCIMLOP_PREC_TF32X3) return false;
+  if (m1 > 128 || n1 > 128 || m2 > 128 || n2 > 128) return false;
+  // every slab costs two 128^3 products whatever its extents: below ~96^2 the one-mode-per-pass path is faster
+  if (n1 * n2 < 96 * 96 || m1 * m2 < 96 * 96) return false;
+  if (n1 % 4 || m1 % 4 || !aligned16(X) || !aligned16(D)) return false;   // TMA strides are multiples of 16 bytes
+  return slabs > 0 && slabs < (1ll << 31);
+}
+
+int launch_kron2_f16(scimlop_context* c, int m1, int n1, int m2, int n2, long long slabs, const float* F1, long long ld1,
+                     bool tr1, const float* F2, long long ld2, bool tr2, const float* X, float* D, float alpha, float beta,
+                     cudaStream_t st) {
+  CUtensorMap tmX, tmD;
+  if (int rc = make_map_f32(c, &tmX, X, n1, n2, slabs, (cuuint64_t)n1 * 4, (cuuint64_t)n1 * n2 * 4, 32, 128, false)) return rc;
+  if (int rc = make_map_f32(c, &tmD, D, m1, m2, slabs, (cuuint64_t)m1 * 4, (cuuint64_t)m1 * m2 * 4, 32, 32, false, true)) return rc;
+  kf16::Params p;
+  memset(&p, 0, sizeof(p));
+  p.n1 = n1; p.n2 = n2; p.m1 = m1; p.m2 = m2; p.slabs = slabs;
+  p.F1 = F1; p.f1_rs = tr1 ? ld1 : 1; p.f1_cs = tr1 ? 1 : ld1;
+  p.F2 = F2; p.f2_rs = tr2 ? ld2 : 1; p.f2_cs = tr2 ? 1 : ld2;
+  p.alpha = alpha; p.beta = beta;
+#ifdef SCIMLOP_KF16_TRACE
+  p.trace = g_kf16_trace;
+#endif
+  const int grid = (int)std::min<long long>(slabs, std::max(1, c->sm_count - c->sm_reserve));
+  kf16::kron2_f16_kernel<<<grid, kf16::THREADS, kf16::SMEM_BYTES, st>>>(tmX, tmD, p);
+  c->launches++;
+  SCIMLOP_CUDA(c, cudaGetLastError());
+  return SCIMLOP_OK;
+}
+
 // ---- hi / lo images of Float32 operands (3xTF32 split) ---------------------------------------------------------
 inline long long split_ld(long long rows) { return (rows + 3) / 4 * 4; }
 inline size_t split_image_bytes(long long rows, long long cols) { return 2 * (size_t)split_ld(rows) * (size_t)cols * sizeof(float); }
@@ -642,6 +682,9 @@ int check_dtype(scimlop_context* c, int dtype) {
 // handle
 // ================================================================================================
 extern "C" int scimlop_version(void) { return SCIMLOP_VERSION; }
+#ifdef SCIMLOP_KF16_TRACE
+extern "C" int scimlop_debug_kf16_trace(void* buf) { g_kf16_trace = static_cast<long long*>(buf); return 0; }
+#endif
 
 extern "C" const char* scimlop_status_string(int s) {
   switch (s) {
@@ -719,6 +762,7 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   auto optin2 = [&](const void* f) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, tf32::SMEM_BYTES);
   };
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)kf16::kron2_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kf16::SMEM_BYTES);
   optin2((const void*)tf32::gemm_tf32x3_kernel<false, false>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<false, true>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<true, false>);
@@ -1060,6 +1104,28 @@ int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* cons
     const T a = last ? alpha : T(1), bt = last ? beta : T(0);
     const bool tr = (kinds[p] & SCIMLOP_TRANS) != 0;
     int rc;
+    if constexpr (std::is_same<T, float>::value) {
+      // the two fastest modes, both small dense Float32 factors: ONE pass with the intermediate kept on chip
+      if (L == 1 && p >= 1 && (kinds[p] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE && (kinds[p - 1] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE &&
+          !g_peers.active()) {
+        const long long m2 = dims[2 * (p - 1)], n2 = dims[2 * (p - 1) + 1];
+        const long long slabs = R / n2;
+        const bool last2 = (done + 1 == pl.nops);
+        float* out2 = last2 ? W : bufs[flip];
+        if (kron2_f16_eligible(precision, m, n, m2, n2, slabs, cur, out2)) {
+          rc = launch_kron2_f16(c, (int)m, (int)n, (int)m2, (int)n2, slabs, static_cast<const float*>(factors[p]), lds[p], tr,
+                                static_cast<const float*>(factors[p - 1]), lds[p - 1], (kinds[p - 1] & SCIMLOP_TRANS) != 0, cur,
+                                out2, last2 ? alpha : 1.f, last2 ? beta : 0.f, st);
+          if (rc) return rc;
+          done++;
+          cur = out2;
+          flip ^= 1;
+          L = m * m2;
+          p--;
+          continue;
+        }
+      }
+    }
     if (kinds[p] == SCIMLOP_BANDED) {
       // mode product with a banded matrix: a 1-D stencil along index (i / L) % n      [HBM-bound]
       const long long total = L * n * R;

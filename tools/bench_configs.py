@@ -88,18 +88,36 @@ def c2(reps):
 
 
 def c3(reps, k=512):
+    """configs[2].  HBM-bound: the roofline fraction is ALGORITHMIC bytes (V read once, W written once; + W read for
+    the 5-arg form) over the measured copy bandwidth.  Passes actually made: 2 (modes C and B fused on chip by
+    kron2_f16_kernel, then mode A), so the traffic floor of this schedule is 2x the algorithmic bytes."""
     F = [dev_rand((128, 128), np.float32, s) for s in (0, 10, 20)]
     n = 128 ** 3
     V = dev_rand((n, k), np.float32, 1)
     W = sb.DeviceArray.empty((n, k), np.float32)
     L = sb.cache_operator(sb.TensorProductOperator(*[sb.MatrixOperator(f) for f in F]), V)
     t = timeit(lambda: sb.mul_(W, L, V), max(2, reps // 3), warm=1)
-    report(f"c3 128^3 three-factor f32 k={k} 3arg", 3 * 2 * 128.0 * n * k, 2.0 * n * k * 4, *t, "f32",
-           {"hbm_frac_3_passes": 3 * 2.0 * n * k * 4 / (t[1] * 1e-3) / 1e9 / PEAKS["hbm_gbs"]})
+    report(f"c3 128^3 three-factor f32 k={k} 3arg", 3 * 2 * 128.0 * n * k, 2.0 * n * k * 4, *t, "hbm",
+           {"hbm_frac_of_2_pass_traffic": 2 * 2.0 * n * k * 4 / (t[1] * 1e-3) / 1e9 / PEAKS["hbm_gbs"]})
     W.t.fill_(0.5)
     t = timeit(lambda: sb.mul_(W, L, V, 0.7, 0.3), max(2, reps // 3), warm=1)
-    report(f"c3 128^3 three-factor f32 k={k} 5arg", 3 * 2 * 128.0 * n * k, 3.0 * n * k * 4, *t, "f32",
-           {"hbm_frac_3_passes": (3 * 2.0 + 1.0) * n * k * 4 / (t[1] * 1e-3) / 1e9 / PEAKS["hbm_gbs"]})
+    report(f"c3 128^3 three-factor f32 k={k} 5arg", 3 * 2 * 128.0 * n * k, 3.0 * n * k * 4, *t, "hbm",
+           {"hbm_frac_of_2_pass_traffic": (2 * 2.0 + 1.0) * n * k * 4 / (t[1] * 1e-3) / 1e9 / PEAKS["hbm_gbs"]})
+
+
+def c3pair(reps, k=32768):
+    """The fused two-mode kernel alone: 128x128 (x) 128x128 Float32 on a 16384 x k batch (one launch)."""
+    F = [dev_rand((128, 128), np.float32, s) for s in (0, 10)]
+    n = 128 ** 2
+    V = dev_rand((n, k), np.float32, 1)
+    W = sb.DeviceArray.empty((n, k), np.float32)
+    L = sb.cache_operator(sb.TensorProductOperator(*[sb.MatrixOperator(f) for f in F]), V)
+    t = timeit(lambda: sb.mul_(W, L, V), max(2, reps // 3), warm=1)
+    report(f"c3pair 128^2 two-factor f32 k={k} 3arg (kron2_f16_kernel)", 2 * 2 * 128.0 * n * k, 2.0 * n * k * 4, *t, "hbm",
+           {"us_per_slab_per_sm": t[1] * 1e3 / (k / 148.0)})
+    W.t.fill_(0.5)
+    t = timeit(lambda: sb.mul_(W, L, V, 0.7, 0.3), max(2, reps // 3), warm=1)
+    report(f"c3pair 128^2 two-factor f32 k={k} 5arg (kron2_f16_kernel)", 2 * 2 * 128.0 * n * k, 3.0 * n * k * 4, *t, "hbm")
 
 
 def c4elt(reps):
@@ -212,7 +230,7 @@ def c5fd(reps, k=8):
     report(f"c5-fd as AddedOperator of two banded TPOs (two passes) k={k}", 10.0 * N * k, 5.0 * nb, *t, "hbm")
 
 
-ALL = {"c5fd": c5fd, "krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
+ALL = {"c5fd": c5fd, "krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c3pair": c3pair, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
