@@ -469,20 +469,22 @@ bool kron2_f16_eligible(int precision, long long m1, long long n1, long long m2,
 int launch_kron2_f16(scimlop_context* c, int m1, int n1, int m2, int n2, long long slabs, const float* F1, long long ld1,
                      bool tr1, const float* F2, long long ld2, bool tr2, const float* X, float* D, float alpha, float beta,
                      cudaStream_t st) {
-  CUtensorMap tmX, tmD;
+  CUtensorMap tmX, tmW;
   if (int rc = make_map_f32(c, &tmX, X, n1, n2, slabs, (cuuint64_t)n1 * 4, (cuuint64_t)n1 * n2 * 4, 32, 128, false)) return rc;
-  if (int rc = make_map_f32(c, &tmD, D, m1, m2, slabs, (cuuint64_t)m1 * 4, (cuuint64_t)m1 * m2 * 4, 32, 32, false, true)) return rc;
+  // beta != 0: the old output is prefetched as 128 x 32 blocks (plain layout: the epilogue lanes read consecutive floats)
+  if (int rc = make_map_f32(c, &tmW, D, m1, m2, slabs, (cuuint64_t)m1 * 4, (cuuint64_t)m1 * m2 * 4, 128, 32, false, false)) return rc;
   kf16::Params p;
   memset(&p, 0, sizeof(p));
   p.n1 = n1; p.n2 = n2; p.m1 = m1; p.m2 = m2; p.slabs = slabs;
   p.F1 = F1; p.f1_rs = tr1 ? ld1 : 1; p.f1_cs = tr1 ? 1 : ld1;
   p.F2 = F2; p.f2_rs = tr2 ? ld2 : 1; p.f2_cs = tr2 ? 1 : ld2;
-  p.alpha = alpha; p.beta = beta;
+  p.D = D; p.alpha = alpha; p.beta = beta;
 #ifdef SCIMLOP_KF16_TRACE
   p.trace = g_kf16_trace;
 #endif
   const int grid = (int)std::min<long long>(slabs, std::max(1, c->sm_count - c->sm_reserve));
-  kf16::kron2_f16_kernel<<<grid, kf16::THREADS, kf16::SMEM_BYTES, st>>>(tmX, tmD, p);
+  if (beta != 0.f) kf16::kron2_f16_kernel<true><<<grid, kf16::THREADS, kf16::SMEM_BYTES, st>>>(tmX, tmW, p);
+  else kf16::kron2_f16_kernel<false><<<grid, kf16::THREADS, kf16::SMEM_BYTES, st>>>(tmX, tmW, p);
   c->launches++;
   SCIMLOP_CUDA(c, cudaGetLastError());
   return SCIMLOP_OK;
@@ -762,7 +764,8 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   auto optin2 = [&](const void* f) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, tf32::SMEM_BYTES);
   };
-  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)kf16::kron2_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kf16::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)kf16::kron2_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kf16::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)kf16::kron2_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kf16::SMEM_BYTES);
   optin2((const void*)tf32::gemm_tf32x3_kernel<false, false>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<false, true>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<true, false>);

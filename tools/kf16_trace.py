@@ -15,13 +15,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 TRACE_LIB = os.path.join(ROOT, "scimloperators.jl_b200", "libscimlop_b200_trace.so")
 
-SLOTS = {0: "prod kk0 slot free", 1: "prod kk1", 2: "prod kk2", 3: "prod kk3", 8: "mma S1 issue start", 14: "mma S1 issued",
-         15: "mma y_full seen, S2 issue start", 16: "mma S2 issued",
-         20: "spl raw_full0", 21: "spl raw_full1", 22: "spl raw_full2", 23: "spl raw_full3", 24: "spl g0 at barrier", 25: "spl g1 at barrier",
-         26: "spl g0 past barrier", 27: "spl g1 past barrier", 28: "spl conv0 done", 29: "spl conv1 done", 30: "spl conv2 done",
-         31: "spl conv3 done", 32: "spl a_free seen (g0)", 34: "spl a_free seen (g1)",
+SLOTS = {0: "prod kk0 slot free", 1: "prod kk1", 2: "prod kk2", 3: "prod kk3", 8: "mma S1 issue start (x_full seen)", 9: "mma S1 issued",
+         15: "mma S2 issue start (y_full seen)", 16: "mma S2 issued",
+         20: "spl raw_full0", 21: "spl raw_full1", 22: "spl raw_full2", 23: "spl raw_full3", 28: "spl g0 scale known", 29: "spl g1 scale known",
+         32: "spl g0 x_free seen", 33: "spl g1 x_free seen",
          52: "spl g0 q0 done", 53: "spl g0 q1 done", 54: "spl g0 q2 done", 55: "spl g0 q3 done", 56: "spl g1 q0 done", 57: "spl g1 q1 done",
-         58: "spl g1 q2 done", 59: "spl g1 q3 done", 40: "drain1 start", 60: "drain1 blk0 loaded", 61: "drain1 blk1 loaded", 62: "drain1 blk2 loaded", 63: "drain1 blk3 loaded", 4: "drain2 blk0 loaded", 5: "drain2 blk1 loaded", 6: "drain2 blk2 loaded", 7: "drain2 blk3 loaded", 17: "drain2 blk2 staging free", 41: "drain1 done", 44: "drain2 start", 45: "drain2 done"}
+         58: "spl g1 q2 done", 59: "spl g1 q3 done", 40: "drain1 start", 41: "drain1 done", 44: "drain2 start", 46: "drain2 accumulator handed back", 45: "drain2 done"}
 
 
 def main():
@@ -60,15 +59,26 @@ def main():
         else:
             sb.mul_(W, L, V)
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        if a.beta:
+            sb.mul_(W, L, V, 1.0, a.beta)
+        else:
+            sb.mul_(W, L, V)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(json.dumps({"ms_per_launch": ms, "us_per_slab_per_sm": ms * 1e3 / (a.k / 148.0)}))
     t = trace.cpu().numpy().reshape(64, 64)
-    period = np.diff(t[8:40, 8])
-    ns = np.diff(t[8:40, 50])
+    period = np.diff(t[8:40, 15])
+    ns = np.diff(t[8:40, 51])
     print(json.dumps({"k": a.k, "slab_period_clk_median": float(np.median(period)), "min": int(period.min()), "max": int(period.max()),
                       "slab_period_ns_median": float(np.median(ns)), "sm_ghz": float(np.sum(period) / max(1, np.sum(ns)))}))
     for it in (20, 21):
-        base = t[it, 8]
+        base = t[it, 15]
         ev = sorted((int(t[it, s] - base), name) for s, name in SLOTS.items() if t[it, s])
-        print(f"--- slab iteration {it} (clk relative to the slab's first MMA; next slab's at {int(t[it + 1, 8] - base)})")
+        print(f"--- slab iteration {it} (clk relative to the slab's stage-2 issue; next slab's at {int(t[it + 1, 15] - base)})")
         for d, name in ev:
             print(f"{d:8d}  {name}")
 
