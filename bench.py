@@ -270,14 +270,20 @@ def strong_legs(torch, dist, sb, h, world, rank, A, B, ms_1gpu_shape):
 
     # the unfused result of EVERY slab, recomputed locally from that rank's (seeded) V: the bit-compare reference
     def check(Wfull, what):
+        # same summation order as the fused kernels: one launch per stage (the split-K tail launch reorders the sums
+        # of the last partial wave; include/scimlop_b200.h, SCIMLOP_OPT_TAIL_SPLIT)
         ref = sb.DeviceArray.empty((n, kper), np.float64)
-        for r in range(world):
-            sb.mul_(ref, L, slab_of(r))
-            if not torch.equal(Wfull.cols(r * kper, (r + 1) * kper).t, ref.t):
-                d = float((Wfull.cols(r * kper, (r + 1) * kper).t - ref.t).abs().max())
-                print(json.dumps({"error": f"{what}: slab {r} on rank {rank} differs from the unfused result", "max_abs_diff": d}),
-                      file=sys.stderr, flush=True)
-                return False
+        h.set_option(sb.OPT_TAIL_SPLIT, 0)
+        try:
+            for r in range(world):
+                sb.mul_(ref, L, slab_of(r))
+                if not torch.equal(Wfull.cols(r * kper, (r + 1) * kper).t, ref.t):
+                    d = float((Wfull.cols(r * kper, (r + 1) * kper).t - ref.t).abs().max())
+                    print(json.dumps({"error": f"{what}: slab {r} on rank {rank} differs from the unfused result", "max_abs_diff": d}),
+                          file=sys.stderr, flush=True)
+                    return False
+        finally:
+            h.set_option(sb.OPT_TAIL_SPLIT, 1)
         return True
 
     ok = True

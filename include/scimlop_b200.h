@@ -86,6 +86,14 @@ int scimlop_create(scimlop_handle_t* out, int device);
 int scimlop_destroy(scimlop_handle_t h);
 /* Copies the text of the last failure recorded on `h` (empty string if none). */
 int scimlop_last_error(scimlop_handle_t h, char* buf, size_t len);
+/* Explicit behaviour switches of a handle (never environment variables).
+ * SCIMLOP_OPT_TAIL_SPLIT (default 1): a Float64 GEMM whose tile count is a few whole waves plus a partial one runs the
+ * partial wave as a second, split-K launch (thread-block clusters divide K and reduce through distributed shared
+ * memory).  Faster (config 2 on 32 columns: 512 tiles = 3.46 waves -> 3 + 0.5), but the tiles of that wave are summed
+ * in a different order than the single-launch schedule; 0 restores one launch and one summation order everywhere
+ * (what the fused compute + all-gather entries always use, so a bit-for-bit comparison against them sets 0). */
+enum { SCIMLOP_OPT_TAIL_SPLIT = 1 };
+int scimlop_set_option(scimlop_handle_t h, int option, int value);
 /* Number of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
 int scimlop_launch_count(scimlop_handle_t h, int64_t* count);
 

@@ -17,6 +17,7 @@ F64, F32 = 0, 1
 PREC_DEFAULT, PREC_TF32X3, PREC_TF32, PREC_FP32_EXACT = 0, 1, 2, 3
 DENSE, IDENTITY, DIAG, BDIAG, NULL, BANDED = 0, 1, 2, 3, 4, 5
 TRANS = 0x100
+OPT_TAIL_SPLIT = 1
 
 
 class Factor(C.Structure):  # scimlop_factor_t
@@ -45,6 +46,7 @@ SIGNATURES = {
     "scimlop_destroy": [_P],
     "scimlop_last_error": [_P, C.c_char_p, _SZ],
     "scimlop_launch_count": [_P, _I64P],
+    "scimlop_set_option": [_P, _INT, _INT],
     "scimlop_matmul": [_P, _INT, _INT, _INT, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P],
     "scimlop_split_bytes": [_I64, _I64, C.POINTER(_SZ)],
     "scimlop_split_attach": [_P, _P, _I64, _I64, _I64, _P, _SZ, _P],
@@ -132,6 +134,10 @@ class Handle:
             buf = C.create_string_buffer(512)
             self.lib.scimlop_last_error(self._h, buf, 512)
             raise ScimlopError(rc, where, buf.value.decode(errors="replace"))
+
+    def set_option(self, option, value):
+        """scimlop_set_option: OPT_TAIL_SPLIT = 1 (include/scimlop_b200.h)."""
+        self.check(self.lib.scimlop_set_option(self._h, int(option), int(value)), "scimlop_set_option")
 
     def launch_count(self):
         n = C.c_int64(0)

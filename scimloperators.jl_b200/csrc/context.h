@@ -32,6 +32,7 @@ struct scimlop_context {
   int device;
   int sm_count;
   int sm_reserve;  // SMs left free by the persistent GEMM kernels (for concurrently running NCCL kernels)
+  int tail_split;  // scimlop_set_option(SCIMLOP_OPT_TAIL_SPLIT): run the last partial wave of a many-tile FP64 GEMM split-K (default 1)
   scimlop_encode_tiled_fn encode_tiled;
   // Float32 streamed GEMM: hi / lo images attached by the caller (cached operators: nothing is split or allocated per
   // call), and a grow-only scratch for the UNCACHED convenience entries (scimlop_matmul & co. on unattached operands)

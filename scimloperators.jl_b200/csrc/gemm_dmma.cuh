@@ -35,7 +35,8 @@ struct Scale {
 struct Params {
   int M, N, K, batch;
   int tiles_m, tiles_n;
-  long long total_tiles;
+  long long total_tiles;   // tiles THIS launch covers: global tile ids tile_base .. tile_base + total_tiles - 1
+  int tile_base;           // != 0 for the split-K launch that takes the last partial wave of a many-tile problem
   double* C;
   long long ldc, strideC;
   double alpha, beta;  // beta == 0: C is never read
@@ -156,8 +157,8 @@ __global__ void __launch_bounds__(THREADS, 1)
       uint32_t phase = 0;
       const int tiles_mn = p.tiles_m * p.tiles_n;
       for (int tile = tile_first; tile < ntiles; tile += tile_step) {
-        const int b = tile / tiles_mn;
-        const int rem = tile - b * tiles_mn;
+        const int b = (tile + p.tile_base) / tiles_mn;
+        const int rem = (tile + p.tile_base) - b * tiles_mn;
         const int nt = rem / p.tiles_m;
         const int mt = rem - nt * p.tiles_m;
         const int m0 = mt * BM, n0 = nt * BN;
@@ -191,8 +192,8 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int tiles_mn = p.tiles_m * p.tiles_n;
       uint32_t tph = 0;
       for (int tile = tile_first; tile < ntiles; tile += tile_step) {
-        const int b = tile / tiles_mn;
-        const int rem = tile - b * tiles_mn;
+        const int b = (tile + p.tile_base) / tiles_mn;
+        const int rem = (tile + p.tile_base) - b * tiles_mn;
         const int nt = rem / p.tiles_m;
         const int mt = rem - nt * p.tiles_m;
         double* base = p.mcC + (long long)b * p.strideC + (long long)(nt * BN) * p.ldc + mt * BM;
@@ -267,8 +268,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 
   for (int tile = tile_first; tile < ntiles; tile += tile_step) {
     const int tiles_mn = p.tiles_m * p.tiles_n;
-    const int b = tile / tiles_mn;
-    const int rem = tile - b * tiles_mn;
+    const int b = (tile + p.tile_base) / tiles_mn;
+    const int rem = (tile + p.tile_base) - b * tiles_mn;
     const int nt = rem / p.tiles_m;
     const int mt = rem - nt * p.tiles_m;
     const bool last_tile = tile + tile_step >= ntiles;

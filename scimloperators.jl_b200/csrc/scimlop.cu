@@ -239,13 +239,56 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
     SCIMLOP_CUDA(c, e);
     return SCIMLOP_OK;
   }
-  const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
+  // Tail-wave quantisation: a few whole waves plus a partial one (512 tiles on 148 SMs = 3.46 waves: the strong-scaled
+  // config-2 share of one of 8 GPUs) leaves most SMs idle for the last tile time.  The last partial wave is then run as
+  // a second launch of the split-K form -- each tile on a cluster of `ts` CTAs that divide K -- so it costs 1 / ts of a
+  // tile time (+ the cluster reduction).  Modelled with the same constants as above; only taken when it saves > 10 us.
+  const int nsm = std::max(1, c->sm_count - c->sm_reserve);
+  long long tail = 0, ts = 1;
+  if (c->tail_split && !g_peers.active() && p.total_tiles > nsm && p.total_tiles % nsm != 0) {
+    const long long rem = p.total_tiles % nsm;
+    const double tile_us = nk_all * 2.2 + 2.0;
+    double best_gain = 10.0;
+    for (long long cand = 2; cand <= 8; cand *= 2) {
+      const long long maxc = c->dmma_max_clusters[cand];
+      if (maxc <= 0 || nk_all < 2 * cand || rem > maxc) continue;
+      const double gain = tile_us - ((double)((nk_all + cand - 1) / cand) * 2.2 + 6.0 + 3.0);
+      if (gain > best_gain) { best_gain = gain; tail = rem; ts = cand; }
+    }
+  }
+  const long long all_tiles = p.total_tiles;
+  p.total_tiles = all_tiles - tail;
+  const int grid = (int)std::min<long long>(p.total_tiles, nsm);
   if (!transA && !transB) dmma::gemm_dmma_kernel<false, false><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p, pmaps);
   else if (!transA && transB) dmma::gemm_dmma_kernel<false, true><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p, pmaps);
   else if (transA && !transB) dmma::gemm_dmma_kernel<true, false><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p, pmaps);
   else dmma::gemm_dmma_kernel<true, true><<<grid, dmma::THREADS, dmma::SMEM_BYTES, st>>>(tmA, tmB, p, pmaps);
   c->launches++;
   SCIMLOP_CUDA(c, cudaGetLastError());
+  if (tail > 0) {
+    p.tile_base = (int)(all_tiles - tail);
+    p.total_tiles = tail;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(ts * tail), 1, 1);
+    cfg.blockDim = dim3(dmma::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = dmma::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ts;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    if (!transA && !transB) e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<false, false, true>, tmA, tmB, p, pmaps);
+    else if (!transA && transB) e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<false, true, true>, tmA, tmB, p, pmaps);
+    else if (transA && !transB) e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<true, false, true>, tmA, tmB, p, pmaps);
+    else e = cudaLaunchKernelEx(&cfg, dmma::gemm_dmma_kernel<true, true, true>, tmA, tmB, p, pmaps);
+    c->launches++;
+    SCIMLOP_CUDA(c, e);
+  }
   return SCIMLOP_OK;
 }
 
@@ -721,6 +764,7 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   c->magic = SCIMLOP_MAGIC;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  c->tail_split = 1;
   scimlop_device_guard guard(device);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -804,6 +848,12 @@ extern "C" int scimlop_last_error(scimlop_handle_t h, char* buf, size_t len) {
   if (!buf || len == 0) return SCIMLOP_ERR_NULL_POINTER;
   snprintf(buf, len, "%s", h->last_error);
   return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_set_option(scimlop_handle_t h, int option, int value) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (option == SCIMLOP_OPT_TAIL_SPLIT) { h->tail_split = value != 0; return SCIMLOP_OK; }
+  return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "scimlop_set_option: unknown option %d", option);
 }
 
 extern "C" int scimlop_launch_count(scimlop_handle_t h, int64_t* count) {

@@ -1181,3 +1181,41 @@ def test_batched_cg_zero_rhs_column_stays_finite(sb):
         assert np.isfinite(x).all() and np.isfinite(rs.numpy()).all(), f"graph={use_graph}"
         assert np.array_equal(x[:, 2], np.zeros(n1 * n2))
         assert R.rel_err(dense @ x, Bm) < 1e-8
+
+
+def test_dmma_tail_wave_runs_split_k_and_option_restores_one_launch(sb):
+    """A Float64 GEMM with a few whole waves plus a partial one (the strong-scaled configs[1] share of one of 8 GPUs:
+    512 x 512 (x) 512 x 512 on 32 columns = 512 tiles per stage on 148 SMs) runs the partial wave as a second,
+    split-K launch: 2 launches per stage, same result within 1e-12; SCIMLOP_OPT_TAIL_SPLIT = 0 restores one launch per
+    stage and the single summation order (bit-identical to the fused all-gather entries, bench.py's check)."""
+    import torch
+    rng = np.random.default_rng(11)
+    A, B = rnd(rng, 512, 512), rnd(rng, 512, 512)
+    n, k = 512 * 512, 32
+    g = torch.Generator(device="cuda").manual_seed(5)
+    V = sb.DeviceArray(torch.rand(n * k, dtype=torch.float64, device="cuda", generator=g), (n, k))
+    L = sb.cache_operator(sb.kron(sb.MatrixOperator(A), sb.MatrixOperator(B)), V)
+    h = sb.handle(0)
+    W1 = sb.DeviceArray.full((n, k), float("nan"), np.float64)
+    sb.mul_(W1, L, V)
+    n0 = h.launch_count()
+    sb.mul_(W1, L, V)
+    split_launches = h.launch_count() - n0
+    h.set_option(sb.OPT_TAIL_SPLIT, 0)
+    try:
+        W0 = sb.DeviceArray.full((n, k), float("nan"), np.float64)
+        n0 = h.launch_count()
+        sb.mul_(W0, L, V)
+        assert h.launch_count() - n0 == 2
+    finally:
+        h.set_option(sb.OPT_TAIL_SPLIT, 1)
+    assert split_launches == 4, f"expected main + tail launch per stage, got {split_launches}"
+    assert torch.isfinite(W1.t).all()
+    err = float((W1.t - W0.t).norm() / W0.t.norm())
+    assert err <= 1e-14, f"split-K tail vs single launch: {err:.3e}"
+    for j in (0, 31):
+        check(W1.cols(j, j + 1).numpy(), R.kron_apply([A, B], V.cols(j, j + 1).numpy()), np.float64, f"column {j}")
+    # 5-arg through the tail launch as well
+    W2 = W1.copy()
+    sb.mul_(W2, L, V, 2.0, -1.0)
+    assert float((W2.t - W1.t).norm() / W1.t.norm()) <= 1e-12
