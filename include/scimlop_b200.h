@@ -57,7 +57,11 @@ enum {
                                  shape is eligible, exact-FP32 FFMA otherwise                               */
   SCIMLOP_PREC_TF32X3 = 1,    /* F32 only: 3xTF32 split on tcgen05 (same as DEFAULT where eligible)          */
   SCIMLOP_PREC_TF32 = 2,      /* F32 only, explicit opt-in: single-pass TF32 on tcgen05 (rel. err ~1e-3)     */
-  SCIMLOP_PREC_FP32_EXACT = 3 /* F32 only: force the exact-FP32 FFMA path                                    */
+  SCIMLOP_PREC_FP32_EXACT = 3,/* F32 only: force the exact-FP32 FFMA path                                    */
+  SCIMLOP_PREC_BF16 = 4       /* F32 only, explicit opt-in: operands rounded to BF16, one tcgen05.mma kind::f16 pass,
+                                 FP32 accumulation (rel. err ~4e-3).  Taken by the fused two-mode Kronecker kernel
+                                 (two adjacent dense factors <= 128); every other Float32 shape runs the single-pass
+                                 TF32 path, which is at least as accurate                                    */
 };
 
 /* ---- factor kinds (kron factors and tree leaves) --------------------------------------------------- */

@@ -35,6 +35,7 @@
 // Warp roles (20 warps): 0 TMA producer, 1 MMA issuer, 4-11 splitters (group g converts k-blocks 2g, 2g+1 of every
 // slab), 12-15 drain-1, 16-19 drain-2 (alpha / beta epilogue).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "gemm_tf32.cuh"
@@ -103,9 +104,10 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
 }
 // instruction descriptor: D = F32, A = B = F16, both K-major (A in TMEM), M = 128, N = 128.  A tcgen05.mma costs ~20 clk on
 // top of its N / 2, so the widest N wins (measured: 79 clk at N = 128, 52 at N = 64).
-__device__ __forceinline__ uint32_t make_idesc_f16() {
+__device__ __forceinline__ uint32_t make_idesc_f16(bool bf16) {
   uint32_t d = 0;
-  d |= 1u << 4;                        // c_format = F32 (a_format = b_format = 0: F16; a_major = b_major = 0: K)
+  d |= 1u << 4;                        // c_format = F32 (a_format = b_format = 0: F16, 1: BF16; a_major = b_major = 0: K)
+  if (bf16) d |= (1u << 7) | (1u << 10);
   d |= (uint32_t)(128 >> 3) << 17;     // N >> 3
   d |= (uint32_t)(128 >> 4) << 24;     // M >> 4
   return d;
@@ -129,6 +131,10 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 // byte offset of element (row n, k) in a 128 x 128 FP16 K-major SWIZZLE_128B operand image: two 64-k panels of 16 KB,
 // rows of 128 B, 16-byte chunks XOR (n & 7)
 __device__ __forceinline__ uint32_t kmajor_off(int n, int k) {
@@ -138,7 +144,9 @@ __device__ __forceinline__ uint32_t kmajor_off(int n, int k) {
 // READW: the 5-arg form (beta != 0).  The slab-wide scale makes a splitter need ALL k-blocks of a slab before it can convert
 // any, so the raw ring has to hold more than one slab for the TMA latency to stay out of the splitters' loop: 6 stages
 // without the old-output ring, 4 with it (that kernel is bound by its 1.5x memory traffic anyway).
-template <bool READW>
+// BF16: the opt-in single-pass mode (SCIMLOP_PREC_BF16): operands rounded to BF16 (no split, no scaling: BF16 has the
+// FP32 exponent range), one tcgen05.mma kind::f16 per k-step with BF16 formats, FP32 accumulation; rel. error ~4e-3.
+template <bool READW, bool BF16 = false>
 __global__ void __launch_bounds__(THREADS, 1)
     kron2_f16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -197,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   // ---- factor images (once per CTA): largest entry -> exact power-of-two scale -> FP16 hi / lo ----
-  {
+  if (!BF16) {
     uint32_t m1b = 0u, m2b = 0u;
     for (int i = threadIdx.x; i < p.m1 * p.n1; i += THREADS) {
       const int r = i % p.m1, c = i / p.m1;
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
   }
   __syncthreads();
-  const int e1 = exp_of_max(fmax_g[0]), e2 = exp_of_max(fmax_g[1]);
+  const int e1 = BF16 ? 0 : exp_of_max(fmax_g[0]), e2 = BF16 ? 0 : exp_of_max(fmax_g[1]);
   {
     // F2 image: B operand of stage 2, element (n = b', k = b) = F2op(b', b) * 2^-e2
     const float sa = pow2f(-(e2 / 2)), sb = pow2f(-(e2 - e2 / 2));   // 2^-e2 in two exact steps
@@ -223,11 +231,15 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int r = i & 127, c = i >> 7;
       float v = 0.f;
       if (r < p.m2 && c < p.n2) v = __ldg(p.F2 + r * p.f2_rs + c * p.f2_cs) * sa * sb;
-      const __half h = __float2half_rn(v);
-      const __half l = __float2half_rn(v - __half2float(h));
       const uint32_t off = kmajor_off(r, c);
-      *reinterpret_cast<__half*>(smem_gen + off) = h;
-      *reinterpret_cast<__half*>(smem_gen + IMG_BYTES + off) = l;
+      if (BF16) {
+        *reinterpret_cast<__nv_bfloat16*>(smem_gen + off) = __float2bfloat16_rn(v);
+      } else {
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn(v - __half2float(h));
+        *reinterpret_cast<__half*>(smem_gen + off) = h;
+        *reinterpret_cast<__half*>(smem_gen + IMG_BYTES + off) = l;
+      }
     }
     fence_async_smem();
   }
@@ -245,7 +257,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         float v0 = 0.f, v1 = 0.f;
         if (row < p.m1 && c < p.n1) v0 = __ldg(p.F1 + row * p.f1_rs + c * p.f1_cs) * sa * sb;
         if (row < p.m1 && c + 1 < p.n1) v1 = __ldg(p.F1 + row * p.f1_rs + (c + 1) * p.f1_cs) * sa * sb;
-        split_pair(v0, v1, hi[j], lo[j]);
+        if (BF16) { hi[j] = pack_bf16(v0, v1); lo[j] = 0u; }
+        else split_pair(v0, v1, hi[j], lo[j]);
       }
       tc_st32(ta + TM_F1HI + 32 * t, hi);
       tc_st32(ta + TM_F1LO + 32 * t, lo);
@@ -299,7 +312,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       // drain-1 turns slab i's accumulator into the A operand of its stage 2, so the tensor pipe always has the next
       // block queued and the ~200 clk round trip of every mbarrier wait (the shared-memory pipe is ~80 % busy) hides
       // behind ~1900 clk of queued MMAs.
-      const uint32_t idesc = make_idesc_f16();
+      const uint32_t idesc = make_idesc_f16(BF16);
       const uint64_t xhi = make_desc_k(sXhi), xlo = make_desc_k(sXlo), f2hi = make_desc_k(sF2hi), f2lo = make_desc_k(sF2lo);
       auto stage1 = [&](long long i) {
         mbar_wait(x_full, (uint32_t)(i & 1));
@@ -311,9 +324,13 @@ __global__ void __launch_bounds__(THREADS, 1)
           for (int k0 = 0; k0 < p.n1; k0 += 16) {
             const uint32_t ahi = tmem_base + TM_F1HI + (k0 >> 1), alo = tmem_base + TM_F1LO + (k0 >> 1);
             const uint64_t koff = (uint64_t)(((k0 >> 6) * 16384 + (k0 & 63) * 2) >> 4);
-            tc_mma_f16_ts(d, alo, xhi + koff, idesc, k0 == 0 ? 0u : 1u);
-            tc_mma_f16_ts(d, ahi, xlo + koff, idesc, 1u);
-            tc_mma_f16_ts(d, ahi, xhi + koff, idesc, 1u);
+            if (BF16) {
+              tc_mma_f16_ts(d, ahi, xhi + koff, idesc, k0 == 0 ? 0u : 1u);
+            } else {
+              tc_mma_f16_ts(d, alo, xhi + koff, idesc, k0 == 0 ? 0u : 1u);
+              tc_mma_f16_ts(d, ahi, xlo + koff, idesc, 1u);
+              tc_mma_f16_ts(d, ahi, xhi + koff, idesc, 1u);
+            }
           }
           tc_commit(acc1_full + 8 * (uint32_t)(i & 1));
           tc_commit(x_free);
@@ -334,9 +351,13 @@ __global__ void __launch_bounds__(THREADS, 1)
           for (int k0 = 0; k0 < p.n2; k0 += 16) {
             const uint32_t ahi = y + (k0 >> 5) * 32 + ((k0 >> 4) & 1) * 8, alo = ahi + 16;
             const uint64_t koff = (uint64_t)(((k0 >> 6) * 16384 + (k0 & 63) * 2) >> 4);
-            tc_mma_f16_ts(tmem_base + TM_ACC2, alo, f2hi + koff, idesc, k0 == 0 ? 0u : 1u);
-            tc_mma_f16_ts(tmem_base + TM_ACC2, ahi, f2lo + koff, idesc, 1u);
-            tc_mma_f16_ts(tmem_base + TM_ACC2, ahi, f2hi + koff, idesc, 1u);
+            if (BF16) {
+              tc_mma_f16_ts(tmem_base + TM_ACC2, ahi, f2hi + koff, idesc, k0 == 0 ? 0u : 1u);
+            } else {
+              tc_mma_f16_ts(tmem_base + TM_ACC2, alo, f2hi + koff, idesc, k0 == 0 ? 0u : 1u);
+              tc_mma_f16_ts(tmem_base + TM_ACC2, ahi, f2lo + koff, idesc, 1u);
+              tc_mma_f16_ts(tmem_base + TM_ACC2, ahi, f2hi + koff, idesc, 1u);
+            }
           }
           tc_commit(acc2_full);
         }
@@ -381,29 +402,34 @@ __global__ void __launch_bounds__(THREADS, 1)
           for (int q = 0; q < 32; q++) x[32 * j + q] = 0.f;
         }
       }
-      // largest |x| of the slab over the 8 splitter warps
-      mx = __reduce_max_sync(0xffffffffu, mx);
-      const int slot = (int)(it & 1);
-      if (lane == 0) wmax_g[8 * slot + (warp - 4)] = mx;
-      bar_sync_named(1, 256);
-      uint32_t all = 0u;
-#pragma unroll
-      for (int q = 0; q < 8; q++) all = max(all, wmax_g[8 * slot + q]);
-      const int ex = exp_of_max(all);
-      if (warp == 4 && lane == 0) sexp_g[it & 7] = ex;
-      // x * 2^(K0 - ex): the exponent spans -122 .. 132, so two exact steps (the first is 1 whenever one step can do it)
-      const int sh = K0 - ex, sh1 = (sh >= -126 && sh <= 127) ? 0 : sh / 2;
-      const float sa = pow2f(sh1), sb = pow2f(sh - sh1);
-      // split before the wait (the FP32 values die here: 64 registers of floats become 32 + 32 of packed halves), so that the
-      // section between "stage 1 of the previous slab has read the split slab" and "the next one is in place" -- the one
-      // dependency of the MMA stream on this warp -- is 16 stores long
       uint32_t hi[32], lo[32];
-      if (sh1 == 0) {
+      if (BF16) {
 #pragma unroll
-        for (int q = 0; q < 32; q++) split_pair(x[2 * q] * sb, x[2 * q + 1] * sb, hi[q], lo[q]);
+        for (int q = 0; q < 32; q++) { hi[q] = pack_bf16(x[2 * q], x[2 * q + 1]); lo[q] = 0u; }
       } else {
+        // largest |x| of the slab over the 8 splitter warps
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        const int slot = (int)(it & 1);
+        if (lane == 0) wmax_g[8 * slot + (warp - 4)] = mx;
+        bar_sync_named(1, 256);
+        uint32_t all = 0u;
 #pragma unroll
-        for (int q = 0; q < 32; q++) split_pair(x[2 * q] * sa * sb, x[2 * q + 1] * sa * sb, hi[q], lo[q]);
+        for (int q = 0; q < 8; q++) all = max(all, wmax_g[8 * slot + q]);
+        const int ex = exp_of_max(all);
+        if (warp == 4 && lane == 0) sexp_g[it & 7] = ex;
+        // x * 2^(K0 - ex): the exponent spans -122 .. 132, so two exact steps (the first is 1 whenever one step can do it)
+        const int sh = K0 - ex, sh1 = (sh >= -126 && sh <= 127) ? 0 : sh / 2;
+        const float sa = pow2f(sh1), sb = pow2f(sh - sh1);
+        // split before the wait (the FP32 values die here: 64 registers of floats become 32 + 32 of packed halves), so that
+        // the section between "stage 1 of the previous slab has read the split slab" and "the next one is in place" -- the
+        // one dependency of the MMA stream on this warp -- is 16 stores long
+        if (sh1 == 0) {
+#pragma unroll
+          for (int q = 0; q < 32; q++) split_pair(x[2 * q] * sb, x[2 * q + 1] * sb, hi[q], lo[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; q++) split_pair(x[2 * q] * sa * sb, x[2 * q + 1] * sa * sb, hi[q], lo[q]);
+        }
       }
       if (quarter == 0) KF16_STAMP(it, 28 + grp);
       mbar_wait(x_free, ph ^ 1);
@@ -413,7 +439,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       for (int j = 0; j < 8; j++) {
         const uint32_t off = (uint32_t)((j ^ (row & 7)) << 4);
         *reinterpret_cast<uint4*>(xh + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-        *reinterpret_cast<uint4*>(xl + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        if (!BF16) *reinterpret_cast<uint4*>(xl + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
       }
       fence_async_smem();
       __syncwarp();
@@ -438,9 +464,12 @@ __global__ void __launch_bounds__(THREADS, 1)
         tc_wait_ld();
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int q = 0; q < 16; q++) split_pair(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]), hi[q], lo[q]);
+        for (int q = 0; q < 16; q++) {
+          if (BF16) hi[q] = pack_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+          else split_pair(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]), hi[q], lo[q]);
+        }
         tc_st16(tl + blk * 32, hi);
-        tc_st16(tl + blk * 32 + 16, lo);
+        if (!BF16) tc_st16(tl + blk * 32 + 16, lo);
       }
       tc_wait_st();
       tc_fence_before();
@@ -470,7 +499,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       // Z = alpha * Z'' * 2^kexp, kexp = ex + e1 + e2 - K0.  One multiplier when 2^kexp * alpha cannot over- / underflow on
       // its own (|kexp| <= 100: whatever it loses the product loses too, since 1 <= |Z''| < 2^23 for the entries that
       // matter); two exact steps otherwise.
-      int kexp = sexp_g[it & 7] + e1 + e2 - K0;
+      int kexp = BF16 ? 0 : sexp_g[it & 7] + e1 + e2 - K0;
       kexp = max(-250, min(250, kexp));
       const bool one = kexp >= -100 && kexp <= 100;
       const float fa = one ? 1.f : pow2f(kexp / 2), fb = (one ? pow2f(kexp) : pow2f(kexp - kexp / 2)) * p.alpha;

@@ -501,7 +501,7 @@ long long* g_kf16_trace = nullptr;   // profiling builds only (tools/kf16_trace.
 #endif
 bool kron2_f16_eligible(int precision, long long m1, long long n1, long long m2, long long n2, long long slabs,
                         const float* X, const float* D) {
-  if (precision != SCIMLOP_PREC_DEFAULT && precision != SCIMLOP_PREC_TF32X3) return false;
+  if (precision != SCIMLOP_PREC_DEFAULT && precision != SCIMLOP_PREC_TF32X3 && precision != SCIMLOP_PREC_BF16) return false;
   if (m1 > 128 || n1 > 128 || m2 > 128 || n2 > 128) return false;
   // every slab costs two 128^3 products whatever its extents: below ~96^2 the one-mode-per-pass path is faster
   if (n1 * n2 < 96 * 96 || m1 * m2 < 96 * 96) return false;
@@ -511,7 +511,7 @@ bool kron2_f16_eligible(int precision, long long m1, long long n1, long long m2,
 
 int launch_kron2_f16(scimlop_context* c, int m1, int n1, int m2, int n2, long long slabs, const float* F1, long long ld1,
                      bool tr1, const float* F2, long long ld2, bool tr2, const float* X, float* D, float alpha, float beta,
-                     cudaStream_t st) {
+                     bool bf16, cudaStream_t st) {
   CUtensorMap tmX, tmW;
   if (int rc = make_map_f32(c, &tmX, X, n1, n2, slabs, (cuuint64_t)n1 * 4, (cuuint64_t)n1 * n2 * 4, 32, 128, false)) return rc;
   // beta != 0: the old output is prefetched as 128 x 32 blocks (plain layout: the epilogue lanes read consecutive floats)
@@ -526,7 +526,9 @@ int launch_kron2_f16(scimlop_context* c, int m1, int n1, int m2, int n2, long lo
   p.trace = g_kf16_trace;
 #endif
   const int grid = (int)std::min<long long>(slabs, std::max(1, c->sm_count - c->sm_reserve));
-  if (beta != 0.f) kf16::kron2_f16_kernel<true><<<grid, kf16::THREADS, kf16::SMEM_BYTES, st>>>(tmX, tmW, p);
+  if (bf16 && beta != 0.f) kf16::kron2_f16_kernel<true, true><<<grid, kf16::THREADS, kf16::SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (bf16) kf16::kron2_f16_kernel<false, true><<<grid, kf16::THREADS, kf16::SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (beta != 0.f) kf16::kron2_f16_kernel<true><<<grid, kf16::THREADS, kf16::SMEM_BYTES, st>>>(tmX, tmW, p);
   else kf16::kron2_f16_kernel<false><<<grid, kf16::THREADS, kf16::SMEM_BYTES, st>>>(tmX, tmW, p);
   c->launches++;
   SCIMLOP_CUDA(c, cudaGetLastError());
@@ -661,8 +663,9 @@ int gemm_dispatch<float>(scimlop_context* c, int precision, bool transA, bool tr
                          long long ldb, long long sB, float beta, float* C, long long ldc, long long sC,
                          long long batch, int nscale, const ScaleArg* scales, cudaStream_t st, const PeerArg& peers) {
   if (peers.active()) return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "peer / multicast targets are Float64 only");
-  if (precision < SCIMLOP_PREC_DEFAULT || precision > SCIMLOP_PREC_FP32_EXACT)
+  if (precision < SCIMLOP_PREC_DEFAULT || precision > SCIMLOP_PREC_BF16)
     return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "unknown precision mode %d", precision);
+  if (precision == SCIMLOP_PREC_BF16) precision = SCIMLOP_PREC_TF32;   // outside the fused Kronecker kernel: single-pass TF32
   if (M <= 0 || N <= 0 || batch <= 0) return SCIMLOP_OK;
   if (precision != SCIMLOP_PREC_FP32_EXACT && nscale == 0 && K >= 8 && K <= tf32::MAXF) {
     const int passes = (precision == SCIMLOP_PREC_TF32) ? 1 : 3;
@@ -810,6 +813,8 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   };
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)kf16::kron2_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kf16::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)kf16::kron2_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kf16::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)kf16::kron2_f16_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kf16::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)kf16::kron2_f16_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kf16::SMEM_BYTES);
   optin2((const void*)tf32::gemm_tf32x3_kernel<false, false>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<false, true>);
   optin2((const void*)tf32::gemm_tf32x3_kernel<true, false>);
@@ -1168,7 +1173,7 @@ int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* cons
         if (kron2_f16_eligible(precision, m, n, m2, n2, slabs, cur, out2)) {
           rc = launch_kron2_f16(c, (int)m, (int)n, (int)m2, (int)n2, slabs, static_cast<const float*>(factors[p]), lds[p], tr,
                                 static_cast<const float*>(factors[p - 1]), lds[p - 1], (kinds[p - 1] & SCIMLOP_TRANS) != 0, cur,
-                                out2, last2 ? alpha : 1.f, last2 ? beta : 0.f, st);
+                                out2, last2 ? alpha : 1.f, last2 ? beta : 0.f, precision == SCIMLOP_PREC_BF16, st);
           if (rc) return rc;
           done++;
           cur = out2;

@@ -198,3 +198,40 @@ def test_precision_modes_bypass_the_fused_kernel(sb):
     sb.mul_(w, L, dv)
     assert h.launch_count() - n0 == 2
     assert err_vs_oracle(w.numpy(), [A, B], v) <= 1e-6
+
+
+def test_bf16_opt_in_mode(sb):
+    """SCIMLOP_PREC_BF16 (explicit opt-in): one tcgen05 pass on BF16-rounded operands, FP32 accumulation.  Error of the
+    order of the BF16 unit roundoff (2^-9) per mode, far from the default mode's 1e-6 -- and finite / unscaled for data
+    far outside the FP16 range (BF16 keeps the FP32 exponent)."""
+    rng = np.random.default_rng(10)
+    A, B = nrm(rng, 128, 128), nrm(rng, 128, 128)
+    v = nrm(rng, 128 * 128, 3)
+    v[:, 1] *= np.float32(1e20)
+    dv = dev(sb, v)
+    h = sb.handle(0)
+    L = sb.cache_operator(sb.TensorProductOperator(A, B), dv)
+    L.precision = 4   # SCIMLOP_PREC_BF16
+    w = sb.DeviceArray.full((128 * 128, 3), float("nan"), np.float32)
+    sb.mul_(w, L, dv)
+    n0 = h.launch_count()
+    sb.mul_(w, L, dv)
+    assert h.launch_count() - n0 == 1
+    got = w.numpy()
+    want = R.kron_apply([A.astype(np.float64), B.astype(np.float64)], v.astype(np.float64))
+    for j in range(3):
+        e = R.rel_err(got[:, j], want[:, j])
+        assert 1e-5 < e <= 1e-2, f"column {j}: rel err {e:.3e} is not BF16-like"
+    w0 = nrm(rng, 128 * 128, 3)
+    dw = dev(sb, w0)
+    sb.mul_(dw, L, dv, 0.5, 2.0)
+    e = R.rel_err(dw.numpy()[:, 0], 0.5 * want[:, 0] + 2.0 * w0[:, 0].astype(np.float64))
+    assert e <= 1e-2
+    # three factors: the fused pair runs BF16, the third mode the single-pass TF32 kernel
+    F = [nrm(rng, 128, 128) for _ in range(3)]
+    v3 = nrm(rng, 128 ** 3, 1)
+    dv3 = dev(sb, v3)
+    L3 = sb.cache_operator(sb.TensorProductOperator(*F), dv3)
+    L3.precision = 4
+    e = err_vs_oracle((L3 * dv3).numpy(), F, v3)
+    assert e <= 1e-2, f"3-factor BF16 mode: {e:.3e}"
