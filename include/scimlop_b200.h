@@ -110,6 +110,18 @@ int scimlop_matmul(scimlop_handle_t h, int dtype, int precision, int transA, int
                    int64_t k, const void* A, int64_t lda, const void* V, int64_t ldv, void* W,
                    int64_t ldw, const void* alpha, const void* beta, void* stream);
 
+/* MatrixOperator over a general sparse matrix, CSR storage (rowptr: rows + 1 entries, colidx / values: nnz entries,
+ * 32-bit indices, `index_base` 0 or 1 -- CUDA.jl's CuSparseMatrixCSR is 1-based):
+ *     W = alpha * op(A) * V + beta * W,   op(A) = A (trans == 0: W is rows x k) or A^T (trans != 0: W is cols x k).
+ * Replaces `mul!(w, L.A, v[, α, β])` (src/matrix.jl:337-350) for sparse L.A -- the `sprand` operators of
+ * test/basic.jl:405-426, test/Downstream/alloccheck.jl:37-45; ext/SciMLOperatorsSparseArraysExt.jl:8-23.  A
+ * SparseMatrixCSC is the CSR form of its transpose: bind it with trans flipped.  trans == 0 gathers per output row
+ * (deterministic, W never read when beta == 0); trans != 0 scatters with atomic adds (two launches; the summation
+ * order, hence the last bits, may differ between runs). */
+int scimlop_csr_mul(scimlop_handle_t h, int dtype, int trans, int64_t rows, int64_t cols, int64_t k,
+                    const int32_t* rowptr, const int32_t* colidx, const void* values, int index_base, const void* V,
+                    int64_t ldv, void* W, int64_t ldw, const void* alpha, const void* beta, void* stream);
+
 /* Float32 operands of the streamed tensor-core GEMM (matrices beyond the 128 x 128 resident-factor kernel: large
  * MatrixOperators, Kronecker factors > 128, dense tree / block-diagonal leaves).  3xTF32 needs the operand as
  * hi + lo halves; for a constant operator that is prepared ONCE: `cache_operator` allocates scimlop_split_bytes

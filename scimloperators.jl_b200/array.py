@@ -9,7 +9,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-_TORCH = {np.dtype("float64"): torch.float64, np.dtype("float32"): torch.float32}
+_TORCH = {np.dtype("float64"): torch.float64, np.dtype("float32"): torch.float32,
+          np.dtype("int32"): torch.int32}   # int32: index arrays of sparse operators only
 
 
 class DeviceArray:
@@ -72,7 +73,7 @@ class DeviceArray:
 
     @property
     def dtype(self):
-        return np.dtype("float64") if self.t.dtype == torch.float64 else np.dtype("float32")
+        return {torch.float64: np.dtype("float64"), torch.float32: np.dtype("float32"), torch.int32: np.dtype("int32")}[self.t.dtype]
 
     @property
     def ptr(self) -> int:

@@ -124,6 +124,46 @@ class BandedMatrix:
         return self.bands.dtype
 
 
+class SparseMatrixCSR:
+    """Device storage of a general sparse m x n matrix in CSR (0-based 32-bit indices): what a `MatrixOperator(sprand(...))`
+    holds (test/basic.jl:405-426, test/Downstream/alloccheck.jl:37-45).  Built from a SciPy sparse matrix, a dense
+    array, or the three CSR arrays."""
+
+    def __init__(self, rowptr, colidx, values, shape):
+        self.rowptr = _as_device(np.ascontiguousarray(rowptr, dtype=np.int32)) if not isinstance(rowptr, DeviceArray) else rowptr
+        self.colidx = _as_device(np.ascontiguousarray(colidx, dtype=np.int32)) if not isinstance(colidx, DeviceArray) else colidx
+        self.values = _as_device(values)
+        self.shape = (int(shape[0]), int(shape[1]))
+        if self.rowptr.shape[0] != self.shape[0] + 1 or self.colidx.shape[0] != self.values.shape[0]:
+            raise ValueError("SparseMatrixCSR: rowptr needs rows + 1 entries, colidx and values nnz entries each")
+
+    @staticmethod
+    def from_scipy(A):
+        A = A.tocsr()
+        A.sum_duplicates()
+        return SparseMatrixCSR(A.indptr, A.indices, np.asarray(A.data), A.shape)
+
+    @staticmethod
+    def from_dense(A):
+        A = np.asarray(A)
+        rows, cols = np.nonzero(A)                    # row-major order: already sorted by row
+        rowptr = np.zeros(A.shape[0] + 1, dtype=np.int32)
+        np.cumsum(np.bincount(rows, minlength=A.shape[0]), out=rowptr[1:])
+        return SparseMatrixCSR(rowptr, cols.astype(np.int32), np.ascontiguousarray(A[rows, cols]), A.shape)
+
+    @property
+    def dtype(self):
+        return self.values.dtype
+
+    @property
+    def nnz(self):
+        return self.values.shape[0]
+
+    @property
+    def device_index(self):
+        return self.values.device_index
+
+
 class ScalarOperator:
     """src/scalar.jl:124-127 -- mutable scalar; `update_func(old, u, p, t)` gives the new value (:267-270)."""
 
@@ -282,9 +322,12 @@ class MatrixOperator(AbstractSciMLOperator):
     device matrix in place (:257-271)."""
 
     def __init__(self, A, trans=False, update_func=None):
+        if hasattr(A, "tocsr"):                      # a SciPy sparse matrix
+            A = SparseMatrixCSR.from_scipy(A)
+        self.sparse = isinstance(A, SparseMatrixCSR)
         self.banded = isinstance(A, BandedMatrix)
-        self.A = A if self.banded else _as_device(A)
-        if not self.banded and self.A.ndim != 2:
+        self.A = A if (self.banded or self.sparse) else _as_device(A)
+        if not (self.banded or self.sparse) and self.A.ndim != 2:
             raise ValueError("MatrixOperator needs a matrix")
         if self.banded and trans:
             raise NotImplementedError("adjoint of a banded MatrixOperator: transpose the bands on the host")
@@ -312,7 +355,7 @@ class MatrixOperator(AbstractSciMLOperator):
     def _attach_split(self):
         """`cache_operator` side of the no-allocation contract (test/Downstream/alloccheck.jl): the 3xTF32 halves of
         a large Float32 matrix are made once here, so that `mul!` is one launch with no scratch allocation."""
-        if self.banded or self._split is not None or self.A.dtype != np.float32:
+        if self.banded or self.sparse or self._split is not None or self.A.dtype != np.float32:
             return self
         m, n = self.A.shape
         if min(m, n) < 16 or max(m, n) <= 128:
@@ -366,6 +409,13 @@ class MatrixOperator(AbstractSciMLOperator):
         _check_vw(self, w, v)
         h = _lib.handle(w.device_index)
         m, n = self.size()
+        if self.sparse:   # general sparse matrix: CSR gather (or, for the lazy adjoint, scatter) kernel
+            A = self.A
+            h.check(h.lib.scimlop_csr_mul(h.ptr, _DT[w.dtype], int(self.trans), A.shape[0], A.shape[1], _ncols(v),
+                                          C.c_void_p(A.rowptr.ptr), C.c_void_p(A.colidx.ptr), C.c_void_p(A.values.ptr), 0,
+                                          C.c_void_p(v.ptr), v.ld, C.c_void_p(w.ptr), w.ld, _scalar(w.dtype, alpha),
+                                          _scalar(w.dtype, beta), _stream()), "scimlop_csr_mul")
+            return w
         if self.banded:   # a one-factor "Kronecker product": the banded mode-product kernel
             nb = self.A.shape[0]
             dims, lds = (C.c_int64 * 2)(nb, nb), (C.c_int64 * 1)(self.A.b)
@@ -617,8 +667,8 @@ def _terms_with_scalars(L, scalars=()):
     """Flatten like src/basic.jl:619-635 (sums) and :936-939 (products); returns [(scalars, leaves)] or None."""
     if isinstance(L, InvertibleOperator):
         return _terms_with_scalars(L.L, scalars)      # mul! of an InvertibleOperator is mul! of L.L
-    if isinstance(L, MatrixOperator) and L.banded:
-        return None    # banded leaves are applied by their own kernel, not by scimlop_tree_mul
+    if isinstance(L, MatrixOperator) and (L.banded or L.sparse):
+        return None    # banded / sparse leaves are applied by their own kernels, not by scimlop_tree_mul
     if isinstance(L, _LEAVES):
         return [(tuple(scalars), [L])]
     if isinstance(L, ScaledOperator):
@@ -673,7 +723,7 @@ class BlockDiagonalOperator(AbstractSciMLOperator):
             raise AssertionError("BlockDiagonalOperator needs at least one block")   # src/block.jl:45
         self.ops = tuple(op if isinstance(op, AbstractSciMLOperator) else MatrixOperator(op) for op in ops)
         for op in self.ops:
-            if not isinstance(op, _LEAVES) or (isinstance(op, MatrixOperator) and op.banded):
+            if not isinstance(op, _LEAVES) or (isinstance(op, MatrixOperator) and (op.banded or op.sparse)):
                 raise NotImplementedError(f"BlockDiagonalOperator block {type(op).__name__}: the B200 backend takes "
                                           "Matrix / Diagonal / BatchedDiagonal / Identity / Null blocks "
                                           "(the Julia wrapper keeps the generic loop for anything else)")
@@ -825,7 +875,7 @@ class WOperator(AbstractSciMLOperator):
     # ---- W \\ x: the reference converts W to a dense matrix and solves (src/woperator.jl:431-445).  Here the concrete
     #      form J - M/γ is assembled on the device and inverted once per (J, M, γ); every solve is then a product. ----
     def has_ldiv(self):
-        return isinstance(self.J, MatrixOperator) and not self.J.banded and \
+        return isinstance(self.J, MatrixOperator) and not self.J.banded and not self.J.sparse and \
             isinstance(self.mass_matrix, (MatrixOperator, IdentityOperator))
 
     def _concrete_inverse(self):
@@ -1010,8 +1060,8 @@ def factorize(L):
     if isinstance(L, InvertibleOperator):
         return L
     if isinstance(L, MatrixOperator):
-        if L.banded:
-            raise NotImplementedError("factorize of a banded MatrixOperator (a banded solve) is not on this path")
+        if L.banded or L.sparse:
+            raise NotImplementedError("factorize of a banded / sparse MatrixOperator (a sparse solve) is not on this path")
         inv = invert_matrix(L.A)
         refresh = (lambda: _invert_into(L.A, inv)) if L.update_func is not None else None
         return InvertibleOperator(L, MatrixOperator(inv, L.trans), refresh)
@@ -1268,6 +1318,9 @@ def _kron_leaf(op):
     """(kind, data_ptr, ld) if `op` can be a native Kronecker factor, else None."""
     while isinstance(op, InvertibleOperator):
         op = op.L
+    if isinstance(op, MatrixOperator) and op.sparse:
+        raise NotImplementedError("a sparse MatrixOperator as a Kronecker factor is not supported by the B200 backend "
+                                  "(the Julia wrapper keeps the generic path for it)")
     if isinstance(op, MatrixOperator) and op.banded:
         return (_lib.BANDED, op.A.bands.ptr, op.A.b)      # lds[] carries the half-bandwidth for banded factors
     if isinstance(op, MatrixOperator):
@@ -1489,7 +1542,7 @@ class TensorProductOperator(AbstractSciMLOperator):
         while isinstance(outer, ScaledOperator):                                   # :755-759 / :800-804 (intended)
             lam *= outer.lam.convert()
             outer = outer.L
-        if not isinstance(outer, MatrixOperator) or outer.banded:
+        if not isinstance(outer, MatrixOperator) or outer.banded or outer.sparse:
             raise NotImplementedError(f"outer factor {type(outer).__name__} is not supported by the B200 backend "
                                       "(the Julia wrapper keeps the generic path for it)")
         a = alpha if lam == 1.0 else lam * (1.0 if alpha is None else float(alpha))
@@ -1518,7 +1571,7 @@ class TensorSumOperator(AbstractSciMLOperator):
             if m != n:
                 raise AssertionError("TensorSumOperator needs square factors")
         self.ops = (outer, inner)
-        both = isinstance(outer, MatrixOperator) and isinstance(inner, MatrixOperator)
+        both = isinstance(outer, MatrixOperator) and isinstance(inner, MatrixOperator) and not (outer.sparse or inner.sparse)
         self._banded = both and outer.banded and inner.banded
         self._native = both and not outer.trans and not inner.trans and (self._banded or not (outer.banded or inner.banded))
         self.products = None

@@ -1,0 +1,103 @@
+"""GPU parity of the sparse (CSR) MatrixOperator: `mul!(w, L.A, v[, α, β])` with a `sprand` matrix
+(src/matrix.jl:337-350; test/basic.jl:405-426, test/Downstream/alloccheck.jl:37-45), through scimlop_csr_mul."""
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as R
+
+pytestmark = pytest.mark.gpu
+TOL = {np.dtype("float64"): 1e-12, np.dtype("float32"): 1e-5}
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    import scimlop_b200 as sb
+    sb.handle(0)
+    return sb
+
+
+def sprand(rng, m, n, density, dtype):
+    A = rng.standard_normal((m, n)) * (rng.random((m, n)) < density)
+    return np.asfortranarray(A.astype(dtype))
+
+
+def csr_of(A):
+    rows, cols = np.nonzero(A)
+    rowptr = np.zeros(A.shape[0] + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=A.shape[0]), out=rowptr[1:])
+    return rowptr, cols, A[rows, cols]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(100, 100, 5 / 100, 7), (100, 100, 2 / 100, 1), (257, 130, 0.05, 9), (64, 300, 0.5, 2),
+                                   (1000, 1000, 0.01, 33), (5, 5, 0.0, 3)])
+def test_sparse_matrix_operator_mul(sb, dtype, shape):
+    m, n, density, k = shape
+    rng = np.random.default_rng(m + n + k)
+    A = sprand(rng, m, n, density, dtype)
+    L = sb.MatrixOperator(sb.SparseMatrixCSR.from_dense(A))
+    assert L.size() == (m, n)
+    v = np.asfortranarray(rng.standard_normal((n, k)).astype(dtype))
+    dv = sb.DeviceArray.from_numpy(v)
+    w = sb.DeviceArray.full((m, k), float("nan"), dtype)
+    sb.mul_(w, L, dv)
+    got = w.numpy()
+    assert np.isfinite(got).all(), "beta == 0 must not read W"
+    rp, ci, va = csr_of(A)
+    want = R.csr_mul(rp, ci, va, (m, n), v)
+    assert R.rel_err(got, want) <= TOL[np.dtype(dtype)]
+    assert R.rel_err(got, A.astype(np.float64) @ v.astype(np.float64)) <= TOL[np.dtype(dtype)]
+    w0 = np.asfortranarray(rng.standard_normal((m, k)).astype(dtype))
+    dw = sb.DeviceArray.from_numpy(w0)
+    sb.mul_(dw, L, dv, 0.7, -1.5)
+    assert R.rel_err(dw.numpy(), R.csr_mul(rp, ci, va, (m, n), v, 0.7, -1.5, w0)) <= TOL[np.dtype(dtype)]
+    # lazy adjoint (src/matrix.jl:174-175): the scatter kernel
+    Lt = L.adjoint()
+    assert Lt.size() == (n, m)
+    vt = np.asfortranarray(rng.standard_normal((m, k)).astype(dtype))
+    dvt = sb.DeviceArray.from_numpy(vt)
+    wt = sb.DeviceArray.full((n, k), float("nan"), dtype)
+    sb.mul_(wt, Lt, dvt)
+    assert np.isfinite(wt.numpy()).all()
+    assert R.rel_err(wt.numpy(), R.csr_mul(rp, ci, va, (m, n), vt, trans=True)) <= TOL[np.dtype(dtype)]
+    wt0 = np.asfortranarray(rng.standard_normal((n, k)).astype(dtype))
+    dwt = sb.DeviceArray.from_numpy(wt0)
+    sb.mul_(dwt, Lt, dvt, 2.0, 0.5)
+    assert R.rel_err(dwt.numpy(), R.csr_mul(rp, ci, va, (m, n), vt, 2.0, 0.5, wt0, trans=True)) <= TOL[np.dtype(dtype)]
+
+
+def test_sparse_operators_in_an_added_tree_with_time_dependent_scalars(sb):
+    """test/basic.jl:405-426 / alloccheck.jl:37-60: MatrixOperator(A) + ScalarOperator(t) * MatrixOperator(A) + ..."""
+    rng = np.random.default_rng(3)
+    N, K = 100, 4
+    A1, A2 = sprand(rng, N, N, 5 / N, np.float64), sprand(rng, N, N, 5 / N, np.float64)
+    D = np.asfortranarray(rng.standard_normal((N, N)))
+    c1 = sb.ScalarOperator(0.0, lambda a, u, p, t: np.sin(p * t))
+    c2 = sb.ScalarOperator(0.0, lambda a, u, p, t: np.cos(p * t))
+    op = sb.MatrixOperator(sb.SparseMatrixCSR.from_dense(A1)) + c1 * sb.MatrixOperator(sb.SparseMatrixCSR.from_dense(A2)) + \
+        c2 * sb.MatrixOperator(D)
+    v = np.asfortranarray(rng.standard_normal((N, K)))
+    dv = sb.DeviceArray.from_numpy(v)
+    op = sb.cache_operator(op, dv)
+    for t in (0.3, 1.7):
+        sb.update_coefficients_(op, None, 2.0, t)
+        want = (A1 + np.sin(2.0 * t) * A2 + np.cos(2.0 * t) * D) @ v
+        assert R.rel_err((op * dv).numpy(), want) <= 1e-12
+        w0 = np.asfortranarray(rng.standard_normal((N, K)))
+        dw = sb.DeviceArray.from_numpy(w0)
+        sb.mul_(dw, op, dv, 0.5, 2.0)
+        assert R.rel_err(dw.numpy(), 0.5 * want + 2.0 * w0) <= 1e-12
+
+
+def test_sparse_from_scipy_and_large_batch(sb):
+    sp = pytest.importorskip("scipy.sparse")
+    rng = np.random.default_rng(5)
+    n, k = 4096, 64
+    A = sp.random(n, n, density=8 / n, format="csr", random_state=7, dtype=np.float64)
+    L = sb.MatrixOperator(A)
+    assert L.sparse and L.A.nnz == A.nnz
+    v = np.asfortranarray(rng.standard_normal((n, k)))
+    got = (L * sb.DeviceArray.from_numpy(v)).numpy()
+    assert R.rel_err(got, A @ v) <= 1e-12

@@ -235,3 +235,20 @@ def test_block_diagonal_and_woperator_restatements():
     b = rng.random(n)
     assert R.rel_err(R.woperator_mul(np.empty(n), M, gamma, J, b), (J - M / gamma) @ b) < RTOL
     assert R.rel_err(R.woperator_mul(np.empty(n), 2.0, gamma, J, b), (J - 2.0 * np.eye(n) / gamma) @ b) < RTOL
+
+
+def test_csr_restatement_matches_the_dense_product():
+    """The reference's own check for sparse MatrixOperators: L * v ≈ Matrix(A) * v (test/basic.jl:405-426)."""
+    rng = np.random.default_rng(21)
+    for m, n, k in ((7, 5, 3), (40, 40, 1), (1, 9, 2), (12, 30, 4)):
+        A = rng.standard_normal((m, n)) * (rng.random((m, n)) < 0.3)
+        rows, cols = np.nonzero(A)
+        rowptr = np.zeros(m + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows, minlength=m), out=rowptr[1:])
+        vals = A[rows, cols]
+        v = rng.standard_normal((n, k))
+        assert np.allclose(R.csr_mul(rowptr, cols, vals, (m, n), v), A @ v, rtol=1e-13, atol=1e-13)
+        w0 = rng.standard_normal((m, k))
+        assert np.allclose(R.csr_mul(rowptr, cols, vals, (m, n), v, 0.3, -2.0, w0), 0.3 * (A @ v) - 2.0 * w0, rtol=1e-13, atol=1e-13)
+        vt = rng.standard_normal((m, k))
+        assert np.allclose(R.csr_mul(rowptr, cols, vals, (m, n), vt, trans=True), A.T @ vt, rtol=1e-13, atol=1e-13)

@@ -230,7 +230,26 @@ def c5fd(reps, k=8):
     report(f"c5-fd as AddedOperator of two banded TPOs (two passes) k={k}", 10.0 * N * k, 5.0 * nb, *t, "hbm")
 
 
-ALL = {"c5fd": c5fd, "krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c3pair": c3pair, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
+def csr(reps, N=65536, K=1024, per_row=16):
+    """Sparse MatrixOperator (CSR gather kernel): N x N with ~per_row nonzeros per row on an N x K Float64 batch.
+    Algorithmic bytes: V read once + W written once + the CSR arrays once per 8-column tile (they are re-read per tile)."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    cols = torch.randint(0, N, (N, per_row), device="cuda", generator=g, dtype=torch.int32)
+    cols, _ = torch.sort(cols, dim=1)
+    rowptr = torch.arange(0, N * per_row + 1, per_row, device="cuda", dtype=torch.int32)
+    vals = torch.rand(N * per_row, device="cuda", generator=g, dtype=torch.float64)
+    A = sb.SparseMatrixCSR(sb.DeviceArray(rowptr, (N + 1,)), sb.DeviceArray(cols.reshape(-1).contiguous(), (N * per_row,)),
+                           sb.DeviceArray(vals, (N * per_row,)), (N, N))
+    L = sb.MatrixOperator(A)
+    V = dev_rand((N, K), np.float64, 1)
+    W = sb.DeviceArray.empty((N, K), np.float64)
+    t = timeit(lambda: sb.mul_(W, L, V), reps)
+    nnz = N * per_row
+    report(f"csr N={N} nnz/row={per_row} f64 k={K} 3arg", 2.0 * nnz * K, 2.0 * N * K * 8 + nnz * 12.0 * (K / 8), *t, "hbm",
+           {"dense_bytes_only_gbs": 2.0 * N * K * 8 / (t[1] * 1e-3) / 1e9})
+
+
+ALL = {"c5fd": c5fd, "krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c3pair": c3pair, "csr": csr, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
