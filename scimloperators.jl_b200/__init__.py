@@ -11,7 +11,7 @@ from .operators import (AbstractSciMLOperator, AddedOperator, BandedMatrix, Batc
                         DiagonalOperator, IdentityOperator, MatrixOperator, NullOperator, ScalarOperator,
                         ScaledOperator, SparseMatrixCSR, TensorProductOperator, TensorSumOperator, adapt, cache_operator, iscached, kron,
                         kronsum, mul_, update_coefficients_, InvertibleOperator, InvertedOperator, factorize, has_ldiv,
-                        inv, invert_matrix, ldiv_, BlockDiagonalOperator, WOperator)
+                        inv, invert_matrix, ldiv_, LUFactorization, BlockDiagonalOperator, WOperator)
 from .distributed import ColumnShard, allgather_cols, shard_columns
 from . import krylov
 

@@ -60,6 +60,9 @@ SIGNATURES = {
     "scimlop_diag_div": [_P, _INT, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P],
     "scimlop_invert_workspace_bytes": [_INT, _I64, C.POINTER(_SZ)],
     "scimlop_invert": [_P, _INT, _I64, _P, _I64, _P, _I64, _P, _SZ, _P],
+    "scimlop_factorize_bytes": [_INT, _I64, C.POINTER(_SZ), C.POINTER(_SZ)],
+    "scimlop_factorize": [_P, _INT, _I64, _P, _I64, _P, _SZ, _P, _I64, _P, _SZ, C.POINTER(C.c_double), _P],
+    "scimlop_kron_ldiv": [_P, _INT, _INT, C.POINTER(_P), _I64P, _I32P, _P, _P, _I64, _P, _SZ, _P],
     "scimlop_kron_workspace_bytes": [_INT, _INT, _I64P, _I32P, _I64, C.POINTER(_SZ)],
     "scimlop_kron_mul": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _I64, _P, _I64, _I64, _P,
                          _P, _P, _SZ, _P],

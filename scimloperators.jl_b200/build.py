@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libscimlop_b200.so")
-SOURCES = ["scimlop.cu", "extras.cu", "solve.cu", "multicast.cu", "sparse.cu"]
+SOURCES = ["scimlop.cu", "extras.cu", "solve.cu", "multicast.cu", "sparse.cu", "lu.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 

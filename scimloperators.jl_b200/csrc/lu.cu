@@ -1,0 +1,549 @@
+// lu.cu -- the factorised solve behind `ldiv!`, Float64.
+//
+// The reference caches an LU (`factorize(L::MatrixOperator)` -> `lu`, src/matrix.jl:513-516; per Kronecker factor,
+// src/tensor.jl:227) and solves with it (`ldiv!`: src/tensor.jl:612-673, outer_div! :864-899 -- LAPACK getrs around two
+// permutedims!).  Round 1 cached an explicit inverse from an unblocked Gauss-Jordan (2n+1 launches, 263 ms at 4096^2,
+// residual ~ cond(A) * eps).  This file is the replacement:
+//
+//   factorise  blocked right-looking LU with partial pivoting, P A = L U.  Panels of 32 columns are factorised by ONE
+//              multi-CTA kernel per panel: every thread owns one row of the panel in registers, a column step is a
+//              block arg-max, a grid barrier, the exchange of the pivot row through global memory, a second barrier and
+//              32 FMAs per thread.  Row swaps + the 32 x w triangular solve of the block row are one more kernel; the
+//              trailing update is the DMMA GEMM (alpha = -1, beta = 1).  3 launches per 32 columns; measured 4.3 / 9.4 /
+//              20 / 46 ms at n = 512 / 1024 / 2048 / 4096 (round 1: 4.4 / 10.8 / 30 / 263), 60 % of it the panel kernel's
+//              ~6 us per column (three dependent L2 round trips: publish, barrier, read the winner's row).
+//   solve      triangular solves as GEMMs: 128 x 128 diagonal blocks of L and U are inverted once (in shared memory),
+//              the off-diagonal block rows are pre-multiplied by them (L' = Dinv L, U' = Dinv U), and a block step is
+//              x_i = Dinv_ii b_i  followed by  x_i -= L'_{i,<i} x_{<i}  -- both DMMA GEMMs, out of place between two
+//              buffers (no in-place hazards for any GEMM kernel the dispatcher may choose), acting along ANY Kronecker
+//              mode exactly like the mode products of mul! (no permutedims).  The row permutation is one gather pass.
+//              Cost: 1.25x the flops of a multiplication by the explicit inverse at n = 512 (block triangles), with the
+//              backward stability of substitution: residual ~ eps * |A| |x| (inverted diagonal blocks only, the scheme of
+//              cuBLAS / MAGMA trsm).
+//   inverse    the explicit inverse is ALSO formed (the solve applied to the identity: GEMM speed) together with
+//              cond_1(A) = |A|_1 |Ainv|_1, returned to the caller: for a well-conditioned factor the host keeps the
+//              round-1 fast path (ldiv! = mul! with the inverse factors, residual cond * eps still inside the 1e-12
+//              budget), for an ill-conditioned one it takes the factorised solve.
+#include <algorithm>
+#include <cstring>
+
+#include "context.h"
+
+namespace {
+
+constexpr int PB = 32;        // panel width
+constexpr int PROWS = 256;    // panel rows per CTA (one per thread)
+constexpr int DB = 128;       // diagonal block of the triangular solves (= DMMA tile rows)
+
+inline long long ld_of(long long n) { return (n + 3) / 4 * 4; }
+inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+// ---- blob layout (device memory, caller-owned) --------------------------------------------------------------------
+struct Blob {
+  int* perm;      // n: row r of P*b is row perm[r] of b
+  double* LU;     // ldf x n: the LAPACK-style factors (unit lower + upper), pivoted
+  double* LUr;    // ldf x n: off-diagonal blocks pre-multiplied by the inverse diagonal block of their block ROW
+  double* DL;     // ldf x DB: inverse diagonal blocks of L, block i at rows i*DB
+  double* DU;     // ldf x DB: inverse diagonal blocks of U
+  long long ldf;
+};
+inline size_t blob_bytes(long long n) {
+  const long long ldf = ld_of(n);
+  return align256((size_t)n * 4) + 2 * align256((size_t)ldf * n * 8) + 2 * align256((size_t)ldf * DB * 8);
+}
+inline Blob blob_at(void* base, long long n) {
+  Blob b;
+  b.ldf = ld_of(n);
+  char* p = static_cast<char*>(base);
+  b.perm = reinterpret_cast<int*>(p); p += align256((size_t)n * 4);
+  b.LU = reinterpret_cast<double*>(p); p += align256((size_t)b.ldf * n * 8);
+  b.LUr = reinterpret_cast<double*>(p); p += align256((size_t)b.ldf * n * 8);
+  b.DL = reinterpret_cast<double*>(p); p += align256((size_t)b.ldf * DB * 8);
+  b.DU = reinterpret_cast<double*>(p);
+  return b;
+}
+// scratch: piv (n ints), sync words, pivot-row exchange, norms / info, two n x n work matrices
+struct Scratch {
+  int* piv;
+  unsigned* bar;        // one counter per panel
+  double* slots;        // [2 parities][max CTAs][PB + 2] candidate rows, then [2][PB] diagonal rows
+  double* norms;        // [0] = |A|_1, [1] = |Ainv|_1 (as doubles; max via atomics on the bit pattern)
+  int* info;
+  double* T1;
+  double* T2;
+};
+inline size_t scratch_bytes(long long n) {
+  const long long ldf = ld_of(n);
+  const long long npan = (n + PB - 1) / PB, ncta = (n + PROWS - 1) / PROWS;
+  return align256((size_t)n * 4) + align256((size_t)npan * 4) + align256((size_t)(2 * ncta * (PB + 2) + 2 * PB) * 8) +
+         256 + 256 + 2 * align256((size_t)ldf * n * 8);
+}
+inline Scratch scratch_at(void* base, long long n) {
+  const long long ldf = ld_of(n);
+  const long long npan = (n + PB - 1) / PB, ncta = (n + PROWS - 1) / PROWS;
+  Scratch s;
+  char* p = static_cast<char*>(base);
+  s.piv = reinterpret_cast<int*>(p); p += align256((size_t)n * 4);
+  s.bar = reinterpret_cast<unsigned*>(p); p += align256((size_t)npan * 4);
+  s.slots = reinterpret_cast<double*>(p); p += align256((size_t)(2 * ncta * (PB + 2) + 2 * PB) * 8);
+  s.norms = reinterpret_cast<double*>(p); p += 256;
+  s.info = reinterpret_cast<int*>(p); p += 256;
+  s.T1 = reinterpret_cast<double*>(p); p += align256((size_t)ldf * n * 8);
+  s.T2 = reinterpret_cast<double*>(p);
+  return s;
+}
+
+// ---- kernels -----------------------------------------------------------------------------------------------------------
+__global__ void copy_matrix_kernel(long long n, const double* __restrict__ A, long long lda, double* __restrict__ B, long long ldb) {
+  const long long total = n * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    B[(i % n) + (i / n) * ldb] = A[(i % n) + (i / n) * lda];
+}
+
+// max column abs-sum of an n x n matrix -> out (non-negative doubles compare like their bit patterns)
+__global__ void norm1_kernel(long long n, const double* __restrict__ A, long long lda, double* out) {
+  __shared__ double part[32];
+  for (long long c = blockIdx.x; c < n; c += gridDim.x) {
+    double s = 0.0;
+    for (long long r = threadIdx.x; r < n; r += blockDim.x) s += fabs(A[r + c * lda]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      s = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(s));
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned v;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+// One panel: columns j0 .. j0 + w - 1, rows j0 .. n - 1.  Thread t of CTA b owns row j0 + PROWS * b + t: its w panel entries
+// live in registers for the whole panel.  All CTAs are co-resident (<= n / 256 of them), so the software barrier is safe.
+// A column step has ONE grid barrier: before it every CTA publishes its candidate pivot (|value|, row) TOGETHER with that
+// row's panel entries, and CTA 0 also publishes the diagonal row; after it every CTA picks the same winner and reads the
+// winner's row from the winner's slot.  Slots are double-buffered by column parity (a CTA runs at most one column ahead).
+__global__ void __launch_bounds__(PROWS) lu_panel_kernel(long long n, double* __restrict__ A, long long lda, int j0, int w,
+                                                         int* __restrict__ piv, unsigned* bar, double* slots, int* info) {
+  // slots: [parity][CTA][PB + 2]: candidate row values, |value|, row index (as a double);  diag: [parity][PB] after them
+  __shared__ double sval[PROWS / 32];
+  __shared__ int srow[PROWS / 32];
+  __shared__ int swin, spiv;
+  constexpr int SL = PB + 2;
+  const int nct = gridDim.x;
+  double* diag = slots + 2 * (size_t)nct * SL;
+  const int i = blockIdx.x * PROWS + threadIdx.x;     // panel-relative row
+  const long long r = (long long)j0 + i;
+  const bool live = r < n;
+  double a[PB];
+#pragma unroll
+  for (int c = 0; c < PB; c++) a[c] = (live && c < w) ? A[r + (long long)(j0 + c) * lda] : 0.0;
+  unsigned epoch = 0;
+  for (int c = 0; c < w; c++) {
+    const int par = c & 1;
+    // ---- local arg-max of |a(:, c)| over rows >= c (first maximum, like idamax) ----
+    double ac = 0.0;
+#pragma unroll
+    for (int q = 0; q < PB; q++) if (q == c) ac = a[q];
+    double best = (live && i >= c) ? fabs(ac) : -1.0;
+    if (best != best) best = 1.0e308;                 // NaN: take it as the pivot so that it propagates like LAPACK's
+    int bi = i;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, best, o);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sval[threadIdx.x >> 5] = best; srow[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int q = 1; q < PROWS / 32; q++)
+        if (sval[q] > best || (sval[q] == best && srow[q] < bi)) { best = sval[q]; bi = srow[q]; }
+      swin = bi;
+      double* sl = slots + ((size_t)par * nct + blockIdx.x) * SL;
+      sl[PB] = best;
+      sl[PB + 1] = (double)bi;
+    }
+    __syncthreads();
+    if (i == swin) {                                   // this CTA's candidate row publishes its entries
+      double* sl = slots + ((size_t)par * nct + blockIdx.x) * SL;
+#pragma unroll
+      for (int q = 0; q < PB; q++) sl[q] = a[q];
+    }
+    if (i == c) {                                      // the diagonal row (always in CTA 0)
+#pragma unroll
+      for (int q = 0; q < PB; q++) diag[par * PB + q] = a[q];
+    }
+    grid_barrier(bar, (++epoch) * nct);
+    // ---- global arg-max (every CTA computes the same answer): warp 0 reads all slots at once ----
+    if (threadIdx.x < 32) {
+      double gb = -1.0;
+      int gi = 0x7fffffff, gw = 0;
+      for (int q = threadIdx.x; q < nct; q += 32) {
+        const double* sl = slots + ((size_t)par * nct + q) * SL;
+        const double v = __ldcg(sl + PB);
+        const int ri = (int)__ldcg(sl + PB + 1);
+        if (v > gb || (v == gb && ri < gi)) { gb = v; gi = ri; gw = q; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, gb, o);
+        const int oi = __shfl_down_sync(0xffffffffu, gi, o);
+        const int ow = __shfl_down_sync(0xffffffffu, gw, o);
+        if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; gw = ow; }
+      }
+      if (threadIdx.x == 0) {
+        spiv = gi;
+        swin = gw;
+        if (blockIdx.x == 0) {
+          piv[j0 + c] = j0 + gi;
+          if (!(gb > 0.0)) atomicCAS(info, 0, j0 + c + 1);
+        }
+      }
+    }
+    __syncthreads();
+    const int p = spiv;
+    const double* win = slots + ((size_t)par * nct + swin) * SL;
+    double pr[PB];
+#pragma unroll
+    for (int q = 0; q < PB; q++) pr[q] = __ldcg(win + q);
+    if (live && p != c) {
+      if (i == c) {
+#pragma unroll
+        for (int q = 0; q < PB; q++) a[q] = pr[q];
+      } else if (i == p) {
+#pragma unroll
+        for (int q = 0; q < PB; q++) a[q] = __ldcg(diag + par * PB + q);
+      }
+    }
+    // ---- eliminate: l = a(i, c) / pivot, a(i, c+1:) -= l * pivot_row(c+1:) ----
+    double pv = 0.0;
+#pragma unroll
+    for (int q = 0; q < PB; q++) if (q == c) pv = pr[q];
+    if (live && i > c && pv != 0.0) {
+      double l = 0.0;
+#pragma unroll
+      for (int q = 0; q < PB; q++) if (q == c) { l = a[q] / pv; a[q] = l; }
+#pragma unroll
+      for (int q = 0; q < PB; q++) if (q > c) a[q] -= l * pr[q];
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < PB; c++) if (c < w) A[r + (long long)(j0 + c) * lda] = a[c];
+  }
+}
+
+// Row swaps of the panel applied to every column outside it, then (columns right of the panel) the w x w unit-lower
+// solve that turns A12 into U12.  One thread per column.  (A variant that loaded all rows up front and emulated the swap
+// sequence in shared memory was slower: 45 vs 34 us per panel at n = 4096.)
+constexpr int ST_THREADS = 128;
+__global__ void __launch_bounds__(ST_THREADS) lu_swap_trsm_kernel(long long n, double* __restrict__ A, long long lda, int j0, int w,
+                                                                  const int* __restrict__ piv) {
+  __shared__ double L11[PB * PB];
+  __shared__ int sp[PB];
+  for (int q = threadIdx.x; q < PB * PB; q += blockDim.x) {
+    const int rr = q % PB, cc = q / PB;
+    L11[q] = (rr < w && cc < w && rr > cc) ? A[(long long)(j0 + rr) + (long long)(j0 + cc) * lda] : 0.0;
+  }
+  if (threadIdx.x < PB) sp[threadIdx.x] = threadIdx.x < w ? piv[j0 + threadIdx.x] : 0;
+  __syncthreads();
+  long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= n - w) return;
+  if (col >= j0) col += w;                         // skip the panel's own columns
+  double* a = A + col * lda;
+  for (int c = 0; c < w; c++) {
+    const int p = sp[c];
+    if (p != j0 + c) {
+      const double t = a[j0 + c];
+      a[j0 + c] = a[p];
+      a[p] = t;
+    }
+  }
+  if (col > j0) {
+    double x[PB];
+#pragma unroll
+    for (int q = 0; q < PB; q++) x[q] = q < w ? a[j0 + q] : 0.0;
+#pragma unroll
+    for (int q = 1; q < PB; q++) {
+      double sacc = x[q];
+#pragma unroll
+      for (int k2 = 0; k2 < PB; k2++) if (k2 < q) sacc -= L11[q + k2 * PB] * x[k2];
+      x[q] = sacc;
+    }
+#pragma unroll
+    for (int q = 0; q < PB; q++) if (q < w) a[j0 + q] = x[q];
+  }
+}
+
+// perm from the pivot sequence (sequential swaps of the identity), in shared memory by one thread
+__global__ void perm_kernel(int n, const int* __restrict__ piv, int* __restrict__ perm) {
+  extern __shared__ int sperm[];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sperm[i] = i;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n; i++) {
+      const int p = piv[i];
+      if (p != i) { const int t = sperm[i]; sperm[i] = sperm[p]; sperm[p] = t; }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = sperm[i];
+}
+
+// Inverse of one DB x DB diagonal block, in place in shared memory (LAPACK trti2 order): blocks [0, nb) are the
+// unit-lower blocks of L, [nb, 2 nb) the upper blocks of U.  One CTA of DB threads per block.
+__global__ void __launch_bounds__(DB) tri_inv_kernel(long long n, const double* __restrict__ LU, long long ldf,
+                                                     double* __restrict__ DL, double* __restrict__ DU, int nblocks) {
+  extern __shared__ double T[];                    // DB x DB, column-major, pitch DB + 1
+  constexpr int P = DB + 1;
+  const bool upper = blockIdx.x >= nblocks;
+  const int blk = upper ? blockIdx.x - nblocks : blockIdx.x;
+  const long long o = (long long)blk * DB;
+  const int sz = (int)(n - o < DB ? n - o : DB);
+  const int t = threadIdx.x;
+  for (int c = 0; c < sz; c++) {
+    double v = 0.0;
+    if (t < sz) {
+      const double x = LU[(o + t) + (o + c) * ldf];
+      if (upper) v = t <= c ? x : 0.0;
+      else v = t > c ? x : (t == c ? 1.0 : 0.0);
+    }
+    T[t + c * P] = v;
+  }
+  __syncthreads();
+  if (upper) {
+    // columns left to right: T(0:j, j) = -Tinv(0:j, 0:j) * T(0:j, j) / T(j, j)
+    for (int j = 0; j < sz; j++) {
+      const double d = 1.0 / T[j + j * P];
+      double s = 0.0;
+      if (t < j) {
+        for (int k2 = t; k2 < j; k2++) s += T[t + k2 * P] * T[k2 + j * P];   // Tinv(t, k2) (already inverted) * T(k2, j)
+      }
+      __syncthreads();
+      if (t < j) T[t + j * P] = -s * d;
+      if (t == j) T[j + j * P] = d;
+      __syncthreads();
+    }
+  } else {
+    // unit lower, columns right to left: T(j+1:, j) = -Tinv(j+1:, j+1:) * T(j+1:, j)
+    for (int j = sz - 1; j >= 0; j--) {
+      double s = 0.0;
+      if (t > j && t < sz) {
+        for (int k2 = j + 1; k2 <= t; k2++) s += T[t + k2 * P] * T[k2 + j * P];
+      }
+      __syncthreads();
+      if (t > j && t < sz) T[t + j * P] = -s;
+      __syncthreads();
+    }
+  }
+  double* D = upper ? DU : DL;
+  for (int c = 0; c < DB; c++)
+    if (t < sz) D[(o + t) + (long long)c * ldf] = c < sz ? T[t + c * P] : 0.0;
+}
+
+// out(l, r, b) = in(l, perm[r], b) for an (Lp x n x R) view: the row permutation of P*b along one Kronecker mode
+__global__ void perm_mode_kernel(long long Lp, long long n, long long R, const int* __restrict__ perm,
+                                 const double* __restrict__ in, double* __restrict__ out) {
+  const long long total = Lp * n * R;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long l = i % Lp, r = (i / Lp) % n, b = i / (Lp * n);
+    out[i] = in[l + Lp * ((long long)perm[r] + n * b)];
+  }
+}
+__global__ void identity_perm_kernel(long long n, long long ldt, const int* __restrict__ perm, double* __restrict__ T) {
+  const long long total = n * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i % n, c = i / n;
+    T[r + c * ldt] = perm[r] == c ? 1.0 : 0.0;
+  }
+}
+
+// ---- host drivers --------------------------------------------------------------------------------------------------------
+int gemm64(scimlop_context* h, bool ta, bool tb, long long M, long long N, long long K, double alpha, const double* A,
+           long long lda, long long sA, const double* B, long long ldb, long long sB, double beta, double* C, long long ldc,
+           long long sC, long long batch, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || batch <= 0) return SCIMLOP_OK;
+  return scimlop_gemm_strided_batched(h, SCIMLOP_F64, SCIMLOP_PREC_DEFAULT, ta, tb, M, N, K, &alpha, A, lda, sA, B, ldb, sB,
+                                      &beta, C, ldc, sC, batch, st);
+}
+
+// One triangular sweep along a mode: dst = T^{-1} src for the (Lp x n x R) view, T = L (forward) or U (backward).
+// inner mode (Lp == 1): the arrays are n x R;  otherwise R slabs of Lp x n and the factor acts from the right.
+int tri_sweep(scimlop_context* h, const Blob& f, long long n, bool upper, long long Lp, long long R, const double* src,
+              double* dst, cudaStream_t st) {
+  const long long nb = (n + DB - 1) / DB;
+  const double* D = upper ? f.DU : f.DL;
+  for (long long s = 0; s < nb; s++) {
+    const long long i = upper ? nb - 1 - s : s;
+    const long long o = i * DB, sz = std::min<long long>(DB, n - o);
+    const long long ko = upper ? o + sz : 0, kw = upper ? n - ko : o;          // already-solved index range
+    int rc;
+    if (Lp == 1) {
+      rc = gemm64(h, false, false, sz, R, sz, 1.0, D + o, f.ldf, 0, src + o, n, 0, 0.0, dst + o, n, 0, 1, st);
+      if (!rc && kw > 0) rc = gemm64(h, false, false, sz, R, kw, -1.0, f.LUr + o + ko * f.ldf, f.ldf, 0, dst + ko, n, 0, 1.0, dst + o, n, 0, 1, st);
+    } else {
+      rc = gemm64(h, false, true, Lp, sz, sz, 1.0, src + Lp * o, Lp, Lp * n, D + o, f.ldf, 0, 0.0, dst + Lp * o, Lp, Lp * n, R, st);
+      if (!rc && kw > 0)
+        rc = gemm64(h, false, true, Lp, sz, kw, -1.0, dst + Lp * ko, Lp, Lp * n, f.LUr + o + ko * f.ldf, f.ldf, 0, 1.0, dst + Lp * o, Lp,
+                    Lp * n, R, st);
+    }
+    if (rc) return rc;
+  }
+  return SCIMLOP_OK;
+}
+
+inline unsigned grid_for(long long total, scimlop_context* h) {
+  return (unsigned)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16));
+}
+
+}  // namespace
+
+extern "C" int scimlop_factorize_bytes(int dtype, int64_t n, size_t* fact_bytes, size_t* scratch) {
+  if (dtype != SCIMLOP_F64) return SCIMLOP_ERR_UNSUPPORTED;
+  if (n < 0) return SCIMLOP_ERR_BAD_SHAPE;
+  if (fact_bytes) *fact_bytes = blob_bytes(n);
+  if (scratch) *scratch = scratch_bytes(n);
+  return SCIMLOP_OK;
+}
+
+extern "C" int scimlop_factorize(scimlop_handle_t h, int dtype, int64_t n, const void* A, int64_t lda, void* fact,
+                                 size_t fact_bytes, void* Ainv, int64_t ldinv, void* scratch, size_t scratch_len,
+                                 double* cond1, void* stream) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (dtype != SCIMLOP_F64) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "factorize: Float64 only (Float32 factors keep scimlop_invert)");
+  if (n < 0 || lda < std::max<int64_t>(1, n) || (Ainv && ldinv < std::max<int64_t>(1, n)))
+    return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "factorize: bad n / lda / ldinv");
+  if (n > 32768) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "factorize: n = %lld above the 32768 rows one panel launch keeps co-resident", (long long)n);
+  if (n == 0) { if (cond1) *cond1 = 0.0; return SCIMLOP_OK; }
+  if (!A || !fact || !scratch) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "factorize: null pointer");
+  if (fact_bytes < blob_bytes(n) || scratch_len < scratch_bytes(n))
+    return scimlop_fail(h, SCIMLOP_ERR_WORKSPACE, "factorize: buffers too small (scimlop_factorize_bytes)");
+  scimlop_device_guard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Blob f = blob_at(fact, n);
+  const Scratch s = scratch_at(scratch, n);
+  const long long npan = (n + PB - 1) / PB;
+  SCIMLOP_CUDA(h, cudaMemsetAsync(s.bar, 0, (size_t)npan * 4, st));
+  SCIMLOP_CUDA(h, cudaMemsetAsync(s.norms, 0, 256, st));
+  SCIMLOP_CUDA(h, cudaMemsetAsync(s.info, 0, 256, st));
+  copy_matrix_kernel<<<grid_for(n * n, h), 256, 0, st>>>(n, static_cast<const double*>(A), lda, f.LU, f.ldf);
+  norm1_kernel<<<(unsigned)std::min<long long>(n, 1024), 256, 0, st>>>(n, f.LU, f.ldf, s.norms);
+  h->launches += 2;
+  // ---- blocked LU ----
+  for (long long p = 0; p < npan; p++) {
+    const int j0 = (int)(p * PB), w = (int)std::min<long long>(PB, n - j0);
+    const unsigned ncta = (unsigned)((n - j0 + PROWS - 1) / PROWS);
+    lu_panel_kernel<<<ncta, PROWS, 0, st>>>(n, f.LU, f.ldf, j0, w, s.piv, s.bar + p, s.slots, s.info);
+    h->launches++;
+    if (n - w > 0) {
+      lu_swap_trsm_kernel<<<(unsigned)((n - w + ST_THREADS - 1) / ST_THREADS), ST_THREADS, 0, st>>>(n, f.LU, f.ldf, j0, w, s.piv);
+      h->launches++;
+    }
+    const long long j1 = j0 + w, rem = n - j1;
+    if (rem > 0) {
+      if (int rc = gemm64(h, false, false, rem, rem, w, -1.0, f.LU + j1 + (long long)j0 * f.ldf, f.ldf, 0, f.LU + j0 + j1 * f.ldf, f.ldf, 0,
+                          1.0, f.LU + j1 + j1 * f.ldf, f.ldf, 0, 1, st))
+        return rc;
+    }
+  }
+  SCIMLOP_CUDA(h, cudaGetLastError());
+  SCIMLOP_CUDA(h, cudaFuncSetAttribute(perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+  perm_kernel<<<1, 256, (size_t)n * 4, st>>>((int)n, s.piv, f.perm);
+  // ---- solve structures: inverse diagonal blocks, pre-multiplied off-diagonal block rows ----
+  const int nb = (int)((n + DB - 1) / DB);
+  SCIMLOP_CUDA(h, cudaFuncSetAttribute(tri_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB * (DB + 1) * 8));
+  tri_inv_kernel<<<2 * nb, DB, DB * (DB + 1) * 8, st>>>(n, f.LU, f.ldf, f.DL, f.DU, nb);
+  h->launches += 2;
+  for (int i = 0; i < nb; i++) {
+    const long long o = (long long)i * DB, sz = std::min<long long>(DB, n - o);
+    if (o > 0)
+      if (int rc = gemm64(h, false, false, sz, o, sz, 1.0, f.DL + o, f.ldf, 0, f.LU + o, f.ldf, 0, 0.0, f.LUr + o, f.ldf, 0, 1, st)) return rc;
+    const long long ko = o + sz, kw = n - ko;
+    if (kw > 0)
+      if (int rc = gemm64(h, false, false, sz, kw, sz, 1.0, f.DU + o, f.ldf, 0, f.LU + o + ko * f.ldf, f.ldf, 0, 0.0, f.LUr + o + ko * f.ldf,
+                          f.ldf, 0, 1, st))
+        return rc;
+  }
+  // ---- explicit inverse = the solve applied to the identity; cond_1 ----
+  identity_perm_kernel<<<grid_for(n * n, h), 256, 0, st>>>(n, n, f.perm, s.T1);     // T1 = P (n x n, ld n)
+  h->launches++;
+  if (int rc = tri_sweep(h, f, n, false, 1, n, s.T1, s.T2, st)) return rc;
+  if (int rc = tri_sweep(h, f, n, true, 1, n, s.T2, s.T1, st)) return rc;
+  if (Ainv) {
+    copy_matrix_kernel<<<grid_for(n * n, h), 256, 0, st>>>(n, s.T1, n, static_cast<double*>(Ainv), ldinv);
+    h->launches++;
+  }
+  norm1_kernel<<<(unsigned)std::min<long long>(n, 1024), 256, 0, st>>>(n, s.T1, n, s.norms + 1);
+  h->launches++;
+  SCIMLOP_CUDA(h, cudaGetLastError());
+  double hn[2];
+  int hinfo = 0;
+  SCIMLOP_CUDA(h, cudaMemcpyAsync(hn, s.norms, 16, cudaMemcpyDeviceToHost, st));
+  SCIMLOP_CUDA(h, cudaMemcpyAsync(&hinfo, s.info, 4, cudaMemcpyDeviceToHost, st));
+  SCIMLOP_CUDA(h, cudaStreamSynchronize(st));
+  if (hinfo != 0) return scimlop_fail(h, SCIMLOP_ERR_SINGULAR, "factorize: zero pivot at column %d", hinfo);
+  if (cond1) *cond1 = hn[0] * hn[1];
+  return SCIMLOP_OK;
+}
+
+// W = (F_1 (x) ... (x) F_n)^{-1} V with every dense factor given by its factorisation blob (kinds: SCIMLOP_DENSE or
+// SCIMLOP_IDENTITY; dims[f] = order of factor f, outermost first).  workspace: one buffer of prod(dims) * k doubles.
+extern "C" int scimlop_kron_ldiv(scimlop_handle_t h, int dtype, int nfactors, void* const* facts, const int64_t* dims,
+                                 const int32_t* kinds, const void* V, void* W, int64_t k, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
+  if (dtype != SCIMLOP_F64) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "kron_ldiv: Float64 only");
+  if (nfactors < 1 || nfactors > 8 || !dims || !kinds || !facts) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_ldiv: bad factor description");
+  long long N = 1;
+  int nops = 0;
+  for (int f = 0; f < nfactors; f++) {
+    if (dims[f] < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kron_ldiv: negative size");
+    if (kinds[f] != SCIMLOP_DENSE && kinds[f] != SCIMLOP_IDENTITY)
+      return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "kron_ldiv: factor %d: only dense (factorised) and identity factors", f);
+    if (kinds[f] == SCIMLOP_DENSE) { nops++; if (!facts[f]) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_ldiv: factor %d has no factorisation", f); }
+    N *= dims[f];
+  }
+  if (k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kron_ldiv: negative k");
+  if (k == 0 || N == 0) return SCIMLOP_OK;
+  if (!V || !W) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_ldiv: V/W null");
+  scimlop_device_guard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bytes = (size_t)N * (size_t)k * 8;
+  if (nops == 0) {
+    SCIMLOP_CUDA(h, cudaMemcpyAsync(W, V, bytes, cudaMemcpyDeviceToDevice, st));
+    return SCIMLOP_OK;
+  }
+  if (!workspace || workspace_bytes < bytes) return scimlop_fail(h, SCIMLOP_ERR_WORKSPACE, "kron_ldiv: workspace %zu B < required %zu B", workspace_bytes, bytes);
+  // three out-of-place passes per factor (row gather, L sweep, U sweep): 3 * nops passes alternate between W and the
+  // workspace and must end in W
+  double* bufs[2] = {static_cast<double*>(W), static_cast<double*>(workspace)};
+  int cur = (3 * nops) % 2 == 1 ? 0 : 1;              // target of the first pass
+  const double* src = static_cast<const double*>(V);
+  long long Lp = 1;
+  for (int fi = nfactors - 1; fi >= 0; fi--) {
+    const long long n = dims[fi];
+    if (kinds[fi] == SCIMLOP_IDENTITY) { Lp *= n; continue; }
+    const long long R = N * k / (Lp * n);
+    const Blob f = blob_at(facts[fi], n);
+    perm_mode_kernel<<<grid_for(N * k, h), 256, 0, st>>>(Lp, n, R, f.perm, src, bufs[cur]);
+    h->launches++;
+    if (int rc = tri_sweep(h, f, n, false, Lp, R, bufs[cur], bufs[cur ^ 1], st)) return rc;
+    if (int rc = tri_sweep(h, f, n, true, Lp, R, bufs[cur ^ 1], bufs[cur], st)) return rc;
+    src = bufs[cur];
+    cur ^= 1;
+    Lp *= n;
+  }
+  SCIMLOP_CUDA(h, cudaGetLastError());
+  return SCIMLOP_OK;
+}

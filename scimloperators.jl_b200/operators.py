@@ -926,11 +926,20 @@ class InvertibleOperator(AbstractSciMLOperator):
     formed once on the device by scimlop_invert), so that ldiv! runs on the same tensor-core path as mul!.
     `refresh` re-forms F after `update_coefficients!` changed L (the reference updates both, :575-579)."""
 
-    def __init__(self, L, F, refresh=None):
+    def __init__(self, L, F, refresh=None, lu=None):
         if L.size() != F.size()[::-1]:
             raise AssertionError(f"InvertibleOperator: L is {L.size()}, F is {F.size()}")
         self.L, self.F, self._refresh = L, F, refresh
+        self.lu = lu                  # LUFactorization of a Float64 matrix leaf (None otherwise)
         self._stash = None
+        self._lu_ws = None
+
+    @property
+    def stable_solve(self):
+        """True when ldiv! runs the factorised (substitution) solve instead of multiplying by the explicit inverse:
+        an ill-conditioned Float64 factor (cond_1 > COND_FAST).  The lazy adjoint keeps the inverse (the transposed
+        sweeps are not built)."""
+        return self.lu is not None and self.lu.stable_needed and not getattr(self.L, "trans", False)
 
     @property
     def dtype(self):
@@ -943,7 +952,7 @@ class InvertibleOperator(AbstractSciMLOperator):
         return (self.L, self.F)
 
     def adjoint(self):   # src/matrix.jl:565
-        return InvertibleOperator(self.L.adjoint(), self.F.adjoint())
+        return InvertibleOperator(self.L.adjoint(), self.F.adjoint(), lu=self.lu)
 
     def iscached(self):
         return self.L.iscached() and self.F.iscached()
@@ -977,6 +986,16 @@ class InvertibleOperator(AbstractSciMLOperator):
                 self._stash = DeviceArray.empty(tuple(v.shape), v.dtype, v.device_index)
             self._stash.t.copy_(v.t)
             src = self._stash
+        if self.stable_solve:
+            k = _ncols(v)
+            need = self.lu.n * k * 8
+            if self._lu_ws is None or self._lu_ws.numel() < need:
+                self._lu_ws = torch.empty(need, dtype=torch.uint8, device=v.t.device)
+            h = _lib.handle(w.device_index)
+            _kron_ldiv(h, [self.lu], [self.lu.n], src, w, k, self._lu_ws)
+            if scale is not None and float(scale) != 1.0:
+                _lmul(w, float(scale), h)
+            return w
         return self.F.mul_(w, src, scale, None if scale is None else False)
 
 
@@ -1054,14 +1073,70 @@ def _invert_into(A, out):
     return out
 
 
+COND_FAST = 1.0e3   # cond_1 up to which ldiv! multiplies by the explicit inverse (residual cond * eps <= 1e-13)
+
+
+class LUFactorization:
+    """The device-side `lu(A)` of a Float64 matrix (scimlop_factorize): the opaque solve blob for scimlop_kron_ldiv, the
+    explicit inverse and cond_1(A).  `refresh()` re-factorises after the matrix changed in place."""
+
+    def __init__(self, A):
+        self.A = A
+        n = A.shape[0]
+        if A.shape[1] != n:
+            raise AssertionError("factorize: only square factors have an ldiv! on this path (test/matrix.jl:646)")
+        self.n = n
+        h = _lib.handle(A.device_index)
+        fb, sbytes = C.c_size_t(0), C.c_size_t(0)
+        h.check(h.lib.scimlop_factorize_bytes(_DT[A.dtype], n, C.byref(fb), C.byref(sbytes)), "scimlop_factorize_bytes")
+        self.blob = torch.empty(max(1, fb.value), dtype=torch.uint8, device=A.t.device)
+        self._fb, self._sb = fb.value, sbytes.value
+        self.inv = DeviceArray.empty((n, n), A.dtype, A.device_index)
+        self.cond = float("nan")
+        self.refresh()
+
+    def refresh(self):
+        A = self.A
+        h = _lib.handle(A.device_index)
+        scratch = torch.empty(max(1, self._sb), dtype=torch.uint8, device=A.t.device)
+        cond = C.c_double(0.0)
+        h.check(h.lib.scimlop_factorize(h.ptr, _DT[A.dtype], self.n, C.c_void_p(A.ptr), A.ld, C.c_void_p(self.blob.data_ptr()),
+                                        self._fb, C.c_void_p(self.inv.ptr), self.inv.ld, C.c_void_p(scratch.data_ptr()),
+                                        self._sb, C.byref(cond), _stream()), "scimlop_factorize")
+        self.cond = cond.value
+        return self
+
+    @property
+    def stable_needed(self):
+        return not (self.cond <= COND_FAST)       # NaN-safe: unknown conditioning takes the substitution path
+
+
+def _kron_ldiv(h, facts, dims, v, w, k, ws):
+    """scimlop_kron_ldiv on LUFactorization blobs (None = identity factor)."""
+    nf = len(dims)
+    cf, cd, ck = (C.c_void_p * nf)(), (C.c_int64 * nf)(), (C.c_int32 * nf)()
+    for i, (f, n) in enumerate(zip(facts, dims)):
+        cd[i] = n
+        ck[i] = _lib.IDENTITY if f is None else _lib.DENSE
+        cf[i] = None if f is None else f.blob.data_ptr()
+    h.check(h.lib.scimlop_kron_ldiv(h.ptr, _lib.F64, nf, cf, cd, ck, C.c_void_p(v.ptr), C.c_void_p(w.ptr), k,
+                                    C.c_void_p(ws.data_ptr()), ws.numel(), _stream()), "scimlop_kron_ldiv")
+    return w
+
+
 def factorize(L):
     """`LinearAlgebra.factorize(L)`: src/matrix.jl:513-516 (leaf), src/basic.jl:500 (Scaled), :1056 (Composed),
-    src/tensor.jl:227 (every Kronecker factor).  Singular factors raise ScimlopError(ERR_SINGULAR)."""
+    src/tensor.jl:227 (every Kronecker factor).  Singular factors raise ScimlopError(ERR_SINGULAR).  Float64 matrices
+    get a blocked LU on the device (+ the explicit inverse and cond_1 from it); Float32 keeps scimlop_invert."""
     if isinstance(L, InvertibleOperator):
         return L
     if isinstance(L, MatrixOperator):
         if L.banded or L.sparse:
             raise NotImplementedError("factorize of a banded / sparse MatrixOperator (a sparse solve) is not on this path")
+        if L.A.dtype == np.float64:
+            lu = LUFactorization(L.A)
+            refresh = lu.refresh if L.update_func is not None else None
+            return InvertibleOperator(L, MatrixOperator(lu.inv, L.trans), refresh, lu=lu)
         inv = invert_matrix(L.A)
         refresh = (lambda: _invert_into(L.A, inv)) if L.update_func is not None else None
         return InvertibleOperator(L, MatrixOperator(inv, L.trans), refresh)
@@ -1432,6 +1507,7 @@ class TensorProductOperator(AbstractSciMLOperator):
     def _flatten_inverse(self):
         """Like _flatten, but every leaf is replaced by the operator that applies its inverse."""
         leaves, scalars = [], []
+        self._inv_owners = []     # the InvertibleOperator (or None for an identity) behind every leaf
 
         def walk(op):
             if isinstance(op, ScaledOperator):
@@ -1441,9 +1517,11 @@ class TensorProductOperator(AbstractSciMLOperator):
                 return all(walk(o) for o in op.ops)
             if isinstance(op, IdentityOperator):
                 leaves.append(op)
+                self._inv_owners.append(None)
                 return True
             if isinstance(op, InvertibleOperator) and _kron_leaf(op.F) is not None and not isinstance(op.F, InvertibleOperator):
                 leaves.append(op.F)
+                self._inv_owners.append(op)
                 return True
             return False
 
@@ -1487,12 +1565,30 @@ class TensorProductOperator(AbstractSciMLOperator):
                 torch.empty(max(1, nbytes.value), dtype=torch.uint8, device=v.t.device)
             self._native_inv = dict(nf=nf, dims=dims, lds=lds, kinds=kinds, ptrs=ptrs, ws=ws, ws_bytes=nbytes.value,
                                     scalars=scalars, dtype=v.dtype, nstages=sum(1 for i in range(nf) if kinds[i] != _lib.IDENTITY),
-                                    ndense=ndense, stash=None)
+                                    ndense=ndense, stash=None, owners=list(self._inv_owners), lu_ws=None)
         nat = self._native_inv
         a = scale
         for s in nat["scalars"]:
             a = (1.0 if a is None else float(a)) / s.convert()
         src = v
+        owners = nat["owners"]
+        if any(o is not None and o.stable_solve for o in owners) and \
+                all(o is None or (o.lu is not None and not getattr(o.L, "trans", False)) for o in owners):
+            # an ill-conditioned factor: the factorised solve (substitution sweeps as GEMMs along every mode)
+            need = v.t.numel() * 8
+            if nat["lu_ws"] is None or nat["lu_ws"].numel() < need:
+                nat["lu_ws"] = torch.empty(need, dtype=torch.uint8, device=v.t.device)
+            if w.t.data_ptr() == v.t.data_ptr():
+                if nat["stash"] is None or nat["stash"].shape != tuple(v.shape):
+                    nat["stash"] = DeviceArray.empty(tuple(v.shape), v.dtype, v.device_index)
+                nat["stash"].t.copy_(v.t)
+                src = nat["stash"]
+            h = _lib.handle(w.device_index)
+            dims_n = [leaf.size()[0] for leaf in self._flatten_inverse()[0]]
+            _kron_ldiv(h, [None if o is None else o.lu for o in owners], dims_n, src, w, k, nat["lu_ws"])
+            if a is not None and float(a) != 1.0:
+                _lmul(w, float(a), h)
+            return w
         if w.t.data_ptr() == v.t.data_ptr() and nat["nstages"] == 1 and nat["ndense"] == 1:
             # two-argument form with a single GEMM stage: a GEMM cannot run in place, stage v once
             if nat["stash"] is None or nat["stash"].shape != tuple(v.shape):
