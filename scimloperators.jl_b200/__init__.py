@@ -9,7 +9,7 @@ from ._lib import Handle, ScimlopError, handle, load, OPT_TAIL_SPLIT
 from .array import DeviceArray
 from .operators import (AbstractSciMLOperator, AddedOperator, BandedMatrix, BatchedDiagonalOperator, ComposedOperator,
                         DiagonalOperator, IdentityOperator, MatrixOperator, NullOperator, ScalarOperator,
-                        ScaledOperator, SparseMatrixCSR, TensorProductOperator, TensorSumOperator, adapt, cache_operator, iscached, kron,
+                        ScaledOperator, SparseMatrixCSR, TensorProductOperator, TensorSumOperator, adapt, cache_operator, copy, iscached, kron,
                         kronsum, mul_, update_coefficients_, InvertibleOperator, InvertedOperator, factorize, has_ldiv,
                         inv, invert_matrix, ldiv_, LUFactorization, BlockDiagonalOperator, WOperator)
 from .distributed import ColumnShard, allgather_cols, shard_columns

@@ -604,9 +604,12 @@ class _TreePlan:
         nt = len(terms)
         self.c_terms = (_lib.Term * nt)()
         self._keep = []
+        self._promoted = []
         for i, (_, leaves) in enumerate(terms):
             arr = (_lib.Factor * len(leaves))()
             for j, leaf in enumerate(leaves):
+                leaf = _promote_leaf(leaf, self.dtype) if isinstance(leaf, (MatrixOperator, _VectorDiagonalOperator)) else leaf
+                self._promoted.append(leaf)
                 m, n = leaf.size()
                 f = arr[j]
                 f.rows, f.cols, f.trans, f.data, f.ld = m, n, 0, None, 0
@@ -731,11 +734,9 @@ class BlockDiagonalOperator(AbstractSciMLOperator):
         self._packed = None
 
     @property
-    def dtype(self):
-        for op in self.ops:
-            if op.dtype is not None:
-                return op.dtype
-        return None
+    def dtype(self):   # reduce(_promote_operator_eltype, ops), src/interface.jl:444
+        dts = [op.dtype for op in self.ops if op.dtype is not None]
+        return None if not dts else np.dtype(np.result_type(*dts))
 
     def size(self):   # src/block.jl:66-69
         return (sum(op.size()[0] for op in self.ops), sum(op.size()[1] for op in self.ops))
@@ -1239,11 +1240,9 @@ class AddedOperator(_TreeMixin, AbstractSciMLOperator):
         self.ops = tuple(flat)
 
     @property
-    def dtype(self):
-        for op in self.ops:
-            if op.dtype is not None:
-                return op.dtype
-        return None
+    def dtype(self):   # reduce(_promote_operator_eltype, ops), src/interface.jl:444
+        dts = [op.dtype for op in self.ops if op.dtype is not None]
+        return None if not dts else np.dtype(np.result_type(*dts))
 
     def size(self):
         return self.ops[0].size()
@@ -1312,11 +1311,9 @@ class ComposedOperator(_TreeMixin, AbstractSciMLOperator):
         self.cache = None
 
     @property
-    def dtype(self):
-        for op in self.ops:
-            if op.dtype is not None:
-                return op.dtype
-        return None
+    def dtype(self):   # reduce(_promote_operator_eltype, ops), src/interface.jl:444
+        dts = [op.dtype for op in self.ops if op.dtype is not None]
+        return None if not dts else np.dtype(np.result_type(*dts))
 
     def size(self):
         return (self.ops[0].size()[0], self.ops[-1].size()[1])
@@ -1407,6 +1404,22 @@ def _kron_leaf(op):
     return None
 
 
+def _promote_leaf(op, dtype):
+    """Mixed element types (`_promote_operator_eltype`, src/interface.jl:444; src/tensor.jl:99): a constant dense /
+    diagonal leaf whose eltype differs from the arrays' is applied through a converted copy made once at cache time
+    (Float32 -> Float64 is exact; Float64 -> Float32 rounds the operator to the arrays' precision).  Time-dependent
+    leaves keep the error: their copy would go stale."""
+    if op.dtype is None or op.dtype == dtype:
+        return op
+    tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    if isinstance(op, MatrixOperator) and not (op.banded or op.sparse) and op.update_func is None:
+        return MatrixOperator(DeviceArray(op.A.t.to(tdt), op.A.shape), op.trans)
+    if isinstance(op, _VectorDiagonalOperator) and op.update_func is None:
+        return _VectorDiagonalOperator(DeviceArray(op.diag.t.to(tdt), op.diag.shape))
+    raise TypeError(f"operator eltype {op.dtype} != array eltype {np.dtype(dtype)} (only constant dense / diagonal "
+                    "leaves are promoted)")
+
+
 class TensorProductOperator(AbstractSciMLOperator):
     """src/tensor.jl:88-107.  `ops = (outer, inner)`; matrices are wrapped in MatrixOperator (:109-118); the
     N-ary constructor is a right fold (:121).  `mul!` :543-610 needs `cache_operator` first (:548,:583)."""
@@ -1424,11 +1437,9 @@ class TensorProductOperator(AbstractSciMLOperator):
         self._k = None
 
     @property
-    def dtype(self):
-        for op in self.ops:
-            if op.dtype is not None:
-                return op.dtype
-        return None
+    def dtype(self):   # reduce(_promote_operator_eltype, ops), src/tensor.jl:99
+        dts = [op.dtype for op in self.ops if op.dtype is not None]
+        return None if not dts else np.dtype(np.result_type(*dts))
 
     def size(self):
         (mo, no), (mi, ni) = self.ops[0].size(), self.ops[1].size()
@@ -1471,6 +1482,8 @@ class TensorProductOperator(AbstractSciMLOperator):
         flat = self._flatten()
         if flat is not None:
             leaves, scalars = flat
+            leaves = [_promote_leaf(op, v.dtype) for op in leaves]
+            self._promoted = leaves      # keeps converted copies alive
             nf = len(leaves)
             dims = (C.c_int64 * (2 * nf))()
             lds = (C.c_int64 * nf)()
@@ -1480,8 +1493,6 @@ class TensorProductOperator(AbstractSciMLOperator):
                 m, n = op.size()
                 dims[2 * i], dims[2 * i + 1] = m, n
                 kinds[i], ptrs[i], lds[i] = _kron_leaf(op)
-                if op.dtype is not None and op.dtype != v.dtype:
-                    raise TypeError(f"factor eltype {op.dtype} != array eltype {v.dtype}")
                 if isinstance(op, MatrixOperator):
                     op._attach_split()
             nbytes = C.c_size_t(0)
@@ -1734,7 +1745,27 @@ def kronsum(outer, inner):
 
 
 def cache_operator(L, v):
-    return L.cache_operator(v)
+    L = L.cache_operator(v)
+    try:
+        L._cached_for = (tuple(v.shape), v.dtype, v.device_index)
+    except AttributeError:
+        pass
+    return L
+
+
+def copy(L):
+    """`Base.copy(L)`: a deep copy that shares no storage with L -- operator arrays AND caches
+    (src/tensor.jl:210-215 copies the ops and deep-copies the cache; the leaves copy their arrays).  A cached operator
+    yields a cached copy (its workspace is allocated anew for the same input shape)."""
+    new = adapt(L, to=lambda a: DeviceArray(a.t.clone(), a.shape))
+    for attr in ("precision",):
+        if attr in getattr(L, "__dict__", {}):
+            setattr(new, attr, getattr(L, attr))
+    cf = getattr(L, "_cached_for", None)
+    if cf is not None:
+        shape, dtype, dev = cf
+        new = cache_operator(new, DeviceArray.empty(shape, dtype, dev))
+    return new
 
 
 def adapt(L, device=None, to=None):
@@ -1748,6 +1779,10 @@ def adapt(L, device=None, to=None):
         dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         to = lambda a: DeviceArray(a.t.to(dev, copy=True), a.shape)
     if isinstance(L, MatrixOperator):
+        if L.banded:
+            return MatrixOperator(BandedMatrix(to(L.A.bands), L.A.b), L.trans, L.update_func)
+        if L.sparse:
+            return MatrixOperator(SparseMatrixCSR(to(L.A.rowptr), to(L.A.colidx), to(L.A.values), L.A.shape), L.trans, L.update_func)
         return MatrixOperator(to(L.A), L.trans, L.update_func)
     if isinstance(L, _VectorDiagonalOperator):
         return _VectorDiagonalOperator(to(L.diag), L.update_func)
@@ -1756,6 +1791,8 @@ def adapt(L, device=None, to=None):
     if isinstance(L, (IdentityOperator, NullOperator)):
         return type(L)(L.len)
     if isinstance(L, InvertibleOperator):
+        if L.lu is not None:                      # re-factorise on the new home (the blob is device-local)
+            return factorize(adapt(L.L, to=to))
         return InvertibleOperator(adapt(L.L, to=to), adapt(L.F, to=to))
     if isinstance(L, BlockDiagonalOperator):
         return BlockDiagonalOperator(*[adapt(op, to=to) for op in L.ops])

@@ -1219,3 +1219,37 @@ def test_dmma_tail_wave_runs_split_k_and_option_restores_one_launch(sb):
     W2 = W1.copy()
     sb.mul_(W2, L, V, 2.0, -1.0)
     assert float((W2.t - W1.t).norm() / W1.t.norm()) <= 1e-12
+
+
+def test_mixed_eltype_factors_are_promoted(sb):
+    """`_promote_operator_eltype` (src/interface.jl:444, src/tensor.jl:99): a Float32 factor next to Float64 arrays is
+    applied at Float64 (exactly the promoted values), in a Kronecker product and in an operator tree."""
+    rng = np.random.default_rng(12)
+    A32, B = rnd(rng, 6, 5, dtype=np.float32), rnd(rng, 7, 4)
+    v = rnd(rng, 20, 3)
+    dv = dev(sb, v)
+    L = sb.TensorProductOperator(A32, B)
+    assert L.dtype == np.float64
+    L = sb.cache_operator(L, dv)
+    check((L * dv).numpy(), np.kron(A32.astype(np.float64), B) @ v, np.float64, "promoted kron")
+    M32, D = rnd(rng, 9, 9, dtype=np.float32), rnd(rng, 9, 9)
+    T = sb.cache_operator(sb.MatrixOperator(M32) + 2.0 * sb.MatrixOperator(D), dev(sb, rnd(rng, 9, 2)))
+    x = rnd(rng, 9, 2)
+    check((T * dev(sb, x)).numpy(), (M32.astype(np.float64) + 2.0 * D) @ x, np.float64, "promoted tree")
+
+
+def test_copy_shares_no_storage_and_stays_cached(sb):
+    """`Base.copy(L)` (src/tensor.jl:210-215): ops and cache are copied; mutating the original leaves the copy alone."""
+    rng = np.random.default_rng(13)
+    A, B = rnd(rng, 5, 5), rnd(rng, 6, 6)
+    v = rnd(rng, 30, 4)
+    dv = dev(sb, v)
+    L = sb.cache_operator(sb.TensorProductOperator(A, B), dv)
+    Lc = sb.copy(L)
+    assert sb.iscached(Lc)
+    want = np.kron(A, B) @ v
+    L.ops[0].A.t.zero_()                      # wreck the original's outer factor in place
+    check((Lc * dv).numpy(), want, np.float64, "copy after the original changed")
+    assert np.abs((L * dv).numpy()).max() == 0.0
+    Tc = sb.copy(sb.cache_operator(sb.MatrixOperator(A) + sb.DiagonalOperator(rnd(rng, 5)), dev(sb, rnd(rng, 5, 2))))
+    assert sb.iscached(Tc)
