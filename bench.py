@@ -329,6 +329,45 @@ def strong_legs(torch, dist, sb, h, world, rank, A, B, ms_1gpu_shape):
     return out
 
 
+def c3_leg(torch, dist, sb, world, rank):
+    """configs[2]: kron(A, B, C) with 128 x 128 Float32 factors on a 2097152 x 512 batch per GPU (column-sharded like the
+    headline): modes (C, B) fused on chip by kron2_f16_kernel, mode A by the resident-factor tcgen05 kernel.  HBM-bound:
+    the fraction is ALGORITHMIC bytes (V once + W once) over the measured copy bandwidth; the schedule moves 2.0x that."""
+    n, k = 128 ** 3, 512
+    g = torch.Generator(device="cuda").manual_seed(33 + rank)
+    F = [sb.DeviceArray(torch.rand(128 * 128, dtype=torch.float32, device="cuda", generator=g) - 0.5, (128, 128)) for _ in range(3)]
+    V = sb.DeviceArray(torch.rand(n * k, dtype=torch.float32, device="cuda", generator=g), (n, k))
+    W = sb.DeviceArray.empty((n, k), np.float32)
+    L = sb.cache_operator(sb.TensorProductOperator(*[sb.MatrixOperator(f) for f in F]), V)
+    ms = _timed_max(torch, dist, world, lambda: sb.mul_(W, L, V), reps=5, warm=2)
+    # parity spot check: one column against the Float64 product of the three modes, on the device
+    j = 7
+    X = V.cols(j, j + 1).t.double().reshape(128, 128, 128)               # [a][b][c]
+    Fd = [f.t.double().reshape(128, 128).t() for f in F]                  # row-major views of the column-major factors
+    Y = X @ Fd[2].t()                                                     # mode C: [a][b][c'] 
+    Y = (Y.transpose(1, 2) @ Fd[1].t()).transpose(1, 2)                  # mode B: [a][b'][c']
+    ref = torch.tensordot(Fd[0], Y, dims=([1], [0])).reshape(-1)         # mode A: [a'][b'][c']
+    got = W.cols(j, j + 1).t.double()
+    err = float((got - ref).norm() / ref.norm())
+    peak = hbm_peak_gbs()
+    gbs = 2.0 * n * k * 4 / (ms * 1e-3) / 1e9
+    out = {"workload": "configs[2]: TensorProductOperator of three 128x128 Float32 MatrixOperators, 2097152 x 512 batch per GPU",
+           "ms": ms, "tflops_fp32_equiv_aggregate": 3 * 2 * 128.0 * n * k * world / (ms * 1e-3) / 1e12,
+           "algorithmic_gbs_per_gpu": gbs, "frac_of_hbm_copy_peak": gbs / peak[0], "hbm_peak": peak[1],
+           "passes": 2, "parity_rel_err_vs_f64_column": err}
+    del V, W, L
+    torch.cuda.empty_cache()
+    return out
+
+
+def hbm_peak_gbs():
+    try:
+        mp = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))
+        return float(mp["hbm_gbs"]), "MEASURED_PEAKS.json (copy bandwidth measured on this pool)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
 def c5_leg(torch, dist, sb, world, rank):
     """configs[4]: kron(Dxx, I) + kron(I, Dyy) on a 4096 x 4096 grid (dense spectral-style factors, Float64), batch-
     sharded: ONE column per GPU, C5_MATVECS dependent matvecs (w -> v ping-pong) captured in one CUDA graph."""
@@ -480,6 +519,7 @@ def run_gpu(args):
     del L
     strong = strong_legs(torch, dist, sb, h, world, rank, A, B, ms)
     c5 = c5_leg(torch, dist, sb, world, rank)
+    c3 = c3_leg(torch, dist, sb, world, rank)
     if world > 1 and not strong.get("all_ranks_bit_identical", True):
         if rank == 0:
             print(json.dumps({"error": "a fused compute + all-gather variant differs from the unfused result", "strong": strong}))
@@ -527,7 +567,7 @@ def run_gpu(args):
                    "global_batch_columns": KCOLS * world, "parallelism": f"column-sharded x{world}, factors replicated, "
                    "no data-path collective", "l2": "inputs larger than L2: V, W and the intermediate are 537 MB "
                    "each vs 126 MB L2", "ms_per_step_5arg": ms5, "parity_rel_err_vs_oracle": err,
-                   "e2e_vs_resident_max_abs_diff": mism, "strong": strong, "c5": c5},
+                   "e2e_vs_resident_max_abs_diff": mism, "strong": strong, "c5": c5, "c3": c3},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": int(Vh.numel() * 8 + Ah.nbytes + Bh.nbytes),
                 "d2h_bytes_per_step": int(Wh.numel() * 8), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,

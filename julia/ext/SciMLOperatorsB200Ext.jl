@@ -332,49 +332,86 @@ end
 # on the inverse factors -- the same two tensor-core mode products as `mul!`.
 struct DeviceInverse{T} <: AbstractMatrix{T}      # what `F` holds: inv(A), applied by multiplication
     inv::CuMatrix{T}
+    blob::Union{Nothing, CuVector{UInt8}}         # Float64: the LU solve structures of scimlop_factorize
+    cond::Float64                                 # cond_1(A) from the factorisation (NaN for Float32)
 end
 Base.size(F::DeviceInverse) = size(F.inv)
 SciMLOperators.has_ldiv(::DeviceInverse) = true
 SciMLOperators.has_ldiv!(::DeviceInverse) = true
-LinearAlgebra.ldiv!(w::DevMat{T}, F::DeviceInverse{T}, v::DevMat{T}) where {T <: F} = mul!(w, F.inv, v, true, false)
+const COND_FAST = 1.0e3       # up to here ldiv! multiplies by the inverse (residual cond * eps <= 1e-13)
+stable_solve(F::DeviceInverse) = F.blob !== nothing && !(F.cond <= COND_FAST)
 
-function LinearAlgebra.factorize(L::MatrixOperator{T, <:CuMatrix{T}}) where {T <: F}
+function kron_ldiv!(w::DevMat{Float64}, blobs, dims::Vector{Int64}, kinds::Vector{Cint}, v::DevMat{Float64})
+    ws = CUDA.zeros(UInt8, sizeof(v))             # a real extension keeps this in the operator's cache
+    ptrs = Ptr{Cvoid}[b === nothing ? C_NULL : dptr(b) for b in blobs]
+    check(ccall((:scimlop_kron_ldiv, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Cint}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid},
+                 Csize_t, Ptr{Cvoid}),
+                handle(), 0, length(dims), ptrs, dims, kinds, dptr(v), dptr(w), size(v, 2), dptr(ws), sizeof(ws),
+                stream_ptr()), "scimlop_kron_ldiv")
+    w
+end
+function LinearAlgebra.ldiv!(w::DevMat{T}, F::DeviceInverse{T}, v::DevMat{T}) where {T <: F}
+    stable_solve(F) || return mul!(w, F.inv, v, true, false)
+    kron_ldiv!(w, (F.blob,), Int64[size(F, 1)], Cint[DENSE], v)
+end
+
+function LinearAlgebra.factorize(L::MatrixOperator{Float64, <:CuMatrix{Float64}})
+    n = LinearAlgebra.checksquare(L.A)
+    fb = Ref{Csize_t}(0); sb = Ref{Csize_t}(0)
+    ccall((:scimlop_factorize_bytes, LIB), Cint, (Cint, Int64, Ref{Csize_t}, Ref{Csize_t}), 0, n, fb, sb)
+    blob, scratch, Ainv, cond = CUDA.zeros(UInt8, fb[]), CUDA.zeros(UInt8, sb[]), similar(L.A), Ref(0.0)
+    check(ccall((:scimlop_factorize, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Csize_t,
+                 Ref{Float64}, Ptr{Cvoid}),
+                handle(), 0, n, dptr(L.A), stride(L.A, 2), dptr(blob), fb[], dptr(Ainv), stride(Ainv, 2), dptr(scratch),
+                sb[], cond, stream_ptr()), "scimlop_factorize")   # status 9 (singular) -> error, like SingularException
+    SciMLOperators.InvertibleOperator(L, DeviceInverse{Float64}(Ainv, blob, cond[]))
+end
+function LinearAlgebra.factorize(L::MatrixOperator{Float32, <:CuMatrix{Float32}})
     n = LinearAlgebra.checksquare(L.A)
     Ainv = similar(L.A)
     nbytes = Ref{Csize_t}(0)
-    ccall((:scimlop_invert_workspace_bytes, LIB), Cint, (Cint, Int64, Ref{Csize_t}), dtype(T), n, nbytes)
+    ccall((:scimlop_invert_workspace_bytes, LIB), Cint, (Cint, Int64, Ref{Csize_t}), 1, n, nbytes)
     ws = CUDA.zeros(UInt8, nbytes[])
     check(ccall((:scimlop_invert, LIB), Cint,
                 (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
-                handle(), dtype(T), n, dptr(L.A), stride(L.A, 2), dptr(Ainv), stride(Ainv, 2), dptr(ws), sizeof(ws),
-                stream_ptr()), "scimlop_invert")           # status 9 (singular) -> error, like SingularException
-    SciMLOperators.InvertibleOperator(L, DeviceInverse{T}(Ainv))
+                handle(), 1, n, dptr(L.A), stride(L.A, 2), dptr(Ainv), stride(Ainv, 2), dptr(ws), sizeof(ws),
+                stream_ptr()), "scimlop_invert")
+    SciMLOperators.InvertibleOperator(L, DeviceInverse{Float32}(Ainv, nothing, NaN))
 end
 
 # like `flatten`, with every factorised leaf replaced by its cached device inverse and every λ by 1/λ
 function flatten_inverse(L::TensorProductOperator, T)
-    kinds = Cint[]; ptrs = Ptr{Cvoid}[]; dims = Int64[]; lds = Int64[]; λinv = one(T)
+    kinds = Cint[]; ptrs = Ptr{Cvoid}[]; dims = Int64[]; lds = Int64[]; λinv = one(T); blobs = Any[]
     function walk(op)
         if op isa ScaledOperator
             λinv /= convert(Number, op.λ); return walk(op.L)
         elseif op isa TensorProductOperator
             return all(walk, op.ops)
         elseif op isa IdentityOperator
-            push!(kinds, IDENTITY); push!(ptrs, C_NULL); push!(lds, 0)
+            push!(kinds, IDENTITY); push!(ptrs, C_NULL); push!(lds, 0); push!(blobs, nothing)
         elseif op isa SciMLOperators.InvertibleOperator && op.F isa DeviceInverse{T}
-            push!(kinds, DENSE); push!(ptrs, dptr(op.F.inv)); push!(lds, stride(op.F.inv, 2))
+            push!(kinds, DENSE); push!(ptrs, dptr(op.F.inv)); push!(lds, stride(op.F.inv, 2)); push!(blobs, op.F)
         else
             return false                      # not factorised on the device: the generic ldiv! runs
         end
         append!(dims, size(op)); true
     end
-    walk(L) ? (kinds, ptrs, dims, lds, λinv) : nothing
+    walk(L) ? (kinds, ptrs, dims, lds, λinv, blobs) : nothing
 end
 function LinearAlgebra.ldiv!(w::DevMat{T}, L::TensorProductOperator, v::DevMat{T}) where {T <: F}
     @assert iscached(L)                                                            # src/tensor.jl:617
     fl = flatten_inverse(L, T)
     fl === nothing && return invoke(ldiv!, Tuple{AbstractVecOrMat, TensorProductOperator, AbstractVecOrMat}, w, L, v)
-    kinds, ptrs, dims, lds, λinv = fl
+    kinds, ptrs, dims, lds, λinv, blobs = fl
+    if T === Float64 && any(b -> b !== nothing && stable_solve(b), blobs) && all(b -> b === nothing || b.blob !== nothing, blobs)
+        # an ill-conditioned factor: substitution sweeps along every mode (scimlop_kron_ldiv), then 1/λ
+        src = dptr(w) == dptr(v) ? copy(v) : v
+        kron_ldiv!(w, Any[b === nothing ? nothing : b.blob for b in blobs], dims[1:2:end], kinds, src)
+        isone(λinv) || CUDA.@sync(w .*= λinv)
+        return w
+    end
     ws = L.cache[1]
     check(ccall((:scimlop_kron_mul, LIB), Cint,
                 (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}, Ptr{Cint}, Ptr{Cvoid}, Int64,
@@ -401,5 +438,21 @@ function col_dot!(out::CuVector{T}, x::CuMatrix{T}, y::CuMatrix{T}) where {T <: 
                 stream_ptr()), "scimlop_col_dot")
     out
 end
+
+# ---- sparse MatrixOperator (test/basic.jl:405-426, test/Downstream/alloccheck.jl:37-45) ---------------------------------
+# CUDA.jl's CuSparseMatrixCSR stores 1-based Int32 rowPtr / colVal; a CuSparseMatrixCSC is the CSR form of the transpose.
+using CUDA.CUSPARSE: CuSparseMatrixCSR, CuSparseMatrixCSC
+function csr_mul!(w::DevMat{T}, rowptr, colval, nzval, rows, cols, trans, v::DevMat{T}, α, β) where {T <: F}
+    check(ccall((:scimlop_csr_mul, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64,
+                 Ptr{Cvoid}, Int64, Ref{T}, Ref{T}, Ptr{Cvoid}),
+                handle(), dtype(T), trans, rows, cols, size(v, 2), dptr(rowptr), dptr(colval), dptr(nzval), 1, dptr(v),
+                stride(v, 2), dptr(w), stride(w, 2), T(α), T(β), stream_ptr()), "scimlop_csr_mul")
+    w
+end
+mul!(w::DevMat{T}, L::MatrixOperator{T, <:CuSparseMatrixCSR{T, Int32}}, v::DevMat{T}, α::Number, β::Number) where {T <: F} =
+    csr_mul!(w, L.A.rowPtr, L.A.colVal, L.A.nzVal, size(L.A, 1), size(L.A, 2), 0, v, α, β)
+mul!(w::DevMat{T}, L::MatrixOperator{T, <:CuSparseMatrixCSC{T, Int32}}, v::DevMat{T}, α::Number, β::Number) where {T <: F} =
+    csr_mul!(w, L.A.colPtr, L.A.rowVal, L.A.nzVal, size(L.A, 2), size(L.A, 1), 1, v, α, β)
 
 end # module
