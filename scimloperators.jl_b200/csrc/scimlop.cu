@@ -1259,13 +1259,21 @@ static int kron_mul_impl_peers(scimlop_context* h, int dtype, int precision, int
       return eltwise_axpby<double>(h, pl.rows, k, nullptr, 0, (double*)W, ldw, 0.0, scalar_or<double>(beta, 0.0), st);
     return eltwise_axpby<float>(h, pl.rows, k, nullptr, 0, (float*)W, ldw, 0.f, scalar_or<float>(beta, 0.f), st);
   }
+  // the fused compute + all-gather entries keep ONE summation order in every stage (their last stage cannot take the
+  // split-K tail launch, so no stage does: results are bit-identical to the SCIMLOP_OPT_TAIL_SPLIT = 0 schedule)
+  const int saved_tail_split = h->tail_split;
+  if (peers.active()) h->tail_split = 0;
+  int rc;
   if (dtype == SCIMLOP_F64)
-    return kron_mul_t<double>(h, precision, nfactors, factors, dims, lds, kinds, (const double*)V, (double*)W, k,
-                              scalar_or<double>(alpha, 1.0), scalar_or<double>(beta, 0.0), workspace, workspace_bytes,
-                              pl, st, peers);
-  return kron_mul_t<float>(h, precision, nfactors, factors, dims, lds, kinds, (const float*)V, (float*)W, k,
+    rc = kron_mul_t<double>(h, precision, nfactors, factors, dims, lds, kinds, (const double*)V, (double*)W, k,
+                            scalar_or<double>(alpha, 1.0), scalar_or<double>(beta, 0.0), workspace, workspace_bytes,
+                            pl, st, peers);
+  else
+    rc = kron_mul_t<float>(h, precision, nfactors, factors, dims, lds, kinds, (const float*)V, (float*)W, k,
                            scalar_or<float>(alpha, 1.f), scalar_or<float>(beta, 0.f), workspace, workspace_bytes, pl,
                            st, peers);
+  h->tail_split = saved_tail_split;
+  return rc;
 }
 
 int scimlop_kron_mul_impl(scimlop_context* h, int dtype, int precision, int nfactors, const void* const* factors,
