@@ -28,8 +28,14 @@
 #include <cstring>
 
 #include "context.h"
+#include "ptx.cuh"
 
 namespace {
+
+using scimlop::cluster_sync_all;
+using scimlop::ld_cluster;
+using scimlop::map_to_rank;
+using scimlop::smem_u32;
 
 constexpr int PB = 32;        // panel width
 constexpr int PROWS = 256;    // panel rows per CTA (one per thread)
@@ -151,12 +157,14 @@ __global__ void __launch_bounds__(PROWS) lu_panel_kernel(long long n, double* __
 #pragma unroll
   for (int c = 0; c < PB; c++) a[c] = (live && c < w) ? A[r + (long long)(j0 + c) * lda] : 0.0;
   unsigned epoch = 0;
-  for (int c = 0; c < w; c++) {
+  // the column loop is fully unrolled: a[c] / pr[c] are then plain registers (a run-time c costs a 32-long select chain
+  // per access: ~1500 instructions per warp and column, measured)
+#pragma unroll
+  for (int c = 0; c < PB; c++) {
+    if (c >= w) break;
     const int par = c & 1;
     // ---- local arg-max of |a(:, c)| over rows >= c (first maximum, like idamax) ----
-    double ac = 0.0;
-#pragma unroll
-    for (int q = 0; q < PB; q++) if (q == c) ac = a[q];
+    const double ac = a[c];
     double best = (live && i >= c) ? fabs(ac) : -1.0;
     if (best != best) best = 1.0e308;                 // NaN: take it as the pivot so that it propagates like LAPACK's
     int bi = i;
@@ -227,13 +235,10 @@ __global__ void __launch_bounds__(PROWS) lu_panel_kernel(long long n, double* __
       }
     }
     // ---- eliminate: l = a(i, c) / pivot, a(i, c+1:) -= l * pivot_row(c+1:) ----
-    double pv = 0.0;
-#pragma unroll
-    for (int q = 0; q < PB; q++) if (q == c) pv = pr[q];
+    const double pv = pr[c];
     if (live && i > c && pv != 0.0) {
-      double l = 0.0;
-#pragma unroll
-      for (int q = 0; q < PB; q++) if (q == c) { l = a[q] / pv; a[q] = l; }
+      const double l = a[c] / pv;
+      a[c] = l;
 #pragma unroll
       for (int q = 0; q < PB; q++) if (q > c) a[q] -= l * pr[q];
     }
@@ -242,6 +247,114 @@ __global__ void __launch_bounds__(PROWS) lu_panel_kernel(long long n, double* __
 #pragma unroll
     for (int c = 0; c < PB; c++) if (c < w) A[r + (long long)(j0 + c) * lda] = a[c];
   }
+}
+
+// The same panel step with the CTAs of ONE thread-block cluster (panels of up to 16 x 256 = 4096 rows): candidates and
+// the diagonal row live in each CTA's shared memory and are read through distributed shared memory after one cluster
+// barrier per column -- ~0.3 us round trips instead of the ~1 us L2 round trips of the grid-barrier form above.
+__global__ void __launch_bounds__(PROWS) lu_panel_cluster_kernel(long long n, double* __restrict__ A, long long lda, int j0, int w,
+                                                                 int* __restrict__ piv, int* info) {
+  __shared__ double slot[2][PB + 2];     // this CTA's candidate row: entries, |value|, row index
+  __shared__ double diag[2][PB];         // the diagonal row (rank 0's copy is the one that is read)
+  __shared__ double prow[PB], drow[PB];
+  __shared__ double sval[PROWS / 32];
+  __shared__ int srow[PROWS / 32];
+  __shared__ int swin, spiv;
+  const int nct = gridDim.x;             // = cluster size
+  const int i = blockIdx.x * PROWS + threadIdx.x;
+  const long long r = (long long)j0 + i;
+  const bool live = r < n;
+  double a[PB];
+#pragma unroll
+  for (int c = 0; c < PB; c++) a[c] = (live && c < w) ? A[r + (long long)(j0 + c) * lda] : 0.0;
+#pragma unroll
+  for (int c = 0; c < PB; c++) {
+    if (c >= w) break;
+    const int par = c & 1;
+    const double ac = a[c];
+    double best = (live && i >= c) ? fabs(ac) : -1.0;
+    if (best != best) best = 1.0e308;
+    int bi = i;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, best, o);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sval[threadIdx.x >> 5] = best; srow[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int q = 1; q < PROWS / 32; q++)
+        if (sval[q] > best || (sval[q] == best && srow[q] < bi)) { best = sval[q]; bi = srow[q]; }
+      swin = bi;
+      slot[par][PB] = best;
+      slot[par][PB + 1] = (double)bi;
+    }
+    __syncthreads();
+    if (i == swin) {
+#pragma unroll
+      for (int q = 0; q < PB; q++) slot[par][q] = a[q];
+    }
+    if (i == c) {
+#pragma unroll
+      for (int q = 0; q < PB; q++) diag[par][q] = a[q];
+    }
+    cluster_sync_all();
+    if (threadIdx.x < 32) {
+      double gb = -1.0;
+      int gi = 0x7fffffff, gw = 0;
+      for (int q = threadIdx.x; q < nct; q += 32) {
+        const double v = ld_cluster<double>(map_to_rank(smem_u32(&slot[par][PB]), (uint32_t)q));
+        const int ri = (int)ld_cluster<double>(map_to_rank(smem_u32(&slot[par][PB + 1]), (uint32_t)q));
+        if (v > gb || (v == gb && ri < gi)) { gb = v; gi = ri; gw = q; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, gb, o);
+        const int oi = __shfl_down_sync(0xffffffffu, gi, o);
+        const int ow = __shfl_down_sync(0xffffffffu, gw, o);
+        if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; gw = ow; }
+      }
+      gw = __shfl_sync(0xffffffffu, gw, 0);
+      gi = __shfl_sync(0xffffffffu, gi, 0);
+      gb = __shfl_sync(0xffffffffu, gb, 0);
+      // lane q fetches entry q of the winner's row and of the diagonal row into local shared memory
+      prow[threadIdx.x] = ld_cluster<double>(map_to_rank(smem_u32(&slot[par][threadIdx.x]), (uint32_t)gw));
+      drow[threadIdx.x] = ld_cluster<double>(map_to_rank(smem_u32(&diag[par][threadIdx.x]), 0u));
+      if (threadIdx.x == 0) {
+        spiv = gi;
+        if (blockIdx.x == 0) {
+          piv[j0 + c] = j0 + gi;
+          if (!(gb > 0.0)) atomicCAS(info, 0, j0 + c + 1);
+        }
+      }
+    }
+    __syncthreads();
+    const int p = spiv;
+    double pr[PB];
+#pragma unroll
+    for (int q = 0; q < PB; q++) pr[q] = prow[q];
+    if (live && p != c) {
+      if (i == c) {
+#pragma unroll
+        for (int q = 0; q < PB; q++) a[q] = pr[q];
+      } else if (i == p) {
+#pragma unroll
+        for (int q = 0; q < PB; q++) a[q] = drow[q];
+      }
+    }
+    const double pv = pr[c];
+    if (live && i > c && pv != 0.0) {
+      const double l = a[c] / pv;
+      a[c] = l;
+#pragma unroll
+      for (int q = 0; q < PB; q++) if (q > c) a[q] -= l * pr[q];
+    }
+    __syncthreads();     // prow / drow are rewritten by warp 0 in the next column
+  }
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < PB; c++) if (c < w) A[r + (long long)(j0 + c) * lda] = a[c];
+  }
+  cluster_sync_all();    // no CTA may exit while a peer can still read its shared memory
 }
 
 // Row swaps of the panel applied to every column outside it, then (columns right of the panel) the w x w unit-lower
@@ -434,6 +547,10 @@ extern "C" int scimlop_factorize(scimlop_handle_t h, int dtype, int64_t n, const
   const Blob f = blob_at(fact, n);
   const Scratch s = scratch_at(scratch, n);
   const long long npan = (n + PB - 1) / PB;
+  // clusters of up to 16 CTAs (non-portable size: opt in; fall back to the grid-barrier panel kernel if refused)
+  static int cluster_fits[17] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+  const bool cluster16_ok = cudaFuncSetAttribute(lu_panel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+  if (!cluster16_ok) cudaGetLastError();
   SCIMLOP_CUDA(h, cudaMemsetAsync(s.bar, 0, (size_t)npan * 4, st));
   SCIMLOP_CUDA(h, cudaMemsetAsync(s.norms, 0, 256, st));
   SCIMLOP_CUDA(h, cudaMemsetAsync(s.info, 0, 256, st));
@@ -444,7 +561,30 @@ extern "C" int scimlop_factorize(scimlop_handle_t h, int dtype, int64_t n, const
   for (long long p = 0; p < npan; p++) {
     const int j0 = (int)(p * PB), w = (int)std::min<long long>(PB, n - j0);
     const unsigned ncta = (unsigned)((n - j0 + PROWS - 1) / PROWS);
-    lu_panel_kernel<<<ncta, PROWS, 0, st>>>(n, f.LU, f.ldf, j0, w, s.piv, s.bar + p, s.slots, s.info);
+    bool clustered = false;
+    if (ncta <= 16 && (ncta <= 8 || cluster16_ok)) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(ncta, 1, 1);
+      cfg.blockDim = dim3(PROWS, 1, 1);
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (cluster_fits[ncta] < 0) {       // once per cluster size: can the device place such a cluster at all?
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, lu_panel_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+        cluster_fits[ncta] = nc > 0 ? 1 : 0;
+      }
+      if (cluster_fits[ncta] == 1) {
+        SCIMLOP_CUDA(h, cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel, (long long)n, f.LU, f.ldf, j0, w, s.piv, s.info));
+        clustered = true;
+      }
+    }
+    if (!clustered) {
+      lu_panel_kernel<<<ncta, PROWS, 0, st>>>(n, f.LU, f.ldf, j0, w, s.piv, s.bar + p, s.slots, s.info);
+    }
     h->launches++;
     if (n - w > 0) {
       lu_swap_trsm_kernel<<<(unsigned)((n - w + ST_THREADS - 1) / ST_THREADS), ST_THREADS, 0, st>>>(n, f.LU, f.ldf, j0, w, s.piv);

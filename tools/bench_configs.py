@@ -75,6 +75,22 @@ def c1(reps):
     for tag, fn in (("3arg", lambda: sb.mul_(W, L, V)), ("5arg", lambda: sb.mul_(W, L, V, 0.7, 0.3))):
         t = timeit(fn, reps)
         report(f"c1 100x100(x)100x100 f64 k=100 {tag}", 4.0e8, 1.616e7 + (8e6 if tag == "5arg" else 0), *t, "f64")
+    # the same mul! as a captured CUDA graph (krylov.CapturedMul: what a solver loop replays): the eager number above is
+    # bound by the host work between two 10-us launches, not by the kernels
+    cm = sb.krylov.CapturedMul(L, W, V)
+    t = timeit(cm.replay, reps)
+    report("c1 100x100(x)100x100 f64 k=100 3arg, CUDA-graph replay", 4.0e8, 1.616e7, *t, "f64")
+    # 20 replays inside ONE graph: per-matvec device time without any launch gap
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(20):
+                sb.mul_(W, L, V)
+    torch.cuda.current_stream().wait_stream(side)
+    t = timeit(g.replay, reps)
+    report("c1 100x100(x)100x100 f64 k=100 3arg, 20 matvecs in one graph (per matvec)", 4.0e8, 1.616e7, t[0] / 20, t[1] / 20, "f64")
 
 
 def c2(reps):
