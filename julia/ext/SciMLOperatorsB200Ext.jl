@@ -445,9 +445,11 @@ using CUDA.CUSPARSE: CuSparseMatrixCSR, CuSparseMatrixCSC
 function csr_mul!(w::DevMat{T}, rowptr, colval, nzval, rows, cols, trans, v::DevMat{T}, α, β) where {T <: F}
     check(ccall((:scimlop_csr_mul, LIB), Cint,
                 (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64,
-                 Ptr{Cvoid}, Int64, Ref{T}, Ref{T}, Ptr{Cvoid}),
+                 Ptr{Cvoid}, Int64, Ref{T}, Ref{T}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
                 handle(), dtype(T), trans, rows, cols, size(v, 2), dptr(rowptr), dptr(colval), dptr(nzval), 1, dptr(v),
-                stride(v, 2), dptr(w), stride(w, 2), T(α), T(β), stream_ptr()), "scimlop_csr_mul")
+                stride(v, 2), dptr(w), stride(w, 2), T(α), T(β), C_NULL, 0, stream_ptr()), "scimlop_csr_mul")
+    # (C_NULL workspace: the direct gather; `cache_operator` may keep a scimlop_csr_workspace_bytes buffer for the
+    #  row-contiguous staging copy of v and pass it here)
     w
 end
 mul!(w::DevMat{T}, L::MatrixOperator{T, <:CuSparseMatrixCSR{T, Int32}}, v::DevMat{T}, α::Number, β::Number) where {T <: F} =

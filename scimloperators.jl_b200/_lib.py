@@ -48,7 +48,8 @@ SIGNATURES = {
     "scimlop_launch_count": [_P, _I64P],
     "scimlop_set_option": [_P, _INT, _INT],
     "scimlop_matmul": [_P, _INT, _INT, _INT, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P],
-    "scimlop_csr_mul": [_P, _INT, _INT, _I64, _I64, _I64, _P, _P, _P, _INT, _P, _I64, _P, _I64, _P, _P, _P],
+    "scimlop_csr_workspace_bytes": [_INT, _INT, _I64, _I64, _I64, C.POINTER(_SZ)],
+    "scimlop_csr_mul": [_P, _INT, _INT, _I64, _I64, _I64, _P, _P, _P, _INT, _P, _I64, _P, _I64, _P, _P, _P, _SZ, _P],
     "scimlop_split_bytes": [_I64, _I64, C.POINTER(_SZ)],
     "scimlop_split_attach": [_P, _P, _I64, _I64, _I64, _P, _SZ, _P],
     "scimlop_split_refresh": [_P, _P, _P],

@@ -378,6 +378,12 @@ class MatrixOperator(AbstractSciMLOperator):
         return self
 
     def cache_operator(self, v):
+        if self.sparse:
+            nbytes = C.c_size_t(0)
+            _lib.load().scimlop_csr_workspace_bytes(_DT[v.dtype], int(self.trans), self.A.shape[0], self.A.shape[1], _ncols(v),
+                                                    C.byref(nbytes))
+            self._csr_ws = torch.empty(nbytes.value, dtype=torch.uint8, device=v.t.device) if nbytes.value else None
+            return self
         return self._attach_split()
 
     def __del__(self):
@@ -411,10 +417,12 @@ class MatrixOperator(AbstractSciMLOperator):
         m, n = self.size()
         if self.sparse:   # general sparse matrix: CSR gather (or, for the lazy adjoint, scatter) kernel
             A = self.A
+            ws = getattr(self, "_csr_ws", None)     # allocated by cache_operator (row-contiguous staging copy of V)
             h.check(h.lib.scimlop_csr_mul(h.ptr, _DT[w.dtype], int(self.trans), A.shape[0], A.shape[1], _ncols(v),
                                           C.c_void_p(A.rowptr.ptr), C.c_void_p(A.colidx.ptr), C.c_void_p(A.values.ptr), 0,
                                           C.c_void_p(v.ptr), v.ld, C.c_void_p(w.ptr), w.ld, _scalar(w.dtype, alpha),
-                                          _scalar(w.dtype, beta), _stream()), "scimlop_csr_mul")
+                                          _scalar(w.dtype, beta), None if ws is None else C.c_void_p(ws.data_ptr()),
+                                          0 if ws is None else ws.numel(), _stream()), "scimlop_csr_mul")
             return w
         if self.banded:   # a one-factor "Kronecker product": the banded mode-product kernel
             nb = self.A.shape[0]

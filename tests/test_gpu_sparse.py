@@ -91,6 +91,30 @@ def test_sparse_operators_in_an_added_tree_with_time_dependent_scalars(sb):
         assert R.rel_err(dw.numpy(), 0.5 * want + 2.0 * w0) <= 1e-12
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_cached_sparse_operator_uses_the_staged_gather(sb, dtype):
+    """cache_operator allocates the row-contiguous staging copy of V (k a multiple of 8): two launches, same numbers."""
+    rng = np.random.default_rng(8)
+    m, n, k = 300, 257, 40
+    A = sprand(rng, m, n, 0.05, dtype)
+    v = np.asfortranarray(rng.standard_normal((n, k)).astype(dtype))
+    dv = sb.DeviceArray.from_numpy(v)
+    L = sb.cache_operator(sb.MatrixOperator(sb.SparseMatrixCSR.from_dense(A)), dv)
+    assert L._csr_ws is not None
+    h = sb.handle(0)
+    w = sb.DeviceArray.full((m, k), float("nan"), dtype)
+    sb.mul_(w, L, dv)
+    n0 = h.launch_count()
+    sb.mul_(w, L, dv)
+    assert h.launch_count() - n0 == 2
+    want = A.astype(np.float64) @ v.astype(np.float64)
+    assert R.rel_err(w.numpy(), want) <= TOL[np.dtype(dtype)]
+    w0 = np.asfortranarray(rng.standard_normal((m, k)).astype(dtype))
+    dw = sb.DeviceArray.from_numpy(w0)
+    sb.mul_(dw, L, dv, -0.5, 2.0)
+    assert R.rel_err(dw.numpy(), -0.5 * want + 2.0 * w0.astype(np.float64)) <= TOL[np.dtype(dtype)]
+
+
 def test_sparse_from_scipy_and_large_batch(sb):
     sp = pytest.importorskip("scipy.sparse")
     rng = np.random.default_rng(5)

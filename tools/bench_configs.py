@@ -259,10 +259,14 @@ def csr(reps, N=65536, K=1024, per_row=16):
     L = sb.MatrixOperator(A)
     V = dev_rand((N, K), np.float64, 1)
     W = sb.DeviceArray.empty((N, K), np.float64)
-    t = timeit(lambda: sb.mul_(W, L, V), reps)
     nnz = N * per_row
-    report(f"csr N={N} nnz/row={per_row} f64 k={K} 3arg", 2.0 * nnz * K, 2.0 * N * K * 8 + nnz * 12.0 * (K / 8), *t, "hbm",
+    t = timeit(lambda: sb.mul_(W, L, V), reps)
+    report(f"csr N={N} nnz/row={per_row} f64 k={K} 3arg, direct gather (uncached)", 2.0 * nnz * K, 2.0 * N * K * 8 + nnz * 12.0 * (K / 8), *t, "hbm",
            {"dense_bytes_only_gbs": 2.0 * N * K * 8 / (t[1] * 1e-3) / 1e9})
+    L = sb.cache_operator(L, V)
+    t = timeit(lambda: sb.mul_(W, L, V), reps)
+    report(f"csr N={N} nnz/row={per_row} f64 k={K} 3arg, cached (row-contiguous staging of V)", 2.0 * nnz * K,
+           4.0 * N * K * 8 + nnz * 12.0 * (K / 8), *t, "hbm", {"dense_bytes_only_gbs": 2.0 * N * K * 8 / (t[1] * 1e-3) / 1e9})
 
 
 ALL = {"c5fd": c5fd, "krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c3pair": c3pair, "csr": csr, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}

@@ -11,7 +11,7 @@ ptrs = (C.c_void_p * 2)(A.ctypes.data, B.ctypes.data); dims = (C.c_int64 * 4)(51
 lds = (C.c_int64 * 2)(512, 512); kinds = (C.c_int32 * 2)(0, 0)
 def call(chunk):
     h.check(h.lib.scimlop_kron_mul_host(h.ptr, 0, 0, 2, ptrs, dims, lds, kinds, C.c_void_p(Vh.data_ptr()), n, C.c_void_p(Wh.data_ptr()), n, k, None, None, chunk), "host")
-for chunk in (2, 4, 8, 16, 32, 64):
+for chunk in (0, 2, 4, 6, 8, 12, 16, 32):
     call(chunk); call(chunk); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(5): call(chunk)
