@@ -108,3 +108,56 @@ def test_column_shards_cover_every_column_once():
             s = sb.ColumnShard(k, world, r)
             seen.extend(range(s.first, s.first + s.count))
         assert seen == list(range(k))
+
+
+def test_sparse_matrix_csr_from_dense_layout():
+    """SparseMatrixCSR.from_dense builds 0-based CSR arrays (rows + 1 pointers, column indices sorted within a row)."""
+    import importlib
+    ops = importlib.import_module("scimlop_b200.operators")
+
+    class FakeDev:      # stands in for DeviceArray on a CPU-only box: keeps the numpy array
+        def __init__(self, a):
+            self.a = np.asarray(a)
+            self.shape = self.a.shape
+            self.ndim = self.a.ndim
+            self.dtype = self.a.dtype
+    orig = ops._as_device
+    ops._as_device = lambda a: FakeDev(a)
+    try:
+        A = np.array([[0.0, 2.0, 0.0], [1.0, 0.0, 3.0], [0.0, 0.0, 0.0], [4.0, 5.0, 6.0]])
+        S = ops.SparseMatrixCSR.from_dense(A)
+        assert S.shape == (4, 3) and S.nnz == 6
+        assert S.rowptr.a.tolist() == [0, 1, 3, 3, 6]
+        assert S.colidx.a.tolist() == [1, 0, 2, 0, 1, 2]
+        assert S.values.a.tolist() == [2.0, 1.0, 3.0, 4.0, 5.0, 6.0]
+        with pytest.raises(ValueError):
+            ops.SparseMatrixCSR(np.zeros(3, dtype=np.int32), np.zeros(2, dtype=np.int32), np.zeros(2), (4, 3))
+    finally:
+        ops._as_device = orig
+
+
+def test_factorisation_and_option_entry_points_are_declared_and_exported():
+    """The round-2 entry points are in the header, the binding table and the library (no GPU needed to resolve them)."""
+    from scimlop_b200 import _lib
+    lib = _lib.load()
+    for name in ("scimlop_factorize", "scimlop_factorize_bytes", "scimlop_kron_ldiv", "scimlop_csr_mul",
+                 "scimlop_csr_workspace_bytes", "scimlop_set_option"):
+        assert name in _lib.SIGNATURES and hasattr(lib, name)
+    import ctypes as C
+    fb, sbytes = C.c_size_t(0), C.c_size_t(0)
+    assert lib.scimlop_factorize_bytes(_lib.F64, 512, C.byref(fb), C.byref(sbytes)) == _lib.OK
+    assert fb.value >= 2 * 512 * 512 * 8 and sbytes.value >= 2 * 512 * 512 * 8
+    assert lib.scimlop_factorize_bytes(_lib.F32, 512, C.byref(fb), C.byref(sbytes)) == _lib.ERR_UNSUPPORTED
+    nb = C.c_size_t(1)
+    assert lib.scimlop_csr_workspace_bytes(_lib.F64, 0, 100, 200, 16, C.byref(nb)) == _lib.OK and nb.value == 200 * 16 * 8
+    assert lib.scimlop_csr_workspace_bytes(_lib.F64, 1, 100, 200, 16, C.byref(nb)) == _lib.OK and nb.value == 0
+    assert lib.scimlop_set_option(None, 1, 0) == _lib.ERR_BAD_HANDLE
+
+
+def test_mixed_eltype_products_report_the_promoted_eltype():
+    rng = np.random.default_rng(8)
+    A32 = DeviceArray.from_numpy(np.asfortranarray(rng.random((3, 3)).astype(np.float32)))
+    B64 = DeviceArray.from_numpy(np.asfortranarray(rng.random((4, 4))))
+    L = sb.TensorProductOperator(sb.MatrixOperator(A32), sb.MatrixOperator(B64))
+    assert L.dtype == np.float64
+    assert (sb.MatrixOperator(A32) + sb.MatrixOperator(A32)).dtype == np.float32
