@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(THREADS, 1)
           // so a parity wait can never be two phases behind.
           const long long n = it * nkb1 + kk;
           const uint32_t stage = (uint32_t)(n % RS), use = (uint32_t)(n / RS);
-          mbar_wait(raw_full + 8 * stage, use & 1);
+          mbar_wait_relaxed(raw_full + 8 * stage, use & 1);
           if (quarter == 0) KF16_STAMP(it, 20 + kk);
           const uint8_t* g = smem_gen + (sX - smem) + stage * XT_BYTES + row * 128;
 #pragma unroll
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
       }
       if (quarter == 0) KF16_STAMP(it, 28 + grp);
-      mbar_wait(x_free, ph ^ 1);
+      mbar_wait_relaxed(x_free, ph ^ 1);
       if (quarter == 0) KF16_STAMP(it, 32 + grp);
       // row b of panel g: 8 chunks of 8 k, chunk j at (j ^ (b & 7)) * 16
 #pragma unroll
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     const uint32_t tl0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + TM_ACC1;
     for (long long it = 0; it < nmine; it++) {
       const uint32_t tl = tl0 + (uint32_t)(it & 1) * 128;
-      mbar_wait(acc1_full + 8 * (uint32_t)(it & 1), (uint32_t)((it >> 1) & 1));
+      mbar_wait_relaxed(acc1_full + 8 * (uint32_t)(it & 1), (uint32_t)((it >> 1) & 1));
       if (quarter == 0) KF16_STAMP(it, 40);
       tc_fence_after();
       // columns b = 32 blk .. 32 blk + 31 (FP32)  ->  16 columns of hi pairs, 16 columns of lo pairs, same 32 columns
