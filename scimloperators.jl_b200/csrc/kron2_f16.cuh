@@ -404,6 +404,9 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       uint32_t hi[32], lo[32];
       if (BF16) {
+        // no slab scale to agree on, but the two groups still meet here once per slab: ring stages are served by both
+        // groups in turn, and a parity wait is only safe while they stay within one slab of each other
+        bar_sync_named(1, 256);
 #pragma unroll
         for (int q = 0; q < 32; q++) { hi[q] = pack_bf16(x[2 * q], x[2 * q + 1]); lo[q] = 0u; }
       } else {

@@ -235,3 +235,28 @@ def test_bf16_opt_in_mode(sb):
     L3.precision = 4
     e = err_vs_oracle((L3 * dv3).numpy(), F, v3)
     assert e <= 1e-2, f"3-factor BF16 mode: {e:.3e}"
+
+
+def test_bf16_mode_many_slabs_per_cta(sb):
+    """The BF16 mode on a batch large enough for every CTA to run dozens of slabs (the splitter groups share the raw ring:
+    they must stay within one slab of each other in this mode too)."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(3)
+    k = 148 * 24
+    F = [sb.DeviceArray(torch.rand(128 * 128, dtype=torch.float32, device="cuda", generator=g) - 0.5, (128, 128)) for _ in range(2)]
+    V = sb.DeviceArray(torch.rand(128 * 128 * k, dtype=torch.float32, device="cuda", generator=g) - 0.5, (128 * 128, k))
+    L = sb.cache_operator(sb.TensorProductOperator(*[sb.MatrixOperator(f) for f in F]), V)
+    L.precision = 4
+    W = sb.DeviceArray.full((128 * 128, k), float("nan"), np.float32)
+    for _ in range(3):
+        sb.mul_(W, L, V)
+    torch.cuda.synchronize()
+    assert torch.isfinite(W.t).all()
+    for j in (0, k // 2, k - 1):
+        want = R.kron_apply([f.numpy().astype(np.float64) for f in F], V.cols(j, j + 1).numpy().astype(np.float64))
+        assert R.rel_err(W.cols(j, j + 1).numpy(), want) <= 2e-2
+    L.precision = 0
+    sb.mul_(W, L, V)
+    for j in (1, k - 2):
+        want = R.kron_apply([f.numpy().astype(np.float64) for f in F], V.cols(j, j + 1).numpy().astype(np.float64))
+        assert R.rel_err(W.cols(j, j + 1).numpy(), want) <= 1e-5

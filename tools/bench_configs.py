@@ -159,7 +159,7 @@ def c4elt(reps):
     report("IdentityOperator 5-arg (axpby)", 2.0 * N * K, 3.0 * nb, *t, "hbm")
 
 
-def c4dense(reps, N=32768, K=1024):
+def c4dense(reps, N=65536, K=1024):   # configs[3] at its named size: the matrix is 34 GB
     Mm = dev_rand((N, N), np.float64, 6)
     d = dev_rand((N,), np.float64, 3)
     V, W = dev_rand((N, K), np.float64, 1), dev_rand((N, K), np.float64, 2)
@@ -269,7 +269,19 @@ def csr(reps, N=65536, K=1024, per_row=16):
            4.0 * N * K * 8 + nnz * 12.0 * (K / 8), *t, "hbm", {"dense_bytes_only_gbs": 2.0 * N * K * 8 / (t[1] * 1e-3) / 1e9})
 
 
-ALL = {"c5fd": c5fd, "krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c3pair": c3pair, "csr": csr, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
+def c3bf16(reps, k=32768):
+    """The opt-in BF16 single-pass mode of the fused two-mode kernel (SCIMLOP_PREC_BF16)."""
+    F = [dev_rand((128, 128), np.float32, s) for s in (0, 10)]
+    n = 128 ** 2
+    V = dev_rand((n, k), np.float32, 1)
+    W = sb.DeviceArray.empty((n, k), np.float32)
+    L = sb.cache_operator(sb.TensorProductOperator(*[sb.MatrixOperator(f) for f in F]), V)
+    L.precision = 4
+    t = timeit(lambda: sb.mul_(W, L, V), max(2, reps // 3), warm=1)
+    report(f"c3pair 128^2 two-factor f32 k={k} 3arg, SCIMLOP_PREC_BF16 (opt-in)", 2 * 2 * 128.0 * n * k, 2.0 * n * k * 4, *t, "hbm")
+
+
+ALL = {"c3bf16": c3bf16, "c5fd": c5fd, "krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c3pair": c3pair, "csr": csr, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
