@@ -457,4 +457,26 @@ mul!(w::DevMat{T}, L::MatrixOperator{T, <:CuSparseMatrixCSR{T, Int32}}, v::DevMa
 mul!(w::DevMat{T}, L::MatrixOperator{T, <:CuSparseMatrixCSC{T, Int32}}, v::DevMat{T}, α::Number, β::Number) where {T <: F} =
     csr_mul!(w, L.A.colPtr, L.A.rowVal, L.A.nzVal, size(L.A, 2), size(L.A, 1), 1, v, α, β)
 
+# ---- ComplexF32 / ComplexF64 (test/basic.jl:405-426, alloccheck.jl:37): dtype codes 2 / 3, interleaved storage as is ----
+# A complex MatrixOperator mul! is the one-factor case of scimlop_kron_mul's complex planner; the workspace
+# (scimlop_kron_workspace_bytes with the complex dtype) belongs in the operator's cache.
+const CF = Union{ComplexF32, ComplexF64}
+cdtype(::Type{ComplexF32}) = Cint(2)
+cdtype(::Type{ComplexF64}) = Cint(3)
+function mul!(w::DevMat{T}, L::MatrixOperator{T, <:DenseDev{T}}, v::DevMat{T}, α::Number, β::Number) where {T <: CF}
+    A, trans = _stored(L.A)
+    dims = Int64[size(L, 1), size(L, 2)]; lds = Int64[stride(A, 2)]; kinds = Cint[DENSE | (trans == 1 ? TRANS : 0)]
+    ptrs = Ptr{Cvoid}[dptr(A)]
+    nbytes = Ref{Csize_t}(0)
+    ccall((:scimlop_kron_workspace_bytes, LIB), Cint, (Cint, Cint, Ptr{Int64}, Ptr{Cint}, Int64, Ref{Csize_t}),
+          cdtype(T), 1, dims, kinds, size(v, 2), nbytes)
+    ws = CUDA.zeros(UInt8, nbytes[])
+    check(ccall((:scimlop_kron_mul, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}, Ptr{Cint}, Ptr{Cvoid}, Int64,
+                 Ptr{Cvoid}, Int64, Int64, Ref{T}, Ref{T}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                handle(), cdtype(T), 0, 1, ptrs, dims, lds, kinds, dptr(v), size(v, 1), dptr(w), size(w, 1), size(v, 2),
+                T(α), T(β), dptr(ws), sizeof(ws), stream_ptr()), "scimlop_kron_mul")
+    w
+end
+
 end # module

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libscimlop_b200.so")
 OK = 0
 (ERR_NULL_POINTER, ERR_BAD_SHAPE, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_BAD_HANDLE, ERR_NO_DEVICE,
  ERR_SINGULAR) = range(1, 10)
-F64, F32 = 0, 1
+F64, F32, C64, C128 = 0, 1, 2, 3
 PREC_DEFAULT, PREC_TF32X3, PREC_TF32, PREC_FP32_EXACT, PREC_BF16 = 0, 1, 2, 3, 4
 DENSE, IDENTITY, DIAG, BDIAG, NULL, BANDED = 0, 1, 2, 3, 4, 5
 TRANS = 0x100

@@ -10,7 +10,8 @@ import numpy as np
 import torch
 
 _TORCH = {np.dtype("float64"): torch.float64, np.dtype("float32"): torch.float32,
-          np.dtype("int32"): torch.int32}   # int32: index arrays of sparse operators only
+          np.dtype("int32"): torch.int32,   # int32: index arrays of sparse operators only
+          np.dtype("complex64"): torch.complex64, np.dtype("complex128"): torch.complex128}   # interleaved, as Julia stores them
 
 
 class DeviceArray:
@@ -28,7 +29,7 @@ class DeviceArray:
     def from_numpy(a, device=None) -> "DeviceArray":
         a = np.asarray(a)
         if a.dtype not in _TORCH:
-            raise TypeError(f"unsupported dtype {a.dtype}: the B200 backend takes Float64 / Float32")
+            raise TypeError(f"unsupported dtype {a.dtype}: the B200 backend takes Float64 / Float32 / ComplexF64 / ComplexF32")
         flat = np.ascontiguousarray(a.reshape(-1, order="F"))
         dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         return DeviceArray(torch.from_numpy(flat).to(dev), a.shape)
@@ -73,7 +74,8 @@ class DeviceArray:
 
     @property
     def dtype(self):
-        return {torch.float64: np.dtype("float64"), torch.float32: np.dtype("float32"), torch.int32: np.dtype("int32")}[self.t.dtype]
+        return {torch.float64: np.dtype("float64"), torch.float32: np.dtype("float32"), torch.int32: np.dtype("int32"),
+                torch.complex64: np.dtype("complex64"), torch.complex128: np.dtype("complex128")}[self.t.dtype]
 
     @property
     def ptr(self) -> int:

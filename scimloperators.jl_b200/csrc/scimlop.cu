@@ -1219,11 +1219,129 @@ int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* cons
   return SCIMLOP_OK;
 }
 
+
+// ---- complex element types (ComplexF32 / ComplexF64: test/basic.jl:405-426, test/Downstream/alloccheck.jl:37) ---------------
+// Julia's Complex arrays interleave (re, im).  A complex mode product is four real GEMMs on PLANAR data
+//     Yr = op(Fr) Xr - s op(Fi) Xi,   Yi = s op(Fi) Xr + op(Fr) Xi          (s = -1 for the lazy adjoint F^H)
+// -- exactly the 8 m n k real flops of a complex product -- so the planner de-interleaves V once, runs every mode of the
+// Kronecker product as 4 tensor-core GEMMs between two planar ping-pong buffers (the same strided-batched shapes as the
+// real path: no permutedims), and re-interleaves into W with the complex alpha / beta applied in that last pass.
+template <typename T>
+__global__ void cplx_split_kernel(long long rows, long long cols, const T* __restrict__ Z, long long ldz, T* __restrict__ re,
+                                  T* __restrict__ im) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i % rows, c = i / rows;
+    const T* z = Z + 2 * (r + c * ldz);
+    re[i] = z[0];
+    im[i] = z[1];
+  }
+}
+template <typename T>
+__global__ void cplx_merge_kernel(long long rows, long long cols, const T* __restrict__ re, const T* __restrict__ im, T* W,
+                                  long long ldw, T ar, T ai, T br, T bi, int readw) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i % rows, c = i / rows;
+    T* w = W + 2 * (r + c * ldw);
+    const T yr = re[i], yi = im[i];
+    T outr = ar * yr - ai * yi, outi = ar * yi + ai * yr;
+    if (readw) {
+      const T wr = w[0], wi = w[1];
+      outr += br * wr - bi * wi;
+      outi += br * wi + bi * wr;
+    }
+    w[0] = outr;
+    w[1] = outi;
+  }
+}
+
+struct CplxLayout {
+  size_t plane;            // bytes of one plane of one ping-pong buffer
+  size_t fac_off[MAX_KRON_FACTORS];
+  size_t total;
+};
+inline CplxLayout cplx_layout(int nfactors, const int64_t* dims, const int32_t* kinds, long long k, const KronPlan& pl, size_t es) {
+  CplxLayout L;
+  long long maxe = std::max(pl.rows, pl.cols) * k;
+  maxe = std::max(maxe, pl.max_inter);
+  L.plane = align_up((size_t)maxe * es, 256);
+  size_t off = 4 * L.plane;                                 // two buffers x (re, im)
+  for (int f = 0; f < nfactors; f++) {
+    L.fac_off[f] = off;
+    if (kinds[f] != SCIMLOP_IDENTITY) off += 2 * align_up((size_t)dims[2 * f] * (size_t)dims[2 * f + 1] * es, 256);
+  }
+  L.total = off;
+  return L;
+}
+
+template <typename T>
+int kron_mul_complex_t(scimlop_context* c, int precision, int nfactors, const void* const* factors, const int64_t* dims,
+                       const int64_t* lds, const int32_t* kinds, const T* V, long long ldv, T* W, long long ldw, long long k,
+                       const T* alpha, const T* beta, void* workspace, size_t ws_bytes, const KronPlan& pl, cudaStream_t st) {
+  for (int f = 0; f < nfactors; f++)
+    if (kinds[f] != SCIMLOP_IDENTITY && (kinds[f] & ~SCIMLOP_TRANS) != SCIMLOP_DENSE)
+      return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "kron (complex): factor %d: only dense and identity factors", f);
+  const CplxLayout lay = cplx_layout(nfactors, dims, kinds, k, pl, sizeof(T));
+  if (!workspace || ws_bytes < lay.total)
+    return scimlop_fail(c, SCIMLOP_ERR_WORKSPACE, "kron (complex): workspace %zu B < required %zu B", ws_bytes, lay.total);
+  char* base = static_cast<char*>(workspace);
+  T* buf[2][2] = {{reinterpret_cast<T*>(base), reinterpret_cast<T*>(base + lay.plane)},
+                  {reinterpret_cast<T*>(base + 2 * lay.plane), reinterpret_cast<T*>(base + 3 * lay.plane)}};
+  auto grid_of = [&](long long total) {
+    return (unsigned)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16));
+  };
+  const T ar = alpha ? alpha[0] : T(1), ai = alpha ? alpha[1] : T(0), br = beta ? beta[0] : T(0), bi = beta ? beta[1] : T(0);
+  const int readw = (br != T(0) || bi != T(0)) ? 1 : 0;
+  // V -> planar
+  cplx_split_kernel<T><<<grid_of(pl.cols * k), 256, 0, st>>>(pl.cols, k, V, ldv, buf[0][0], buf[0][1]);
+  c->launches++;
+  int cur = 0;
+  long long L = 1;
+  for (int p = nfactors - 1; p >= 0; p--) {
+    const long long m = dims[2 * p], n = dims[2 * p + 1];
+    if (kinds[p] == SCIMLOP_IDENTITY) { L *= m; continue; }
+    long long R = k;
+    for (int q = 0; q < p; q++) R *= dims[2 * q + 1];
+    const bool tr = (kinds[p] & SCIMLOP_TRANS) != 0;
+    const long long srows = tr ? n : m, scols = tr ? m : n;          // stored shape
+    T* Fr = reinterpret_cast<T*>(base + lay.fac_off[p]);
+    T* Fi = reinterpret_cast<T*>(base + lay.fac_off[p] + align_up((size_t)m * (size_t)n * sizeof(T), 256));
+    cplx_split_kernel<T><<<grid_of(srows * scols), 256, 0, st>>>(srows, scols, static_cast<const T*>(factors[p]), lds[p], Fr, Fi);
+    c->launches++;
+    const T sgn = tr ? T(-1) : T(1);                                  // lazy adjoint: conjugate transpose
+    const T *Xr = buf[cur][0], *Xi = buf[cur][1];
+    T *Yr = buf[cur ^ 1][0], *Yi = buf[cur ^ 1][1];
+    auto gemm = [&](const T* F, const T* X, T* Y, T a, T b) -> int {
+      if (L == 1)   // innermost applied mode: Y(m x R) = op(F)(m x n) X(n x R)
+        return gemm_dispatch<T>(c, precision, tr, false, m, R, n, a, F, srows, 0, X, n, 0, b, Y, m, 0, 1, 0, nullptr, st, NO_PEERS);
+      return gemm_dispatch<T>(c, precision, false, !tr, L, m, n, a, X, L, L * n, F, srows, 0, b, Y, L, L * m, R, 0, nullptr, st, NO_PEERS);
+    };
+    int rc = gemm(Fr, Xr, Yr, T(1), T(0));
+    if (!rc) rc = gemm(Fi, Xi, Yr, -sgn, T(1));
+    if (!rc) rc = gemm(Fi, Xr, Yi, sgn, T(0));
+    if (!rc) rc = gemm(Fr, Xi, Yi, T(1), T(1));
+    if (rc) return rc;
+    cur ^= 1;
+    L *= m;
+  }
+  cplx_merge_kernel<T><<<grid_of(pl.rows * k), 256, 0, st>>>(pl.rows, k, buf[cur][0], buf[cur][1], W, ldw, ar, ai, br, bi, readw);
+  c->launches++;
+  SCIMLOP_CUDA(c, cudaGetLastError());
+  return SCIMLOP_OK;
+}
+
 }  // namespace
 
 extern "C" int scimlop_kron_workspace_bytes(int dtype, int nfactors, const int64_t* dims, const int32_t* kinds,
                                             int64_t k, size_t* bytes) {
   if (!bytes) return SCIMLOP_ERR_NULL_POINTER;
+  if (dtype == SCIMLOP_C64 || dtype == SCIMLOP_C128) {
+    KronPlan plc;
+    if (int rc = kron_plan(nullptr, nfactors, dims, kinds, k, &plc)) return rc;
+    *bytes = cplx_layout(nfactors, dims, kinds, k, plc, dtype == SCIMLOP_C128 ? 8 : 4).total;
+    return SCIMLOP_OK;
+  }
   if (dtype != SCIMLOP_F64 && dtype != SCIMLOP_F32) return SCIMLOP_ERR_UNSUPPORTED;
   KronPlan pl;
   if (int rc = kron_plan(nullptr, nfactors, dims, kinds, k, &pl)) return rc;
@@ -1236,7 +1354,10 @@ static int kron_mul_impl_peers(scimlop_context* h, int dtype, int precision, int
                                const int64_t* dims, const int64_t* lds, const int32_t* kinds, const void* V, int64_t ldv,
                                void* W, int64_t ldw, int64_t k, const void* alpha, const void* beta, void* workspace,
                                size_t workspace_bytes, cudaStream_t st, const PeerArg& peers) {
-  if (int rc = check_dtype(h, dtype)) return rc;
+  const bool is_complex = dtype == SCIMLOP_C64 || dtype == SCIMLOP_C128;
+  if (!is_complex)
+    if (int rc = check_dtype(h, dtype)) return rc;
+  if (is_complex && peers.active()) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "peer targets: real element types only");
   KronPlan pl;
   if (int rc = kron_plan(h, nfactors, dims, kinds, k, &pl)) return rc;
   if (!factors || !lds) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron: factors/lds null");
@@ -1254,6 +1375,15 @@ static int kron_mul_impl_peers(scimlop_context* h, int dtype, int precision, int
     return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE,
                         "kron: V and W must be contiguous (ldv=%lld, cols=%lld; ldw=%lld, rows=%lld)", (long long)ldv,
                         pl.cols, (long long)ldw, pl.rows);
+  if (is_complex) {
+    if (pl.cols == 0) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "kron (complex): empty contraction");
+    if (dtype == SCIMLOP_C128)
+      return kron_mul_complex_t<double>(h, SCIMLOP_PREC_DEFAULT, nfactors, factors, dims, lds, kinds, (const double*)V, ldv,
+                                        (double*)W, ldw, k, (const double*)alpha, (const double*)beta, workspace,
+                                        workspace_bytes, pl, st);
+    return kron_mul_complex_t<float>(h, precision, nfactors, factors, dims, lds, kinds, (const float*)V, ldv, (float*)W, ldw, k,
+                                     (const float*)alpha, (const float*)beta, workspace, workspace_bytes, pl, st);
+  }
   if (pl.cols == 0) {  // empty contraction: W = beta * W
     if (dtype == SCIMLOP_F64)
       return eltwise_axpby<double>(h, pl.rows, k, nullptr, 0, (double*)W, ldw, 0.0, scalar_or<double>(beta, 0.0), st);

@@ -39,8 +39,22 @@ import torch
 from . import _lib
 from .array import DeviceArray
 
-_DT = {np.dtype("float64"): _lib.F64, np.dtype("float32"): _lib.F32}
-_CT = {np.dtype("float64"): C.c_double, np.dtype("float32"): C.c_float}
+_DT = {np.dtype("float64"): _lib.F64, np.dtype("float32"): _lib.F32,
+       np.dtype("complex64"): _lib.C64, np.dtype("complex128"): _lib.C128}
+_CT = {np.dtype("float64"): C.c_double, np.dtype("float32"): C.c_float,
+       np.dtype("complex64"): C.c_float, np.dtype("complex128"): C.c_double}
+
+
+def _is_complex(dtype):
+    return dtype is not None and np.dtype(dtype).kind == "c"
+
+
+def _num(x):
+    """A host scalar as Python float, or complex when it has an imaginary part (complex operators / λ = -1im)."""
+    if isinstance(x, complex) or (hasattr(x, "imag") and not isinstance(x, (int, float)) and np.iscomplexobj(x)):
+        x = complex(x)
+        return x if x.imag != 0.0 else x.real
+    return float(x)
 
 
 def _stream():
@@ -51,6 +65,9 @@ def _scalar(dtype, x):
     """Host scalar in the operand dtype, by reference (the ABI takes α/β as host pointers). None -> NULL."""
     if x is None:
         return None
+    if _is_complex(dtype):            # (re, im) pair in the real base type
+        z = complex(x)
+        return (_CT[np.dtype(dtype)] * 2)(z.real, z.imag)
     return C.byref(_CT[np.dtype(dtype)](float(x)))
 
 
@@ -298,12 +315,15 @@ class AbstractSciMLOperator:
 
 
 def _beta_is_zero(beta):
-    return beta is None or beta is False or float(beta) == 0.0
+    return beta is None or beta is False or beta == 0
 
 
 def _lmul(w, beta, h):
     """lmul!(β, w) with a strong zero (src/basic.jl:251,263) -> scimlop_axpby with V == NULL."""
     n, k = w.shape[0], _ncols(w)
+    if _is_complex(w.dtype):
+        w.t.mul_(0 if _beta_is_zero(beta) else complex(beta))    # complex arrays: torch is the allocator AND this scale
+        return w
     b = 0.0 if _beta_is_zero(beta) else float(beta)
     h.check(h.lib.scimlop_axpby(h.ptr, _DT[w.dtype], n, k, None, 0, C.c_void_p(w.ptr), w.ld, None,
                                 _scalar(w.dtype, b), _stream()), "scimlop_axpby")
@@ -415,6 +435,23 @@ class MatrixOperator(AbstractSciMLOperator):
         _check_vw(self, w, v)
         h = _lib.handle(w.device_index)
         m, n = self.size()
+        if _is_complex(w.dtype):   # ComplexF32 / ComplexF64: the one-factor case of the complex Kronecker planner
+            if self.banded or self.sparse:
+                raise NotImplementedError("complex banded / sparse MatrixOperator is outside the B200 backend")
+            k = _ncols(v)
+            sm, sn = self.A.shape
+            dims, lds = (C.c_int64 * 2)(m, n), (C.c_int64 * 1)(self.A.ld)
+            kinds = (C.c_int32 * 1)(_lib.DENSE | (_lib.TRANS if self.trans else 0))
+            ptrs = (C.c_void_p * 1)(self.A.ptr)
+            nbytes = C.c_size_t(0)
+            h.check(h.lib.scimlop_kron_workspace_bytes(_DT[w.dtype], 1, dims, kinds, k, C.byref(nbytes)), "scimlop_kron_workspace_bytes")
+            ws = getattr(self, "_cplx_ws", None)
+            if ws is None or ws.numel() < nbytes.value:
+                ws = self._cplx_ws = torch.empty(max(1, nbytes.value), dtype=torch.uint8, device=w.t.device)
+            h.check(h.lib.scimlop_kron_mul(h.ptr, _DT[w.dtype], self.precision, 1, ptrs, dims, lds, kinds, C.c_void_p(v.ptr), n,
+                                           C.c_void_p(w.ptr), m, k, _scalar(w.dtype, alpha), _scalar(w.dtype, beta),
+                                           C.c_void_p(ws.data_ptr()), ws.numel(), _stream()), "scimlop_kron_mul")
+            return w
         if self.sparse:   # general sparse matrix: CSR gather (or, for the lazy adjoint, scatter) kernel
             A = self.A
             ws = getattr(self, "_csr_ws", None)     # allocated by cache_operator (row-contiguous staging copy of V)
@@ -709,7 +746,7 @@ class _TreeMixin:
     _plan = None
 
     def _try_plan(self, v):
-        terms = _terms_with_scalars(self)
+        terms = None if _is_complex(v.dtype) or _is_complex(self.dtype) else _terms_with_scalars(self)
         if terms is None:
             self._plan = None
             return False
@@ -1231,7 +1268,7 @@ class ScaledOperator(_TreeMixin, AbstractSciMLOperator):
         lam = self.lam.convert()
         if lam == 0:
             return _lmul(w, beta, _lib.handle(w.device_index))
-        a = lam if alpha is None else lam * float(alpha)
+        a = lam if alpha is None else lam * _num(alpha)
         return self.L.mul_(w, v, a, False if beta is None else beta)
 
 
@@ -1419,7 +1456,8 @@ def _promote_leaf(op, dtype):
     leaves keep the error: their copy would go stale."""
     if op.dtype is None or op.dtype == dtype:
         return op
-    tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    tdt = {np.dtype("float64"): torch.float64, np.dtype("float32"): torch.float32, np.dtype("complex64"): torch.complex64,
+           np.dtype("complex128"): torch.complex128}[np.dtype(dtype)]
     if isinstance(op, MatrixOperator) and not (op.banded or op.sparse) and op.update_func is None:
         return MatrixOperator(DeviceArray(op.A.t.to(tdt), op.A.shape), op.trans)
     if isinstance(op, _VectorDiagonalOperator) and op.update_func is None:
@@ -1635,7 +1673,7 @@ class TensorProductOperator(AbstractSciMLOperator):
             nat = self._native
             a = alpha
             for s in nat["scalars"]:  # ScaledOperator factors fold into α (the intended src/tensor.jl:800-804)
-                a = s.convert() * (1.0 if a is None else float(a))
+                a = s.convert() * (1.0 if a is None else _num(a))
             m, n = self.size()
             h.check(h.lib.scimlop_kron_mul(h.ptr, _DT[w.dtype], self.precision, nat["nf"], nat["ptrs"], nat["dims"],
                                            nat["lds"], nat["kinds"], C.c_void_p(v.ptr), n, C.c_void_p(w.ptr), m, k,
@@ -1660,7 +1698,7 @@ class TensorProductOperator(AbstractSciMLOperator):
         if not isinstance(outer, MatrixOperator) or outer.banded or outer.sparse:
             raise NotImplementedError(f"outer factor {type(outer).__name__} is not supported by the B200 backend "
                                       "(the Julia wrapper keeps the generic path for it)")
-        a = alpha if lam == 1.0 else lam * (1.0 if alpha is None else float(alpha))
+        a = alpha if lam == 1.0 else lam * (1.0 if alpha is None else _num(alpha))
         if outer.trans:
             # W_j = C1_j * op(A)^T with op(A) = A^T  ->  plain (non-transposed B) batched GEMM
             h.check(h.lib.scimlop_gemm_strided_batched(

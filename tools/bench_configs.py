@@ -281,7 +281,23 @@ def c3bf16(reps, k=32768):
     report(f"c3pair 128^2 two-factor f32 k={k} 3arg, SCIMLOP_PREC_BF16 (opt-in)", 2 * 2 * 128.0 * n * k, 2.0 * n * k * 4, *t, "hbm")
 
 
-ALL = {"c3bf16": c3bf16, "c5fd": c5fd, "krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c3pair": c3pair, "csr": csr, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
+def c2c(reps, k=128):
+    """Complex variant of config 2: 512 x 512 (x) 512 x 512 ComplexF64 on 262144 x 128 (same bytes as the Float64 config):
+    4 planar real DMMA GEMMs per mode between a de-interleave and an interleave pass."""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    def crand(shape):
+        n = int(np.prod(shape))
+        t = torch.complex(torch.rand(n, dtype=torch.float64, device="cuda", generator=g) - 0.5,
+                          torch.rand(n, dtype=torch.float64, device="cuda", generator=g) - 0.5)
+        return sb.DeviceArray(t, shape)
+    A, B = crand((512, 512)), crand((512, 512))
+    V, W = crand((512 * 512, k)), crand((512 * 512, k))
+    L = sb.cache_operator(sb.kron(sb.MatrixOperator(A), sb.MatrixOperator(B)), V)
+    t = timeit(lambda: sb.mul_(W, L, V), reps)
+    report(f"c2 complex: 512x512(x)512x512 ComplexF64 k={k} 3arg", 4 * 1.374e11 * k / 256, 2 * 512.0 * 512 * k * 16, *t, "f64")
+
+
+ALL = {"c2c": c2c, "c3bf16": c3bf16, "c5fd": c5fd, "krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c3pair": c3pair, "csr": csr, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
