@@ -22,6 +22,7 @@
 #include "gemm_skinny.cuh"
 #include "gemm_tf32.cuh"
 #include "kron2_f16.cuh"
+#include "kron2_f64_small.cuh"
 
 using namespace scimlop;
 
@@ -535,6 +536,31 @@ int launch_kron2_f16(scimlop_context* c, int m1, int n1, int m2, int n2, long lo
   return SCIMLOP_OK;
 }
 
+// ---- two fused Kronecker mode products, Float64, small problems (kron2_f64_small.cuh) -----------------------------------
+// Taken when the slab count is too small to fill the persistent 128 x 128-tile GEMM (fewer than two waves of tiles):
+// config 1, vector-like batches of small-factor products.
+bool kron2_f64_small_eligible(const scimlop_context* c, long long m1, long long n1, long long m2, long long n2, long long slabs) {
+  if (m1 > k2s::MAXD || n1 > k2s::MAXD || m2 > k2s::MAXD || n2 > k2s::MAXD) return false;
+  if (m1 < 8 || n1 < 8 || m2 < 8 || n2 < 8) return false;
+  return slabs >= 1 && slabs <= 2ll * c->sm_count;
+}
+int launch_kron2_f64_small(scimlop_context* c, int m1, int n1, int m2, int n2, long long slabs, const double* F1, long long ld1,
+                           bool tr1, const double* F2, long long ld2, bool tr2, const double* X, double* D, double alpha,
+                           double beta, cudaStream_t st) {
+  k2s::Params p;
+  memset(&p, 0, sizeof(p));
+  p.n1 = n1; p.n2 = n2; p.m1 = m1; p.m2 = m2; p.slabs = slabs;
+  p.F1 = F1; p.f1_rs = tr1 ? ld1 : 1; p.f1_cs = tr1 ? 1 : ld1;
+  p.F2 = F2; p.f2_rs = tr2 ? ld2 : 1; p.f2_cs = tr2 ? 1 : ld2;
+  p.V = X; p.W = D; p.alpha = alpha; p.beta = beta;
+  const size_t smem = k2s::smem_bytes(n1, n2, m1, m2);
+  const int grid = (int)std::min<long long>(slabs, c->sm_count);
+  k2s::kron2_f64_small_kernel<<<grid, k2s::THREADS, smem, st>>>(p);
+  c->launches++;
+  SCIMLOP_CUDA(c, cudaGetLastError());
+  return SCIMLOP_OK;
+}
+
 // ---- hi / lo images of Float32 operands (3xTF32 split) ---------------------------------------------------------
 inline long long split_ld(long long rows) { return (rows + 3) / 4 * 4; }
 inline size_t split_image_bytes(long long rows, long long cols) { return 2 * (size_t)split_ld(rows) * (size_t)cols * sizeof(float); }
@@ -811,6 +837,8 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   auto optin2 = [&](const void* f) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, tf32::SMEM_BYTES);
   };
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)k2s::kron2_f64_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)k2s::smem_bytes(k2s::MAXD, k2s::MAXD, k2s::MAXD, k2s::MAXD));
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)kf16::kron2_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kf16::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)kf16::kron2_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kf16::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)kf16::kron2_f16_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kf16::SMEM_BYTES);
@@ -1174,6 +1202,28 @@ int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* cons
           rc = launch_kron2_f16(c, (int)m, (int)n, (int)m2, (int)n2, slabs, static_cast<const float*>(factors[p]), lds[p], tr,
                                 static_cast<const float*>(factors[p - 1]), lds[p - 1], (kinds[p - 1] & SCIMLOP_TRANS) != 0, cur,
                                 out2, last2 ? alpha : 1.f, last2 ? beta : 0.f, precision == SCIMLOP_PREC_BF16, st);
+          if (rc) return rc;
+          done++;
+          cur = out2;
+          flip ^= 1;
+          L = m * m2;
+          p--;
+          continue;
+        }
+      }
+    }
+    if constexpr (std::is_same<T, double>::value) {
+      // small problem, two small dense factors: one launch, intermediate in shared memory
+      if (L == 1 && p >= 1 && (kinds[p] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE && (kinds[p - 1] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE &&
+          !g_peers.active()) {
+        const long long m2 = dims[2 * (p - 1)], n2 = dims[2 * (p - 1) + 1];
+        const long long slabs = n2 > 0 ? R / n2 : 0;
+        if (kron2_f64_small_eligible(c, m, n, m2, n2, slabs)) {
+          const bool last2 = (done + 1 == pl.nops);
+          double* out2 = last2 ? W : bufs[flip];
+          rc = launch_kron2_f64_small(c, (int)m, (int)n, (int)m2, (int)n2, slabs, static_cast<const double*>(factors[p]), lds[p], tr,
+                                      static_cast<const double*>(factors[p - 1]), lds[p - 1], (kinds[p - 1] & SCIMLOP_TRANS) != 0,
+                                      cur, out2, last2 ? alpha : 1.0, last2 ? beta : 0.0, st);
           if (rc) return rc;
           done++;
           cur = out2;

@@ -1253,3 +1253,30 @@ def test_copy_shares_no_storage_and_stays_cached(sb):
     assert np.abs((L * dv).numpy()).max() == 0.0
     Tc = sb.copy(sb.cache_operator(sb.MatrixOperator(A) + sb.DiagonalOperator(rnd(rng, 5)), dev(sb, rnd(rng, 5, 2))))
     assert sb.iscached(Tc)
+
+
+@pytest.mark.parametrize("case", [((100, 100), (100, 100), 100), ((9, 13), (17, 11), 5), ((128, 128), (128, 128), 3),
+                                  ((8, 8), (8, 8), 1), ((33, 64), (120, 50), 250), ((100, 37), (64, 128), 7)])
+def test_small_float64_kron_is_one_fused_launch(sb, case):
+    """configs[0]-like problems (two dense Float64 factors <= 128, fewer than two waves of slabs): ONE launch of
+    kron2_f64_small_kernel with the intermediate in shared memory; 3-arg (NaN-prefilled W), 5-arg, adjoint factors."""
+    (ma, na), (mb, nb), k = case
+    rng = np.random.default_rng(ma + nb + k)
+    A, B = rnd(rng, ma, na) - 0.5, rnd(rng, mb, nb) - 0.5
+    v = rnd(rng, na * nb, k) - 0.5
+    dv = dev(sb, v)
+    h = sb.handle(0)
+    L = sb.cache_operator(sb.kron(sb.MatrixOperator(A), sb.MatrixOperator(B)), dv)
+    w = sb.DeviceArray.full((ma * mb, k), float("nan"), np.float64)
+    sb.mul_(w, L, dv)
+    n0 = h.launch_count()
+    sb.mul_(w, L, dv)
+    assert h.launch_count() - n0 == 1
+    want = R.kron_apply([A, B], v)
+    check(w.numpy(), want, np.float64, f"{case} 3-arg")
+    w0 = rnd(rng, ma * mb, k)
+    check(sb.mul_(dev(sb, w0), L, dv, 0.7, -0.3).numpy(), 0.7 * want - 0.3 * w0, np.float64, f"{case} 5-arg")
+    vt = rnd(rng, ma * mb, k) - 0.5
+    dvt = dev(sb, vt)
+    Lt = sb.cache_operator(sb.kron(sb.MatrixOperator(A), sb.MatrixOperator(B)).adjoint(), dvt)
+    check((Lt * dvt).numpy(), R.kron_apply([A.T.copy(), B.T.copy()], vt), np.float64, f"{case} adjoint")
