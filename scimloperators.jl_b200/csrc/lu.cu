@@ -124,6 +124,20 @@ __global__ void norm1_kernel(long long n, const double* __restrict__ A, long lon
   }
 }
 
+// a[c] of a register array with a run-time c: a jump table (BRX), a handful of executed instructions.  (A chain of 32
+// selects costs ~100 per access; unrolling the whole column loop instead made the panel kernels instruction-cache bound:
+// "no_instructions" 46 % of the stalls, profiles/r02_lu_panel_ncu_summary.txt.)
+#define LU_CASE(k) case k: return a[k];
+__device__ __forceinline__ double reg_get(const double (&a)[PB], int c) {
+  switch (c) {
+    LU_CASE(0) LU_CASE(1) LU_CASE(2) LU_CASE(3) LU_CASE(4) LU_CASE(5) LU_CASE(6) LU_CASE(7) LU_CASE(8) LU_CASE(9) LU_CASE(10)
+    LU_CASE(11) LU_CASE(12) LU_CASE(13) LU_CASE(14) LU_CASE(15) LU_CASE(16) LU_CASE(17) LU_CASE(18) LU_CASE(19) LU_CASE(20)
+    LU_CASE(21) LU_CASE(22) LU_CASE(23) LU_CASE(24) LU_CASE(25) LU_CASE(26) LU_CASE(27) LU_CASE(28) LU_CASE(29) LU_CASE(30)
+    default: return a[31];
+  }
+}
+#undef LU_CASE
+
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -157,14 +171,10 @@ __global__ void __launch_bounds__(PROWS) lu_panel_kernel(long long n, double* __
 #pragma unroll
   for (int c = 0; c < PB; c++) a[c] = (live && c < w) ? A[r + (long long)(j0 + c) * lda] : 0.0;
   unsigned epoch = 0;
-  // the column loop is fully unrolled: a[c] / pr[c] are then plain registers (a run-time c costs a 32-long select chain
-  // per access: ~1500 instructions per warp and column, measured)
-#pragma unroll
-  for (int c = 0; c < PB; c++) {
-    if (c >= w) break;
+  for (int c = 0; c < w; c++) {
     const int par = c & 1;
     // ---- local arg-max of |a(:, c)| over rows >= c (first maximum, like idamax) ----
-    const double ac = a[c];
+    const double ac = reg_get(a, c);
     double best = (live && i >= c) ? fabs(ac) : -1.0;
     if (best != best) best = 1.0e308;                 // NaN: take it as the pivot so that it propagates like LAPACK's
     int bi = i;
@@ -235,12 +245,14 @@ __global__ void __launch_bounds__(PROWS) lu_panel_kernel(long long n, double* __
       }
     }
     // ---- eliminate: l = a(i, c) / pivot, a(i, c+1:) -= l * pivot_row(c+1:) ----
-    const double pv = pr[c];
+    const double pv = reg_get(pr, c);
     if (live && i > c && pv != 0.0) {
-      const double l = a[c] / pv;
-      a[c] = l;
+      const double l = reg_get(a, c) / pv;
 #pragma unroll
-      for (int q = 0; q < PB; q++) if (q > c) a[q] -= l * pr[q];
+      for (int q = 0; q < PB; q++) {
+        if (q == c) a[q] = l;
+        if (q > c) a[q] -= l * pr[q];
+      }
     }
   }
   if (live) {
@@ -267,11 +279,9 @@ __global__ void __launch_bounds__(PROWS) lu_panel_cluster_kernel(long long n, do
   double a[PB];
 #pragma unroll
   for (int c = 0; c < PB; c++) a[c] = (live && c < w) ? A[r + (long long)(j0 + c) * lda] : 0.0;
-#pragma unroll
-  for (int c = 0; c < PB; c++) {
-    if (c >= w) break;
+  for (int c = 0; c < w; c++) {
     const int par = c & 1;
-    const double ac = a[c];
+    const double ac = reg_get(a, c);
     double best = (live && i >= c) ? fabs(ac) : -1.0;
     if (best != best) best = 1.0e308;
     int bi = i;
@@ -341,12 +351,14 @@ __global__ void __launch_bounds__(PROWS) lu_panel_cluster_kernel(long long n, do
         for (int q = 0; q < PB; q++) a[q] = drow[q];
       }
     }
-    const double pv = pr[c];
+    const double pv = reg_get(pr, c);
     if (live && i > c && pv != 0.0) {
-      const double l = a[c] / pv;
-      a[c] = l;
+      const double l = reg_get(a, c) / pv;
 #pragma unroll
-      for (int q = 0; q < PB; q++) if (q > c) a[q] -= l * pr[q];
+      for (int q = 0; q < PB; q++) {
+        if (q == c) a[q] = l;
+        if (q > c) a[q] -= l * pr[q];
+      }
     }
     __syncthreads();     // prow / drow are rewritten by warp 0 in the next column
   }
