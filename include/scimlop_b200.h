@@ -54,7 +54,8 @@ enum { SCIMLOP_F64 = 0, SCIMLOP_F32 = 1,
        /* ComplexF32 / ComplexF64, interleaved (re, im) as Julia stores them; alpha / beta point to (re, im) pairs; leading
         * dimensions count complex elements.  Taken by scimlop_kron_workspace_bytes / scimlop_kron_mul with dense
         * (SCIMLOP_DENSE, | SCIMLOP_TRANS = the lazy adjoint F^H) and identity factors -- one factor is a complex
-        * MatrixOperator mul! (test/basic.jl:405-426, test/Downstream/alloccheck.jl:37).  Every other entry answers
+        * MatrixOperator mul! (test/basic.jl:405-426, test/Downstream/alloccheck.jl:37) -- and by scimlop_csr_mul (sparse
+        * complex operators, the direct gather / scatter kernels).  Every other entry answers
         * SCIMLOP_ERR_UNSUPPORTED for them. */
        SCIMLOP_C64 = 2, SCIMLOP_C128 = 3 };
 enum {

@@ -18,6 +18,34 @@
 
 namespace {
 
+// ComplexF32 / ComplexF64 values (interleaved re, im): the `sprand(ComplexF64, ...)` operators of alloccheck.jl:37-45
+template <typename R>
+struct cplx {
+  R re, im;
+  __host__ __device__ constexpr cplx(R r = R(0), R i = R(0)) : re(r), im(i) {}
+  __host__ __device__ cplx operator*(const cplx& o) const { return cplx(re * o.re - im * o.im, re * o.im + im * o.re); }
+  __host__ __device__ cplx operator+(const cplx& o) const { return cplx(re + o.re, im + o.im); }
+  __host__ __device__ cplx& operator+=(const cplx& o) { re += o.re; im += o.im; return *this; }
+  __host__ __device__ bool operator!=(const cplx& o) const { return re != o.re || im != o.im; }
+  __host__ __device__ bool operator==(const cplx& o) const { return re == o.re && im == o.im; }
+};
+template <typename T> __device__ __forceinline__ T ldg_any(const T* p) { return __ldg(p); }
+template <> __device__ __forceinline__ cplx<double> ldg_any(const cplx<double>* p) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return cplx<double>(v.x, v.y);
+}
+template <> __device__ __forceinline__ cplx<float> ldg_any(const cplx<float>* p) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return cplx<float>(v.x, v.y);
+}
+template <typename T> __device__ __forceinline__ void atomic_add_any(T* p, T v) { atomicAdd(p, v); }
+template <typename R> __device__ __forceinline__ void atomic_add_any(cplx<R>* p, cplx<R> v) {
+  atomicAdd(&p->re, v.re);
+  atomicAdd(&p->im, v.im);
+}
+template <typename T> struct is_cplx { static constexpr bool value = false; };
+template <typename R> struct is_cplx<cplx<R>> { static constexpr bool value = true; };
+
 template <typename T, int C>
 __global__ void csr_gather_kernel(long long m, long long k, const int* __restrict__ rowptr, const int* __restrict__ colidx,
                                   const T* __restrict__ vals, int base, const T* __restrict__ V, long long ldv, T* W,
@@ -35,7 +63,7 @@ __global__ void csr_gather_kernel(long long m, long long k, const int* __restric
         const T a = vals[j];
         const T* vp = v0 + (colidx[j] - base);
 #pragma unroll
-        for (int c = 0; c < C; c++) acc[c] += a * __ldg(vp + c * ldv);
+        for (int c = 0; c < C; c++) acc[c] += a * ldg_any(vp + c * ldv);
       }
     } else {
       for (int j = j0; j < j1; j++) {
@@ -43,7 +71,7 @@ __global__ void csr_gather_kernel(long long m, long long k, const int* __restric
         const T* vp = v0 + (colidx[j] - base);
 #pragma unroll
         for (int c = 0; c < C; c++)
-          if (c0 + c < k) acc[c] += a * __ldg(vp + c * ldv);
+          if (c0 + c < k) acc[c] += a * ldg_any(vp + c * ldv);
       }
     }
 #pragma unroll
@@ -134,7 +162,7 @@ __global__ void csr_scatter_kernel(long long m, long long k, const int* __restri
       T* wp = W + (colidx[j] - base) + c0 * ldw;
 #pragma unroll
       for (int c = 0; c < C; c++)
-        if (c0 + c < k) atomicAdd(wp + c * ldw, a * x[c]);
+        if (c0 + c < k) atomic_add_any(wp + c * ldw, a * x[c]);
     }
   }
 }
@@ -146,7 +174,7 @@ int csr_mul_t(scimlop_context* h, bool trans, long long m, long long n, long lon
   constexpr int THREADS = 128;
   const unsigned gx = (unsigned)((m + THREADS - 1) / THREADS);
   if (!trans) {
-    if (workspace && k >= 8 && k % 8 == 0 && ws_bytes >= (size_t)n * (size_t)k * sizeof(T) &&
+    if (!is_cplx<T>::value && workspace && k >= 8 && k % 8 == 0 && ws_bytes >= (size_t)n * (size_t)k * sizeof(T) &&
         (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0 && (n + 31) / 32 <= 2147483647LL && (k + 31) / 32 <= 65535) {
       // enough columns to pay for a transposed staging copy of V (one extra read + write of V)
       T* Vt = static_cast<T*>(workspace);
@@ -187,6 +215,7 @@ int csr_mul_t(scimlop_context* h, bool trans, long long m, long long n, long lon
 
 extern "C" int scimlop_csr_workspace_bytes(int dtype, int trans, int64_t rows, int64_t cols, int64_t k, size_t* bytes) {
   if (!bytes) return SCIMLOP_ERR_NULL_POINTER;
+  if (dtype == SCIMLOP_C64 || dtype == SCIMLOP_C128) { *bytes = 0; return SCIMLOP_OK; }   // complex: the direct gather
   if (dtype != SCIMLOP_F64 && dtype != SCIMLOP_F32) return SCIMLOP_ERR_UNSUPPORTED;
   if (rows < 0 || cols < 0 || k < 0) return SCIMLOP_ERR_BAD_SHAPE;
   // the transposed staging copy of V pays off from 8 columns on (non-transposed form, k a multiple of 8)
@@ -199,7 +228,8 @@ extern "C" int scimlop_csr_mul(scimlop_handle_t h, int dtype, int trans, int64_t
                                const void* V, int64_t ldv, void* W, int64_t ldw, const void* alpha, const void* beta,
                                void* workspace, size_t workspace_bytes, void* stream) {
   if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
-  if (dtype != SCIMLOP_F64 && dtype != SCIMLOP_F32) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "csr_mul: unsupported dtype %d", dtype);
+  if (dtype != SCIMLOP_F64 && dtype != SCIMLOP_F32 && dtype != SCIMLOP_C64 && dtype != SCIMLOP_C128)
+    return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "csr_mul: unsupported dtype %d", dtype);
   if (rows < 0 || cols < 0 || k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "csr_mul: negative size");
   if (index_base != 0 && index_base != 1) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "csr_mul: index_base must be 0 or 1");
   const int64_t out_rows = trans ? cols : rows, in_rows = trans ? rows : cols;
@@ -209,6 +239,22 @@ extern "C" int scimlop_csr_mul(scimlop_handle_t h, int dtype, int trans, int64_t
   if (!W || (rows > 0 && !rowptr)) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "csr_mul: null pointer");
   scimlop_device_guard guard(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SCIMLOP_C128 || dtype == SCIMLOP_C64) {       // (re, im) pairs; alpha / beta point to one pair each
+    if (dtype == SCIMLOP_C128) {
+      using Z = cplx<double>;
+      const double* ap = static_cast<const double*>(alpha);
+      const double* bp = static_cast<const double*>(beta);
+      return csr_mul_t<Z>(h, trans != 0, rows, cols, k, rowptr, colidx, static_cast<const Z*>(values), index_base,
+                          static_cast<const Z*>(V), ldv, static_cast<Z*>(W), ldw, ap ? Z(ap[0], ap[1]) : Z(1.0), bp ? Z(bp[0], bp[1]) : Z(0.0),
+                          nullptr, 0, st);
+    }
+    using Z = cplx<float>;
+    const float* ap = static_cast<const float*>(alpha);
+    const float* bp = static_cast<const float*>(beta);
+    return csr_mul_t<Z>(h, trans != 0, rows, cols, k, rowptr, colidx, static_cast<const Z*>(values), index_base,
+                        static_cast<const Z*>(V), ldv, static_cast<Z*>(W), ldw, ap ? Z(ap[0], ap[1]) : Z(1.f), bp ? Z(bp[0], bp[1]) : Z(0.f),
+                        nullptr, 0, st);
+  }
   if (dtype == SCIMLOP_F64) {
     const double a = alpha ? *static_cast<const double*>(alpha) : 1.0, b = beta ? *static_cast<const double*>(beta) : 0.0;
     return csr_mul_t<double>(h, trans != 0, rows, cols, k, rowptr, colidx, static_cast<const double*>(values), index_base,

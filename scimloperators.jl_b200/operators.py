@@ -366,6 +366,11 @@ class MatrixOperator(AbstractSciMLOperator):
     def adjoint(self):
         if self.update_func is not None:
             raise NotImplementedError("adjoint of a time-dependent MatrixOperator builds an AdjointOperator (src/left.jl) -- out of scope")
+        if self.sparse and _is_complex(self.A.dtype):
+            # the CSR kernels' `trans` is the plain transpose: the adjoint of a complex sparse matrix conjugates a copy
+            A = self.A
+            return MatrixOperator(SparseMatrixCSR(A.rowptr, A.colidx, DeviceArray(A.values.t.conj().resolve_conj().clone(), A.values.shape),
+                                                  A.shape), not self.trans)
         return MatrixOperator(self.A, not self.trans)
 
     # ---- Float32 matrices beyond the resident-factor kernel: hi / lo image prepared once (scimlop_split_attach) ----
@@ -435,9 +440,9 @@ class MatrixOperator(AbstractSciMLOperator):
         _check_vw(self, w, v)
         h = _lib.handle(w.device_index)
         m, n = self.size()
-        if _is_complex(w.dtype):   # ComplexF32 / ComplexF64: the one-factor case of the complex Kronecker planner
-            if self.banded or self.sparse:
-                raise NotImplementedError("complex banded / sparse MatrixOperator is outside the B200 backend")
+        if _is_complex(w.dtype) and not self.sparse:   # ComplexF32 / ComplexF64: the one-factor case of the complex Kronecker planner
+            if self.banded:
+                raise NotImplementedError("complex banded MatrixOperator is outside the B200 backend")
             k = _ncols(v)
             sm, sn = self.A.shape
             dims, lds = (C.c_int64 * 2)(m, n), (C.c_int64 * 1)(self.A.ld)
