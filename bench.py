@@ -290,6 +290,9 @@ def strong_legs(torch, dist, sb, h, world, rank, A, B, ms_1gpu_shape):
     try:
         win = sd.PeerWindow(h, W, rank, world, gather_obj)
         out["replicated_fused_peer_ms"] = _timed_max(torch, dist, world, lambda: sd.kron_mul_peers(h, L, V, win, kper), reps=20)
+        h.set_option(sb.OPT_PEER_PIPELINE, 0)      # both stages over all columns in turn (the round-1 schedule)
+        out["replicated_fused_peer_unpipelined_ms"] = _timed_max(torch, dist, world, lambda: sd.kron_mul_peers(h, L, V, win, kper), reps=20)
+        h.set_option(sb.OPT_PEER_PIPELINE, 1)
         W.t.zero_()
         torch.cuda.synchronize()
         dist.barrier()
@@ -311,6 +314,9 @@ def strong_legs(torch, dist, sb, h, world, rank, A, B, ms_1gpu_shape):
         out["replicated_fused_multicast_unavailable"] = str(e)[:160]
     if mcw is not None:
         out["replicated_fused_multicast_ms"] = _timed_max(torch, dist, world, lambda: sd.kron_mul_mc(h, L, V, mcw, kper), reps=20)
+        h.set_option(sb.OPT_PEER_PIPELINE, 0)
+        out["replicated_fused_multicast_unpipelined_ms"] = _timed_max(torch, dist, world, lambda: sd.kron_mul_mc(h, L, V, mcw, kper), reps=20)
+        h.set_option(sb.OPT_PEER_PIPELINE, 1)
         mcw.W.t.zero_()
         torch.cuda.synchronize()
         dist.barrier()

@@ -102,8 +102,13 @@ int scimlop_last_error(scimlop_handle_t h, char* buf, size_t len);
  * partial wave as a second, split-K launch (thread-block clusters divide K and reduce through distributed shared
  * memory).  Faster (config 2 on 32 columns: 512 tiles = 3.46 waves -> 3 + 0.5), but the tiles of that wave are summed
  * in a different order than the single-launch schedule; 0 restores one launch and one summation order everywhere
- * (what the fused compute + all-gather entries always use, so a bit-for-bit comparison against them sets 0). */
-enum { SCIMLOP_OPT_TAIL_SPLIT = 1 };
+ * (what the fused compute + all-gather entries always use, so a bit-for-bit comparison against them sets 0).
+ * SCIMLOP_OPT_PEER_PIPELINE (0 = off, 1 = automatic (default), 2 = always): scimlop_kron_mul_peers / _mc with two dense
+ * Float64 factors may run as a pipeline of 2 or 4 column chunks on two streams -- the last stage of a chunk, which is
+ * bound by NVLink ingress when many ranks gather, on a share of the SMs, the first stage of the next chunk on the rest.
+ * Automatic takes it where the estimated gather time is at least twice the last stage's arithmetic (8 ranks on config
+ * 2, not 2 ranks).  Same numbers bit for bit as the unchunked schedule. */
+enum { SCIMLOP_OPT_TAIL_SPLIT = 1, SCIMLOP_OPT_PEER_PIPELINE = 2 };
 int scimlop_set_option(scimlop_handle_t h, int option, int value);
 /* Number of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
 int scimlop_launch_count(scimlop_handle_t h, int64_t* count);

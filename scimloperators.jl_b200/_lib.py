@@ -18,6 +18,7 @@ PREC_DEFAULT, PREC_TF32X3, PREC_TF32, PREC_FP32_EXACT, PREC_BF16 = 0, 1, 2, 3, 4
 DENSE, IDENTITY, DIAG, BDIAG, NULL, BANDED = 0, 1, 2, 3, 4, 5
 TRANS = 0x100
 OPT_TAIL_SPLIT = 1
+OPT_PEER_PIPELINE = 2
 
 
 class Factor(C.Structure):  # scimlop_factor_t
@@ -141,7 +142,7 @@ class Handle:
             raise ScimlopError(rc, where, buf.value.decode(errors="replace"))
 
     def set_option(self, option, value):
-        """scimlop_set_option: OPT_TAIL_SPLIT = 1 (include/scimlop_b200.h)."""
+        """scimlop_set_option: OPT_TAIL_SPLIT = 1, OPT_PEER_PIPELINE = 2 (include/scimlop_b200.h)."""
         self.check(self.lib.scimlop_set_option(self._h, int(option), int(value)), "scimlop_set_option")
 
     def launch_count(self):

@@ -32,6 +32,13 @@ struct scimlop_context {
   int device;
   int sm_count;
   int sm_reserve;  // SMs left free by the persistent GEMM kernels (for concurrently running NCCL kernels)
+  int peer_pipeline;  // scimlop_set_option(SCIMLOP_OPT_PEER_PIPELINE): column-chunk pipeline of the fused all-gather entries (default 1)
+  int grid_limit;     // != 0: persistent GEMM kernels launch at most this many CTAs (set per stage by that pipeline)
+  int stage_limit[2]; // grid limits of the first / the last stage of a kron_mul call (0 = none)
+  cudaEvent_t stage_event;   // != nullptr: recorded after the first stage of a kron_mul call
+  cudaStream_t s_side;       // second stream + events of the pipeline (created on first use)
+  cudaEvent_t ev_pipe[10];
+  bool pipe_ready;
   int tail_split;  // scimlop_set_option(SCIMLOP_OPT_TAIL_SPLIT): run the last partial wave of a many-tile FP64 GEMM split-K (default 1)
   scimlop_encode_tiled_fn encode_tiled;
   // Float32 streamed GEMM: hi / lo images attached by the caller (cached operators: nothing is split or allocated per

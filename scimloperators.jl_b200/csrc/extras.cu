@@ -366,6 +366,11 @@ extern "C" int scimlop_destroy(scimlop_handle_t h) {
     }
     cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_comp); cudaStreamDestroy(h->s_d2h);
   }
+  if (h->pipe_ready) {
+    cudaStreamSynchronize(h->s_side);
+    for (int i = 0; i < 10; i++) cudaEventDestroy(h->ev_pipe[i]);
+    cudaStreamDestroy(h->s_side);
+  }
   if (h->stage) cudaFree(h->stage);
   if (h->comm_scratch) cudaFree(h->comm_scratch);
   if (h->split_scratch) { cudaDeviceSynchronize(); cudaFree(h->split_scratch); }

@@ -196,7 +196,8 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
       if (r != CUDA_SUCCESS) return scimlop_fail(c, SCIMLOP_ERR_CUDA, "cuTensorMapEncodeTiled(peer C %d) failed (CUresult %d)", q, (int)r);
     }
     if (!peer_bulk) memset(&peer_maps, 0, sizeof(peer_maps));
-    const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
+    int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
+    if (c->grid_limit > 0) grid = std::min(grid, c->grid_limit);
     if (!transB) dmma::gemm_dmma_kernel<false, false, false, true><<<grid, dmma::THREADS, dmma::PEER_SMEM_BYTES, st>>>(tmA, tmB, p, peer_maps);
     else dmma::gemm_dmma_kernel<false, true, false, true><<<grid, dmma::THREADS, dmma::PEER_SMEM_BYTES, st>>>(tmA, tmB, p, peer_maps);
     c->launches++;
@@ -244,7 +245,8 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
   // config-2 share of one of 8 GPUs) leaves most SMs idle for the last tile time.  The last partial wave is then run as
   // a second launch of the split-K form -- each tile on a cluster of `ts` CTAs that divide K -- so it costs 1 / ts of a
   // tile time (+ the cluster reduction).  Modelled with the same constants as above; only taken when it saves > 10 us.
-  const int nsm = std::max(1, c->sm_count - c->sm_reserve);
+  int nsm = std::max(1, c->sm_count - c->sm_reserve);
+  if (c->grid_limit > 0) nsm = std::min(nsm, c->grid_limit);
   long long tail = 0, ts = 1;
   if (c->tail_split && !g_peers.active() && p.total_tiles > nsm && p.total_tiles % nsm != 0) {
     const long long rem = p.total_tiles % nsm;
@@ -794,6 +796,7 @@ extern "C" int scimlop_create(scimlop_handle_t* out, int device) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   c->tail_split = 1;
+  c->peer_pipeline = 1;
   scimlop_device_guard guard(device);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -886,6 +889,7 @@ extern "C" int scimlop_last_error(scimlop_handle_t h, char* buf, size_t len) {
 extern "C" int scimlop_set_option(scimlop_handle_t h, int option, int value) {
   if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
   if (option == SCIMLOP_OPT_TAIL_SPLIT) { h->tail_split = value != 0; return SCIMLOP_OK; }
+  if (option == SCIMLOP_OPT_PEER_PIPELINE) { h->peer_pipeline = value < 0 ? 0 : (value > 2 ? 2 : value); return SCIMLOP_OK; }
   return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "scimlop_set_option: unknown option %d", option);
 }
 
@@ -1190,6 +1194,7 @@ int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* cons
     const T a = last ? alpha : T(1), bt = last ? beta : T(0);
     const bool tr = (kinds[p] & SCIMLOP_TRANS) != 0;
     int rc;
+    c->grid_limit = last ? c->stage_limit[1] : (done == 1 ? c->stage_limit[0] : 0);
     if constexpr (std::is_same<T, float>::value) {
       // the two fastest modes, both small dense Float32 factors: ONE pass with the intermediate kept on chip
       if (L == 1 && p >= 1 && (kinds[p] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE && (kinds[p - 1] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE &&
@@ -1261,7 +1266,9 @@ int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* cons
       rc = gemm_dispatch<T>(c, precision, false, !tr, L, m, n, a, cur, L, L * n, static_cast<const T*>(factors[p]),
                             lds[p], 0, bt, out, L, L * m, R, 0, nullptr, st, last ? g_peers : NO_PEERS);
     }
+    c->grid_limit = 0;
     if (rc) return rc;
+    if (done == 1 && c->stage_event) SCIMLOP_CUDA(c, cudaEventRecord(c->stage_event, st));
     cur = out;
     flip ^= 1;
     L *= m;
@@ -1443,6 +1450,69 @@ static int kron_mul_impl_peers(scimlop_context* h, int dtype, int precision, int
   // split-K tail launch, so no stage does: results are bit-identical to the SCIMLOP_OPT_TAIL_SPLIT = 0 schedule)
   const int saved_tail_split = h->tail_split;
   if (peers.active()) h->tail_split = 0;
+  // Column-chunk pipeline of the fused all-gather: the last stage of a chunk is bound by NVLink ingress, not by the SMs,
+  // so it runs on a third of them while the first stage of the NEXT chunk computes on the rest (second stream), instead
+  // of the whole first stage running before any store is on the wire.  Columns are independent: same numbers, bit for bit.
+  // Chunks keep >= sm_count tiles in the first stage, so that no chunk takes the few-tile split-K launch the whole
+  // problem would not have taken; chunk offsets keep the 256 B alignment of the workspace and 16 B of V / W.
+  int nch = 0;
+  double ingress_us = 0.0, stage2_us = 1.0;
+  if (peers.active() && h->peer_pipeline && dtype == SCIMLOP_F64 && nfactors == 2 && (kinds[0] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE &&
+      (kinds[1] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE && scalar_or<double>(beta, 0.0) == 0.0 && (pl.max_inter / k) % 32 == 0 &&
+      pl.rows % 2 == 0 && pl.cols % 2 == 0) {
+    const long long mt = (dims[2] + 127) / 128;
+    for (int cand = 4; cand >= 2 && !nch; cand -= 2)
+      if (k % cand == 0 && mt * ((k / cand * dims[1] + 127) / 128) >= h->sm_count) nch = cand;
+    // worth it only where the gather, not the arithmetic, bounds the last stage: bytes this GPU receives at ~600 GB/s
+    // (NVLink 5 ingress as NCCL's all-gather reaches it here) against the stage's flops at ~35 TFLOP/s (DMMA, measured)
+    const int npeers = peers.n > 0 ? peers.n : std::max(0, h->nranks - 1);
+    ingress_us = (double)npeers * (double)pl.rows * (double)k * 8.0 / 6.0e5;
+    stage2_us = 2.0 * (double)dims[1] * (double)pl.rows * (double)k / 35.0e6;
+    if (h->peer_pipeline == 1 && ingress_us < 2.0 * stage2_us) nch = 0;
+  }
+  if (nch) {
+    if (!h->pipe_ready) {
+      SCIMLOP_CUDA(h, cudaStreamCreateWithFlags(&h->s_side, cudaStreamNonBlocking));
+      for (int i = 0; i < 10; i++) SCIMLOP_CUDA(h, cudaEventCreateWithFlags(&h->ev_pipe[i], cudaEventDisableTiming));
+      h->pipe_ready = true;
+    }
+    const int nsm = std::max(1, h->sm_count - h->sm_reserve);
+    // SMs of the last stage: enough that its arithmetic keeps up with the wire (30 % margin), between 1/4 and 1/2 of all
+    const int g2 = std::min(std::max((int)(1.3 * nsm * stage2_us / std::max(ingress_us, 1.0)) + 1, nsm / 4), nsm / 2), g1 = nsm - g2;
+    const long long inter_per_col = pl.max_inter / k;
+    const double a = scalar_or<double>(alpha, 1.0);
+    SCIMLOP_CUDA(h, cudaEventRecord(h->ev_pipe[8], st));
+    SCIMLOP_CUDA(h, cudaStreamWaitEvent(h->s_side, h->ev_pipe[8], 0));
+    int rc = SCIMLOP_OK;
+    long long c0 = 0;
+    for (int i = 0; i < nch && rc == SCIMLOP_OK; i++) {
+      const long long nc = (k * (i + 1)) / nch - c0;
+      cudaStream_t si = (i % 2 == 0) ? st : h->s_side;
+      if (i > 0) SCIMLOP_CUDA(h, cudaStreamWaitEvent(si, h->ev_pipe[i - 1], 0));   // S1(i) starts when S1(i-1) is done
+      KronPlan plc;
+      if ((rc = kron_plan(h, nfactors, dims, kinds, nc, &plc))) break;
+      PeerArg pc;
+      pc.n = peers.n;
+      for (int q = 0; q < peers.n; q++) pc.ptr[q] = static_cast<double*>(peers.ptr[q]) + c0 * pl.rows;
+      if (peers.mc) pc.mc = static_cast<double*>(peers.mc) + c0 * pl.rows;
+      h->stage_event = h->ev_pipe[i];
+      h->stage_limit[0] = i == 0 ? 0 : g1;
+      h->stage_limit[1] = i == nch - 1 ? 0 : g2;
+      rc = kron_mul_t<double>(h, precision, nfactors, factors, dims, lds, kinds, static_cast<const double*>(V) + c0 * pl.cols,
+                              static_cast<double*>(W) + c0 * pl.rows, nc, a, 0.0 /* checked above */,
+                              static_cast<char*>(workspace) + (size_t)c0 * (size_t)inter_per_col * 8,
+                              workspace_bytes - (size_t)c0 * (size_t)inter_per_col * 8, plc, si, pc);
+      c0 += nc;
+    }
+    h->stage_event = nullptr;
+    h->stage_limit[0] = h->stage_limit[1] = 0;
+    h->grid_limit = 0;
+    h->tail_split = saved_tail_split;
+    if (rc) return rc;
+    SCIMLOP_CUDA(h, cudaEventRecord(h->ev_pipe[9], h->s_side));
+    SCIMLOP_CUDA(h, cudaStreamWaitEvent(st, h->ev_pipe[9], 0));
+    return SCIMLOP_OK;
+  }
   int rc;
   if (dtype == SCIMLOP_F64)
     rc = kron_mul_t<double>(h, precision, nfactors, factors, dims, lds, kinds, (const double*)V, (double*)W, k,

@@ -77,7 +77,11 @@ def main():
     Vc = sb.DeviceArray(torch.rand(512 * 512 * kc, dtype=torch.float64, device="cuda", generator=g), (512 * 512, kc))
     Lc = sb.cache_operator(sb.kron(Ac, Bc), Vc)
     plain = sb.DeviceArray.zeros((512 * 512, kc), np.float64)
+    # one summation order, as the fused entries use (512 tiles: the default would run the last partial wave split-K)
+    h.set_option(sb.OPT_TAIL_SPLIT, 0)
     sb.mul_(plain, Lc, Vc)
+    h.set_option(sb.OPT_TAIL_SPLIT, 1)
+    h.set_option(sb.OPT_PEER_PIPELINE, 2)    # column-chunk pipeline forced on: must stay bit-identical
     slabs = [torch.empty_like(plain.t) for _ in range(world)]
     dist.all_gather(slabs, plain.t)
     want4 = torch.cat(slabs)

@@ -1221,6 +1221,63 @@ def test_dmma_tail_wave_runs_split_k_and_option_restores_one_launch(sb):
     assert float((W2.t - W1.t).norm() / W1.t.norm()) <= 1e-12
 
 
+@pytest.mark.parametrize("k,launches", [(32, 4), (64, 8), (8, 2)])
+def test_fused_all_gather_column_pipeline_is_bit_identical(sb, k, launches):
+    """scimlop_kron_mul_peers (include/scimlop_b200.h) on ONE device: the "peer" copy of W is a second buffer of the same
+    GPU, so the column-chunk pipeline (SCIMLOP_OPT_PEER_PIPELINE: last stage of chunk i beside the first stage of chunk
+    i + 1, two streams, per-stage grid limits) runs without a second rank.  Both copies must equal the plain mul_ with
+    one summation order (SCIMLOP_OPT_TAIL_SPLIT = 0) bit for bit, pipelined (2 chunks at 32 columns, 4 at 64, none at
+    8) and not, repeatedly; the launch count shows which schedule ran."""
+    import types
+    import torch
+    from scimlop_b200 import distributed as sd
+    rng = np.random.default_rng(23)
+    A, B = rnd(rng, 512, 512), rnd(rng, 512, 512)
+    n = 512 * 512
+    g = torch.Generator(device="cuda").manual_seed(77)
+    V = sb.DeviceArray(torch.rand(n * k, dtype=torch.float64, device="cuda", generator=g), (n, k))
+    L = sb.cache_operator(sb.kron(sb.MatrixOperator(A), sb.MatrixOperator(B)), V)
+    h = sb.handle(0)
+    h.set_option(sb.OPT_TAIL_SPLIT, 0)
+    try:
+        want = sb.DeviceArray.zeros((n, k), np.float64)
+        sb.mul_(want, L, V)
+    finally:
+        h.set_option(sb.OPT_TAIL_SPLIT, 1)
+    if k == 8:   # few tiles: the first stage of the plain path runs split-K; compare to tolerance only
+        check(want.cols(0, 1).numpy(), R.kron_apply([A, B], V.cols(0, 1).numpy()), np.float64, "plain")
+    # "rank 0 of 2": own slab = columns 0 .. k of a 2k-column W, peer = another buffer on this device
+    W0 = sb.DeviceArray.zeros((n, 2 * k), np.float64)
+    W1 = sb.DeviceArray.zeros((n, 2 * k), np.float64)
+    win = types.SimpleNamespace(W=W0, rank=0, world=2, base=[W0.ptr, W1.ptr])
+    for pipelined in (2, 0, 2):   # 2 = always (automatic would decline: one local "peer" is not ingress-bound)
+        h.set_option(sb.OPT_PEER_PIPELINE, pipelined)
+        try:
+            for rep in range(3):
+                W0.t.zero_(); W1.t.zero_()
+                n0 = h.launch_count()
+                sd.kron_mul_peers(h, L, V, win, k, barrier=False)
+                torch.cuda.synchronize()
+                assert h.launch_count() - n0 == (launches if pipelined else 2)
+                for name, Wx in (("own", W0), ("peer", W1)):
+                    got = Wx.cols(0, k).t
+                    if k == 8:
+                        err = float((got - want.t).norm() / want.t.norm())
+                        assert err <= 1e-14, f"{name} copy, pipelined={pipelined}: {err:.3e}"
+                    else:
+                        assert torch.equal(got, want.t), \
+                            f"{name} copy, pipelined={pipelined}, rep {rep}: max diff {float((got - want.t).abs().max()):.3e}"
+                    assert float(Wx.cols(k, 2 * k).t.abs().max()) == 0.0, "stored outside the slab"
+        finally:
+            h.set_option(sb.OPT_PEER_PIPELINE, 1)
+    # alpha rides along; beta is not part of the entry.  Automatic mode: unchunked here
+    n0 = h.launch_count()
+    sd.kron_mul_peers(h, L, V, win, k, alpha=-0.5, barrier=False)
+    torch.cuda.synchronize()
+    assert h.launch_count() - n0 == 2
+    assert float((W1.cols(0, k).t + 0.5 * want.t).norm() / want.t.norm()) <= 1e-13
+
+
 def test_mixed_eltype_factors_are_promoted(sb):
     """`_promote_operator_eltype` (src/interface.jl:444, src/tensor.jl:99): a Float32 factor next to Float64 arrays is
     applied at Float64 (exactly the promoted values), in a Kronecker product and in an operator tree."""
