@@ -19,6 +19,8 @@ DENSE, IDENTITY, DIAG, BDIAG, NULL, BANDED = 0, 1, 2, 3, 4, 5
 TRANS = 0x100
 OPT_TAIL_SPLIT = 1
 OPT_PEER_PIPELINE = 2
+OPT_PEER_CHUNKS = 3
+OPT_PEER_STAGE2_SMS = 4
 
 
 class Factor(C.Structure):  # scimlop_factor_t

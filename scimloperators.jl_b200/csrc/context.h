@@ -34,6 +34,8 @@ struct scimlop_context {
   int sm_reserve;  // SMs left free by the persistent GEMM kernels (for concurrently running NCCL kernels)
   int peer_pipeline;  // scimlop_set_option(SCIMLOP_OPT_PEER_PIPELINE): column-chunk pipeline of the fused all-gather entries (default 1)
   int grid_limit;     // != 0: persistent GEMM kernels launch at most this many CTAs (set per stage by that pipeline)
+  int peer_chunks, peer_stage2_sms;  // SCIMLOP_OPT_PEER_CHUNKS / _STAGE2_SMS: explicit pipeline shape (0 = chosen by the library)
+  int no_small_splitk; // != 0: a GEMM with fewer tiles than SMs still runs the plain persistent kernel (chunks of that pipeline keep the summation order of the whole problem)
   int stage_limit[2]; // grid limits of the first / the last stage of a kron_mul call (0 = none)
   cudaEvent_t stage_event;   // != nullptr: recorded after the first stage of a kron_mul call
   cudaStream_t s_side;       // second stream + events of the pipeline (created on first use)

@@ -209,7 +209,7 @@ int launch_dmma(scimlop_context* c, bool transA, bool transB, long long M, long 
   // co-resident clusters comes from the occupancy query at handle creation (8-CTA clusters do not tile all SMs).
   const long long nk_all = (K + dmma::BK - 1) / dmma::BK;
   long long ks = 1;
-  if (!g_peers.active() && p.total_tiles < c->sm_count) {
+  if (!g_peers.active() && !c->no_small_splitk && p.total_tiles < c->sm_count) {
     double best = (double)((p.total_tiles + c->sm_count - 1) / c->sm_count) * (nk_all * 2.2 + 2.0);
     for (long long cand = 2; cand <= 8; cand *= 2) {
       const long long maxc = c->dmma_max_clusters[cand];
@@ -889,6 +889,8 @@ extern "C" int scimlop_last_error(scimlop_handle_t h, char* buf, size_t len) {
 extern "C" int scimlop_set_option(scimlop_handle_t h, int option, int value) {
   if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
   if (option == SCIMLOP_OPT_TAIL_SPLIT) { h->tail_split = value != 0; return SCIMLOP_OK; }
+  if (option == SCIMLOP_OPT_PEER_CHUNKS) { h->peer_chunks = (value == 2 || value == 4 || value == 8) ? value : 0; return SCIMLOP_OK; }
+  if (option == SCIMLOP_OPT_PEER_STAGE2_SMS) { h->peer_stage2_sms = value > 0 ? value : 0; return SCIMLOP_OK; }
   if (option == SCIMLOP_OPT_PEER_PIPELINE) { h->peer_pipeline = value < 0 ? 0 : (value > 2 ? 2 : value); return SCIMLOP_OK; }
   return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "scimlop_set_option: unknown option %d", option);
 }
@@ -1451,18 +1453,25 @@ static int kron_mul_impl_peers(scimlop_context* h, int dtype, int precision, int
   const int saved_tail_split = h->tail_split;
   if (peers.active()) h->tail_split = 0;
   // Column-chunk pipeline of the fused all-gather: the last stage of a chunk is bound by NVLink ingress, not by the SMs,
-  // so it runs on a third of them while the first stage of the NEXT chunk computes on the rest (second stream), instead
+  // so it runs on a share of them while the first stage of the NEXT chunk computes on the rest (second stream), instead
   // of the whole first stage running before any store is on the wire.  Columns are independent: same numbers, bit for bit.
-  // Chunks keep >= sm_count tiles in the first stage, so that no chunk takes the few-tile split-K launch the whole
-  // problem would not have taken; chunk offsets keep the 256 B alignment of the workspace and 16 B of V / W.
+  // The whole problem must have >= sm_count tiles in its first stage (it then runs the plain persistent kernel, and so
+  // do the chunks: no_small_splitk), a chunk at least 3/4 of that; chunk offsets keep the 256 B alignment of the
+  // workspace and 16 B of V / W.
   int nch = 0;
   double ingress_us = 0.0, stage2_us = 1.0;
+  long long t1c = 0, t2c = 0;   // tiles of one chunk in the first / the last stage
   if (peers.active() && h->peer_pipeline && dtype == SCIMLOP_F64 && nfactors == 2 && (kinds[0] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE &&
       (kinds[1] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE && scalar_or<double>(beta, 0.0) == 0.0 && (pl.max_inter / k) % 32 == 0 &&
       pl.rows % 2 == 0 && pl.cols % 2 == 0) {
     const long long mt = (dims[2] + 127) / 128;
-    for (int cand = 4; cand >= 2 && !nch; cand -= 2)
-      if (k % cand == 0 && mt * ((k / cand * dims[1] + 127) / 128) >= h->sm_count) nch = cand;
+    if (mt * ((k * dims[1] + 127) / 128) >= h->sm_count)
+      for (int cand = h->peer_chunks ? h->peer_chunks : 2; cand >= 2 && !nch; cand -= 2)
+        if (k % cand == 0 && (h->peer_chunks || mt * ((k / cand * dims[1] + 127) / 128) >= h->sm_count)) nch = cand;
+    if (nch) {
+      t1c = mt * ((k / nch * dims[1] + 127) / 128);
+      t2c = mt * ((dims[0] + 127) / 128) * (k / nch);
+    }
     // worth it only where the gather, not the arithmetic, bounds the last stage: bytes this GPU receives at ~600 GB/s
     // (NVLink 5 ingress as NCCL's all-gather reaches it here) against the stage's flops at ~35 TFLOP/s (DMMA, measured)
     const int npeers = peers.n > 0 ? peers.n : std::max(0, h->nranks - 1);
@@ -1477,8 +1486,30 @@ static int kron_mul_impl_peers(scimlop_context* h, int dtype, int precision, int
       h->pipe_ready = true;
     }
     const int nsm = std::max(1, h->sm_count - h->sm_reserve);
-    // SMs of the last stage: enough that its arithmetic keeps up with the wire (30 % margin), between 1/4 and 1/2 of all
-    const int g2 = std::min(std::max((int)(1.3 * nsm * stage2_us / std::max(ingress_us, 1.0)) + 1, nsm / 4), nsm / 2), g1 = nsm - g2;
+    // SMs of the last stage of a non-final chunk.  The next chunk's first stage is on the critical path (its last stage
+    // starts when it ends and then shares the wire), so: fewest waves for that first stage on the remaining SMs, among
+    // the splits whose own waves still fit the gather time of a chunk; of those the smallest share + 4 SMs of slack.
+    // Measured on 8 GPUs (profiles/r02_peer_pipeline_sweep.jsonl): 2 chunks x 56 SMs 0.996 ms, 64..100 SMs 1.06-1.07,
+    // 4 chunks 1.09-1.14, unchunked 1.14.
+    int g2 = nsm / 3;
+    {
+      const double tile_us = stage2_us / std::max(1.0, (double)(t2c * nch) / nsm);
+      const double wire = ingress_us / nch / std::max(tile_us, 1e-3);
+      const int lo = std::max(1, nsm / 4), hi = std::max(lo, nsm / 2);
+      auto w2 = [&](int s) { return (double)((t2c + s - 1) / s); };
+      auto w1 = [&](int s) { return (double)((t1c + (nsm - s) - 1) / (nsm - s)); };
+      const double w2_ok = std::max(wire, w2(hi));
+      double best = 1e30;
+      for (int s = lo; s <= hi; s++)
+        if (w2(s) <= w2_ok) best = std::min(best, w1(s));
+      int first = 0, last = 0;
+      for (int s = lo; s <= hi; s++)
+        if (w2(s) <= w2_ok && w1(s) == best) { if (!first) first = s; last = s; }
+      if (first) g2 = std::min(first + 4, last);
+    }
+    if (h->peer_stage2_sms > 0) g2 = std::min(h->peer_stage2_sms, nsm - 1);
+    const int g1 = nsm - g2;
+    h->no_small_splitk = 1;
     const long long inter_per_col = pl.max_inter / k;
     const double a = scalar_or<double>(alpha, 1.0);
     SCIMLOP_CUDA(h, cudaEventRecord(h->ev_pipe[8], st));
@@ -1505,6 +1536,7 @@ static int kron_mul_impl_peers(scimlop_context* h, int dtype, int precision, int
       c0 += nc;
     }
     h->stage_event = nullptr;
+    h->no_small_splitk = 0;
     h->stage_limit[0] = h->stage_limit[1] = 0;
     h->grid_limit = 0;
     h->tail_split = saved_tail_split;

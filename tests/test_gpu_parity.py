@@ -1221,13 +1221,14 @@ def test_dmma_tail_wave_runs_split_k_and_option_restores_one_launch(sb):
     assert float((W2.t - W1.t).norm() / W1.t.norm()) <= 1e-12
 
 
-@pytest.mark.parametrize("k,launches", [(32, 4), (64, 8), (8, 2)])
-def test_fused_all_gather_column_pipeline_is_bit_identical(sb, k, launches):
+@pytest.mark.parametrize("k,chunks,launches", [(32, 0, 4), (64, 0, 4), (64, 4, 8), (32, 4, 8), (8, 0, 2)])
+def test_fused_all_gather_column_pipeline_is_bit_identical(sb, k, chunks, launches):
     """scimlop_kron_mul_peers (include/scimlop_b200.h) on ONE device: the "peer" copy of W is a second buffer of the same
     GPU, so the column-chunk pipeline (SCIMLOP_OPT_PEER_PIPELINE: last stage of chunk i beside the first stage of chunk
     i + 1, two streams, per-stage grid limits) runs without a second rank.  Both copies must equal the plain mul_ with
-    one summation order (SCIMLOP_OPT_TAIL_SPLIT = 0) bit for bit, pipelined (2 chunks at 32 columns, 4 at 64, none at
-    8) and not, repeatedly; the launch count shows which schedule ran."""
+    one summation order (SCIMLOP_OPT_TAIL_SPLIT = 0) bit for bit, pipelined (2 chunks, or the 4 that
+    SCIMLOP_OPT_PEER_CHUNKS asks for -- 128-tile chunks then stay off the few-tile split-K launch; none at 8 columns)
+    and not, repeatedly; the launch count shows which schedule ran."""
     import types
     import torch
     from scimlop_b200 import distributed as sd
@@ -1252,6 +1253,7 @@ def test_fused_all_gather_column_pipeline_is_bit_identical(sb, k, launches):
     win = types.SimpleNamespace(W=W0, rank=0, world=2, base=[W0.ptr, W1.ptr])
     for pipelined in (2, 0, 2):   # 2 = always (automatic would decline: one local "peer" is not ingress-bound)
         h.set_option(sb.OPT_PEER_PIPELINE, pipelined)
+        h.set_option(sb.OPT_PEER_CHUNKS, chunks)
         try:
             for rep in range(3):
                 W0.t.zero_(); W1.t.zero_()
@@ -1270,6 +1272,7 @@ def test_fused_all_gather_column_pipeline_is_bit_identical(sb, k, launches):
                     assert float(Wx.cols(k, 2 * k).t.abs().max()) == 0.0, "stored outside the slab"
         finally:
             h.set_option(sb.OPT_PEER_PIPELINE, 1)
+            h.set_option(sb.OPT_PEER_CHUNKS, 0)
     # alpha rides along; beta is not part of the entry.  Automatic mode: unchunked here
     n0 = h.launch_count()
     sd.kron_mul_peers(h, L, V, win, k, alpha=-0.5, barrier=False)
