@@ -207,8 +207,9 @@ int scimlop_invert(scimlop_handle_t h, int dtype, int64_t n, const void* A, int6
  *   returns SCIMLOP_ERR_SINGULAR (LAPACK info > 0).  The caller picks the solve per operator: multiplication by Ainv
  *   (scimlop_kron_mul: one GEMM per mode, residual ~ cond * eps -- inside the 1e-12 budget for well-conditioned factors)
  *   or scimlop_kron_ldiv (substitution: residual ~ eps |A| |x| at any cond, 1.25x the flops at n = 512).
- * scimlop_kron_ldiv: W = (F_1 (x) ... (x) F_n)^{-1} V, factor f given by its blob facts[f] (kinds[f] = SCIMLOP_DENSE) or
- *   an identity (SCIMLOP_IDENTITY, facts[f] ignored); dims[f] = order of factor f, outermost first; V, W contiguous
+ * scimlop_kron_ldiv: W = (F_1 (x) ... (x) F_n)^{-1} V, factor f given by its blob facts[f] (kinds[f] = SCIMLOP_DENSE, or
+ *   SCIMLOP_DENSE | SCIMLOP_TRANS to solve with the TRANSPOSE of the factorised matrix -- the lazy adjoint of
+ *   src/matrix.jl:565: U^T and L^T sweeps, then P^T) or an identity (SCIMLOP_IDENTITY, facts[f] ignored); dims[f] = order of factor f, outermost first; V, W contiguous
  *   prod(dims) x k and distinct; workspace = prod(dims) * k * 8 bytes.  Every triangular sweep is a sequence of GEMMs
  *   along the factor's mode (no permutedims), out of place between W and the workspace. */
 int scimlop_factorize_bytes(int dtype, int64_t n, size_t* fact_bytes, size_t* scratch_bytes);

@@ -355,6 +355,13 @@ function LinearAlgebra.ldiv!(w::DevMat{T}, F::DeviceInverse{T}, v::DevMat{T}) wh
     stable_solve(F) || return mul!(w, F.inv, v, true, false)
     kron_ldiv!(w, (F.blob,), Int64[size(F, 1)], Cint[DENSE], v)
 end
+# adjoint(::InvertibleOperator) wraps F lazily (src/matrix.jl:565): the same blob, transposed sweeps (getrs('T'))
+function LinearAlgebra.ldiv!(w::DevMat{T}, Ft::Union{Adjoint{T, <:DeviceInverse{T}}, Transpose{T, <:DeviceInverse{T}}},
+                             v::DevMat{T}) where {T <: F}
+    F = parent(Ft)
+    stable_solve(F) || return mul!(w, transpose(F.inv), v, true, false)
+    kron_ldiv!(w, (F.blob,), Int64[size(F, 1)], Cint[DENSE | TRANS], v)
+end
 
 function LinearAlgebra.factorize(L::MatrixOperator{Float64, <:CuMatrix{Float64}})
     n = LinearAlgebra.checksquare(L.A)

@@ -486,6 +486,15 @@ __global__ void perm_mode_kernel(long long Lp, long long n, long long R, const i
     out[i] = in[l + Lp * ((long long)perm[r] + n * b)];
   }
 }
+// out(l, perm[r], b) = in(l, r, b): P^T along one mode (the last pass of a transposed solve)
+__global__ void perm_mode_scatter_kernel(long long Lp, long long n, long long R, const int* __restrict__ perm,
+                                         const double* __restrict__ in, double* __restrict__ out) {
+  const long long total = Lp * n * R;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long l = i % Lp, r = (i / Lp) % n, b = i / (Lp * n);
+    out[l + Lp * ((long long)perm[r] + n * b)] = in[i];
+  }
+}
 __global__ void identity_perm_kernel(long long n, long long ldt, const int* __restrict__ perm, double* __restrict__ T) {
   const long long total = n * n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -522,6 +531,34 @@ int tri_sweep(scimlop_context* h, const Blob& f, long long n, bool upper, long l
       if (!rc && kw > 0)
         rc = gemm64(h, false, true, Lp, sz, kw, -1.0, dst + Lp * ko, Lp, Lp * n, f.LUr + o + ko * f.ldf, f.ldf, 0, 1.0, dst + Lp * o, Lp,
                     Lp * n, R, st);
+    }
+    if (rc) return rc;
+  }
+  return SCIMLOP_OK;
+}
+
+// The sweeps of the TRANSPOSED solve (A^T x = b: U^T y = b forward, L^T z = y backward).  dst = T^{-T} src with
+// T = U (`unit_lower` false: forward over the lower-triangular U^T) or T = L (true: backward over the unit upper L^T).
+// The pre-multiplied block rows of the blob belong to the other orientation, so a block step is the two GEMMs in the
+// other order, on the plain factors:  t_i = b_i - T_{solved, i}^T y_solved  (INTO src: the sweep consumes its input),
+// then  y_i = Dinv_ii^T t_i  into dst.  Same flops, same stability argument (inverted diagonal blocks only).
+int tri_sweep_t(scimlop_context* h, const Blob& f, long long n, bool unit_lower, long long Lp, long long R, double* src,
+                double* dst, cudaStream_t st) {
+  const long long nb = (n + DB - 1) / DB;
+  const double* D = unit_lower ? f.DL : f.DU;
+  for (long long s = 0; s < nb; s++) {
+    const long long i = unit_lower ? nb - 1 - s : s;
+    const long long o = i * DB, sz = std::min<long long>(DB, n - o);
+    const long long ko = unit_lower ? o + sz : 0, kw = unit_lower ? n - ko : o;   // already-solved index range
+    const double* M = f.LU + ko + o * f.ldf;                                      // T_{solved, i}: kw x sz
+    int rc = SCIMLOP_OK;
+    if (Lp == 1) {
+      if (kw > 0) rc = gemm64(h, true, false, sz, R, kw, -1.0, M, f.ldf, 0, dst + ko, n, 0, 1.0, src + o, n, 0, 1, st);
+      if (!rc) rc = gemm64(h, true, false, sz, R, sz, 1.0, D + o, f.ldf, 0, src + o, n, 0, 0.0, dst + o, n, 0, 1, st);
+    } else {
+      if (kw > 0)
+        rc = gemm64(h, false, false, Lp, sz, kw, -1.0, dst + Lp * ko, Lp, Lp * n, M, f.ldf, 0, 1.0, src + Lp * o, Lp, Lp * n, R, st);
+      if (!rc) rc = gemm64(h, false, false, Lp, sz, sz, 1.0, src + Lp * o, Lp, Lp * n, D + o, f.ldf, 0, 0.0, dst + Lp * o, Lp, Lp * n, R, st);
     }
     if (rc) return rc;
   }
@@ -649,8 +686,8 @@ extern "C" int scimlop_factorize(scimlop_handle_t h, int dtype, int64_t n, const
   return SCIMLOP_OK;
 }
 
-// W = (F_1 (x) ... (x) F_n)^{-1} V with every dense factor given by its factorisation blob (kinds: SCIMLOP_DENSE or
-// SCIMLOP_IDENTITY; dims[f] = order of factor f, outermost first).  workspace: one buffer of prod(dims) * k doubles.
+// W = (F_1 (x) ... (x) F_n)^{-1} V with every dense factor given by its factorisation blob (kinds: SCIMLOP_DENSE,
+// SCIMLOP_DENSE | SCIMLOP_TRANS for the transposed factor, or SCIMLOP_IDENTITY; dims[f] = order of factor f, outermost first).  workspace: one buffer of prod(dims) * k doubles.
 extern "C" int scimlop_kron_ldiv(scimlop_handle_t h, int dtype, int nfactors, void* const* facts, const int64_t* dims,
                                  const int32_t* kinds, const void* V, void* W, int64_t k, void* workspace,
                                  size_t workspace_bytes, void* stream) {
@@ -661,9 +698,9 @@ extern "C" int scimlop_kron_ldiv(scimlop_handle_t h, int dtype, int nfactors, vo
   int nops = 0;
   for (int f = 0; f < nfactors; f++) {
     if (dims[f] < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kron_ldiv: negative size");
-    if (kinds[f] != SCIMLOP_DENSE && kinds[f] != SCIMLOP_IDENTITY)
+    if ((kinds[f] & ~SCIMLOP_TRANS) != SCIMLOP_DENSE && kinds[f] != SCIMLOP_IDENTITY)
       return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "kron_ldiv: factor %d: only dense (factorised) and identity factors", f);
-    if (kinds[f] == SCIMLOP_DENSE) { nops++; if (!facts[f]) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_ldiv: factor %d has no factorisation", f); }
+    if (kinds[f] != SCIMLOP_IDENTITY) { nops++; if (!facts[f]) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_ldiv: factor %d has no factorisation", f); }
     N *= dims[f];
   }
   if (k < 0) return scimlop_fail(h, SCIMLOP_ERR_BAD_SHAPE, "kron_ldiv: negative k");
@@ -677,21 +714,41 @@ extern "C" int scimlop_kron_ldiv(scimlop_handle_t h, int dtype, int nfactors, vo
     return SCIMLOP_OK;
   }
   if (!workspace || workspace_bytes < bytes) return scimlop_fail(h, SCIMLOP_ERR_WORKSPACE, "kron_ldiv: workspace %zu B < required %zu B", workspace_bytes, bytes);
-  // three out-of-place passes per factor (row gather, L sweep, U sweep): 3 * nops passes alternate between W and the
-  // workspace and must end in W
+  // three out-of-place passes per factor -- row gather, L sweep, U sweep; for a transposed factor (SCIMLOP_TRANS: the
+  // lazy adjoint, A^T = U^T L^T P) U^T sweep, L^T sweep, row scatter -- alternate between W and the workspace and must
+  // end in W.  The transposed sweeps consume their source, so if the first factor applied is transposed V is copied first.
+  int first_op = -1;
+  for (int fi = nfactors - 1; fi >= 0 && first_op < 0; fi--)
+    if (kinds[fi] != SCIMLOP_IDENTITY) first_op = fi;
+  const bool copy_first = (kinds[first_op] & SCIMLOP_TRANS) != 0;
+  const int passes = 3 * nops + (copy_first ? 1 : 0);
   double* bufs[2] = {static_cast<double*>(W), static_cast<double*>(workspace)};
-  int cur = (3 * nops) % 2 == 1 ? 0 : 1;              // target of the first pass
+  int cur = passes % 2 == 1 ? 0 : 1;              // target of the first pass
   const double* src = static_cast<const double*>(V);
+  if (copy_first) {
+    SCIMLOP_CUDA(h, cudaMemcpyAsync(bufs[cur], V, bytes, cudaMemcpyDeviceToDevice, st));
+    src = bufs[cur];
+    cur ^= 1;
+  }
   long long Lp = 1;
   for (int fi = nfactors - 1; fi >= 0; fi--) {
     const long long n = dims[fi];
     if (kinds[fi] == SCIMLOP_IDENTITY) { Lp *= n; continue; }
     const long long R = N * k / (Lp * n);
     const Blob f = blob_at(facts[fi], n);
-    perm_mode_kernel<<<grid_for(N * k, h), 256, 0, st>>>(Lp, n, R, f.perm, src, bufs[cur]);
-    h->launches++;
-    if (int rc = tri_sweep(h, f, n, false, Lp, R, bufs[cur], bufs[cur ^ 1], st)) return rc;
-    if (int rc = tri_sweep(h, f, n, true, Lp, R, bufs[cur ^ 1], bufs[cur], st)) return rc;
+    if (kinds[fi] & SCIMLOP_TRANS) {
+      // src is bufs[cur ^ 1] here (a buffer, never V): sweep into bufs[cur], back into bufs[cur ^ 1], scatter into bufs[cur]
+      double* a = bufs[cur ^ 1];
+      if (int rc = tri_sweep_t(h, f, n, false, Lp, R, a, bufs[cur], st)) return rc;
+      if (int rc = tri_sweep_t(h, f, n, true, Lp, R, bufs[cur], a, st)) return rc;
+      perm_mode_scatter_kernel<<<grid_for(N * k, h), 256, 0, st>>>(Lp, n, R, f.perm, a, bufs[cur]);
+      h->launches++;
+    } else {
+      perm_mode_kernel<<<grid_for(N * k, h), 256, 0, st>>>(Lp, n, R, f.perm, src, bufs[cur]);
+      h->launches++;
+      if (int rc = tri_sweep(h, f, n, false, Lp, R, bufs[cur], bufs[cur ^ 1], st)) return rc;
+      if (int rc = tri_sweep(h, f, n, true, Lp, R, bufs[cur ^ 1], bufs[cur], st)) return rc;
+    }
     src = bufs[cur];
     cur ^= 1;
     Lp *= n;

@@ -988,9 +988,13 @@ class InvertibleOperator(AbstractSciMLOperator):
     @property
     def stable_solve(self):
         """True when ldiv! runs the factorised (substitution) solve instead of multiplying by the explicit inverse:
-        an ill-conditioned Float64 factor (cond_1 > COND_FAST).  The lazy adjoint keeps the inverse (the transposed
-        sweeps are not built)."""
-        return self.lu is not None and self.lu.stable_needed and not getattr(self.L, "trans", False)
+        an ill-conditioned Float64 factor (cond_1 > COND_FAST).  The lazy adjoint solves with the same blob through the
+        transposed sweeps (U^T, L^T, then P^T)."""
+        return self.lu is not None and self.lu.stable_needed
+
+    @property
+    def _trans(self):
+        return bool(getattr(self.L, "trans", False))
 
     @property
     def dtype(self):
@@ -1043,7 +1047,7 @@ class InvertibleOperator(AbstractSciMLOperator):
             if self._lu_ws is None or self._lu_ws.numel() < need:
                 self._lu_ws = torch.empty(need, dtype=torch.uint8, device=v.t.device)
             h = _lib.handle(w.device_index)
-            _kron_ldiv(h, [self.lu], [self.lu.n], src, w, k, self._lu_ws)
+            _kron_ldiv(h, [self.lu], [self.lu.n], src, w, k, self._lu_ws, [self._trans])
             if scale is not None and float(scale) != 1.0:
                 _lmul(w, float(scale), h)
             return w
@@ -1162,13 +1166,13 @@ class LUFactorization:
         return not (self.cond <= COND_FAST)       # NaN-safe: unknown conditioning takes the substitution path
 
 
-def _kron_ldiv(h, facts, dims, v, w, k, ws):
-    """scimlop_kron_ldiv on LUFactorization blobs (None = identity factor)."""
+def _kron_ldiv(h, facts, dims, v, w, k, ws, trans=None):
+    """scimlop_kron_ldiv on LUFactorization blobs (None = identity factor; trans[i]: solve with the transposed factor)."""
     nf = len(dims)
     cf, cd, ck = (C.c_void_p * nf)(), (C.c_int64 * nf)(), (C.c_int32 * nf)()
     for i, (f, n) in enumerate(zip(facts, dims)):
         cd[i] = n
-        ck[i] = _lib.IDENTITY if f is None else _lib.DENSE
+        ck[i] = _lib.IDENTITY if f is None else (_lib.DENSE | (_lib.TRANS if trans is not None and trans[i] else 0))
         cf[i] = None if f is None else f.blob.data_ptr()
     h.check(h.lib.scimlop_kron_ldiv(h.ptr, _lib.F64, nf, cf, cd, ck, C.c_void_p(v.ptr), C.c_void_p(w.ptr), k,
                                     C.c_void_p(ws.data_ptr()), ws.numel(), _stream()), "scimlop_kron_ldiv")
@@ -1635,7 +1639,7 @@ class TensorProductOperator(AbstractSciMLOperator):
         src = v
         owners = nat["owners"]
         if any(o is not None and o.stable_solve for o in owners) and \
-                all(o is None or (o.lu is not None and not getattr(o.L, "trans", False)) for o in owners):
+                all(o is None or o.lu is not None for o in owners):
             # an ill-conditioned factor: the factorised solve (substitution sweeps as GEMMs along every mode)
             need = v.t.numel() * 8
             if nat["lu_ws"] is None or nat["lu_ws"].numel() < need:
@@ -1647,7 +1651,8 @@ class TensorProductOperator(AbstractSciMLOperator):
                 src = nat["stash"]
             h = _lib.handle(w.device_index)
             dims_n = [leaf.size()[0] for leaf in self._flatten_inverse()[0]]
-            _kron_ldiv(h, [None if o is None else o.lu for o in owners], dims_n, src, w, k, nat["lu_ws"])
+            _kron_ldiv(h, [None if o is None else o.lu for o in owners], dims_n, src, w, k, nat["lu_ws"],
+                       [o is not None and o._trans for o in owners])
             if a is not None and float(a) != 1.0:
                 _lmul(w, float(a), h)
             return w

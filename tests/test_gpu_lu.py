@@ -130,6 +130,86 @@ def test_kron_ldiv_with_ill_conditioned_factors(sb, shape):
     assert np.array_equal(dv2.numpy(), got)
 
 
+@pytest.mark.parametrize("kappa", [1e6, 1e10])
+@pytest.mark.parametrize("n,k", [(96, 7), (300, 5), (512, 64), (700, 33)])
+def test_adjoint_of_ill_conditioned_factorisation_solves_with_transposed_sweeps(sb, kappa, n, k):
+    """`adjoint(::InvertibleOperator)` (src/matrix.jl:565) shares the factorisation; its ldiv! is LAPACK getrs('T'): U^T
+    and L^T sweeps, then P^T (scimlop_kron_ldiv with SCIMLOP_DENSE | SCIMLOP_TRANS).  Backward error of A^T x = b like
+    numpy.linalg.solve(A.T, b)."""
+    rng = np.random.default_rng(int(np.log10(kappa)) * 7 + n)
+    A = with_cond(rng, n, kappa)
+    At = np.ascontiguousarray(A.T)
+    b = np.asfortranarray(rng.standard_normal((n, k)))
+    b[:, : k // 2] = At @ rng.standard_normal((n, k // 2))
+    L = sb.factorize(sb.MatrixOperator(A))
+    Lt = L.adjoint()
+    assert Lt.stable_solve and Lt.lu is L.lu
+    db = sb.DeviceArray.from_numpy(b)
+    x = sb.DeviceArray.full((n, k), float("nan"), np.float64)
+    sb.ldiv_(x, Lt, db)
+    got = x.numpy()
+    assert np.isfinite(got).all()
+    xl = np.linalg.solve(At, b)
+    for j in range(k):
+        be = backward_error(At, got[:, j:j + 1], b[:, j:j + 1])
+        be_lapack = backward_error(At, xl[:, j:j + 1], b[:, j:j + 1])
+        assert be <= max(50 * EPS, 20 * be_lapack), f"cond {kappa:.0e} column {j}: backward error {be:.3e} (LAPACK {be_lapack:.3e})"
+    assert R.rel_err(got, xl) <= 200 * kappa * EPS
+    # mul! of the adjoint is A^T v; the forward operator still solves with A
+    w = sb.DeviceArray.full((n, k), float("nan"), np.float64)
+    sb.mul_(w, Lt, db)
+    assert R.rel_err(w.numpy(), At @ b) <= 1e-12
+    sb.ldiv_(x, L, db)
+    assert backward_error(A, x.numpy(), b) <= 1e3 * EPS
+    # two-argument form
+    sb.ldiv_(Lt, db)
+    assert np.array_equal(db.numpy(), got)
+
+
+@pytest.mark.parametrize("which", ["both", "outer", "inner"])
+def test_kron_ldiv_with_transposed_factors(sb, which):
+    """(A (x) B)' \\ v = (A' (x) B') \\ v (src/tensor.jl:181-191 + :612-673) and the mixed cases, ill-conditioned factors:
+    transposed sweeps along the inner (first applied: V is copied, the sweeps consume their source) and the outer mode."""
+    rng = np.random.default_rng(len(which))
+    na, nb, k = 130, 96, 5
+    A, B = with_cond(rng, na, 1e8), with_cond(rng, nb, 1e6)
+    v = np.asfortranarray(rng.standard_normal((na * nb, k)))
+    dv = sb.DeviceArray.from_numpy(v)
+    FA, FB = sb.factorize(sb.MatrixOperator(A)), sb.factorize(sb.MatrixOperator(B))
+    if which == "both":
+        L = sb.factorize(sb.TensorProductOperator(A, B)).adjoint()
+        Ae, Be = A.T, B.T
+    elif which == "outer":
+        L = sb.TensorProductOperator(FA.adjoint(), FB)
+        Ae, Be = A.T, B
+    else:
+        L = sb.TensorProductOperator(FA, FB.adjoint())
+        Ae, Be = A, B.T
+    Ae, Be = np.asfortranarray(Ae), np.asfortranarray(Be)
+    L = sb.cache_operator(L, dv)
+    x = sb.DeviceArray.full((na * nb, k), float("nan"), np.float64)
+    sb.ldiv_(x, L, dv)
+    got = x.numpy()
+    assert np.isfinite(got).all()
+    r = v - R.kron_apply([Ae, Be], got)
+    scale = np.linalg.norm(Ae, np.inf) * np.linalg.norm(Be, np.inf) * np.abs(got).max() + np.abs(v).max()
+    assert np.abs(r).max() / scale <= 200 * EPS, f"{which}: Kronecker backward error {np.abs(r).max() / scale:.3e}"
+    X = got.reshape(nb, na, k, order="F")
+    Vt = v.reshape(nb, na, k, order="F")
+    want = np.empty_like(X)
+    for j in range(k):
+        want[:, :, j] = np.linalg.solve(Ae, np.linalg.solve(Be, Vt[:, :, j]).T).T
+    assert R.rel_err(X, want) <= 500 * 1e8 * 1e6 * EPS
+    assert np.array_equal(dv.numpy(), v), "ldiv! modified its right-hand side"
+    # the operator itself applies the transposed factors
+    w = sb.DeviceArray.full((na * nb, k), float("nan"), np.float64)
+    sb.mul_(w, L, dv)
+    assert R.rel_err(w.numpy(), R.kron_apply([Ae, Be], v)) <= 1e-12
+    dv2 = sb.DeviceArray.from_numpy(v)
+    sb.ldiv_(L, dv2)
+    assert np.array_equal(dv2.numpy(), got)
+
+
 def test_three_factor_ldiv_with_identity_and_scaling(sb):
     rng = np.random.default_rng(9)
     A, Cm = with_cond(rng, 40, 1e8), with_cond(rng, 48, 1e6)
