@@ -101,6 +101,16 @@ struct scimlop_device_guard {
 
 inline bool scimlop_valid(scimlop_context* c) { return c && c->magic == SCIMLOP_MAGIC; }
 
+// the handle's second stream + events (column-chunk pipeline of the fused all-gather, look-ahead of the LU): created on
+// first use, destroyed with the handle
+inline int scimlop_ensure_side_stream(scimlop_context* c) {
+  if (c->pipe_ready) return SCIMLOP_OK;
+  SCIMLOP_CUDA(c, cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking));
+  for (int i = 0; i < 10; i++) SCIMLOP_CUDA(c, cudaEventCreateWithFlags(&c->ev_pipe[i], cudaEventDisableTiming));
+  c->pipe_ready = true;
+  return SCIMLOP_OK;
+}
+
 // internal entry shared between scimlop.cu and extras.cu
 int scimlop_kron_mul_impl(scimlop_context* c, int dtype, int precision, int nfactors,
                           const void* const* factors, const int64_t* dims, const int64_t* lds,

@@ -9,9 +9,14 @@
 //              multi-CTA kernel per panel: every thread owns one row of the panel in registers, a column step is a
 //              block arg-max, a grid barrier, the exchange of the pivot row through global memory, a second barrier and
 //              32 FMAs per thread.  Row swaps + the 32 x w triangular solve of the block row are one more kernel; the
-//              trailing update is the DMMA GEMM (alpha = -1, beta = 1).  3 launches per 32 columns; measured 4.3 / 9.4 /
-//              20 / 46 ms at n = 512 / 1024 / 2048 / 4096 (round 1: 4.4 / 10.8 / 30 / 263), 60 % of it the panel kernel's
-//              ~6 us per column (three dependent L2 round trips: publish, barrier, read the winner's row).
+//              trailing update is the DMMA GEMM (alpha = -1, beta = 1).  With LOOK-AHEAD: the panel kernel (16 CTAs,
+//              ~3.3 us of barriers per column) is the critical path, so only the next panel's 32 columns are brought up
+//              to date on the caller's stream (one small kernel for their swaps + block-row solve; their rank-32 update
+//              rides in the next panel kernel's load phase), while the swaps, block-row solve and trailing update of
+//              every other column run on the handle's side stream on the remaining SMs.  Measured 2.5 / 4.9 / 10.3 /
+//              23.7 ms at n = 512 / 1024 / 2048 / 4096 including the solve structures, the explicit inverse and
+//              cond_1 (sequential: 2.9 / 5.7 / 12.2 / 30.1; round 1: 4.4 / 10.8 / 30 / 263); timeline in
+//              profiles/r02_lu_trace.txt (tools/lu_trace.py): 137 us per panel step = 113 panel + 18 prep + gaps.
 //   solve      triangular solves as GEMMs: 128 x 128 diagonal blocks of L and U are inverted once (in shared memory),
 //              the off-diagonal block rows are pre-multiplied by them (L' = Dinv L, U' = Dinv U), and a block step is
 //              x_i = Dinv_ii b_i  followed by  x_i -= L'_{i,<i} x_{<i}  -- both DMMA GEMMs, out of place between two
@@ -24,6 +29,7 @@
 //              cond_1(A) = |A|_1 |Ainv|_1, returned to the caller: for a well-conditioned factor the host keeps the
 //              round-1 fast path (ldiv! = mul! with the inverse factors, residual cond * eps still inside the 1e-12
 //              budget), for an ill-conditioned one it takes the factorised solve.
+#include <cstdio>
 #include <algorithm>
 #include <cstring>
 
@@ -150,13 +156,39 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
   __syncthreads();
 }
 
+// Look-ahead, fused into the panel kernels: the rows of this panel lie below the previous panel (columns [jp, jp + wp)),
+// whose rank-wp update of THIS panel's columns is applied to the register copy right after the load:
+// a(c) -= sum_k L(r, jp + k) U(jp + k, j0 + c), U (already swapped and solved by lu_lookahead_prep_kernel) staged in
+// shared memory.  The panel kernel stores its columns at the end, so the un-updated values in memory are simply replaced.
+__device__ __forceinline__ void panel_apply_previous(double (&a)[PB], const double* __restrict__ A, long long lda, long long r, bool live,
+                                                     int j0, int w, int jp, int wp, double* Us /* PB * PB */) {
+  if (wp <= 0) return;                              // uniform over the grid
+  for (int q = threadIdx.x; q < PB * PB; q += blockDim.x) {
+    const int k = q % PB, cc = q / PB;
+    Us[q] = (k < wp && cc < w) ? A[(long long)(jp + k) + (long long)(j0 + cc) * lda] : 0.0;
+  }
+  double l[PB];
+#pragma unroll
+  for (int k = 0; k < PB; k++) l[k] = (live && k < wp) ? A[r + (long long)(jp + k) * lda] : 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < PB; c++) {
+    double acc = a[c];
+#pragma unroll
+    for (int k = 0; k < PB; k++) acc -= l[k] * Us[k + c * PB];
+    a[c] = acc;
+  }
+  __syncthreads();                                  // Us may alias the kernel's other shared arrays later: done with it
+}
+
 // One panel: columns j0 .. j0 + w - 1, rows j0 .. n - 1.  Thread t of CTA b owns row j0 + PROWS * b + t: its w panel entries
 // live in registers for the whole panel.  All CTAs are co-resident (<= n / 256 of them), so the software barrier is safe.
 // A column step has ONE grid barrier: before it every CTA publishes its candidate pivot (|value|, row) TOGETHER with that
 // row's panel entries, and CTA 0 also publishes the diagonal row; after it every CTA picks the same winner and reads the
 // winner's row from the winner's slot.  Slots are double-buffered by column parity (a CTA runs at most one column ahead).
 __global__ void __launch_bounds__(PROWS) lu_panel_kernel(long long n, double* __restrict__ A, long long lda, int j0, int w,
-                                                         int* __restrict__ piv, unsigned* bar, double* slots, int* info) {
+                                                         int* __restrict__ piv, unsigned* bar, double* slots, int* info, int jp, int wp) {
+  __shared__ double Us[PB * PB];
   // slots: [parity][CTA][PB + 2]: candidate row values, |value|, row index (as a double);  diag: [parity][PB] after them
   __shared__ double sval[PROWS / 32];
   __shared__ int srow[PROWS / 32];
@@ -170,6 +202,7 @@ __global__ void __launch_bounds__(PROWS) lu_panel_kernel(long long n, double* __
   double a[PB];
 #pragma unroll
   for (int c = 0; c < PB; c++) a[c] = (live && c < w) ? A[r + (long long)(j0 + c) * lda] : 0.0;
+  panel_apply_previous(a, A, lda, r, live, j0, w, jp, wp, Us);
   unsigned epoch = 0;
   for (int c = 0; c < w; c++) {
     const int par = c & 1;
@@ -265,7 +298,8 @@ __global__ void __launch_bounds__(PROWS) lu_panel_kernel(long long n, double* __
 // the diagonal row live in each CTA's shared memory and are read through distributed shared memory after one cluster
 // barrier per column -- ~0.3 us round trips instead of the ~1 us L2 round trips of the grid-barrier form above.
 __global__ void __launch_bounds__(PROWS) lu_panel_cluster_kernel(long long n, double* __restrict__ A, long long lda, int j0, int w,
-                                                                 int* __restrict__ piv, int* info) {
+                                                                 int* __restrict__ piv, int* info, int jp, int wp) {
+  __shared__ double Us[PB * PB];
   __shared__ double slot[2][PB + 2];     // this CTA's candidate row: entries, |value|, row index
   __shared__ double diag[2][PB];         // the diagonal row (rank 0's copy is the one that is read)
   __shared__ double prow[PB], drow[PB];
@@ -279,6 +313,7 @@ __global__ void __launch_bounds__(PROWS) lu_panel_cluster_kernel(long long n, do
   double a[PB];
 #pragma unroll
   for (int c = 0; c < PB; c++) a[c] = (live && c < w) ? A[r + (long long)(j0 + c) * lda] : 0.0;
+  panel_apply_previous(a, A, lda, r, live, j0, w, jp, wp, Us);
   for (int c = 0; c < w; c++) {
     const int par = c & 1;
     const double ac = reg_get(a, c);
@@ -374,7 +409,8 @@ __global__ void __launch_bounds__(PROWS) lu_panel_cluster_kernel(long long n, do
 // sequence in shared memory was slower: 45 vs 34 us per panel at n = 4096.)
 constexpr int ST_THREADS = 128;
 __global__ void __launch_bounds__(ST_THREADS) lu_swap_trsm_kernel(long long n, double* __restrict__ A, long long lda, int j0, int w,
-                                                                  const int* __restrict__ piv) {
+                                                                  const int* __restrict__ piv, long long ncols, long long skip0,
+                                                                  long long skipw) {
   __shared__ double L11[PB * PB];
   __shared__ int sp[PB];
   for (int q = threadIdx.x; q < PB * PB; q += blockDim.x) {
@@ -384,8 +420,8 @@ __global__ void __launch_bounds__(ST_THREADS) lu_swap_trsm_kernel(long long n, d
   if (threadIdx.x < PB) sp[threadIdx.x] = threadIdx.x < w ? piv[j0 + threadIdx.x] : 0;
   __syncthreads();
   long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= n - w) return;
-  if (col >= j0) col += w;                         // skip the panel's own columns
+  if (col >= ncols) return;
+  if (col >= skip0) col += skipw;                  // skip the panel's own columns (and, with look-ahead, the next panel's)
   double* a = A + col * lda;
   for (int c = 0; c < w; c++) {
     const int p = sp[c];
@@ -411,6 +447,90 @@ __global__ void __launch_bounds__(ST_THREADS) lu_swap_trsm_kernel(long long n, d
   }
 }
 
+// ---- look-ahead: the NEXT panel's columns, on the critical path ------------------------------------------------------------
+// Panel p's row swaps, block-row solve and rank-w update applied to the wn columns [c0, c0 + wn) of panel p + 1 only, so
+// that panel p + 1 can start while a second stream does the same for all other columns.  The generic kernels cost
+// ~35 us (w dependent swap steps per column) + a GEMM launch here; these two take a few us:
+//   prep    (one CTA) the w swaps touch at most 2 w rows: their net permutation is formed once in shared memory, every
+//           affected element is loaded (independent loads), then stored; then the w x w unit-lower solve per column.
+//   update  rows below the panel: C(r, :) -= L(r, 0..w) U(0..w, :) is applied by the NEXT panel kernel to its register
+//           copy of those rows while it loads them (panel_apply_previous): no launch, no extra pass.
+constexpr int LA_THREADS = 256;
+__global__ void __launch_bounds__(LA_THREADS) lu_lookahead_prep_kernel(double* __restrict__ A, long long lda, int j0, int w, int c0, int wn,
+                                                                       const int* __restrict__ piv) {
+  __shared__ double L11[PB * PB];
+  __shared__ double T[2 * PB][PB + 1];             // the affected rows of the wn columns, after the permutation
+  __shared__ int rows[2 * PB], cur[2 * PB];
+  __shared__ int nrows_s;
+  for (int q = threadIdx.x; q < PB * PB; q += blockDim.x) {
+    const int rr = q % PB, cc = q / PB;
+    L11[q] = (rr < w && cc < w && rr > cc) ? A[(long long)(j0 + rr) + (long long)(j0 + cc) * lda] : 0.0;
+  }
+  if (threadIdx.x < 32) {
+    // net permutation of the <= 2 w rows the w swaps touch, by one warp: lane i holds rows[w + i] (the pivot rows below
+    // the panel met so far) in a register, so "seen before?" is one ballot instead of a scan
+    const int lane = threadIdx.x;
+    const int myp = lane < w ? piv[j0 + lane] : 0;
+    int extra = -1, nr = w;                         // extra: the row id stored at rows[w + lane]
+    int mycur = lane;                               // cur[lane] for lane < w; cur[w + lane] kept in xcur
+    int xcur = w + lane;
+    for (int c = 0; c < w; c++) {
+      const int p = __shfl_sync(0xffffffffu, myp, c);
+      if (p == j0 + c) continue;
+      int b;
+      if (p < j0 + w) b = p - j0;
+      else {
+        const unsigned hit = __ballot_sync(0xffffffffu, extra == p);
+        if (hit) b = w + (__ffs(hit) - 1);
+        else { b = nr; if (lane == nr - w) extra = p; nr++; }
+      }
+      // swap cur[c] <-> cur[b]
+      const int vc = __shfl_sync(0xffffffffu, mycur, c);
+      const int vb = b < w ? __shfl_sync(0xffffffffu, mycur, b) : __shfl_sync(0xffffffffu, xcur, b - w);
+      if (lane == c) mycur = vb;
+      if (b < w) { if (lane == b) mycur = vc; }
+      else if (lane == b - w) xcur = vc;
+    }
+    if (lane < w) { rows[lane] = j0 + lane; cur[lane] = mycur; }
+    if (lane < nr - w) { rows[w + lane] = extra; cur[w + lane] = xcur; }
+    if (lane == 0) nrows_s = nr;
+  }
+  __syncthreads();
+  const int nr = nrows_s, total = nr * wn;        // <= 64 * 32 elements: new content of rows[i] = old content of rows[cur[i]]
+  double v[2 * PB * PB / LA_THREADS];
+#pragma unroll
+  for (int u = 0; u < 2 * PB * PB / LA_THREADS; u++) {
+    const int idx = threadIdx.x + u * LA_THREADS;
+    v[u] = idx < total ? A[(long long)rows[cur[idx % nr]] + (long long)(c0 + idx / nr) * lda] : 0.0;
+  }
+#pragma unroll
+  for (int u = 0; u < 2 * PB * PB / LA_THREADS; u++) {
+    const int idx = threadIdx.x + u * LA_THREADS;
+    if (idx < total) T[idx % nr][idx / nr] = v[u];
+  }
+  __syncthreads();                                 // every load of the old content has completed (values are in T)
+  if (threadIdx.x < wn) {                          // w x w unit-lower solve on the panel rows of column threadIdx.x
+    const int cc = threadIdx.x;
+    double x[PB];
+#pragma unroll
+    for (int q = 0; q < PB; q++) x[q] = q < w ? T[q][cc] : 0.0;
+#pragma unroll
+    for (int q = 1; q < PB; q++) {
+      double sacc = x[q];
+#pragma unroll
+      for (int k2 = 0; k2 < PB; k2++) if (k2 < q) sacc -= L11[q + k2 * PB] * x[k2];
+      x[q] = sacc;
+    }
+#pragma unroll
+    for (int q = 0; q < PB; q++) if (q < w) T[q][cc] = x[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 2 * PB * PB / LA_THREADS; u++) {
+    const int idx = threadIdx.x + u * LA_THREADS;
+    if (idx < total) A[(long long)rows[idx % nr] + (long long)(c0 + idx / nr) * lda] = T[idx % nr][idx / nr];
+  }
+}
 // perm from the pivot sequence (sequential swaps of the identity), in shared memory by one thread
 __global__ void perm_kernel(int n, const int* __restrict__ piv, int* __restrict__ perm) {
   extern __shared__ int sperm[];
@@ -606,11 +726,29 @@ extern "C" int scimlop_factorize(scimlop_handle_t h, int dtype, int64_t n, const
   copy_matrix_kernel<<<grid_for(n * n, h), 256, 0, st>>>(n, static_cast<const double*>(A), lda, f.LU, f.ldf);
   norm1_kernel<<<(unsigned)std::min<long long>(n, 1024), 256, 0, st>>>(n, f.LU, f.ldf, s.norms);
   h->launches += 2;
-  // ---- blocked LU ----
+#ifdef SCIMLOP_LU_TRACE
+  // timing build (tools/lu_trace.py): timed events at the phase boundaries of every panel step
+  static cudaEvent_t tev[1024][7];
+  static bool tev_ready = false;
+  if (!tev_ready) { for (auto& r : tev) for (auto& e : r) cudaEventCreate(&e); tev_ready = true; }
+#define LU_TEV(p, i, stream) do { if ((p) < 1024) cudaEventRecord(tev[p][i], stream); } while (0)
+#else
+#define LU_TEV(p, i, stream) do { } while (0)
+#endif
+  // ---- blocked LU with look-ahead ----
+  // Panel p + 1 (16 CTAs, ~100 us of barriers at n = 4096: the critical path) runs on the caller's stream right after the
+  // updates of ITS columns; panel p's swaps, block-row solve and trailing update of every other column run beside it on
+  // the handle's side stream (sequentially they were 11 of 30 ms at n = 4096).
+  if (int rc = scimlop_ensure_side_stream(h)) return rc;
+  cudaStream_t sB = h->s_side;
+  SCIMLOP_CUDA(h, cudaEventRecord(h->ev_pipe[0], st));
+  SCIMLOP_CUDA(h, cudaStreamWaitEvent(sB, h->ev_pipe[0], 0));
+  int prev_j0 = 0, prev_w = 0;
   for (long long p = 0; p < npan; p++) {
     const int j0 = (int)(p * PB), w = (int)std::min<long long>(PB, n - j0);
     const unsigned ncta = (unsigned)((n - j0 + PROWS - 1) / PROWS);
     bool clustered = false;
+    LU_TEV(p, 0, st);                              // panel start
     if (ncta <= 16 && (ncta <= 8 || cluster16_ok)) {
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
@@ -627,28 +765,61 @@ extern "C" int scimlop_factorize(scimlop_handle_t h, int dtype, int64_t n, const
         cluster_fits[ncta] = nc > 0 ? 1 : 0;
       }
       if (cluster_fits[ncta] == 1) {
-        SCIMLOP_CUDA(h, cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel, (long long)n, f.LU, f.ldf, j0, w, s.piv, s.info));
+        SCIMLOP_CUDA(h, cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel, (long long)n, f.LU, f.ldf, j0, w, s.piv, s.info, prev_j0, prev_w));
         clustered = true;
       }
     }
     if (!clustered) {
-      lu_panel_kernel<<<ncta, PROWS, 0, st>>>(n, f.LU, f.ldf, j0, w, s.piv, s.bar + p, s.slots, s.info);
+      lu_panel_kernel<<<ncta, PROWS, 0, st>>>(n, f.LU, f.ldf, j0, w, s.piv, s.bar + p, s.slots, s.info, prev_j0, prev_w);
     }
     h->launches++;
-    if (n - w > 0) {
-      lu_swap_trsm_kernel<<<(unsigned)((n - w + ST_THREADS - 1) / ST_THREADS), ST_THREADS, 0, st>>>(n, f.LU, f.ldf, j0, w, s.piv);
-      h->launches++;
-    }
+    // ---- look-ahead: the next panel's columns on this stream, every other column on the side stream ----
     const long long j1 = j0 + w, rem = n - j1;
-    if (rem > 0) {
-      if (int rc = gemm64(h, false, false, rem, rem, w, -1.0, f.LU + j1 + (long long)j0 * f.ldf, f.ldf, 0, f.LU + j0 + j1 * f.ldf, f.ldf, 0,
-                          1.0, f.LU + j1 + j1 * f.ldf, f.ldf, 0, 1, st))
-        return rc;
+    const int wn = (int)std::min<long long>(PB, rem);              // width of the next panel (0 after the last)
+    if (n - w > 0) {
+      cudaEvent_t evP = h->ev_pipe[0], evB = h->ev_pipe[1 + (p & 1)], evBprev = h->ev_pipe[1 + ((p + 1) & 1)];
+      SCIMLOP_CUDA(h, cudaEventRecord(evP, st));
+      LU_TEV(p, 1, st);                            // panel end
+      if (wn > 0) {
+        if (p > 0) SCIMLOP_CUDA(h, cudaStreamWaitEvent(st, evBprev, 0));   // those columns carry every earlier update
+        lu_lookahead_prep_kernel<<<1, LA_THREADS, 0, st>>>(f.LU, f.ldf, j0, w, (int)j1, wn, s.piv);
+        LU_TEV(p, 6, st);                          // swaps + block-row solve of the next panel's columns done
+        h->launches++;                             // (the rank-w update of those columns rides in the next panel kernel)
+      }
+      LU_TEV(p, 2, st);                            // next panel's columns ready
+      SCIMLOP_CUDA(h, cudaStreamWaitEvent(sB, evP, 0));
+      LU_TEV(p, 3, sB);                            // side stream released
+      const long long ncolsB = n - w - wn;
+      if (ncolsB > 0) {
+        lu_swap_trsm_kernel<<<(unsigned)((ncolsB + ST_THREADS - 1) / ST_THREADS), ST_THREADS, 0, sB>>>(n, f.LU, f.ldf, j0, w, s.piv, ncolsB, j0,
+                                                                                                   (long long)w + wn);
+        h->launches++;
+      }
+      LU_TEV(p, 4, sB);                            // swaps + block-row solve done
+      const long long j2 = j1 + wn, remB = n - j2;
+      if (rem > 0 && remB > 0) {
+        // leave the SMs of the next panel's cluster free (the panel kernel is the critical path)
+        const int nsm = std::max(1, h->sm_count - h->sm_reserve);
+        const int next_ctas = (int)std::min<long long>((rem + PROWS - 1) / PROWS, nsm / 2);
+        h->grid_limit = std::max(1, nsm - next_ctas);
+        const int rc = gemm64(h, false, false, rem, remB, w, -1.0, f.LU + j1 + (long long)j0 * f.ldf, f.ldf, 0, f.LU + j0 + j2 * f.ldf, f.ldf, 0,
+                              1.0, f.LU + j1 + j2 * f.ldf, f.ldf, 0, 1, sB);
+        h->grid_limit = 0;
+        if (rc) return rc;
+      }
+      SCIMLOP_CUDA(h, cudaEventRecord(evB, sB));
+      LU_TEV(p, 5, sB);                            // trailing update done
     }
+    prev_j0 = j0; prev_w = w;
   }
+  if (npan > 0 && n > PB) SCIMLOP_CUDA(h, cudaStreamWaitEvent(st, h->ev_pipe[1 + ((npan - 1) & 1)], 0));   // join
   SCIMLOP_CUDA(h, cudaGetLastError());
   SCIMLOP_CUDA(h, cudaFuncSetAttribute(perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
-  perm_kernel<<<1, 256, (size_t)n * 4, st>>>((int)n, s.piv, f.perm);
+  // (a serial pass of one thread, ~0.2 ms at n = 4096: on the side stream, beside the inversion of the diagonal blocks)
+  SCIMLOP_CUDA(h, cudaEventRecord(h->ev_pipe[0], st));
+  SCIMLOP_CUDA(h, cudaStreamWaitEvent(sB, h->ev_pipe[0], 0));
+  perm_kernel<<<1, 256, (size_t)n * 4, sB>>>((int)n, s.piv, f.perm);
+  SCIMLOP_CUDA(h, cudaEventRecord(h->ev_pipe[1], sB));
   // ---- solve structures: inverse diagonal blocks, pre-multiplied off-diagonal block rows ----
   const int nb = (int)((n + DB - 1) / DB);
   SCIMLOP_CUDA(h, cudaFuncSetAttribute(tri_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB * (DB + 1) * 8));
@@ -665,6 +836,7 @@ extern "C" int scimlop_factorize(scimlop_handle_t h, int dtype, int64_t n, const
         return rc;
   }
   // ---- explicit inverse = the solve applied to the identity; cond_1 ----
+  SCIMLOP_CUDA(h, cudaStreamWaitEvent(st, h->ev_pipe[1], 0));                       // perm is ready
   identity_perm_kernel<<<grid_for(n * n, h), 256, 0, st>>>(n, n, f.perm, s.T1);     // T1 = P (n x n, ld n)
   h->launches++;
   if (int rc = tri_sweep(h, f, n, false, 1, n, s.T1, s.T2, st)) return rc;
@@ -681,6 +853,15 @@ extern "C" int scimlop_factorize(scimlop_handle_t h, int dtype, int64_t n, const
   SCIMLOP_CUDA(h, cudaMemcpyAsync(hn, s.norms, 16, cudaMemcpyDeviceToHost, st));
   SCIMLOP_CUDA(h, cudaMemcpyAsync(&hinfo, s.info, 4, cudaMemcpyDeviceToHost, st));
   SCIMLOP_CUDA(h, cudaStreamSynchronize(st));
+#ifdef SCIMLOP_LU_TRACE
+  for (long long p = 0; p + 1 < npan && p < 1024; p += (npan > 16 ? npan / 16 : 1)) {
+    float t[7];
+    for (int i = 0; i < 7; i++) cudaEventElapsedTime(&t[i], tev[0][0], tev[p][i]);
+    fprintf(stderr, "lu_trace n=%lld panel %3lld: P %8.1f..%8.1f us | prep %8.1f cols ready %8.1f | side: released %8.1f swaps %8.1f update %8.1f\n",
+            (long long)n, p, t[0] * 1e3, t[1] * 1e3, t[6] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3);
+  }
+  { float t; cudaEventElapsedTime(&t, tev[0][0], tev[std::min<long long>(npan, 1024) - 2][5]); fprintf(stderr, "lu_trace last side-stream update ends at %.1f us\n", t * 1e3); }
+#endif
   if (hinfo != 0) return scimlop_fail(h, SCIMLOP_ERR_SINGULAR, "factorize: zero pivot at column %d", hinfo);
   if (cond1) *cond1 = hn[0] * hn[1];
   return SCIMLOP_OK;

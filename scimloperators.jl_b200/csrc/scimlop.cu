@@ -1480,11 +1480,7 @@ static int kron_mul_impl_peers(scimlop_context* h, int dtype, int precision, int
     if (h->peer_pipeline == 1 && ingress_us < 2.0 * stage2_us) nch = 0;
   }
   if (nch) {
-    if (!h->pipe_ready) {
-      SCIMLOP_CUDA(h, cudaStreamCreateWithFlags(&h->s_side, cudaStreamNonBlocking));
-      for (int i = 0; i < 10; i++) SCIMLOP_CUDA(h, cudaEventCreateWithFlags(&h->ev_pipe[i], cudaEventDisableTiming));
-      h->pipe_ready = true;
-    }
+    if (int rc0 = scimlop_ensure_side_stream(h)) { h->tail_split = saved_tail_split; return rc0; }
     const int nsm = std::max(1, h->sm_count - h->sm_reserve);
     // SMs of the last stage of a non-final chunk.  The next chunk's first stage is on the critical path (its last stage
     // starts when it ends and then shares the wire), so: fewest waves for that first stage on the remaining SMs, among
