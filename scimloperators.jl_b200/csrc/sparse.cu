@@ -137,6 +137,70 @@ __global__ void csr_gather_t_kernel(long long m, long long k, const int* __restr
   }
 }
 
+// The same gather with one WARP per row and the lanes across columns: a nonzero costs the warp ONE fully coalesced read
+// of 512 contiguous bytes of the row-contiguous copy (the thread-per-row form above touches 32 different lines per load
+// instruction, half a sector used each: 3.5 TB/s of L2 traffic, 89 % of the stalls on the scoreboard).  The (index,
+// value) pairs of a row are loaded 32 at a time, one per lane, and broadcast by shuffle, so the gathers of a row do not
+// depend on each other: 8 in flight per warp.  A CTA owns 32 rows x 32 * VEC columns; the tile goes through shared
+// memory so that W (column-major) is written with 256 contiguous bytes per column.
+template <typename T>
+__global__ void __launch_bounds__(256) csr_gather_rows_kernel(long long m, long long k, const int* __restrict__ rowptr,
+                                                              const int* __restrict__ colidx, const T* __restrict__ vals, int base,
+                                                              const T* __restrict__ Vt, T* W, long long ldw, T alpha, T beta) {
+  constexpr int VEC = 16 / (int)sizeof(T);       // columns per lane: one 16-byte load
+  constexpr int CB = 32 * VEC;                   // columns per CTA
+  __shared__ T tile[32][CB + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)blockIdx.x * 32;
+  for (long long c0 = (long long)blockIdx.y * CB; c0 < k; c0 += (long long)gridDim.y * CB) {   // k % CB == 0 on this path
+    for (int rr = 0; rr < 4; rr++) {
+      const long long r = row0 + warp + 8 * rr;
+      T acc[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; e++) acc[e] = T(0);
+      if (r < m) {
+        const int j0 = rowptr[r] - base, j1 = rowptr[r + 1] - base;
+        const T* vbase = Vt + c0 + lane * VEC;
+        for (int jb = j0; jb < j1; jb += 32) {
+          const int cnt = min(32, j1 - jb);
+          const int myc = lane < cnt ? colidx[jb + lane] - base : 0;
+          const T mya = lane < cnt ? vals[jb + lane] : T(0);
+          for (int q = 0; q < cnt; q += 8) {
+            float4 x[8];
+            T a[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const int cu = __shfl_sync(0xffffffffu, myc, (q + u) & 31);
+              a[u] = __shfl_sync(0xffffffffu, mya, (q + u) & 31);
+              if (q + u < cnt) x[u] = __ldg(reinterpret_cast<const float4*>(vbase + (long long)cu * k));
+              else { x[u] = make_float4(0.f, 0.f, 0.f, 0.f); a[u] = T(0); }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const T* xv = reinterpret_cast<const T*>(&x[u]);
+#pragma unroll
+              for (int e = 0; e < VEC; e++) acc[e] += a[u] * xv[e];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; e++) tile[warp + 8 * rr][lane * VEC + e] = acc[e];
+    }
+    __syncthreads();
+    const long long r = row0 + lane;
+    if (r < m) {
+      for (int c = warp; c < CB; c += 8) {
+        T* w = W + r + (c0 + c) * ldw;
+        T v = alpha * tile[lane][c];
+        if (beta != T(0)) v += beta * *w;
+        *w = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T>
 __global__ void scale_cols_kernel(long long n, long long k, T* W, long long ldw, T beta) {
   const long long total = n * k;
@@ -179,7 +243,17 @@ int csr_mul_t(scimlop_context* h, bool trans, long long m, long long n, long lon
       // enough columns to pay for a transposed staging copy of V (one extra read + write of V)
       T* Vt = static_cast<T*>(workspace);
       transpose_kernel<T><<<dim3((unsigned)((n + 31) / 32), (unsigned)((k + 31) / 32)), dim3(32, 8), 0, st>>>(n, k, V, ldv, Vt);
-      if (k % 16 == 0) {   // 16 columns per thread: a gathered row is a full 128-byte line (Float64)
+      bool by_rows = false;
+      if constexpr (!is_cplx<T>::value) {
+        if (k % (512 / (long long)sizeof(T)) == 0) {   // a warp per row, 512-byte coalesced gathers
+          const unsigned gr = (unsigned)((m + 31) / 32);
+          const unsigned gy = (unsigned)std::min<long long>(k / (512 / (long long)sizeof(T)), 65535);
+          csr_gather_rows_kernel<T><<<dim3(gr, gy), 256, 0, st>>>(m, k, rowptr, colidx, vals, base, Vt, W, ldw, alpha, beta);
+          by_rows = true;
+        }
+      }
+      if (by_rows) {
+      } else if (k % 16 == 0) {   // 16 columns per thread: a gathered row is a full 128-byte line (Float64)
         const unsigned gy = (unsigned)std::min<long long>(k / 16, 65535);
         csr_gather_t_kernel<T, 16><<<dim3(gx, gy), THREADS, 0, st>>>(m, k, rowptr, colidx, vals, base, Vt, W, ldw, alpha, beta);
       } else {

@@ -92,11 +92,16 @@ def test_sparse_operators_in_an_added_tree_with_time_dependent_scalars(sb):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_cached_sparse_operator_uses_the_staged_gather(sb, dtype):
-    """cache_operator allocates the row-contiguous staging copy of V (k a multiple of 8): two launches, same numbers."""
+@pytest.mark.parametrize("shape", [(300, 257, 40, 0.05), (300, 257, 128, 0.3), (1000, 500, 256, 0.004), (33, 2000, 384, 0.05)])
+def test_cached_sparse_operator_uses_the_staged_gather(sb, dtype, shape):
+    """cache_operator allocates the row-contiguous staging copy of V (k a multiple of 8): two launches, same numbers.
+    k a multiple of 512 bytes of elements takes the warp-per-row kernel (csr_gather_rows_kernel): row counts that are not
+    a multiple of the 32-row tile, rows with more than 32 nonzeros (density 0.3 of 257 columns), empty rows (0.004)."""
     rng = np.random.default_rng(8)
-    m, n, k = 300, 257, 40
-    A = sprand(rng, m, n, 0.05, dtype)
+    m, n, k, density = shape
+    A = sprand(rng, m, n, density, dtype)
+    if density < 0.01:
+        A[::7, :] = 0            # some rows without any nonzero
     v = np.asfortranarray(rng.standard_normal((n, k)).astype(dtype))
     dv = sb.DeviceArray.from_numpy(v)
     L = sb.cache_operator(sb.MatrixOperator(sb.SparseMatrixCSR.from_dense(A)), dv)
