@@ -463,6 +463,10 @@ mul!(w::DevMat{T}, L::MatrixOperator{T, <:CuSparseMatrixCSR{T, Int32}}, v::DevMa
     csr_mul!(w, L.A.rowPtr, L.A.colVal, L.A.nzVal, size(L.A, 1), size(L.A, 2), 0, v, α, β)
 mul!(w::DevMat{T}, L::MatrixOperator{T, <:CuSparseMatrixCSC{T, Int32}}, v::DevMat{T}, α::Number, β::Number) where {T <: F} =
     csr_mul!(w, L.A.colPtr, L.A.rowVal, L.A.nzVal, size(L.A, 2), size(L.A, 1), 1, v, α, β)
+# trans = 1 is the scatter kernel (atomic adds: the last bits vary from run to run).  A CACHED operator should convert
+# once instead -- `cache_operator(L::MatrixOperator{T, <:CuSparseMatrixCSC}, v)` keeping `CuSparseMatrixCSR(L.A)` (CUSPARSE
+# csr2csc) next to the staging workspace -- and call the gather (trans = 0) on that: deterministic and 2-4x faster; the
+# Python mirror does exactly this for lazy adjoints (operators.py, `_csr_transpose`).
 
 # ---- ComplexF32 / ComplexF64 (test/basic.jl:405-426, alloccheck.jl:37): dtype codes 2 / 3, interleaved storage as is ----
 # A complex MatrixOperator mul! is the one-factor case of scimlop_kron_mul's complex planner; the workspace

@@ -181,6 +181,23 @@ class SparseMatrixCSR:
         return self.values.device_index
 
 
+def _csr_transpose(A):
+    """CSR form of A^T (= the CSC form of A) on A's device: entries sorted by (column, row).  One-time set-up work of
+    cache_operator for a lazy adjoint, not part of mul!."""
+    m, n = A.shape
+    rowptr, colidx, vals = A.rowptr.t, A.colidx.t, A.values.t
+    dev = vals.device
+    counts = (rowptr[1:] - rowptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(m, device=dev), counts)
+    order = torch.argsort(colidx.long() * max(m, 1) + rows, stable=True)
+    new_rowptr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    if colidx.numel():
+        new_rowptr[1:] = torch.cumsum(torch.bincount(colidx.long(), minlength=n), 0).to(torch.int32)
+    nnz = int(colidx.numel())
+    return SparseMatrixCSR(DeviceArray(new_rowptr, (n + 1,)), DeviceArray(rows[order].to(torch.int32).contiguous(), (nnz,)),
+                           DeviceArray(vals[order].contiguous(), (nnz,)), (n, m))
+
+
 class ScalarOperator:
     """src/scalar.jl:124-127 -- mutable scalar; `update_func(old, u, p, t)` gives the new value (:267-270)."""
 
@@ -405,7 +422,14 @@ class MatrixOperator(AbstractSciMLOperator):
     def cache_operator(self, v):
         if self.sparse:
             nbytes = C.c_size_t(0)
-            _lib.load().scimlop_csr_workspace_bytes(_DT[v.dtype], int(self.trans), self.A.shape[0], self.A.shape[1], _ncols(v),
+            A, trans = self.A, int(self.trans)
+            if self.trans:
+                # The lazy adjoint is constant (adjoint() refuses time-dependent matrices): build the CSR form of A^T
+                # once -- what CUSPARSE's CSR -> CSC conversion gives a Julia caller -- so that mul! is the gather kernel
+                # on it (deterministic, staged, coalesced) instead of the atomic scatter.
+                self._csr_T = A = _csr_transpose(self.A)
+                trans = 0
+            _lib.load().scimlop_csr_workspace_bytes(_DT[v.dtype], trans, A.shape[0], A.shape[1], _ncols(v),
                                                     C.byref(nbytes))
             self._csr_ws = torch.empty(nbytes.value, dtype=torch.uint8, device=v.t.device) if nbytes.value else None
             return self
@@ -458,9 +482,11 @@ class MatrixOperator(AbstractSciMLOperator):
                                            C.c_void_p(ws.data_ptr()), ws.numel(), _stream()), "scimlop_kron_mul")
             return w
         if self.sparse:   # general sparse matrix: CSR gather (or, for the lazy adjoint, scatter) kernel
-            A = self.A
+            A, trans = self.A, int(self.trans)
+            if self.trans and getattr(self, "_csr_T", None) is not None:
+                A, trans = self._csr_T, 0           # cached adjoint: gather on the CSR form of A^T
             ws = getattr(self, "_csr_ws", None)     # allocated by cache_operator (row-contiguous staging copy of V)
-            h.check(h.lib.scimlop_csr_mul(h.ptr, _DT[w.dtype], int(self.trans), A.shape[0], A.shape[1], _ncols(v),
+            h.check(h.lib.scimlop_csr_mul(h.ptr, _DT[w.dtype], trans, A.shape[0], A.shape[1], _ncols(v),
                                           C.c_void_p(A.rowptr.ptr), C.c_void_p(A.colidx.ptr), C.c_void_p(A.values.ptr), 0,
                                           C.c_void_p(v.ptr), v.ld, C.c_void_p(w.ptr), w.ld, _scalar(w.dtype, alpha),
                                           _scalar(w.dtype, beta), None if ws is None else C.c_void_p(ws.data_ptr()),

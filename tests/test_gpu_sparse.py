@@ -120,6 +120,52 @@ def test_cached_sparse_operator_uses_the_staged_gather(sb, dtype, shape):
     assert R.rel_err(dw.numpy(), -0.5 * want + 2.0 * w0.astype(np.float64)) <= TOL[np.dtype(dtype)]
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.complex128])
+@pytest.mark.parametrize("shape", [(300, 257, 40, 0.05), (257, 300, 128, 0.2), (64, 50, 3, 0.0)])
+def test_cached_sparse_adjoint_gathers_on_the_transposed_structure(sb, dtype, shape):
+    """cache_operator of the lazy adjoint (src/matrix.jl:174-175) builds the CSR form of A^T once; mul! is then the gather
+    kernel on it: same numbers as the scatter kernel of the uncached adjoint within tolerance, and -- unlike the atomic
+    scatter -- bit-identical from call to call.  Complex: the adjoint conjugates."""
+    import torch
+    rng = np.random.default_rng(21)
+    m, n, k, density = shape
+    A = sprand(rng, m, n, density, np.float64)
+    if np.issubdtype(dtype, np.complexfloating):
+        A = A + 1j * sprand(rng, m, n, density, np.float64) * (A != 0)
+    A = np.asfortranarray(A.astype(dtype))
+    real = np.float32 if dtype == np.float32 else np.float64
+    v = rng.standard_normal((m, k)).astype(real)
+    if np.issubdtype(dtype, np.complexfloating):
+        v = v + 1j * rng.standard_normal((m, k))
+    v = np.asfortranarray(v.astype(dtype))
+    dv = sb.DeviceArray.from_numpy(v)
+    L = sb.MatrixOperator(sb.SparseMatrixCSR.from_dense(A))
+    plain = sb.DeviceArray.full((n, k), float("nan"), dtype)
+    sb.mul_(plain, L.adjoint(), dv)                      # uncached: scatter kernel
+    Lt = sb.cache_operator(L.adjoint(), dv)
+    assert Lt._csr_T.shape == (n, m) and Lt._csr_T.nnz == L.A.nnz
+    w = sb.DeviceArray.full((n, k), float("nan"), dtype)
+    sb.mul_(w, Lt, dv)
+    want = A.conj().T.astype(np.complex128 if np.issubdtype(dtype, np.complexfloating) else np.float64) @ v
+    tol = 1e-5 if dtype == np.float32 else 1e-12
+
+    def err(got, ref):          # norm-wise, on the complex values themselves (R.rel_err is for real arrays)
+        ref = np.asarray(ref)
+        return float(np.linalg.norm(np.asarray(got) - ref) / max(np.linalg.norm(ref), 1e-300)) if ref.size else 0.0
+    assert err(w.numpy(), want) <= tol
+    assert err(plain.numpy(), want) <= tol
+    first = w.t.clone()
+    for _ in range(3):
+        w.t.fill_(float("nan"))
+        sb.mul_(w, Lt, dv)
+        assert torch.equal(w.t, first), "the gather on the transposed structure must be deterministic"
+    if not np.issubdtype(dtype, np.complexfloating):
+        w0 = np.asfortranarray(rng.standard_normal((n, k)).astype(dtype))
+        dw = sb.DeviceArray.from_numpy(w0)
+        sb.mul_(dw, Lt, dv, -2.0, 0.5)
+        assert R.rel_err(dw.numpy(), -2.0 * want + 0.5 * w0.astype(np.float64)) <= tol
+
+
 def test_sparse_from_scipy_and_large_batch(sb):
     sp = pytest.importorskip("scipy.sparse")
     rng = np.random.default_rng(5)
