@@ -78,10 +78,21 @@ enum {
   SCIMLOP_DIAG = 2,     /* DiagonalOperator(::Vector): data = n entries  src/matrix.jl:438-459        */
   SCIMLOP_BDIAG = 3,    /* BatchedDiagonalOperator: data = n x k, ld     src/batch.jl:11-28           */
   SCIMLOP_NULL = 4,     /* NullOperator                                  src/basic.jl:185-188         */
-  SCIMLOP_BANDED = 5    /* MatrixOperator over a banded (tridiagonal, ...) n x n matrix, kron factors only:
+  SCIMLOP_BANDED = 5,   /* MatrixOperator over a banded (tridiagonal, ...) n x n matrix, kron factors only:
                            data = n x (2b+1) column-major, diagonal d in column d+b aligned by row
                            (data[i + n*(d+b)] = A[i, i+d]); lds[f] carries the half-bandwidth b (<= 4)  */
+  SCIMLOP_CSR = 6       /* MatrixOperator over a general sparse m x n matrix (CSR), kron factors of scimlop_kron_mul only:
+                           factors[f] points to a HOST scimlop_csr_factor describing device arrays; Float32 / Float64,
+                           not combinable with SCIMLOP_TRANS (convert once: a CSC matrix is the CSR form of its transpose) */
 };
+/* A sparse Kronecker factor (`TensorProductOperator(sprand(...), B)`): device pointers, read on the host at call time. */
+typedef struct {
+  const int32_t* rowptr;   /* rows + 1 entries */
+  const int32_t* colidx;   /* nnz entries */
+  const void* values;      /* nnz entries of the call's dtype */
+  int32_t index_base;      /* 0, or 1 for CUDA.jl's CuSparseMatrixCSR */
+  int32_t reserved;
+} scimlop_csr_factor;
 /* OR-ed into a kron factor kind: the factor is the lazy adjoint/transpose of the stored matrix
  * (`adjoint(::MatrixOperator)` wraps the array, src/matrix.jl:174-175; TPO adjoint maps over factors,
  * src/tensor.jl:181-191).  dims[] are those of the OPERATOR; the stored matrix is cols x rows. */

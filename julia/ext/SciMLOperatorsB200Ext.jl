@@ -468,6 +468,15 @@ mul!(w::DevMat{T}, L::MatrixOperator{T, <:CuSparseMatrixCSC{T, Int32}}, v::DevMa
 # csr2csc) next to the staging workspace -- and call the gather (trans = 0) on that: deterministic and 2-4x faster; the
 # Python mirror does exactly this for lazy adjoints (operators.py, `_csr_transpose`).
 
+# A sparse matrix as a Kronecker FACTOR: kind SCIMLOP_CSR = 6, factors[f] = pointer to a host struct of device pointers
+# (include/scimlop_b200.h, scimlop_csr_factor).  `flatten` pushes this for MatrixOperator{T, <:CuSparseMatrixCSR}; keep the
+# Ref alive for the duration of the ccall (GC.@preserve).
+struct CsrFactor
+    rowptr::Ptr{Cvoid}; colidx::Ptr{Cvoid}; values::Ptr{Cvoid}; index_base::Int32; reserved::Int32
+end
+const CSR = Cint(6)
+csr_factor(A::CuSparseMatrixCSR) = Ref(CsrFactor(dptr(A.rowPtr), dptr(A.colVal), dptr(A.nzVal), Int32(1), Int32(0)))
+
 # ---- ComplexF32 / ComplexF64 (test/basic.jl:405-426, alloccheck.jl:37): dtype codes 2 / 3, interleaved storage as is ----
 # A complex MatrixOperator mul! is the one-factor case of scimlop_kron_mul's complex planner; the workspace
 # (scimlop_kron_workspace_bytes with the complex dtype) belongs in the operator's cache.

@@ -15,7 +15,7 @@ OK = 0
  ERR_SINGULAR) = range(1, 10)
 F64, F32, C64, C128 = 0, 1, 2, 3
 PREC_DEFAULT, PREC_TF32X3, PREC_TF32, PREC_FP32_EXACT, PREC_BF16 = 0, 1, 2, 3, 4
-DENSE, IDENTITY, DIAG, BDIAG, NULL, BANDED = 0, 1, 2, 3, 4, 5
+DENSE, IDENTITY, DIAG, BDIAG, NULL, BANDED, CSR = 0, 1, 2, 3, 4, 5, 6
 TRANS = 0x100
 OPT_TAIL_SPLIT = 1
 OPT_PEER_PIPELINE = 2
@@ -98,6 +98,12 @@ SIGNATURES = {
     "scimlop_kron_mul_mc": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _I64, _P, _P, _P, _P, _SZ, _P],
     "scimlop_kron_mul_allgather": [_P, _INT, _INT, _INT, C.POINTER(_P), _I64P, _I64P, _I32P, _P, _P, _I64, _P, _I64, _P, _SZ, _P],
 }
+
+class CsrFactor(C.Structure):
+    """scimlop_csr_factor (include/scimlop_b200.h): a sparse Kronecker factor, device pointers in a host struct."""
+    _fields_ = [("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("values", C.c_void_p), ("index_base", C.c_int32),
+                ("reserved", C.c_int32)]
+
 
 _lib = None
 

@@ -117,3 +117,10 @@ int scimlop_kron_mul_impl(scimlop_context* c, int dtype, int precision, int nfac
                           const int32_t* kinds, const void* V, int64_t ldv, void* W, int64_t ldw, int64_t k,
                           const void* alpha, const void* beta, void* workspace, size_t workspace_bytes,
                           cudaStream_t stream);
+
+// internal entry of sparse.cu used by the Kronecker planner (scimlop.cu): one mode product with a CSR factor,
+// Y(l, i, r) = alpha * sum_j A(i, j) X(l, j, r) + beta * Y(l, i, r) over the (L x n x R) -> (L x m x R) views.
+// `stage`: optional buffer of n * R elements for the innermost mode (L == 1): the row-contiguous copy of X.
+int scimlop_csr_mode_impl(scimlop_context* c, int dtype, const void* csr_factor_desc, long long L, long long m, long long n,
+                          long long R, const void* X, void* Y, const void* alpha, const void* beta, void* stage,
+                          size_t stage_bytes, cudaStream_t stream);

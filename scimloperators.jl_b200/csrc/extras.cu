@@ -77,6 +77,8 @@ extern "C" int scimlop_kron_mul_host(scimlop_handle_t h, int dtype, int precisio
       if (!factors[f]) return scimlop_fail(h, SCIMLOP_ERR_NULL_POINTER, "kron_mul_host: null banded factor %d", f);
       if (lds[f] < 0 || lds[f] > 4) return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "kron_mul_host: bad half-bandwidth");
       off += align_up((size_t)dims[2 * f] * (size_t)(2 * lds[f] + 1) * es, 256);
+    } else if (kinds[f] == SCIMLOP_CSR) {
+      return scimlop_fail(h, SCIMLOP_ERR_UNSUPPORTED, "kron_mul_host: sparse factor %d: upload the CSR arrays and call scimlop_kron_mul", f);
     }
   }
   const size_t vslot = align_up((size_t)cols * cc * es, 256), wslot = align_up((size_t)rows * cc * es, 256);

@@ -1138,6 +1138,7 @@ struct KronPlan {
   int nops;                // non-identity factors
   long long rows, cols;    // prod of factor rows / cols
   long long max_inter;     // largest intermediate (elements per k column count included)
+  long long csr_stage;     // elements of the staging copy an innermost SCIMLOP_CSR factor gathers from (0: none)
 };
 
 int kron_plan(scimlop_context* c, int nfactors, const int64_t* dims, const int32_t* kinds, int64_t k, KronPlan* pl) {
@@ -1151,12 +1152,16 @@ int kron_plan(scimlop_context* c, int nfactors, const int64_t* dims, const int32
     if (m < 0 || n < 0) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "kron: negative factor size");
     if (kinds[f] == SCIMLOP_IDENTITY || kinds[f] == SCIMLOP_DIAG || kinds[f] == SCIMLOP_BANDED) {
       if (m != n) return scimlop_fail(c, SCIMLOP_ERR_BAD_SHAPE, "kron: identity/diagonal/banded factor %d must be square", f);
+    } else if (kinds[f] == SCIMLOP_CSR) {
+      // general sparse factor: any shape
     } else if ((kinds[f] & ~SCIMLOP_TRANS) != SCIMLOP_DENSE) {
       return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "kron: factor kind %d not supported inside a tensor product", kinds[f]);
     }
     if (kinds[f] != SCIMLOP_IDENTITY) pl->nops++;
     pl->rows *= m; pl->cols *= n;
   }
+  // an innermost sparse factor gathers from a row-contiguous copy of the input (csrc/sparse.cu): cols * k elements
+  pl->csr_stage = (kinds[nfactors - 1] == SCIMLOP_CSR) ? pl->cols * k : 0;
   // intermediates: after applying modes nfactors-1 .. p the tensor has prod_{q>=p} m_q * prod_{q<p} n_q * k entries
   long long done = 0;
   for (int p = nfactors - 1; p >= 0; p--) {
@@ -1241,7 +1246,18 @@ int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* cons
         }
       }
     }
-    if (kinds[p] == SCIMLOP_BANDED) {
+    if (kinds[p] == SCIMLOP_CSR) {
+      // mode product with a general sparse matrix: gather kernels of csrc/sparse.cu                [L2 / HBM-bound]
+      if (g_peers.active() && last) return scimlop_fail(c, SCIMLOP_ERR_UNSUPPORTED, "kron: peer targets need a dense outermost factor");
+      char* stage = nullptr;
+      size_t stage_bytes = 0;
+      if (L == 1 && workspace && ws_bytes >= buf_bytes * nbuf + (size_t)pl.csr_stage * sizeof(T)) {
+        stage = static_cast<char*>(workspace) + buf_bytes * nbuf;
+        stage_bytes = ws_bytes - buf_bytes * nbuf;
+      }
+      rc = scimlop_csr_mode_impl(c, std::is_same<T, double>::value ? SCIMLOP_F64 : SCIMLOP_F32, factors[p], L, m, n, R, cur, out, &a, &bt,
+                                 stage, stage_bytes, st);
+    } else if (kinds[p] == SCIMLOP_BANDED) {
       // mode product with a banded matrix: a 1-D stencil along index (i / L) % n      [HBM-bound]
       const long long total = L * n * R;
       const int b = (int)lds[p];
@@ -1405,7 +1421,7 @@ extern "C" int scimlop_kron_workspace_bytes(int dtype, int nfactors, const int64
   KronPlan pl;
   if (int rc = kron_plan(nullptr, nfactors, dims, kinds, k, &pl)) return rc;
   const int nbuf = pl.nops >= 3 ? 2 : (pl.nops == 2 ? 1 : 0);
-  *bytes = nbuf * align_up((size_t)pl.max_inter * elem_size(dtype), 256);
+  *bytes = nbuf * align_up((size_t)pl.max_inter * elem_size(dtype), 256) + align_up((size_t)pl.csr_stage * elem_size(dtype), 256);
   return SCIMLOP_OK;
 }
 

@@ -1471,8 +1471,20 @@ def _kron_leaf(op):
     while isinstance(op, InvertibleOperator):
         op = op.L
     if isinstance(op, MatrixOperator) and op.sparse:
-        raise NotImplementedError("a sparse MatrixOperator as a Kronecker factor is not supported by the B200 backend "
-                                  "(the Julia wrapper keeps the generic path for it)")
+        # SCIMLOP_CSR: factors[f] is a host descriptor of the device arrays (kept alive on the operator).  The lazy adjoint
+        # (constant by construction) is converted once to the CSR form of A^T; complex sparse factors are not built.
+        if _is_complex(op.A.dtype):
+            raise NotImplementedError("a complex sparse MatrixOperator as a Kronecker factor is not supported by the B200 backend")
+        A = op.A
+        if op.trans:
+            if getattr(op, "_csr_T", None) is None:
+                op._csr_T = _csr_transpose(op.A)
+            A = op._csr_T
+        d = getattr(op, "_csr_desc", None)
+        if d is None:                               # ONE struct per operator: native plans keep its address
+            d = op._csr_desc = _lib.CsrFactor()
+        d.rowptr, d.colidx, d.values, d.index_base, d.reserved = A.rowptr.ptr, A.colidx.ptr, A.values.ptr, 0, 0
+        return (_lib.CSR, C.addressof(d), 0)
     if isinstance(op, MatrixOperator) and op.banded:
         return (_lib.BANDED, op.A.bands.ptr, op.A.b)      # lds[] carries the half-bandwidth for banded factors
     if isinstance(op, MatrixOperator):

@@ -166,6 +166,57 @@ def test_cached_sparse_adjoint_gathers_on_the_transposed_structure(sb, dtype, sh
         assert R.rel_err(dw.numpy(), -2.0 * want + 0.5 * w0.astype(np.float64)) <= tol
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", ["sparse_inner", "sparse_outer", "both", "three", "adjoint", "staged_inner"])
+def test_sparse_kronecker_factors(sb, dtype, case):
+    """`TensorProductOperator(sprand(...), B)`: a general sparse matrix as a Kronecker factor (SCIMLOP_CSR), along the
+    innermost mode (the SpMM, staged when the workspace and the column count allow), along outer modes (gather over the
+    contiguous mode rows, no copy), rectangular, next to dense / identity factors, as a lazy adjoint (converted once) --
+    against the dense Kronecker definition (test/matrix.jl:625-644 style) through the oracle's mode products."""
+    rng = np.random.default_rng(sum(map(ord, case)))
+    tol = TOL[np.dtype(dtype)]
+    S = lambda m, n, d: sprand(rng, m, n, d, dtype)
+    D = lambda m, n: np.asfortranarray(rng.standard_normal((m, n)).astype(dtype))
+    sp = lambda A: sb.MatrixOperator(sb.SparseMatrixCSR.from_dense(A))
+    k = 5
+    if case == "sparse_inner":
+        mats = [D(7, 9), S(40, 33, 0.2)]; ops = [sb.MatrixOperator(mats[0]), sp(mats[1])]
+    elif case == "sparse_outer":
+        mats = [S(37, 41, 0.15), D(12, 10)]; ops = [sp(mats[0]), sb.MatrixOperator(mats[1])]
+    elif case == "both":
+        mats = [S(30, 30, 0.5), S(150, 140, 0.02)]; ops = [sp(mats[0]), sp(mats[1])]      # > 32 nonzeros in a row of the outer factor? 0.5 * 30 = 15; inner rows sparse incl. empty ones
+        mats[0][3, :] = rng.standard_normal(30).astype(dtype); ops[0] = sp(mats[0])
+    elif case == "three":
+        mats = [S(6, 5, 0.6), np.asfortranarray(np.eye(4, dtype=dtype)), S(20, 25, 0.3)]
+        ops = [sp(mats[0]), sb.IdentityOperator(4), sp(mats[2])]
+    elif case == "adjoint":
+        A0, B0 = S(21, 17, 0.3), S(19, 26, 0.2)
+        mats = [np.asfortranarray(A0.T), np.asfortranarray(B0.T)]; ops = [sp(A0).adjoint(), sp(B0).adjoint()]
+    else:   # inner factor with R = k * (columns of the outer factor) = 64: the staged, warp-per-row gather
+        k = 8
+        mats = [D(5, 8), S(300, 260, 0.1)]; ops = [sb.MatrixOperator(mats[0]), sp(mats[1])]
+    ncols = int(np.prod([M.shape[1] for M in mats]))
+    nrows = int(np.prod([M.shape[0] for M in mats]))
+    v = np.asfortranarray(rng.standard_normal((ncols, k)).astype(dtype))
+    dv = sb.DeviceArray.from_numpy(v)
+    L = sb.cache_operator(sb.TensorProductOperator(*ops), dv)
+    assert L._native is not None, "sparse factors must take the native Kronecker path"
+    want = R.kron_apply([M.astype(np.float64) for M in mats], v.astype(np.float64))
+    w = sb.DeviceArray.full((nrows, k), float("nan"), dtype)
+    sb.mul_(w, L, dv)
+    assert np.isfinite(w.numpy()).all()
+    assert R.rel_err(w.numpy(), want) <= tol, f"{case}: {R.rel_err(w.numpy(), want):.3e}"
+    w0 = np.asfortranarray(rng.standard_normal((nrows, k)).astype(dtype))
+    dw = sb.DeviceArray.from_numpy(w0)
+    sb.mul_(dw, L, dv, 0.5, -2.0)
+    assert R.rel_err(dw.numpy(), 0.5 * want - 2.0 * w0.astype(np.float64)) <= tol
+    # a vector input (k = 1) through a fresh cache
+    v1 = np.asfortranarray(rng.standard_normal((ncols, 1)).astype(dtype))
+    L1 = sb.cache_operator(sb.TensorProductOperator(*ops), sb.DeviceArray.from_numpy(v1))
+    got1 = (L1 * sb.DeviceArray.from_numpy(v1)).numpy()
+    assert R.rel_err(got1, R.kron_apply([M.astype(np.float64) for M in mats], v1.astype(np.float64))) <= tol
+
+
 def test_sparse_from_scipy_and_large_batch(sb):
     sp = pytest.importorskip("scipy.sparse")
     rng = np.random.default_rng(5)

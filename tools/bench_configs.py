@@ -269,6 +269,27 @@ def csr(reps, N=65536, K=1024, per_row=16):
            4.0 * N * K * 8 + nnz * 12.0 * (K / 8), *t, "hbm", {"dense_bytes_only_gbs": 2.0 * N * K * 8 / (t[1] * 1e-3) / 1e9})
 
 
+def spkron(reps, N=4096, per_row=16, nd=128, K=64):
+    """A general sparse matrix as a Kronecker FACTOR (SCIMLOP_CSR): S (N x N, per_row nonzeros per row) next to a dense
+    nd x nd factor, Float64, K columns -- S as the outer factor (gather over contiguous mode rows of nd entries) and as
+    the inner one (the staged SpMM on nd * K columns).  Algorithmic bytes: input + output + ONE intermediate round trip."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    cols, _ = torch.sort(torch.randint(0, N, (N, per_row), device="cuda", generator=g, dtype=torch.int32), dim=1)
+    rowptr = torch.arange(0, N * per_row + 1, per_row, device="cuda", dtype=torch.int32)
+    vals = torch.rand(N * per_row, device="cuda", generator=g, dtype=torch.float64)
+    S = sb.MatrixOperator(sb.SparseMatrixCSR(sb.DeviceArray(rowptr, (N + 1,)), sb.DeviceArray(cols.reshape(-1).contiguous(), (N * per_row,)),
+                                             sb.DeviceArray(vals, (N * per_row,)), (N, N)))
+    B = sb.MatrixOperator(dev_rand((nd, nd), np.float64, 5))
+    n = N * nd
+    V = dev_rand((n, K), np.float64, 1)
+    W = sb.DeviceArray.empty((n, K), np.float64)
+    flops = (2.0 * N * per_row * nd + 2.0 * nd * nd * N) * K
+    for tag, ops in (("S (x) B (sparse outer factor)", (S, B)), ("B (x) S (sparse inner factor, staged)", (B, S))):
+        L = sb.cache_operator(sb.TensorProductOperator(*ops), V)
+        t = timeit(lambda: sb.mul_(W, L, V), reps)
+        report(f"spkron {tag}: S {N}^2 {per_row} nnz/row, B {nd}^2 dense, f64 k={K}", flops, 4.0 * n * K * 8, *t, "hbm")
+
+
 def c3bf16(reps, k=32768):
     """The opt-in BF16 single-pass mode of the fused two-mode kernel (SCIMLOP_PREC_BF16)."""
     F = [dev_rand((128, 128), np.float32, s) for s in (0, 10)]
@@ -297,7 +318,7 @@ def c2c(reps, k=128):
     report(f"c2 complex: 512x512(x)512x512 ComplexF64 k={k} 3arg", 4 * 1.374e11 * k / 256, 2 * 512.0 * 512 * k * 16, *t, "f64")
 
 
-ALL = {"c2c": c2c, "c3bf16": c3bf16, "c5fd": c5fd, "krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c3pair": c3pair, "csr": csr, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
+ALL = {"c2c": c2c, "c3bf16": c3bf16, "c5fd": c5fd, "krylov": krylov, "c1": c1, "c2": c2, "c3": c3, "c3pair": c3pair, "csr": csr, "spkron": spkron, "c4elt": c4elt, "c4dense": c4dense, "c5": c5}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
