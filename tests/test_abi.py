@@ -32,6 +32,37 @@ def test_header_declares_what_the_binding_binds(lib):
     assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES and include/scimlop_b200.h disagree"
 
 
+def header_constants():
+    """Every `SCIMLOP_X = n` enumerator and `#define SCIMLOP_X n` of the header."""
+    src = open(os.path.join(ROOT, "include", "scimlop_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"\b(SCIMLOP_[A-Z0-9_]+)\s*=\s*(0x[0-9a-fA-F]+|\d+)", src)}
+    out.update({m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+(SCIMLOP_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+|\d+)\b", src)})
+    return out
+
+
+def test_header_constants_match_the_binding():
+    """The numeric codes a binding hard-codes (dtypes, precisions, factor kinds, options, SCIMLOP_TRANS, the sparse
+    factor descriptor) are the header's: a renumbered enum would otherwise pass every symbol check and corrupt calls."""
+    from scimlop_b200 import _lib
+    hc = header_constants()
+    pairs = {"SCIMLOP_F64": _lib.F64, "SCIMLOP_F32": _lib.F32, "SCIMLOP_C64": _lib.C64, "SCIMLOP_C128": _lib.C128,
+             "SCIMLOP_PREC_DEFAULT": _lib.PREC_DEFAULT, "SCIMLOP_PREC_TF32X3": _lib.PREC_TF32X3, "SCIMLOP_PREC_TF32": _lib.PREC_TF32,
+             "SCIMLOP_PREC_FP32_EXACT": _lib.PREC_FP32_EXACT, "SCIMLOP_PREC_BF16": _lib.PREC_BF16,
+             "SCIMLOP_DENSE": _lib.DENSE, "SCIMLOP_IDENTITY": _lib.IDENTITY, "SCIMLOP_DIAG": _lib.DIAG, "SCIMLOP_BDIAG": _lib.BDIAG,
+             "SCIMLOP_NULL": _lib.NULL, "SCIMLOP_BANDED": _lib.BANDED, "SCIMLOP_CSR": _lib.CSR, "SCIMLOP_TRANS": _lib.TRANS,
+             "SCIMLOP_OPT_TAIL_SPLIT": _lib.OPT_TAIL_SPLIT, "SCIMLOP_OPT_PEER_PIPELINE": _lib.OPT_PEER_PIPELINE,
+             "SCIMLOP_OPT_PEER_CHUNKS": _lib.OPT_PEER_CHUNKS, "SCIMLOP_OPT_PEER_STAGE2_SMS": _lib.OPT_PEER_STAGE2_SMS,
+             "SCIMLOP_ERR_SINGULAR": _lib.ERR_SINGULAR, "SCIMLOP_ERR_UNSUPPORTED": _lib.ERR_UNSUPPORTED}
+    missing = [k for k in pairs if k not in hc]
+    assert not missing, f"not found in the header: {missing}"
+    wrong = {k: (hc[k], v) for k, v in pairs.items() if hc[k] != v}
+    assert not wrong, f"header vs binding: {wrong}"
+    # scimlop_csr_factor: three pointers + two int32 (include/scimlop_b200.h)
+    assert C.sizeof(_lib.CsrFactor) == 3 * C.sizeof(C.c_void_p) + 8
+    assert [f[0] for f in _lib.CsrFactor._fields_] == ["rowptr", "colidx", "values", "index_base", "reserved"]
+
+
 def test_library_exports_every_declared_symbol(lib):
     for name in header_functions():
         assert hasattr(lib, name), f"libscimlop_b200.so does not export {name}"
@@ -84,6 +115,17 @@ def test_workspace_queries_need_no_gpu(lib):
     assert lib.scimlop_kron_workspace_bytes(_lib.F64, 2, dims, kinds, 1, None) == _lib.ERR_NULL_POINTER
     bad = (C.c_int32 * 2)(_lib.BDIAG, _lib.DENSE)
     assert lib.scimlop_kron_workspace_bytes(_lib.F64, 2, dims, bad, 1, C.byref(nbytes)) == _lib.ERR_UNSUPPORTED
+    # a sparse innermost factor (rectangular 40 x 33) next to a dense 7 x 9 one, k = 5: the intermediate (40 * 9 * 5) plus
+    # the row-contiguous staging copy of the input (33 * 9 * 5); a sparse OUTER factor needs no staging
+    dimss = (C.c_int64 * 4)(7, 9, 40, 33)
+    assert lib.scimlop_kron_workspace_bytes(_lib.F64, 2, dimss, (C.c_int32 * 2)(_lib.DENSE, _lib.CSR), 5, C.byref(nbytes)) == 0
+    up = lambda b: (b + 255) // 256 * 256
+    assert nbytes.value == up(40 * 9 * 5 * 8) + up(33 * 9 * 5 * 8)
+    dimso = (C.c_int64 * 4)(40, 33, 7, 9)
+    assert lib.scimlop_kron_workspace_bytes(_lib.F64, 2, dimso, (C.c_int32 * 2)(_lib.CSR, _lib.DENSE), 5, C.byref(nbytes)) == 0
+    assert nbytes.value == up(7 * 33 * 5 * 8)
+    assert lib.scimlop_kron_workspace_bytes(_lib.F64, 2, dimss, (C.c_int32 * 2)(_lib.DENSE, _lib.CSR | _lib.TRANS), 5,
+                                            C.byref(nbytes)) == _lib.ERR_UNSUPPORTED
 
 
 def test_tree_workspace_query(lib):
