@@ -136,6 +136,33 @@ def test_sparse_matrix_csr_from_dense_layout():
         ops._as_device = orig
 
 
+def test_csr_transpose_builds_the_csc_form():
+    """operators._csr_transpose (the one-time conversion behind cached sparse adjoints and adjoint sparse Kronecker
+    factors): the CSR arrays of A^T, columns sorted within each row, empty rows / columns kept, duplicates summing the
+    same -- checked against the dense transpose on CPU tensors (the function is pure tensor bookkeeping, no launch)."""
+    from scimlop_b200 import operators as ops
+    rng = np.random.default_rng(12)
+    for m, n, density in ((7, 5, 0.4), (1, 9, 0.5), (6, 6, 0.0), (40, 33, 0.1)):
+        A = rng.standard_normal((m, n)) * (rng.random((m, n)) < density)
+        if m > 3:
+            A[2, :] = 0.0                       # an empty row -> an empty column of A^T
+        rows, cols = np.nonzero(A)
+        rowptr = np.zeros(m + 1, dtype=np.int32)
+        np.cumsum(np.bincount(rows, minlength=m), out=rowptr[1:])
+        wrap = lambda a: DeviceArray(torch.from_numpy(np.ascontiguousarray(a)), a.shape)
+        S = ops.SparseMatrixCSR(wrap(rowptr), wrap(cols.astype(np.int32)), wrap(A[rows, cols]), (m, n))
+        T = ops._csr_transpose(S)
+        assert T.shape == (n, m) and T.nnz == S.nnz
+        rp, ci, va = T.rowptr.t.numpy(), T.colidx.t.numpy(), T.values.t.numpy()
+        assert rp.dtype == np.int32 and ci.dtype == np.int32 and rp[0] == 0 and rp[-1] == S.nnz
+        back = np.zeros((n, m))
+        for r in range(n):
+            seg = ci[rp[r]:rp[r + 1]]
+            assert np.all(np.diff(seg) > 0), "column indices of a row must be strictly increasing"
+            back[r, seg] = va[rp[r]:rp[r + 1]]
+        assert np.array_equal(back, A.T)
+
+
 def test_factorisation_and_option_entry_points_are_declared_and_exported():
     """The round-2 entry points are in the header, the binding table and the library (no GPU needed to resolve them)."""
     from scimlop_b200 import _lib
