@@ -35,7 +35,7 @@ def main():
     demangle = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
     print(f"# cuobjdump -sass {os.path.relpath(LIB, ROOT)} : instructions per kernel (sm_100a)")
     for (name, cnt), dn in zip(kernels.items(), demangle):
-        short = re.sub(r"\(.*", "", dn)
+        short = re.sub(r"\(.*", "", dn.replace("(anonymous namespace)::", ""))
         hits = ", ".join(f"{k} x{v}" for k, v in sorted(cnt.items()) if k != "_total")
         print(f"{short}\n    total {cnt['_total']}; {hits or '-'}")
 
