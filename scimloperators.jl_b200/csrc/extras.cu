@@ -3,6 +3,8 @@
 // scimlop_kron_mul_host streams the columns of V through the device in chunks (H2D copy, the kron kernels
 // and the D2H copy of the previous chunks overlap on three streams): columns are independent units of the
 // operator (src/SciMLOperators.jl:177-198), so chunking is exact.
+#include <chrono>
+#include <cstdio>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -128,6 +130,18 @@ extern "C" int scimlop_kron_mul_host(scimlop_handle_t h, int dtype, int precisio
     for (auto it = ramp.rbegin(); it != ramp.rend(); ++it) sizes.push_back(*it);
   }
   const long long nchunks = (long long)sizes.size();
+#ifdef SCIMLOP_HOST_TRACE
+  // timing build (tools/e2e_trace.py): timed events around every transfer and compute of a chunk + host enqueue times
+  static cudaEvent_t tev[64][6];
+  static bool tev_ready = false;
+  if (!tev_ready) { for (auto& r : tev) for (auto& e : r) cudaEventCreate(&e); tev_ready = true; }
+  static double host_us[64];
+  const auto host_t0 = std::chrono::steady_clock::now();
+  cudaEventRecord(tev[63][0], h->s_h2d);
+#define HOST_TEV(ci, i, stream) do { if ((ci) < 63) cudaEventRecord(tev[ci][i], stream); } while (0)
+#else
+#define HOST_TEV(ci, i, stream) do { } while (0)
+#endif
   long long c0 = 0;
   for (long long ci = 0; ci < nchunks; c0 += sizes[ci], ci++) {
     const int slot = (int)(ci % SCIMLOP_HOST_SLOTS);
@@ -139,26 +153,48 @@ extern "C" int scimlop_kron_mul_host(scimlop_handle_t h, int dtype, int precisio
       SCIMLOP_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_comp[slot], 0));
       if (readw) SCIMLOP_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_d2h[slot], 0));
     }
+    HOST_TEV(ci, 0, h->s_h2d);
     SCIMLOP_CUDA(h, cudaMemcpyAsync(dV, static_cast<const char*>(V) + (size_t)c0 * cols * es, (size_t)nc * cols * es,
                                     cudaMemcpyHostToDevice, h->s_h2d));
+    HOST_TEV(ci, 1, h->s_h2d);
     if (readw)
       SCIMLOP_CUDA(h, cudaMemcpyAsync(dW, static_cast<const char*>(W) + (size_t)c0 * rows * es, (size_t)nc * rows * es,
                                       cudaMemcpyHostToDevice, h->s_h2d));
     SCIMLOP_CUDA(h, cudaEventRecord(h->ev_h2d[slot], h->s_h2d));
     SCIMLOP_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_h2d[slot], 0));
     if (ci >= SCIMLOP_HOST_SLOTS) SCIMLOP_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_d2h[slot], 0));
+    HOST_TEV(ci, 2, h->s_comp);
+#ifdef SCIMLOP_HOST_TRACE_NOCOMPUTE
+    int rc = SCIMLOP_OK;                            // timing experiment: the chunked copies alone (W is garbage)
+#else
     int rc = scimlop_kron_mul_impl(h, dtype, precision, nfactors, dfac, dims, lds, kinds, dV, cols, dW, rows, nc, alpha,
                                    beta, base + ws_off, ws_bytes, h->s_comp);
+#endif
     if (rc) return rc;
+    HOST_TEV(ci, 3, h->s_comp);
     SCIMLOP_CUDA(h, cudaEventRecord(h->ev_comp[slot], h->s_comp));
     SCIMLOP_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_comp[slot], 0));
+    HOST_TEV(ci, 4, h->s_d2h);
     SCIMLOP_CUDA(h, cudaMemcpyAsync(static_cast<char*>(W) + (size_t)c0 * rows * es, dW, (size_t)nc * rows * es,
                                     cudaMemcpyDeviceToHost, h->s_d2h));
     SCIMLOP_CUDA(h, cudaEventRecord(h->ev_d2h[slot], h->s_d2h));
+    HOST_TEV(ci, 5, h->s_d2h);
+#ifdef SCIMLOP_HOST_TRACE
+    if (ci < 63) host_us[ci] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
+#endif
   }
   SCIMLOP_CUDA(h, cudaStreamSynchronize(h->s_d2h));
   SCIMLOP_CUDA(h, cudaStreamSynchronize(h->s_comp));
   SCIMLOP_CUDA(h, cudaStreamSynchronize(h->s_h2d));
+#ifdef SCIMLOP_HOST_TRACE
+  fprintf(stderr, "e2e_trace: %lld chunks; times in us from the first enqueue on the H2D stream\n", nchunks);
+  for (long long ci = 0; ci < nchunks && ci < 63; ci++) {
+    float t[6];
+    for (int i = 0; i < 6; i++) cudaEventElapsedTime(&t[i], tev[63][0], tev[ci][i]);
+    fprintf(stderr, "e2e_trace chunk %2lld (%3lld cols): H2D %8.1f..%8.1f | compute %8.1f..%8.1f | D2H %8.1f..%8.1f | host enqueued at %8.1f\n", ci,
+            sizes[ci], t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3, host_us[ci]);
+  }
+#endif
   return SCIMLOP_OK;
 }
 
