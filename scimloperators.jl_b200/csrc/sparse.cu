@@ -143,21 +143,25 @@ __global__ void csr_gather_t_kernel(long long m, long long k, const int* __restr
 // value) pairs of a row are loaded 32 at a time, one per lane, and broadcast by shuffle, so the gathers of a row do not
 // depend on each other: 8 in flight per warp.  A CTA owns 32 rows x 32 * VEC columns; the tile goes through shared
 // memory so that W (column-major) is written with 256 contiguous bytes per column.
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(256) csr_gather_rows_kernel(long long m, long long k, const int* __restrict__ rowptr,
                                                               const int* __restrict__ colidx, const T* __restrict__ vals, int base,
                                                               const T* __restrict__ Vt, T* W, long long ldw, T alpha, T beta) {
-  constexpr int VEC = 16 / (int)sizeof(T);       // columns per lane: one 16-byte load
-  constexpr int CB = 32 * VEC;                   // columns per CTA
+  // NV 16-byte loads per lane and nonzero (NV = 2: a 1 KB run per nonzero, half the index / shuffle / address work per
+  // byte: ncu showed the NV = 1 form 56 % issue-bound with the broadcast shuffle as its hottest line)
+  constexpr int VEC = 16 / (int)sizeof(T);       // columns per 16-byte load
+  constexpr int CB = 32 * VEC * NV;              // columns per CTA
   __shared__ T tile[32][CB + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = (long long)blockIdx.x * 32;
   for (long long c0 = (long long)blockIdx.y * CB; c0 < k; c0 += (long long)gridDim.y * CB) {   // k % CB == 0 on this path
     for (int rr = 0; rr < 4; rr++) {
       const long long r = row0 + warp + 8 * rr;
-      T acc[VEC];
+      T acc[NV][VEC];
 #pragma unroll
-      for (int e = 0; e < VEC; e++) acc[e] = T(0);
+      for (int v = 0; v < NV; v++)
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc[v][e] = T(0);
       if (r < m) {
         const int j0 = rowptr[r] - base, j1 = rowptr[r + 1] - base;
         const T* vbase = Vt + c0 + lane * VEC;
@@ -165,27 +169,37 @@ __global__ void __launch_bounds__(256) csr_gather_rows_kernel(long long m, long 
           const int cnt = min(32, j1 - jb);
           const int myc = lane < cnt ? colidx[jb + lane] - base : 0;
           const T mya = lane < cnt ? vals[jb + lane] : T(0);
-          for (int q = 0; q < cnt; q += 8) {
-            float4 x[8];
-            T a[8];
+          constexpr int UQ = 8 / NV;             // nonzeros in flight: 8 loads per lane either way
+          for (int q = 0; q < cnt; q += UQ) {
+            float4 x[UQ][NV];
+            T a[UQ];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
+            for (int u = 0; u < UQ; u++) {
               const int cu = __shfl_sync(0xffffffffu, myc, (q + u) & 31);
               a[u] = __shfl_sync(0xffffffffu, mya, (q + u) & 31);
-              if (q + u < cnt) x[u] = __ldg(reinterpret_cast<const float4*>(vbase + (long long)cu * k));
-              else { x[u] = make_float4(0.f, 0.f, 0.f, 0.f); a[u] = T(0); }
+              const T* xp = vbase + (long long)cu * k;
+#pragma unroll
+              for (int v = 0; v < NV; v++) {
+                if (q + u < cnt) x[u][v] = __ldg(reinterpret_cast<const float4*>(xp + v * 32 * VEC));
+                else x[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              if (q + u >= cnt) a[u] = T(0);
             }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-              const T* xv = reinterpret_cast<const T*>(&x[u]);
+            for (int u = 0; u < UQ; u++)
 #pragma unroll
-              for (int e = 0; e < VEC; e++) acc[e] += a[u] * xv[e];
-            }
+              for (int v = 0; v < NV; v++) {
+                const T* xv = reinterpret_cast<const T*>(&x[u][v]);
+#pragma unroll
+                for (int e = 0; e < VEC; e++) acc[v][e] += a[u] * xv[e];
+              }
           }
         }
       }
 #pragma unroll
-      for (int e = 0; e < VEC; e++) tile[warp + 8 * rr][lane * VEC + e] = acc[e];
+      for (int v = 0; v < NV; v++)
+#pragma unroll
+        for (int e = 0; e < VEC; e++) tile[warp + 8 * rr][(v * 32 + lane) * VEC + e] = acc[v][e];
     }
     __syncthreads();
     const long long r = row0 + lane;
@@ -245,10 +259,15 @@ int csr_mul_t(scimlop_context* h, bool trans, long long m, long long n, long lon
       transpose_kernel<T><<<dim3((unsigned)((n + 31) / 32), (unsigned)((k + 31) / 32)), dim3(32, 8), 0, st>>>(n, k, V, ldv, Vt);
       bool by_rows = false;
       if constexpr (!is_cplx<T>::value) {
-        if (k % (512 / (long long)sizeof(T)) == 0) {   // a warp per row, 512-byte coalesced gathers
-          const unsigned gr = (unsigned)((m + 31) / 32);
-          const unsigned gy = (unsigned)std::min<long long>(k / (512 / (long long)sizeof(T)), 65535);
-          csr_gather_rows_kernel<T><<<dim3(gr, gy), 256, 0, st>>>(m, k, rowptr, colidx, vals, base, Vt, W, ldw, alpha, beta);
+        const long long run = 512 / (long long)sizeof(T);   // columns of one 512-byte coalesced warp load
+        const unsigned gr = (unsigned)((m + 31) / 32);
+        if (k % (2 * run) == 0) {          // a warp per row, two 512-byte gathers per nonzero
+          csr_gather_rows_kernel<T, 2><<<dim3(gr, (unsigned)std::min<long long>(k / (2 * run), 65535)), 256, 0, st>>>(
+              m, k, rowptr, colidx, vals, base, Vt, W, ldw, alpha, beta);
+          by_rows = true;
+        } else if (k % run == 0) {
+          csr_gather_rows_kernel<T, 1><<<dim3(gr, (unsigned)std::min<long long>(k / run, 65535)), 256, 0, st>>>(
+              m, k, rowptr, colidx, vals, base, Vt, W, ldw, alpha, beta);
           by_rows = true;
         }
       }
