@@ -117,8 +117,8 @@ int scimlop_last_error(scimlop_handle_t h, char* buf, size_t len);
  * SCIMLOP_OPT_PEER_PIPELINE (0 = off, 1 = automatic (default), 2 = always): scimlop_kron_mul_peers / _mc with two dense
  * Float64 factors may run as a pipeline of column chunks (2 unless SCIMLOP_OPT_PEER_CHUNKS says otherwise) on two streams -- the last stage of a chunk, which is
  * bound by NVLink ingress when many ranks gather, on a share of the SMs, the first stage of the next chunk on the rest.
- * Automatic takes it where the estimated gather time is at least twice the last stage's arithmetic (8 ranks on config
- * 2, not 2 ranks).  Same numbers bit for bit as the unchunked schedule.
+ * Automatic takes it where the estimated gather time is at least 1.25x the last stage's arithmetic (4 and 8 ranks on
+ * config 2, not 2 ranks).  Same numbers bit for bit as the unchunked schedule.
  * SCIMLOP_OPT_PEER_CHUNKS (0 = chosen by the library; 2, 4 or 8) and SCIMLOP_OPT_PEER_STAGE2_SMS (0 = chosen; else the
  * number of SMs the last stage of a non-final chunk runs on) fix the shape of that pipeline: tuning knobs, measured by
  * tools/bench_peer_pipeline.py. */

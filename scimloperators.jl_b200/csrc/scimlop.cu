@@ -1493,7 +1493,8 @@ static int kron_mul_impl_peers(scimlop_context* h, int dtype, int precision, int
     const int npeers = peers.n > 0 ? peers.n : std::max(0, h->nranks - 1);
     ingress_us = (double)npeers * (double)pl.rows * (double)k * 8.0 / 6.0e5;
     stage2_us = 2.0 * (double)dims[1] * (double)pl.rows * (double)k / 35.0e6;
-    if (h->peer_pipeline == 1 && ingress_us < 2.0 * stage2_us) nch = 0;
+    // measured (profiles/r02_peer_pipeline_sweep*.jsonl): ratio 3.2 (8 ranks) -13 %, 1.37 (4 ranks) -9 %, 0.45 (2 ranks) +21 %
+    if (h->peer_pipeline == 1 && ingress_us < 1.25 * stage2_us) nch = 0;
   }
   if (nch) {
     if (int rc0 = scimlop_ensure_side_stream(h)) { h->tail_split = saved_tail_split; return rc0; }
