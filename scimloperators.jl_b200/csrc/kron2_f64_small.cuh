@@ -43,6 +43,27 @@ inline int pitch_for(int) { return PITCH; }
 inline size_t smem_bytes(int, int n2, int, int) { return (size_t)PITCH * ((n2 + 7) / 8 * 8) * 8; }
 
 // NT column strips of stage 1 / MT row strips of stage 2 as a compile-time count: fully unrolled, no predicates
+// Work split over the 16 warps.  A warp owns one 8-wide strip of the stage's "own" dimension and `cnt` strips of the
+// other one, starting at `first`.  With 13 or 14 own strips (factor extents 97..112: config 1) one strip per warp
+// would leave warps 13..15 idle AND give scheduler sub-partition 0 (warps 0, 4, 8, 12) four strips against three for
+// the others -- the stage then runs at the pace of that sub-partition.  The strips beyond the twelfth are therefore cut
+// along the other dimension among warps 12..15 (13 strips of 13: 4 + 3 + 3 + 3), which puts 43 / 42 / 42 / 42 tiles
+// on the four sub-partitions instead of 52 / 39 / 39 / 39.
+__device__ __forceinline__ void assign_strips(int warp, int own, int other, int& strip, int& first, int& cnt) {
+  strip = -1; first = 0; cnt = 0;
+  const int tail = own - 12;
+  if (tail == 1 || tail == 2) {
+    if (warp < 12) { strip = warp; cnt = other; return; }
+    const int j = warp - 12, per = 4 / tail;          // warps per tail strip: 4 or 2
+    const int part = j % per;
+    strip = 12 + j / per;
+    first = (other * part) / per;
+    cnt = (other * (part + 1)) / per - first;
+  } else if (warp < own) {
+    strip = warp; cnt = other;
+  }
+}
+
 template <int NT>
 __device__ __forceinline__ void stage1_strip(double (&acc)[MAXT][2], const double* __restrict__ F, long long rs, long long cs, int m1,
                                              int n1, int mt, int g, int t, int K1, const double* sm) {
@@ -95,7 +116,25 @@ __global__ void __launch_bounds__(THREADS, 1) kron2_f64_small_kernel(const Param
     // ---- X_s -> shared memory (pitch px, zero padding) ----
     __syncthreads();                                        // the previous slab's stage 2 has finished reading Y
     const double* Vs = p.V + s * (long long)p.n1 * p.n2;
-    {
+    if (p.n1 % 2 == 0 && (reinterpret_cast<uintptr_t>(p.V) & 15u) == 0) {
+      // every column of the slab is a run of n1 / 2 16-byte pieces: all of a thread's cp.async are in flight at once (one
+      // memory latency for the whole slab instead of one per round of the register path below); the padding the DMMA
+      // k-steps and strips read (rows n1 .. 4 K1 - 1, columns n2 .. n2p - 1) is zeroed by ordinary stores
+      const int half = p.n1 >> 1, pieces = half * p.n2;
+      const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm);
+      for (int i = threadIdx.x; i < pieces; i += THREADS) {
+        const int b = i / half, c = (i - b * half) * 2;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)(c + PITCH * b) * 8u),
+                     "l"(Vs + c + (long long)p.n1 * b)
+                     : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      const int rpad = 4 * K1 - p.n1;                       // 0 .. 3 rows below the slab
+      for (int i = threadIdx.x; i < rpad * p.n2; i += THREADS) sm[p.n1 + i % rpad + PITCH * (i / rpad)] = 0.0;
+      const int cpad = n2p - p.n2, rows = 4 * K1;           // whole padded columns
+      for (int i = threadIdx.x; i < cpad * rows; i += THREADS) sm[i % rows + PITCH * (p.n2 + i / rows)] = 0.0;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
       // eight independent loads in flight per thread (a rolled loop pays one L2 / HBM latency per element)
       const int total = PITCH * n2p;
       for (int i0 = threadIdx.x; i0 < total; i0 += 8 * THREADS) {
@@ -119,19 +158,20 @@ __global__ void __launch_bounds__(THREADS, 1) kron2_f64_small_kernel(const Param
     double acc[MAXT][2];
 #pragma unroll
     for (int j = 0; j < MAXT; j++) acc[j][0] = acc[j][1] = 0.0;
-    const int mtA = warp;
-    const bool hasA = mtA < MT1;
+    int mtA, ntA0, ntAc;
+    assign_strips(warp, MT1, NT1, mtA, ntA0, ntAc);
+    const bool hasA = ntAc > 0;
     if (hasA) {
-#define K2S_S1(NT) stage1_strip<NT>(acc, p.F1, p.f1_rs, p.f1_cs, p.m1, p.n1, mtA, g, t, K1, sm)
-      K2S_DISPATCH(NT1, K2S_S1)
+#define K2S_S1(NT) stage1_strip<NT>(acc, p.F1, p.f1_rs, p.f1_cs, p.m1, p.n1, mtA, g, t, K1, sm + PITCH * 8 * ntA0)
+      K2S_DISPATCH(ntAc, K2S_S1)
 #undef K2S_S1
     }
     __syncthreads();                                        // every warp is done reading X: Y may overwrite it
     if (hasA) {
 #pragma unroll
       for (int nt = 0; nt < MAXT; nt++) {
-        if (nt < NT1) {
-          double* y = sm + (8 * mtA + g) + PITCH * (8 * nt + 2 * t);
+        if (nt < ntAc) {
+          double* y = sm + (8 * mtA + g) + PITCH * (8 * (ntA0 + nt) + 2 * t);
           y[0] = acc[nt][0];
           y[PITCH] = acc[nt][1];
         }
@@ -143,18 +183,19 @@ __global__ void __launch_bounds__(THREADS, 1) kron2_f64_small_kernel(const Param
     double z[MAXT][2];
 #pragma unroll
     for (int i = 0; i < MAXT; i++) z[i][0] = z[i][1] = 0.0;
-    const int ntA = warp;
-    const bool hasNA = ntA < NT2;
+    int ntA, mtB0, mtBc;
+    assign_strips(warp, NT2, MT2, ntA, mtB0, mtBc);
+    const bool hasNA = mtBc > 0;
     if (hasNA) {
-#define K2S_S2(MT) stage2_strip<MT>(z, p.F2, p.f2_rs, p.f2_cs, p.m2, p.n2, ntA, g, t, K2, sm)
-      K2S_DISPATCH(MT2, K2S_S2)
+#define K2S_S2(MT) stage2_strip<MT>(z, p.F2, p.f2_rs, p.f2_cs, p.m2, p.n2, ntA, g, t, K2, sm + 8 * mtB0)
+      K2S_DISPATCH(mtBc, K2S_S2)
 #undef K2S_S2
       // ---- epilogue: Z_s = alpha * Z + beta * Z_s (beta == 0: never read) ----
       double* Ws = p.W + s * (long long)p.m1 * p.m2;
 #pragma unroll
       for (int mt = 0; mt < MAXT; mt++) {
-        if (mt < MT2) {
-          const int r = 8 * mt + g;
+        if (mt < mtBc) {
+          const int r = 8 * (mtB0 + mt) + g;
 #pragma unroll
           for (int e = 0; e < 2; e++) {
             const int c = 8 * ntA + 2 * t + e;

@@ -1316,7 +1316,11 @@ def test_copy_shares_no_storage_and_stays_cached(sb):
 
 
 @pytest.mark.parametrize("case", [((100, 100), (100, 100), 100), ((9, 13), (17, 11), 5), ((128, 128), (128, 128), 3),
-                                  ((8, 8), (8, 8), 1), ((33, 64), (120, 50), 250), ((100, 37), (64, 128), 7)])
+                                  ((8, 8), (8, 8), 1), ((33, 64), (120, 50), 250), ((100, 37), (64, 128), 7),
+                                  # 13 and 14 strips of 8 in either dimension: the strips beyond the twelfth are cut among
+                                  # warps 12..15 (kron2_f64_small.cuh, assign_strips); 15 strips are not
+                                  ((97, 104), (104, 97), 9), ((112, 105), (109, 112), 4), ((105, 100), (100, 113), 6),
+                                  ((120, 99), (101, 120), 3)])
 def test_small_float64_kron_is_one_fused_launch(sb, case):
     """configs[0]-like problems (two dense Float64 factors <= 128, fewer than two waves of slabs): ONE launch of
     kron2_f64_small_kernel with the intermediate in shared memory; 3-arg (NaN-prefilled W), 5-arg, adjoint factors."""
