@@ -308,11 +308,13 @@ int csr_mul_t(scimlop_context* h, bool trans, long long m, long long n, long lon
 // (L x n x R) -> (L x m x R) views.  The L entries of one (j, r) are contiguous, which is exactly the row-contiguous form
 // the staged gather wants: no copy.  One warp per (i, r), lanes across l (coalesced runs of 32 elements, 4 per lane in
 // flight), the (index, value) pairs of row i loaded 32 at a time and broadcast by shuffle.
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256) csr_mode_kernel(long long L, long long m, long long n, long long R, const int* __restrict__ rowptr,
                                                        const int* __restrict__ colidx, const T* __restrict__ vals, int base,
                                                        const T* __restrict__ X, T* Y, T alpha, T beta) {
-  constexpr int U = 4;
+  // VEC elements per load: 16 bytes when L and the pointers allow (half the instructions per byte), else 1
+  constexpr int U = 4 / (VEC > 1 ? 2 : 1);        // loads in flight per lane and nonzero: 4 scalar or 2 vector
+  constexpr int SPAN = 32 * VEC * U;              // elements of a mode row one pass of the warp covers
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = (long long)blockIdx.x * 8 + warp;
   if (i >= m) return;
@@ -320,10 +322,12 @@ __global__ void __launch_bounds__(256) csr_mode_kernel(long long L, long long m,
   for (long long r = blockIdx.y; r < R; r += gridDim.y) {
     const T* Xr = X + L * n * r;
     T* Yr = Y + L * (i + m * r);
-    for (long long l0 = 0; l0 < L; l0 += 32 * U) {
-      T acc[U];
+    for (long long l0 = 0; l0 < L; l0 += SPAN) {
+      T acc[U][VEC];
 #pragma unroll
-      for (int u = 0; u < U; u++) acc[u] = T(0);
+      for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc[u][e] = T(0);
       for (int jb = j0; jb < j1; jb += 32) {
         const int cnt = min(32, j1 - jb);
         const int myc = lane < cnt ? colidx[jb + lane] - base : 0;
@@ -331,19 +335,32 @@ __global__ void __launch_bounds__(256) csr_mode_kernel(long long L, long long m,
         for (int q = 0; q < cnt; q++) {
           const long long cq = __shfl_sync(0xffffffffu, myc, q);
           const T aq = __shfl_sync(0xffffffffu, mya, q);
-          const T* xp = Xr + L * cq + l0 + lane;
+          const T* xp = Xr + L * cq + l0 + lane * VEC;
 #pragma unroll
-          for (int u = 0; u < U; u++)
-            if (l0 + lane + 32 * u < L) acc[u] += aq * __ldg(xp + 32 * u);
+          for (int u = 0; u < U; u++) {
+            if (l0 + (lane + 32 * u) * VEC < L) {
+              if constexpr (VEC > 1) {
+                const float4 x4 = __ldg(reinterpret_cast<const float4*>(xp + 32 * VEC * u));
+                const T* xv = reinterpret_cast<const T*>(&x4);
+#pragma unroll
+                for (int e = 0; e < VEC; e++) acc[u][e] += aq * xv[e];
+              } else {
+                acc[u][0] += aq * __ldg(xp + 32 * u);
+              }
+            }
+          }
         }
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const long long l = l0 + lane + 32 * u;
+        const long long l = l0 + (lane + 32 * u) * VEC;
         if (l < L) {
-          T v = alpha * acc[u];
-          if (beta != T(0)) v += beta * Yr[l];
-          Yr[l] = v;
+#pragma unroll
+          for (int e = 0; e < VEC; e++) {
+            T v = alpha * acc[u][e];
+            if (beta != T(0)) v += beta * Yr[l + e];
+            Yr[l + e] = v;
+          }
         }
       }
     }
@@ -360,8 +377,13 @@ int csr_mode_t(scimlop_context* h, const scimlop_csr_factor* d, long long L, lon
     return csr_mul_t<T>(h, false, m, n, R, d->rowptr, d->colidx, static_cast<const T*>(d->values), d->index_base, X, n, Y, m, alpha, beta,
                         stage, stage_bytes, st);
   const unsigned gx = (unsigned)((m + 7) / 8), gy = (unsigned)std::min<long long>(R, 65535);
-  csr_mode_kernel<T><<<dim3(gx, gy), 256, 0, st>>>(L, m, n, R, d->rowptr, d->colidx, static_cast<const T*>(d->values), d->index_base, X, Y,
-                                                   alpha, beta);
+  constexpr int VMAX = 16 / (int)sizeof(T);
+  if (L % VMAX == 0 && (reinterpret_cast<uintptr_t>(X) & 15u) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0)
+    csr_mode_kernel<T, VMAX><<<dim3(gx, gy), 256, 0, st>>>(L, m, n, R, d->rowptr, d->colidx, static_cast<const T*>(d->values), d->index_base,
+                                                           X, Y, alpha, beta);
+  else
+    csr_mode_kernel<T, 1><<<dim3(gx, gy), 256, 0, st>>>(L, m, n, R, d->rowptr, d->colidx, static_cast<const T*>(d->values), d->index_base, X,
+                                                        Y, alpha, beta);
   h->launches++;
   SCIMLOP_CUDA(h, cudaGetLastError());
   return SCIMLOP_OK;
