@@ -121,8 +121,12 @@ int scimlop_last_error(scimlop_handle_t h, char* buf, size_t len);
  * config 2, not 2 ranks).  Same numbers bit for bit as the unchunked schedule.
  * SCIMLOP_OPT_PEER_CHUNKS (0 = chosen by the library; 2, 4 or 8) and SCIMLOP_OPT_PEER_STAGE2_SMS (0 = chosen; else the
  * number of SMs the last stage of a non-final chunk runs on) fix the shape of that pipeline: tuning knobs, measured by
- * tools/bench_peer_pipeline.py. */
-enum { SCIMLOP_OPT_TAIL_SPLIT = 1, SCIMLOP_OPT_PEER_PIPELINE = 2, SCIMLOP_OPT_PEER_CHUNKS = 3, SCIMLOP_OPT_PEER_STAGE2_SMS = 4 };
+ * tools/bench_peer_pipeline.py.
+ * SCIMLOP_OPT_MODE_PIPELINE (0 = off (default), 2 .. 8 = column chunks): scimlop_kron_mul on three small dense Float32
+ * factors runs its two passes (fused two-mode pass, third-mode pass) as a pipeline over that many column chunks on two
+ * streams with an SM share each.  Same numbers as the unchunked call. */
+enum { SCIMLOP_OPT_TAIL_SPLIT = 1, SCIMLOP_OPT_PEER_PIPELINE = 2, SCIMLOP_OPT_PEER_CHUNKS = 3, SCIMLOP_OPT_PEER_STAGE2_SMS = 4,
+       SCIMLOP_OPT_MODE_PIPELINE = 5 };
 int scimlop_set_option(scimlop_handle_t h, int option, int value);
 /* Number of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
 int scimlop_launch_count(scimlop_handle_t h, int64_t* count);

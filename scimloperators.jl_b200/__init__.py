@@ -5,7 +5,7 @@ The product is `libscimlop_b200.so` (csrc/, C ABI in include/scimlop_b200.h); th
 mirror of the reference's operator interface over that ABI.  The directory name contains a dot, so import it
 through the `scimlop_b200` shim at the repo root (`import scimlop_b200 as sb`)."""
 from . import _lib
-from ._lib import Handle, ScimlopError, handle, load, OPT_TAIL_SPLIT, OPT_PEER_PIPELINE, OPT_PEER_CHUNKS, OPT_PEER_STAGE2_SMS
+from ._lib import Handle, ScimlopError, handle, load, OPT_TAIL_SPLIT, OPT_PEER_PIPELINE, OPT_PEER_CHUNKS, OPT_PEER_STAGE2_SMS, OPT_MODE_PIPELINE
 from .array import DeviceArray
 from .operators import (AbstractSciMLOperator, AddedOperator, BandedMatrix, BatchedDiagonalOperator, ComposedOperator,
                         DiagonalOperator, IdentityOperator, MatrixOperator, NullOperator, ScalarOperator,

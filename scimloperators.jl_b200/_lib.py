@@ -21,6 +21,7 @@ OPT_TAIL_SPLIT = 1
 OPT_PEER_PIPELINE = 2
 OPT_PEER_CHUNKS = 3
 OPT_PEER_STAGE2_SMS = 4
+OPT_MODE_PIPELINE = 5
 
 
 class Factor(C.Structure):  # scimlop_factor_t

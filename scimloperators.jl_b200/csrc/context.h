@@ -34,6 +34,8 @@ struct scimlop_context {
   int sm_reserve;  // SMs left free by the persistent GEMM kernels (for concurrently running NCCL kernels)
   int peer_pipeline;  // scimlop_set_option(SCIMLOP_OPT_PEER_PIPELINE): column-chunk pipeline of the fused all-gather entries (default 1)
   int grid_limit;     // != 0: persistent GEMM kernels launch at most this many CTAs (set per stage by that pipeline)
+  int mode_pipeline;   // SCIMLOP_OPT_MODE_PIPELINE: column chunks of the two-pass Float32 three-factor pipeline (0 = off)
+  cudaStream_t split_stream;  // != nullptr: kron_mul_t continues on this stream after its first (fused two-mode) pass
   int peer_chunks, peer_stage2_sms;  // SCIMLOP_OPT_PEER_CHUNKS / _STAGE2_SMS: explicit pipeline shape (0 = chosen by the library)
   int no_small_splitk; // != 0: a GEMM with fewer tiles than SMs still runs the plain persistent kernel (chunks of that pipeline keep the summation order of the whole problem)
   int stage_limit[2]; // grid limits of the first / the last stage of a kron_mul call (0 = none)

@@ -486,7 +486,8 @@ int launch_tf32(scimlop_context* c, bool x_mn, bool f_k, long long rows, int m, 
   else rc = make_map_f32(c, &tmD, D, m, rows, 1, d_rs * 4, 0, 32, 32, false, /*swizzle=*/true);
   if (!p.tma_store) tmD = tmX;   // unused by the kernel
   else if (rc) return rc;
-  const int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
+  int grid = (int)std::min<long long>(p.total_tiles, std::max(1, c->sm_count - c->sm_reserve));
+  if (c->grid_limit > 0) grid = std::min(grid, c->grid_limit);
   if (x_mn && f_k) tf32::gemm_tf32x3_kernel<true, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmF, tmD, p);
   else if (x_mn) tf32::gemm_tf32x3_kernel<true, false><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmF, tmD, p);
   else if (f_k) tf32::gemm_tf32x3_kernel<false, true><<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(tmX, tmF, tmF, tmD, p);
@@ -528,7 +529,8 @@ int launch_kron2_f16(scimlop_context* c, int m1, int n1, int m2, int n2, long lo
 #ifdef SCIMLOP_KF16_TRACE
   p.trace = g_kf16_trace;
 #endif
-  const int grid = (int)std::min<long long>(slabs, std::max(1, c->sm_count - c->sm_reserve));
+  int grid = (int)std::min<long long>(slabs, std::max(1, c->sm_count - c->sm_reserve));
+  if (c->grid_limit > 0) grid = std::min(grid, c->grid_limit);
   if (bf16 && beta != 0.f) kf16::kron2_f16_kernel<true, true><<<grid, kf16::THREADS, kf16::SMEM_BYTES, st>>>(tmX, tmW, p);
   else if (bf16) kf16::kron2_f16_kernel<false, true><<<grid, kf16::THREADS, kf16::SMEM_BYTES, st>>>(tmX, tmW, p);
   else if (beta != 0.f) kf16::kron2_f16_kernel<true><<<grid, kf16::THREADS, kf16::SMEM_BYTES, st>>>(tmX, tmW, p);
@@ -889,6 +891,7 @@ extern "C" int scimlop_last_error(scimlop_handle_t h, char* buf, size_t len) {
 extern "C" int scimlop_set_option(scimlop_handle_t h, int option, int value) {
   if (!scimlop_valid(h)) return SCIMLOP_ERR_BAD_HANDLE;
   if (option == SCIMLOP_OPT_TAIL_SPLIT) { h->tail_split = value != 0; return SCIMLOP_OK; }
+  if (option == SCIMLOP_OPT_MODE_PIPELINE) { h->mode_pipeline = (value >= 2 && value <= 8) ? value : 0; return SCIMLOP_OK; }
   if (option == SCIMLOP_OPT_PEER_CHUNKS) { h->peer_chunks = (value == 2 || value == 4 || value == 8) ? value : 0; return SCIMLOP_OK; }
   if (option == SCIMLOP_OPT_PEER_STAGE2_SMS) { h->peer_stage2_sms = value > 0 ? value : 0; return SCIMLOP_OK; }
   if (option == SCIMLOP_OPT_PEER_PIPELINE) { h->peer_pipeline = value < 0 ? 0 : (value > 2 ? 2 : value); return SCIMLOP_OK; }
@@ -1215,6 +1218,13 @@ int kron_mul_t(scimlop_context* c, int precision, int nfactors, const void* cons
                                 static_cast<const float*>(factors[p - 1]), lds[p - 1], (kinds[p - 1] & SCIMLOP_TRANS) != 0, cur,
                                 out2, last2 ? alpha : 1.f, last2 ? beta : 0.f, precision == SCIMLOP_PREC_BF16, st);
           if (rc) return rc;
+          if (c->split_stream && c->stage_event && !last2) {
+            // two-pass pipeline (kron_mul_impl_peers): the remaining pass of this column chunk runs on the side stream,
+            // beside the fused pass of the next chunk on the caller's
+            SCIMLOP_CUDA(c, cudaEventRecord(c->stage_event, st));
+            SCIMLOP_CUDA(c, cudaStreamWaitEvent(c->split_stream, c->stage_event, 0));
+            st = c->split_stream;
+          }
           done++;
           cur = out2;
           flip ^= 1;
@@ -1557,6 +1567,47 @@ static int kron_mul_impl_peers(scimlop_context* h, int dtype, int precision, int
     SCIMLOP_CUDA(h, cudaEventRecord(h->ev_pipe[9], h->s_side));
     SCIMLOP_CUDA(h, cudaStreamWaitEvent(st, h->ev_pipe[9], 0));
     return SCIMLOP_OK;
+  }
+  // Two-pass pipeline for three small dense Float32 factors (config 3): the fused two-mode pass is bound by the shared-
+  // memory pipe, the third mode's pass by HBM.  Over column chunks, pass 2 of chunk i runs on the side stream on a share
+  // of the SMs beside pass 1 of chunk i + 1 on the rest.  Columns are independent: same numbers as the unchunked call.
+  if (!peers.active() && h->mode_pipeline >= 2 && dtype == SCIMLOP_F32 && nfactors == 3 && k % h->mode_pipeline == 0 &&
+      (kinds[0] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE && (kinds[1] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE &&
+      (kinds[2] & ~SCIMLOP_TRANS) == SCIMLOP_DENSE) {
+    const int nch = h->mode_pipeline;
+    const long long kc = k / nch;
+    KronPlan plc;
+    if (int rc0 = kron_plan(h, nfactors, dims, kinds, kc, &plc)) { h->tail_split = saved_tail_split; return rc0; }
+    const size_t bufc = align_up((size_t)plc.max_inter * 4, 256);
+    const long long slabs_c = kc * dims[1];      // slabs of one chunk's fused pass (inner two modes)
+    if (kron2_f16_eligible(precision, dims[4], dims[5], dims[2], dims[3], slabs_c, (const float*)V, (const float*)workspace) &&
+        workspace && workspace_bytes >= 2 * bufc * (size_t)nch && (pl.rows * kc) % 4 == 0 && (pl.cols * kc) % 4 == 0) {
+      if (int rc0 = scimlop_ensure_side_stream(h)) { h->tail_split = saved_tail_split; return rc0; }
+      const int nsm = std::max(1, h->sm_count - h->sm_reserve);
+      const int g2 = h->peer_stage2_sms > 0 ? std::min(h->peer_stage2_sms, nsm - 1) : (nsm * 2) / 5, g1 = nsm - g2;
+      const float a = scalar_or<float>(alpha, 1.f), b = scalar_or<float>(beta, 0.f);
+      SCIMLOP_CUDA(h, cudaEventRecord(h->ev_pipe[8], st));
+      SCIMLOP_CUDA(h, cudaStreamWaitEvent(h->s_side, h->ev_pipe[8], 0));
+      int rc = SCIMLOP_OK;
+      for (int i = 0; i < nch && rc == SCIMLOP_OK; i++) {
+        h->split_stream = h->s_side;
+        h->stage_event = h->ev_pipe[i];
+        h->stage_limit[0] = i == 0 ? 0 : g1;
+        h->stage_limit[1] = i == nch - 1 ? 0 : g2;
+        rc = kron_mul_t<float>(h, precision, nfactors, factors, dims, lds, kinds, static_cast<const float*>(V) + (size_t)i * kc * pl.cols,
+                               static_cast<float*>(W) + (size_t)i * kc * pl.rows, kc, a, b,
+                               static_cast<char*>(workspace) + (size_t)i * 2 * bufc, 2 * bufc, plc, st, NO_PEERS);
+      }
+      h->split_stream = nullptr;
+      h->stage_event = nullptr;
+      h->stage_limit[0] = h->stage_limit[1] = 0;
+      h->grid_limit = 0;
+      h->tail_split = saved_tail_split;
+      if (rc) return rc;
+      SCIMLOP_CUDA(h, cudaEventRecord(h->ev_pipe[9], h->s_side));
+      SCIMLOP_CUDA(h, cudaStreamWaitEvent(st, h->ev_pipe[9], 0));
+      return SCIMLOP_OK;
+    }
   }
   int rc;
   if (dtype == SCIMLOP_F64)

@@ -53,6 +53,7 @@ def test_header_constants_match_the_binding():
              "SCIMLOP_NULL": _lib.NULL, "SCIMLOP_BANDED": _lib.BANDED, "SCIMLOP_CSR": _lib.CSR, "SCIMLOP_TRANS": _lib.TRANS,
              "SCIMLOP_OPT_TAIL_SPLIT": _lib.OPT_TAIL_SPLIT, "SCIMLOP_OPT_PEER_PIPELINE": _lib.OPT_PEER_PIPELINE,
              "SCIMLOP_OPT_PEER_CHUNKS": _lib.OPT_PEER_CHUNKS, "SCIMLOP_OPT_PEER_STAGE2_SMS": _lib.OPT_PEER_STAGE2_SMS,
+             "SCIMLOP_OPT_MODE_PIPELINE": _lib.OPT_MODE_PIPELINE,
              "SCIMLOP_ERR_SINGULAR": _lib.ERR_SINGULAR, "SCIMLOP_ERR_UNSUPPORTED": _lib.ERR_UNSUPPORTED}
     missing = [k for k in pairs if k not in hc]
     assert not missing, f"not found in the header: {missing}"

@@ -173,6 +173,59 @@ def test_three_factors_fused_pair_then_outer_mode(sb):
     assert e <= TOL, f"5-arg rel err {e:.3e}"
 
 
+@pytest.mark.parametrize("chunks", [2, 4])
+def test_three_factor_two_pass_pipeline_is_bit_identical(sb, chunks):
+    """SCIMLOP_OPT_MODE_PIPELINE (include/scimlop_b200.h): the fused two-mode pass and the third-mode pass of three small
+    dense Float32 factors run as a pipeline over column chunks on two streams with an SM share each.  Columns are
+    independent, so the result must equal the unchunked call bit for bit (3- and 5-argument forms, repeated), stay
+    within 1e-5 of the Float64 oracle, and shapes the pipeline does not take (a column count the chunk count does not
+    divide; 64-wide factors below the fused kernel's size) must run unchanged."""
+    import torch
+    rng = np.random.default_rng(17 + chunks)
+    F = [nrm(rng, 128, 128) for _ in range(3)]
+    k = 8
+    v = nrm(rng, 128 ** 3, k)
+    dv = dev(sb, v)
+    L = sb.cache_operator(sb.TensorProductOperator(*F), dv)
+    h = sb.handle(0)
+    w_ref = sb.DeviceArray.full((128 ** 3, k), float("nan"), np.float32)
+    sb.mul_(w_ref, L, dv)
+    w0 = nrm(rng, 128 ** 3, k)
+    w5_ref = dev(sb, w0)
+    sb.mul_(w5_ref, L, dv, 0.5, -0.25)
+    h.set_option(sb.OPT_MODE_PIPELINE, chunks)
+    try:
+        for rep in range(3):
+            w = sb.DeviceArray.full((128 ** 3, k), float("nan"), np.float32)
+            n0 = h.launch_count()
+            sb.mul_(w, L, dv)
+            assert h.launch_count() - n0 == 2 * chunks, "one fused launch + one third-mode launch per chunk"
+            torch.cuda.synchronize()
+            assert torch.equal(w.t, w_ref.t), f"{chunks} chunks, rep {rep}: differs from the unchunked call"
+            w5 = dev(sb, w0)
+            sb.mul_(w5, L, dv, 0.5, -0.25)
+            assert torch.equal(w5.t, w5_ref.t)
+        # not taken: k = 7 is not divisible; the call must still be the plain two launches and the same numbers
+        v7 = np.asfortranarray(v[:, :7])
+        dv7 = dev(sb, v7)
+        L7 = sb.cache_operator(sb.TensorProductOperator(*F), dv7)
+        w7 = sb.DeviceArray.full((128 ** 3, 7), float("nan"), np.float32)
+        n0 = h.launch_count()
+        sb.mul_(w7, L7, dv7)
+        assert h.launch_count() - n0 == 2
+        assert torch.equal(w7.t, w_ref.t[: 128 ** 3 * 7])
+        # not taken: 64-wide factors
+        G = [nrm(rng, 64, 64) for _ in range(3)]
+        vg = nrm(rng, 64 ** 3, 8)
+        got = apply(sb, G, vg)
+        assert R.rel_err(got, R.kron_apply([g.astype(np.float64) for g in G], vg.astype(np.float64))) <= TOL
+    finally:
+        h.set_option(sb.OPT_MODE_PIPELINE, 0)
+    for j in (0, k - 1):
+        want = R.kron_apply([f.astype(np.float64) for f in F], v[:, j:j + 1].astype(np.float64))
+        assert R.rel_err(w_ref.cols(j, j + 1).numpy(), want) <= TOL
+
+
 def test_same_sign_data_accumulation(sb):
     """All-positive factors and data: the tensor core's truncating FP32 accumulation is at its worst."""
     rng = np.random.default_rng(8)
