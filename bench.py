@@ -50,7 +50,7 @@ FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool: tools/peaks.cu -> prof
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm_dmma_kernel on this workload, from the
 # `ncu --set full` capture summarised in profiles/r01_ncu_dmma_v6_summary.txt (539.0 + 492.1 MB stage 1,
 # 539.2 + 495.2 MB stage 2): the algorithmic 537 MB in + 537 MB out, i.e. no re-reads.
-NCU_DRAM_BYTES_PER_LAUNCH = 0.5 * ((539.041536 + 492.103936) + (539.223808 + 495.223552)) * 1e6
+NCU_DRAM_BYTES_PER_LAUNCH = 0.5 * ((540.313856 + 493.162752) + (539.751424 + 495.018496)) * 1e6   # profiles/r02_ncu_dmma_summary.txt
 REF_COLS = KCOLS                 # --impl reference / cpu_baseline (stdlib variant): the full batch, as benchmarks/tensor.jl:17-24 times it
 LV_SAMPLE_COLS = 32              # cpu_baseline, LoopVectorization variant (single-thread nest): columns timed, unscaled
 C5_N = 4096                      # configs[4]: Dxx, Dyy 4096 x 4096 dense Float64
@@ -584,7 +584,7 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                      "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, profiles/r01_ncu_dmma_v6_summary.txt); "
+                     "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, profiles/r02_ncu_dmma_summary.txt; round 1: r01_ncu_dmma_v6_summary.txt); "
                                      "algorithmic bytes per launch = 1.076e9",
                      "kernel": "scimlop::dmma::gemm_dmma_kernel (2 launches per step: stage 1 B*U, stage 2 batched C1_j*A^T)",
                      "peak_source": "FP64 DMMA.8x8x4 issue-rate microbenchmark on this pool (profiles/r01_peaks_microbench.json); "
